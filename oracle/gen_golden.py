@@ -1,0 +1,123 @@
+"""Generate golden vectors by running the UNMODIFIED reference functions.  TEST INFRASTRUCTURE.
+
+Run in the build container only (needs /root/reference; the GPU box does not have it):
+
+    python oracle/gen_golden.py            # writes tests/golden/*.npz
+
+The reference modules are imported from where they lie; the packages they import but do not
+use on this path (tensorflow, dxchange, h5py, matplotlib, autograd, pyfftw) are replaced by
+stubs that never touch the arithmetic.  Each case stores the seed /
+recipe of its inputs plus the reference output, so the fixtures stay small.
+"""
+import os
+import sys
+import subprocess
+import json
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get('BDOF_REFERENCE', '/root/reference')
+OUT = os.path.join(ROOT, 'tests', 'golden')
+
+# -------------------------------------------------------------------------------------------
+# child scripts: the two reference directories both define `util`, so each runs in its own
+# interpreter.
+# -------------------------------------------------------------------------------------------
+
+CHILD_FFT = r'''
+import sys, json
+import numpy as np
+from unittest.mock import MagicMock
+for m in ("tensorflow", "dxchange", "h5py", "matplotlib", "matplotlib.pyplot"):
+    sys.modules[m] = MagicMock()
+sys.path.insert(0, sys.argv[1] + "/tensorflow_recon")
+import npfuncs, util
+out = sys.argv[2]
+sys.path.insert(0, sys.argv[3]); sys.path.insert(0, sys.argv[3] + "/oracle")
+import multislice_oracle as mo
+
+res = {}
+# a-2: get_kernel on several grids (square, non-square, anisotropic voxels)
+for name, args in {
+    "k64": (1.0, 0.248, [1., 1., 1.], [64, 64, 64]),
+    "k48x80": (1.0, 1240. / 800, [0.67, 0.67, 0.67], [48, 80, 8]),
+    "kaniso": (2.5, 0.248, [1.0, 2.0, 2.5], [32, 40, 4]),
+    "kfree": (1e-4 * 1e7, 0.248, [1., 1., 1.], [64, 64, 64]),
+}.items():
+    res["kernel_" + name] = util.get_kernel(*args)
+    res["kernel_" + name + "_args"] = np.array(json.dumps(args))
+
+def run(tag, gd, gb, pr, pi, energy, psize, free):
+    psi = npfuncs.multislice_propagate_batch_numpy(gd, gb, pr, pi, energy, psize,
+                                                   free_prop_cm=free, obj_batch_shape=gd.shape)
+    res["psi_" + tag] = psi
+
+# a-1 case A: the reference's own 64^3 delta fixture, beta = 0.1 delta, plane wave
+gdf = np.load(sys.argv[1] + "/tensorflow_recon/grid_delta.npy")
+vals, lab = np.unique(gdf, return_inverse=True)      # 3 distinct values: store as labels (12 KB)
+res["fixture64_delta_values"] = vals
+res["fixture64_delta_labels"] = lab.reshape(gdf.shape).astype(np.uint8)
+run("fixture64", gdf[None], 0.1 * gdf[None], np.ones([64, 64]), np.zeros([64, 64]), 5000, 1e-7, None)
+# case B: random phantom, batch 2, non-square 48x80x12, gaussian probe, 800 eV, 0.67 nm
+gd, gb = mo.random_phantom((2, 48, 80, 12), seed=11, delta_scale=3e-4, beta_scale=3e-5)
+pr, pi = mo.gaussian_probe((48, 80), 9., 9., 0.5)
+run("rand48x80", gd.astype(np.float64), gb.astype(np.float64), pr, pi, 800, 0.67e-7, None)
+# case C: far field
+run("rand48x80_inf", gd.astype(np.float64), gb.astype(np.float64), pr, pi, 800, 0.67e-7, 'inf')
+# case D: finite free-space distance
+gd, gb = mo.random_phantom((1, 64, 64, 8), seed=12, delta_scale=1e-5, beta_scale=1e-6)
+run("rand64_free", gd.astype(np.float64), gb.astype(np.float64), np.ones([64, 64]), np.zeros([64, 64]), 5000, 1e-7, 1e-4)
+# case E: single slice
+gd, gb = mo.random_phantom((3, 32, 32, 1), seed=13, delta_scale=1e-3, beta_scale=1e-4)
+run("rand32_1slice", gd.astype(np.float64), gb.astype(np.float64), np.ones([32, 32]), np.zeros([32, 32]), 5000, 1e-7, None)
+# case F: zone plate 128^2 x 20 (scaled config 1)
+gd, gb = mo.zone_plate_phantom(n=128, n_slice=20, n_zones=8)
+run("zp128", gd, gb, np.ones([128, 128]), np.zeros([128, 128]), 5000, 1e-7, None)
+np.savez_compressed(out, **res)
+'''
+
+CHILD_CNN = r'''
+import sys, types
+import numpy as np
+import scipy.signal
+from unittest.mock import MagicMock
+for m in ("tensorflow", "dxchange", "h5py", "matplotlib", "matplotlib.pyplot", "tqdm"):
+    sys.modules[m] = MagicMock()
+import tqdm
+tqdm.trange = range
+ag = types.ModuleType("autograd"); ag.numpy = np; ag.grad = lambda *a, **k: None
+agn = np
+ags = types.ModuleType("autograd.scipy"); agss = types.ModuleType("autograd.scipy.signal")
+def convolve(A, B, axes=None, mode='valid'):
+    assert axes == ([1, 2], [0, 1]) and mode == 'valid'
+    return np.stack([scipy.signal.convolve(a, B, mode='valid', method='direct') for a in A])
+agss.convolve = convolve; ags.signal = agss; ag.scipy = ags
+sys.modules.update({"autograd": ag, "autograd.numpy": np, "autograd.numpy.random": np.random,
+                    "autograd.scipy": ags, "autograd.scipy.signal": agss})
+sys.path.insert(0, sys.argv[1] + "/cnn_propagator")
+import propagation
+out = sys.argv[2]
+sys.path.insert(0, sys.argv[3] + "/oracle")
+import multislice_oracle as mo
+res = {}
+gd, gb = mo.random_phantom((2, 32, 40, 6), seed=21, delta_scale=1e-4, beta_scale=1e-5)
+for ks in (5, 17):
+    for free in (None, 'inf'):
+        psi = propagation.multislice_propagate_cnn(gd.astype(np.float64), gb.astype(np.float64),
+                                                   np.ones([32, 40]), np.zeros([32, 40]), 5000,
+                                                   [1e-7] * 3, kernel_size=ks, free_prop_cm=free)
+        res["cnn_ks%d_%s" % (ks, free)] = psi
+np.savez_compressed(out, **res)
+'''
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for name, code in (('ref_fft.npz', CHILD_FFT), ('ref_cnn.npz', CHILD_CNN)):
+        path = os.path.join(OUT, name)
+        subprocess.run([sys.executable, '-c', code, REF, path, ROOT], check=True)
+        print('wrote', path, os.path.getsize(path), 'bytes')
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,381 @@
+"""CPU oracle for the Fresnel multislice hot path -- TEST INFRASTRUCTURE ONLY.
+
+This file is a complex128 NumPy restatement of the reference algorithm
+(mdw771/beyond_dof).  It exists to check the CUDA path; it is never the thing
+shipped or measured.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.
+
+Parity pinning: the reference repository has no tests and no golden vectors
+(SURVEY.md section 4).  The restatement is pinned instead against outputs of
+the reference's own functions executed unmodified in the build container
+(``oracle/gen_golden.py`` -> ``tests/golden/*.npz``) for the forward paths
+(a-1 NumPy multislice, a-2 get_kernel, a-5 real-space "cnn" multislice).
+The TF-graph variant (a-3) and every gradient (a-8) cannot be executed here
+(TensorFlow 1.x / HIPS autograd are absent): for those the restatement is
+pinned against torch.autograd (complex128, CPU) and finite differences, i.e.
+"parity unpinned by the reference itself" for a-3 / a-8.
+
+Reference citations (paths relative to the reference checkout):
+  tensorflow_recon/npfuncs.py:16-63      multislice_propagate_batch_numpy
+  tensorflow_recon/util.py:156-185       gen_mesh, get_kernel
+  tensorflow_recon/util.py:432-508       multislice_propagate_batch (TF graph)
+  cnn_propagator/propagation.py:18-133   multislice_propagate_cnn
+  cnn_propagator/fullfield.py:93-121     calculate_loss (full field)
+  tensorflow_recon/ptychography.py:37-97 rotate_and_project (ptychography)
+"""
+import numpy as np
+from numpy.fft import fft2, ifft2, fftshift, ifftshift
+
+# tensorflow_recon/constants.py:90 and cnn_propagator/util.py:20
+PI_TF = 3.14159265359
+PI_CNN = 3.1415927
+
+
+def gen_mesh(max_, shape):
+    """tensorflow_recon/util.py:156-162 -- endpoint-inclusive frequency grid."""
+    yy = np.linspace(-max_[0], max_[0], shape[0])
+    xx = np.linspace(-max_[1], max_[1], shape[1])
+    return np.meshgrid(xx, yy)
+
+
+def get_kernel(dist_nm, lmbda_nm, voxel_nm, grid_shape, pi=PI_TF):
+    """Centred Fresnel transfer function H (tensorflow_recon/util.py:165-185).
+
+    H[v, u] = exp(i k d) exp(-i pi lambda d (u^2 + v^2)); u runs along axis 1
+    over linspace(+-1/(2 voxel[0])), v along axis 0 over +-1/(2 voxel[1]).
+    """
+    k = 2 * pi / lmbda_nm
+    u_max = 1. / (2. * voxel_nm[0])
+    v_max = 1. / (2. * voxel_nm[1])
+    u, v = gen_mesh([v_max, u_max], grid_shape[0:2])
+    return np.exp(1j * k * dist_nm) * np.exp(-1j * pi * lmbda_nm * dist_nm * (u ** 2 + v ** 2))
+
+
+def kernel_factors(dist_nm, lmbda_nm, voxel_nm, grid_shape, pi=PI_TF):
+    """Separable form of get_kernel: H = phase0 * outer(hy, hx).
+
+    Returns (phase0, hy[ny], hx[nx]) in complex128, all centred (DC in the middle).
+    """
+    k = 2 * pi / lmbda_nm
+    u_max = 1. / (2. * voxel_nm[0])
+    v_max = 1. / (2. * voxel_nm[1])
+    yy = np.linspace(-v_max, v_max, grid_shape[0])
+    xx = np.linspace(-u_max, u_max, grid_shape[1])
+    hy = np.exp(-1j * pi * lmbda_nm * dist_nm * yy ** 2)
+    hx = np.exp(-1j * pi * lmbda_nm * dist_nm * xx ** 2)
+    return np.exp(1j * k * dist_nm), hy, hx
+
+
+def _propagate(wavefront, h):
+    """One transfer-function step exactly as written in the reference:
+    ifft2(ifftshift(fftshift(fft2(psi)) * H))   (npfuncs.py:41)."""
+    return ifft2(ifftshift(fftshift(fft2(wavefront), axes=[1, 2]) * h, axes=[1, 2]))
+
+
+def _free_prop(wavefront, free_prop_cm, lmbda_nm, voxel_nm, grid_shape, pi):
+    """Free-space step after the object (npfuncs.py:43-61, util.py:490-507).
+    'inf' -> far field; float -> one more TF-kernel step (the TF/IR switch is
+    forced to 'TF' in the batch functions)."""
+    if free_prop_cm is None:
+        return wavefront
+    if isinstance(free_prop_cm, str):
+        if free_prop_cm != 'inf':
+            raise ValueError('free_prop_cm must be None, "inf" or a float')
+        return fftshift(fft2(wavefront), axes=[1, 2])
+    dist_nm = free_prop_cm * 1e7
+    h = get_kernel(dist_nm, lmbda_nm, voxel_nm, grid_shape, pi=pi)
+    return _propagate(wavefront, h)
+
+
+def multislice_forward(grid_delta_batch, grid_beta_batch, probe_real, probe_imag, energy_ev,
+                       psize_cm, free_prop_cm=None, obj_batch_shape=None, h=None,
+                       propagate_last=False, pi=PI_TF, return_slices=False):
+    """Forward multislice, [B,Y,X,Z] inputs, complex128 arithmetic.
+
+    propagate_last=False : NumPy semantics (npfuncs.py:35-41, last slice only modulates)
+    propagate_last=True  : TF semantics (util.py:464-488, every slice propagates,
+                           except the n_slice == 1 special case which only modulates)
+    return_slices: also return psi entering every slice (for the adjoint).
+    """
+    grid_delta_batch = np.asarray(grid_delta_batch)
+    grid_beta_batch = np.asarray(grid_beta_batch)
+    if obj_batch_shape is None:
+        obj_batch_shape = grid_delta_batch.shape
+    batch = obj_batch_shape[0]
+    grid_shape = list(obj_batch_shape[1:])
+    voxel_nm = np.array([psize_cm] * 3) * 1.e7
+    # npfuncs.py:21-22: the probe is accumulated into a complex64 array (so it is rounded to
+    # fp32 once); the first multiply with the float64-derived c promotes everything to complex128.
+    wavefront = np.zeros([batch, obj_batch_shape[1], obj_batch_shape[2]], dtype=np.complex64)
+    wavefront += (np.asarray(probe_real) + 1j * np.asarray(probe_imag))
+    wavefront = wavefront.astype(np.complex128)
+    lmbda_nm = 1240. / energy_ev
+    n_slice = obj_batch_shape[-1]
+    delta_nm = voxel_nm[-1]
+    if h is None:
+        h = get_kernel(delta_nm, lmbda_nm, voxel_nm, grid_shape, pi=pi)
+    k = 2. * pi * delta_nm / lmbda_nm
+    slices = []
+    for i in range(n_slice):
+        if return_slices:
+            slices.append(wavefront)
+        c = np.exp(1j * k * grid_delta_batch[:, :, :, i]) * np.exp(-k * grid_beta_batch[:, :, :, i])
+        wavefront = wavefront * c
+        if propagate_last:
+            do_prop = n_slice > 1
+        else:
+            do_prop = i < n_slice - 1
+        if do_prop:
+            wavefront = _propagate(wavefront, h)
+    wavefront = _free_prop(wavefront, free_prop_cm, lmbda_nm, voxel_nm, grid_shape, pi)
+    if return_slices:
+        return wavefront, slices
+    return wavefront
+
+
+def multislice_propagate_batch_numpy(grid_delta_batch, grid_beta_batch, probe_real, probe_imag,
+                                     energy_ev, psize_cm, free_prop_cm=None, obj_batch_shape=None):
+    """Restatement of tensorflow_recon/npfuncs.py:16-63 (NumPy semantics)."""
+    return multislice_forward(grid_delta_batch, grid_beta_batch, probe_real, probe_imag, energy_ev,
+                              psize_cm, free_prop_cm, obj_batch_shape, propagate_last=False, pi=PI_TF)
+
+
+def multislice_propagate_batch(grid_delta_batch, grid_beta_batch, probe_real, probe_imag, energy_ev,
+                               psize_cm, h=None, free_prop_cm=None, obj_batch_shape=None):
+    """Restatement of tensorflow_recon/util.py:432-508, type='plane' (TF semantics),
+    evaluated in complex128 instead of TF's complex64."""
+    return multislice_forward(grid_delta_batch, grid_beta_batch, probe_real, probe_imag, energy_ev,
+                              psize_cm, free_prop_cm, obj_batch_shape, h=h, propagate_last=True, pi=PI_TF)
+
+
+# ---------------------------------------------------------------------------------------------
+# loss head and hand adjoint.  No adjoint exists in the reference: it
+# differentiates with TF / autograd.  Pinned against torch.autograd in tests/test_oracle.py.
+# ---------------------------------------------------------------------------------------------
+
+def loss_mag(wavefront, target_mag):
+    """loss = mean((|psi| - |y|)^2)  (fullfield.py:115, cnn fullfield.py:106, ptychography.py:79).
+    Returns (loss, G) with G = dL/dRe + i dL/dIm."""
+    mag = np.abs(wavefront)
+    diff = mag - target_mag
+    loss = np.mean(diff ** 2)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        g = (2.0 / diff.size) * diff * np.where(mag > 0, wavefront / mag, 0)
+    return loss, g
+
+
+def multislice_adjoint(grid_delta_batch, grid_beta_batch, slices, grad_exit, energy_ev, psize_cm,
+                       free_prop_cm=None, h=None, propagate_last=False, pi=PI_TF):
+    """Back-propagate G = dL/dRe(psi_out) + i dL/dIm(psi_out) through the chain.
+
+    Returns (grad_delta, grad_beta, grad_probe) with grad_* in [B,Y,X,Z] and
+    grad_probe = G at the entrance plane summed over the batch (the probe is shared).
+    """
+    grid_delta_batch = np.asarray(grid_delta_batch)
+    grid_beta_batch = np.asarray(grid_beta_batch)
+    batch, ny, nx, n_slice = grid_delta_batch.shape
+    voxel_nm = np.array([psize_cm] * 3) * 1.e7
+    lmbda_nm = 1240. / energy_ev
+    delta_nm = voxel_nm[-1]
+    grid_shape = [ny, nx, n_slice]
+    if h is None:
+        h = get_kernel(delta_nm, lmbda_nm, voxel_nm, grid_shape, pi=pi)
+    k = 2. * pi * delta_nm / lmbda_nm
+    g = np.asarray(grad_exit, dtype=np.complex128)
+
+    def adj_propagate(g, hh):
+        # adjoint of ifft2(ifftshift(fftshift(fft2(.)) * H)) = same chain with conj(H)
+        return ifft2(ifftshift(fftshift(fft2(g), axes=[1, 2]) * np.conj(hh), axes=[1, 2]))
+
+    if free_prop_cm is not None:
+        if isinstance(free_prop_cm, str):
+            # psi_out = fftshift(fft2 psi): adjoint = N * ifft2(ifftshift(G))
+            g = ifft2(ifftshift(g, axes=[1, 2])) * (ny * nx)
+        else:
+            hf = get_kernel(free_prop_cm * 1e7, lmbda_nm, voxel_nm, grid_shape, pi=pi)
+            g = adj_propagate(g, hf)
+    gd = np.zeros(grid_delta_batch.shape, dtype=np.float64)
+    gb = np.zeros(grid_delta_batch.shape, dtype=np.float64)
+    for i in range(n_slice - 1, -1, -1):
+        if propagate_last:
+            do_prop = n_slice > 1
+        else:
+            do_prop = i < n_slice - 1
+        if do_prop:
+            g = adj_propagate(g, h)
+        t = np.exp(1j * k * grid_delta_batch[:, :, :, i]) * np.exp(-k * grid_beta_batch[:, :, :, i])
+        u = slices[i] * t
+        w = np.conj(g) * u
+        gd[:, :, :, i] = -k * w.imag
+        gb[:, :, :, i] = -k * w.real
+        g = np.conj(t) * g
+    return gd, gb, g.sum(axis=0)
+
+
+def loss_and_grad(grid_delta_batch, grid_beta_batch, probe_real, probe_imag, energy_ev, psize_cm,
+                  target_mag, free_prop_cm=None, h=None, propagate_last=False, pi=PI_TF):
+    """loss = mean((|psi_out| - target)^2) and its gradient w.r.t. delta, beta."""
+    psi, slices = multislice_forward(grid_delta_batch, grid_beta_batch, probe_real, probe_imag,
+                                     energy_ev, psize_cm, free_prop_cm, None, h=h,
+                                     propagate_last=propagate_last, pi=pi, return_slices=True)
+    loss, g = loss_mag(psi, target_mag)
+    gd, gb, gp = multislice_adjoint(grid_delta_batch, grid_beta_batch, slices, g, energy_ev, psize_cm,
+                                    free_prop_cm, h=h, propagate_last=propagate_last, pi=pi)
+    return loss, gd, gb, psi
+
+
+# ---------------------------------------------------------------------------------------------
+# real-space ("cnn") multislice, cnn_propagator/propagation.py:18-133
+# ---------------------------------------------------------------------------------------------
+
+def cnn_kernel(energy_ev, psize_cm, grid_shape_yxz, kernel_size):
+    """Truncated real-space propagator (propagation.py:35-44): IFFT of H built on the
+    (grid_shape - 1) grid, centred, cropped to kernel_size^2."""
+    lmbda_nm = 1240. / energy_ev
+    voxel_nm = np.array(psize_cm) * 1.e7
+    delta_nm = voxel_nm[-1]
+    gs = np.array(grid_shape_yxz) - 1
+    kern = get_kernel(delta_nm, lmbda_nm, voxel_nm, gs, pi=PI_CNN)
+    kern = fftshift(ifft2(ifftshift(kern)))
+    mid = ((np.array(kern.shape) - 1) / 2).astype('int')
+    half = int((kernel_size - 1) / 2)
+    return kern[mid[0] - half:mid[0] + half + 1, mid[1] - half:mid[1] + half + 1]
+
+
+def multislice_propagate_cnn(grid_delta, grid_beta, probe_real, probe_imag, energy_ev, psize_cm,
+                             kernel_size=17, free_prop_cm=None):
+    """Restatement of cnn_propagator/propagation.py:18-133 (FFT-free direct convolution is
+    replaced by an equivalent explicit shift-and-add; arithmetic order differs only in the
+    summation order of the kernel taps)."""
+    assert kernel_size % 2 == 1, 'kernel_size must be an odd number.'
+    grid_delta = np.asarray(grid_delta)
+    grid_beta = np.asarray(grid_beta)
+    n_batch, shape_y, shape_x, n_slice = grid_delta.shape
+    lmbda_nm = 1240. / energy_ev
+    voxel_nm = np.array(psize_cm) * 1.e7
+    delta_nm = voxel_nm[-1]
+    k = 2. * np.pi * delta_nm / lmbda_nm        # propagation.py:25 uses full-precision pi here
+    grid_shape = np.array(grid_delta.shape[1:])
+    kern = cnn_kernel(energy_ev, psize_cm, grid_shape, kernel_size)
+    pad = (kernel_size - 1) // 2
+    probe = np.tile(np.asarray(probe_real) + 1j * np.asarray(probe_imag), [n_batch, 1, 1]).astype(np.complex128)
+    edge_val = 1.0
+    initial = probe[0, 0, 0]
+    ksum = kern.sum()
+    for i in range(n_slice):
+        c = np.exp(1j * k * grid_delta[:, :, :, i] - k * grid_beta[:, :, :, i])
+        probe = probe * c
+        padded = np.pad(probe, [[0, 0], [pad, pad], [pad, pad]], mode='constant', constant_values=edge_val)
+        out = np.zeros_like(probe)
+        # true convolution, 'valid': out[y,x] = sum_{a,b} kern[a,b] * padded[y + 2p - a, x + 2p - b]
+        for a in range(kernel_size):
+            for b in range(kernel_size):
+                out += kern[a, b] * padded[:, 2 * pad - a:2 * pad - a + shape_y, 2 * pad - b:2 * pad - b + shape_x]
+        probe = out
+        edge_val = ksum * edge_val
+    final = probe[0, 0, 0]
+    probe = probe * (initial / final)
+    if free_prop_cm is not None:
+        if isinstance(free_prop_cm, str):
+            probe = fftshift(fft2(probe), axes=[1, 2])
+        else:
+            hf = get_kernel(free_prop_cm * 1e7, lmbda_nm, voxel_nm, grid_shape, pi=PI_CNN)
+            probe = _propagate(probe, hf)
+    return probe
+
+
+# ---------------------------------------------------------------------------------------------
+# model heads (rotation = identity, theta = 0: rotation is a "next" row)
+# ---------------------------------------------------------------------------------------------
+
+def fullfield_loss(obj_delta, obj_beta, prj_batch, probe_real, probe_imag, energy_ev, psize_cm,
+                   free_prop_cm=None, minibatch_size=1, propagate_last=True):
+    """tensorflow_recon/fullfield.py:92-116 with theta = 0 for every batch element."""
+    d = np.broadcast_to(obj_delta, (minibatch_size,) + obj_delta.shape)
+    b = np.broadcast_to(obj_beta, (minibatch_size,) + obj_beta.shape)
+    psi = multislice_forward(d, b, probe_real, probe_imag, energy_ev, psize_cm, free_prop_cm,
+                             propagate_last=propagate_last)
+    return np.mean((np.abs(psi) - np.abs(prj_batch)) ** 2), psi
+
+
+def gaussian_probe(probe_size, mag_sigma, phase_sigma, phase_max):
+    """tensorflow_recon/ptychography.py:271-281 -- r measured from (size-1)/2."""
+    py = np.arange(probe_size[0]) - (probe_size[0] - 1.) / 2
+    px = np.arange(probe_size[1]) - (probe_size[1] - 1.) / 2
+    pxx, pyy = np.meshgrid(px, py)
+    mag = np.exp(-(pxx ** 2 + pyy ** 2) / (2 * mag_sigma ** 2))
+    phase = phase_max * np.exp(-(pxx ** 2 + pyy ** 2) / (2 * phase_sigma ** 2))
+    return mag * np.cos(phase), mag * np.sin(phase)
+
+
+def ptycho_windows(obj_yxz, probe_pos, probe_size):
+    """Zero-pad and cut one probe_size window per scan position
+    (tensorflow_recon/ptychography.py:45-76; note :59 uses probe_size_half[0] for the x pad)."""
+    probe_pos = np.asarray(probe_pos).astype(int)
+    half = (np.array(probe_size) / 2).astype('int')
+    obj_size = obj_yxz.shape
+    pad_arr = np.array([[0, 0], [0, 0]])
+    o = obj_yxz
+    if probe_pos[:, 0].min() - half[0] < 0:
+        pl = half[0] - probe_pos[:, 0].min()
+        o = np.pad(o, ((pl, 0), (0, 0), (0, 0)), mode='constant'); pad_arr[0, 0] = pl
+    if probe_pos[:, 0].max() + half[0] > obj_size[0]:
+        pl = probe_pos[:, 0].max() + half[0] - obj_size[0]
+        o = np.pad(o, ((0, pl), (0, 0), (0, 0)), mode='constant'); pad_arr[0, 1] = pl
+    if probe_pos[:, 1].min() - half[1] < 0:
+        pl = half[1] - probe_pos[:, 1].min()
+        o = np.pad(o, ((0, 0), (pl, 0), (0, 0)), mode='constant'); pad_arr[1, 0] = pl
+    if probe_pos[:, 1].max() + half[1] > obj_size[1]:
+        pl = probe_pos[:, 1].max() + half[0] - obj_size[1]
+        o = np.pad(o, ((0, 0), (0, pl), (0, 0)), mode='constant'); pad_arr[1, 1] = pl
+    wins = []
+    for pos in probe_pos:
+        y0 = int(pos[0]) + pad_arr[0, 0] - half[0]
+        x0 = int(pos[1]) + pad_arr[1, 0] - half[1]
+        wins.append(o[y0:y0 + probe_size[0], x0:x0 + probe_size[1], :])
+    return np.stack(wins), pad_arr
+
+
+def ptycho_loss(obj_delta, obj_beta, probe_pos, prj, probe_real, probe_imag, probe_size, energy_ev,
+                psize_cm, n_dp_batch=20, scale_by_npos=True):
+    """tensorflow_recon/ptychography.py:37-97 at theta = 0 (TF semantics, far field)."""
+    wd, _ = ptycho_windows(obj_delta, probe_pos, probe_size)
+    wb, _ = ptycho_windows(obj_beta, probe_pos, probe_size)
+    outs = []
+    for s in range(0, len(probe_pos), n_dp_batch):
+        outs.append(multislice_forward(wd[s:s + n_dp_batch], wb[s:s + n_dp_batch], probe_real, probe_imag,
+                                       energy_ev, psize_cm, 'inf', propagate_last=True))
+    ex = np.concatenate(outs, 0)
+    loss = np.mean((np.abs(ex) - np.abs(prj)) ** 2)
+    if scale_by_npos:
+        loss = loss * len(probe_pos)
+    return loss, ex
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic phantoms
+# ---------------------------------------------------------------------------------------------
+
+def zone_plate_phantom(n=512, n_slice=100, lmbda_nm=0.248, focal_nm=7742.0, n_zones=30,
+                       delta=1.0e-4, beta=1.0e-5, voxel_nm=1.0):
+    """Binary Fresnel zone plate, axially invariant, centred at (n-1)/2 (config 1)."""
+    c = (n - 1) / 2.
+    yy, xx = np.meshgrid(np.arange(n) - c, np.arange(n) - c, indexing='ij')
+    r = np.sqrt(xx ** 2 + yy ** 2) * voxel_nm
+    nn = np.arange(n_zones + 1)
+    rn = np.sqrt(nn * lmbda_nm * focal_nm + (nn * lmbda_nm / 2.) ** 2)
+    zone = np.searchsorted(rn, r, side='right')           # zone index 1..n_zones inside, >n_zones outside
+    mask = (zone % 2 == 1) & (zone <= n_zones)
+    d2 = np.where(mask, delta, 0.0)
+    b2 = np.where(mask, beta, 0.0)
+    gd = np.repeat(d2[None, :, :, None], n_slice, axis=3)
+    gb = np.repeat(b2[None, :, :, None], n_slice, axis=3)
+    return gd, gb
+
+
+def random_phantom(shape_byxz, seed=1234, delta_scale=1e-5, beta_scale=1e-6):
+    """Random delta/beta phantom (config 2): float32 uniform draws, fixed seed."""
+    rng = np.random.default_rng(seed)
+    gd = rng.random(shape_byxz, dtype=np.float32) * np.float32(delta_scale)
+    gb = rng.random(shape_byxz, dtype=np.float32) * np.float32(beta_scale)
+    return gd, gb

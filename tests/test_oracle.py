@@ -1,0 +1,178 @@
+"""CPU tier: pin the oracle (oracle/multislice_oracle.py) against the golden vectors produced by
+running the reference's own functions (oracle/gen_golden.py), the known-answer anchors recorded
+in SURVEY.md 8c, and torch.autograd for the hand adjoint."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import multislice_oracle as mo
+from conftest import rel_l2
+
+
+@pytest.fixture(scope='module')
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, 'ref_fft.npz'))
+
+
+@pytest.fixture(scope='module')
+def gold_cnn(golden_dir):
+    return np.load(os.path.join(golden_dir, 'ref_cnn.npz'))
+
+
+def fixture64(gold):
+    return gold['fixture64_delta_values'][gold['fixture64_delta_labels']]
+
+
+@pytest.mark.parametrize('name', ['k64', 'k48x80', 'kaniso', 'kfree'])
+def test_get_kernel_matches_reference(gold, name):
+    args = json.loads(str(gold['kernel_%s_args' % name]))
+    h = mo.get_kernel(*args)
+    assert h.shape == gold['kernel_' + name].shape
+    assert np.array_equal(h, gold['kernel_' + name])          # same float64 ops -> bit exact
+    p0, hy, hx = mo.kernel_factors(*args)
+    assert rel_l2(p0 * np.outer(hy, hx), h) < 1e-13            # separable to rounding; phases reach ~1e3 rad
+
+
+def test_kernel_known_answers():
+    # SURVEY.md 8c anchors
+    h = mo.get_kernel(1.0, 0.248, [1, 1, 1], [64, 64, 64])
+    assert abs(h[0, 0] - (0.9825897919540318 - 0.185788322420254j)) < 1e-14
+    assert abs(h[32, 32] - (0.9795496939908097 + 0.20120237822280107j)) < 1e-14
+
+
+def test_forward_fixture64(gold):
+    gd = fixture64(gold)
+    psi = mo.multislice_propagate_batch_numpy(gd[None], 0.1 * gd[None], np.ones([64, 64]), np.zeros([64, 64]),
+                                              5000, 1e-7, None, (1, 64, 64, 64))
+    assert rel_l2(psi, gold['psi_fixture64']) < 1e-14
+    # SURVEY.md 8c anchors
+    assert abs(np.sum(np.abs(psi) ** 2) - 4095.9518576500595) < 1e-8
+    assert abs(psi[0, 0, 0] - (0.9807559047911851 + 0.19523787326342254j)) < 1e-12
+    assert abs(psi[0, 32, 32] - (0.9807332762611662 + 0.1953300000993423j)) < 1e-12
+
+
+def test_forward_random_cases(gold):
+    gd, gb = mo.random_phantom((2, 48, 80, 12), seed=11, delta_scale=3e-4, beta_scale=3e-5)
+    pr, pi = mo.gaussian_probe((48, 80), 9., 9., 0.5)
+    for free, key in ((None, 'psi_rand48x80'), ('inf', 'psi_rand48x80_inf')):
+        psi = mo.multislice_propagate_batch_numpy(gd.astype(np.float64), gb.astype(np.float64), pr, pi, 800,
+                                                  0.67e-7, free, gd.shape)
+        assert rel_l2(psi, gold[key]) < 1e-14
+    gd, gb = mo.random_phantom((1, 64, 64, 8), seed=12, delta_scale=1e-5, beta_scale=1e-6)
+    psi = mo.multislice_propagate_batch_numpy(gd.astype(np.float64), gb.astype(np.float64), np.ones([64, 64]),
+                                              np.zeros([64, 64]), 5000, 1e-7, 1e-4, gd.shape)
+    assert rel_l2(psi, gold['psi_rand64_free']) < 1e-14
+    gd, gb = mo.random_phantom((3, 32, 32, 1), seed=13, delta_scale=1e-3, beta_scale=1e-4)
+    psi = mo.multislice_propagate_batch_numpy(gd.astype(np.float64), gb.astype(np.float64), np.ones([32, 32]),
+                                              np.zeros([32, 32]), 5000, 1e-7, None, gd.shape)
+    assert rel_l2(psi, gold['psi_rand32_1slice']) < 1e-14
+    gd, gb = mo.zone_plate_phantom(n=128, n_slice=20, n_zones=8)
+    psi = mo.multislice_propagate_batch_numpy(gd, gb, np.ones([128, 128]), np.zeros([128, 128]), 5000, 1e-7,
+                                              None, gd.shape)
+    assert rel_l2(psi, gold['psi_zp128']) < 1e-14
+
+
+def test_cnn_matches_reference(gold_cnn):
+    gd, gb = mo.random_phantom((2, 32, 40, 6), seed=21, delta_scale=1e-4, beta_scale=1e-5)
+    for ks in (5, 17):
+        for free in (None, 'inf'):
+            psi = mo.multislice_propagate_cnn(gd.astype(np.float64), gb.astype(np.float64), np.ones([32, 40]),
+                                              np.zeros([32, 40]), 5000, [1e-7] * 3, kernel_size=ks, free_prop_cm=free)
+            assert rel_l2(psi, gold_cnn['cnn_ks%d_%s' % (ks, free)]) < 1e-12
+
+
+def test_shift_folding_identity():
+    # ifft2(ifftshift(fftshift(fft2 u) H)) == ifft2(fft2(u) * ifftshift(H)), also for odd sizes
+    rng = np.random.default_rng(0)
+    for shape in ((16, 16), (9, 12), (15, 7)):
+        u = rng.standard_normal((2,) + shape) + 1j * rng.standard_normal((2,) + shape)
+        h = mo.get_kernel(1.0, 0.248, [1, 1, 1], list(shape) + [4])
+        a = mo._propagate(u, h)
+        b = np.fft.ifft2(np.fft.fft2(u) * np.fft.ifftshift(h))
+        assert rel_l2(b, a) < 1e-14
+
+
+def _torch_forward(gd, gb, probe, k, h, propagate_last, free, hfree):
+    psi = probe[None].expand(gd.shape[0], -1, -1)
+    n_slice = gd.shape[-1]
+    hs = torch.fft.ifftshift(h)
+    for i in range(n_slice):
+        psi = psi * torch.exp(1j * k * gd[..., i]) * torch.exp(-k * gb[..., i])
+        do_prop = (n_slice > 1) if propagate_last else (i < n_slice - 1)
+        if do_prop:
+            psi = torch.fft.ifft2(torch.fft.fft2(psi) * hs)
+    if free == 'inf':
+        psi = torch.fft.fftshift(torch.fft.fft2(psi), dim=(1, 2))
+    elif free is not None:
+        psi = torch.fft.ifft2(torch.fft.fft2(psi) * torch.fft.ifftshift(hfree))
+    return psi
+
+
+@pytest.mark.parametrize('propagate_last', [False, True])
+@pytest.mark.parametrize('free', [None, 'inf', 1e-4])
+def test_hand_adjoint_vs_torch_autograd(propagate_last, free):
+    shape = (2, 16, 24, 5)
+    gd, gb = mo.random_phantom(shape, seed=3, delta_scale=2e-3, beta_scale=2e-4)
+    gd = gd.astype(np.float64); gb = gb.astype(np.float64)
+    pr, pi = mo.gaussian_probe(shape[1:3], 5., 4., 0.7)
+    energy, psize = 5000, 1e-7
+    rng = np.random.default_rng(5)
+    target = rng.random(shape[:3]) + 0.5
+    loss, g_d, g_b, psi = mo.loss_and_grad(gd, gb, pr, pi, energy, psize, target, free_prop_cm=free,
+                                           propagate_last=propagate_last)
+    lmbda = 1240. / energy
+    h = mo.get_kernel(1.0, lmbda, [1., 1., 1.], list(shape[1:]))
+    hfree = mo.get_kernel(free * 1e7, lmbda, [1., 1., 1.], list(shape[1:])) if isinstance(free, float) else None
+    k = 2 * mo.PI_TF * 1.0 / lmbda
+    tgd = torch.tensor(gd, requires_grad=True); tgb = torch.tensor(gb, requires_grad=True)
+    tpsi = _torch_forward(tgd, tgb, torch.tensor((pr + 1j * pi).astype(np.complex64).astype(np.complex128)), k, torch.tensor(h), propagate_last, free,
+                          None if hfree is None else torch.tensor(hfree))
+    tloss = torch.mean((tpsi.abs() - torch.tensor(target)) ** 2)
+    tloss.backward()
+    assert abs(loss - tloss.item()) < 1e-13 * max(1, abs(loss))
+    assert rel_l2(psi, tpsi.detach().numpy()) < 1e-13
+    assert rel_l2(g_d, tgd.grad.numpy()) < 1e-11
+    assert rel_l2(g_b, tgb.grad.numpy()) < 1e-11
+
+
+def test_adjoint_finite_difference():
+    shape = (1, 8, 8, 3)
+    gd, gb = mo.random_phantom(shape, seed=8, delta_scale=1e-2, beta_scale=1e-3)
+    gd = gd.astype(np.float64); gb = gb.astype(np.float64)
+    one, zero = np.ones(shape[1:3]), np.zeros(shape[1:3])
+    target = np.full(shape[:3], 0.9)
+    loss, g_d, g_b, _ = mo.loss_and_grad(gd, gb, one, zero, 5000, 1e-7, target)
+    eps = 1e-7
+    for idx in [(0, 1, 2, 0), (0, 5, 5, 1), (0, 7, 0, 2)]:
+        for arr, g in ((gd, g_d), (gb, g_b)):
+            a = arr.copy(); a[idx] += eps
+            lp = mo.loss_and_grad(a if arr is gd else gd, a if arr is gb else gb, one, zero, 5000, 1e-7, target)[0]
+            a[idx] -= 2 * eps
+            lm = mo.loss_and_grad(a if arr is gd else gd, a if arr is gb else gb, one, zero, 5000, 1e-7, target)[0]
+            fd = (lp - lm) / (2 * eps)
+            assert abs(fd - g[idx]) < 1e-5 * max(abs(g[idx]), 1e-3)
+
+
+def test_energy_conservation_and_vacuum():
+    # beta = 0 and |H| = 1: energy is conserved; vacuum plane wave picks up exp(i k dz) per propagation
+    gd, _ = mo.random_phantom((1, 32, 32, 6), seed=4, delta_scale=1e-3)
+    psi = mo.multislice_propagate_batch_numpy(gd.astype(np.float64), np.zeros(gd.shape), np.ones([32, 32]),
+                                              np.zeros([32, 32]), 5000, 1e-7, None, gd.shape)
+    assert abs(np.sum(np.abs(psi) ** 2) - 32 * 32) < 1e-9
+    z = np.zeros((1, 32, 32, 6))
+    psi = mo.multislice_propagate_batch_numpy(z, z, np.ones([32, 32]), np.zeros([32, 32]), 5000, 1e-7, None, z.shape)
+    assert np.allclose(np.abs(psi), 1.0, atol=1e-12)
+
+
+def test_ptycho_windows_and_loss_shapes():
+    rng = np.random.default_rng(2)
+    obj = rng.random((24, 28, 3))
+    pos = [(0, 0), (5, 7), (23, 27), (12, 14)]
+    wins, pad = mo.ptycho_windows(obj, pos, (8, 8))
+    assert wins.shape == (4, 8, 8, 3)
+    assert np.array_equal(wins[1], obj[1:9, 3:11])
+    assert np.all(wins[0][:4, :, :] == 0) and np.all(wins[0][:, :4, :] == 0)
+    assert np.array_equal(wins[0][4:, 4:], obj[:4, :4])
