@@ -1,0 +1,31 @@
+"""beyond_dof_b200: B200-native Fresnel multislice engine (drop-in for the multislice hot path of
+mdw771/beyond_dof).  Python here is only the host side; the arithmetic lives in libbdof.so
+(hand-written sm_100a CUDA behind the C ABI of include/bdof.h).
+
+Submodules are imported lazily so that `python -m beyond_dof_b200.build` works before the
+library exists; touching any compute entry point without libbdof.so raises ImportError.
+"""
+import importlib
+
+__version__ = '0.1.0'
+
+_LAZY = {
+    'multislice_propagate_batch_numpy': 'propagation',
+    'multislice_propagate_batch': 'propagation',
+    'multislice_propagate': 'propagation',
+    'multislice_propagate_cnn': 'propagation',
+    'MultislicePlan': 'plan',
+    'fullfield_loss_and_grad': 'models',
+    'ptycho_loss_and_grad': 'models',
+    'get_kernel': 'util',
+    'gen_mesh': 'util',
+}
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        mod = importlib.import_module('.' + _LAZY[name], __name__)
+        return getattr(mod, name)
+    if name in ('capi', 'plan', 'propagation', 'models', 'util', 'build', 'dist'):
+        return importlib.import_module('.' + name, __name__)
+    raise AttributeError(name)

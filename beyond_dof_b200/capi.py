@@ -1,0 +1,73 @@
+"""ctypes binding of libbdof.so (include/bdof.h).  No torch types cross this boundary: only raw
+device/host pointers and sizes.  Import fails loudly if the library has not been built."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libbdof.so')
+
+# plan flags / modes (mirror include/bdof.h)
+PROPAGATE_LAST = 1 << 0
+STORE_SLICES = 1 << 1
+Z_BROADCAST = 1 << 2
+FREE_NONE, FREE_INF, FREE_TF = 0, 1, 2
+
+# every symbol include/bdof.h declares (checked by tests/test_capi.py)
+SYMBOLS = [
+    'bdof_version', 'bdof_last_error', 'bdof_launch_count', 'bdof_size_supported', 'bdof_kernel_factors',
+    'bdof_plan_create', 'bdof_plan_destroy', 'bdof_set_kernel', 'bdof_set_kernel_full', 'bdof_set_free_prop',
+    'bdof_forward', 'bdof_loss_mag', 'bdof_adjoint', 'bdof_pack_db', 'bdof_unpack_db', 'bdof_patch_gather',
+    'bdof_patch_scatter_add', 'bdof_cnn_forward', 'bdof_forward_host', 'bdof_plan_workspace_bytes',
+]
+
+
+class BdofError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__('libbdof error %d: %s' % (code, msg))
+        self.code = code
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError('libbdof.so is missing (%s): build it with `python -m beyond_dof_b200.build`; '
+                          'there is no CPU fallback' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, u32, f64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_double
+    lib.bdof_version.restype = i32
+    lib.bdof_last_error.restype = ctypes.c_char_p
+    lib.bdof_launch_count.restype = ctypes.c_ulonglong
+    lib.bdof_size_supported.argtypes = [i32]
+    lib.bdof_kernel_factors.argtypes = [f64, f64, vp, i32, i32, f64, vp, vp, vp]
+    lib.bdof_plan_create.argtypes = [ctypes.POINTER(vp), i32, i32, i32, i32, u32, vp]
+    lib.bdof_plan_destroy.argtypes = [vp]
+    lib.bdof_plan_destroy.restype = None
+    lib.bdof_set_kernel.argtypes = [vp, vp, vp, f64, f64, f64]
+    lib.bdof_set_kernel_full.argtypes = [vp, vp, f64]
+    lib.bdof_set_free_prop.argtypes = [vp, i32, vp, vp, f64, f64]
+    lib.bdof_forward.argtypes = [vp, vp, vp, vp]
+    lib.bdof_loss_mag.argtypes = [vp, vp, vp, f64, vp, vp]
+    lib.bdof_adjoint.argtypes = [vp, vp, vp, vp, vp]
+    lib.bdof_pack_db.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.bdof_unpack_db.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.bdof_patch_gather.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp, vp]
+    lib.bdof_patch_scatter_add.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp, vp]
+    lib.bdof_cnn_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, i32, f64, vp]
+    lib.bdof_forward_host.argtypes = [vp, vp, vp, vp, vp]
+    lib.bdof_plan_workspace_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
+    for name in SYMBOLS:
+        fn = getattr(lib, name)
+        if fn.restype is ctypes.c_int and name not in ('bdof_version', 'bdof_size_supported'):
+            fn.restype = i32
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    if rc != 0:
+        raise BdofError(rc, lib.bdof_last_error().decode('utf-8', 'replace'))
+
+
+def launch_count():
+    return int(lib.bdof_launch_count())

@@ -1,0 +1,741 @@
+// libbdof: B200-native Fresnel multislice engine -- plan, pass scheduling and the C ABI.
+// See include/bdof.h for the boundary and DESIGN.md for the data layout.
+#include "../../include/bdof.h"
+#include "common.h"
+#include "regfft.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <complex>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+using namespace bdof;
+
+// ------------------------------------------------------------------------------------------
+// errors / bookkeeping
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+int bdof_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int bdof_launch_check(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return bdof_fail(int(e), "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+#define fail bdof_fail
+#define launch_check bdof_launch_check
+
+extern "C" int bdof_version(void) { return 100; }
+extern "C" const char* bdof_last_error(void) { return g_err; }
+extern "C" unsigned long long bdof_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------
+// line-kernel dispatch: one translation unit per FFT length (line_inst.cu, -DBDOF_N=...)
+// ------------------------------------------------------------------------------------------
+extern "C" int bdof_size_supported(int n) {
+    switch (n) { case 64: case 128: case 256: case 512: case 1024: case 2048: case 4096: case 8192: return 1; }
+    return 0;
+}
+
+static int launch_variant(int n, int variant, const LineParams& p, long long n_lines, cudaStream_t st) {
+    switch (n) {
+        case 64:   return bdof_launch_line_64(variant, p, n_lines, st);
+        case 128:  return bdof_launch_line_128(variant, p, n_lines, st);
+        case 256:  return bdof_launch_line_256(variant, p, n_lines, st);
+        case 512:  return bdof_launch_line_512(variant, p, n_lines, st);
+        case 1024: return bdof_launch_line_1024(variant, p, n_lines, st);
+        case 2048: return bdof_launch_line_2048(variant, p, n_lines, st);
+        case 4096: return bdof_launch_line_4096(variant, p, n_lines, st);
+        case 8192: return bdof_launch_line_8192(variant, p, n_lines, st);
+    }
+    return bdof_fail(BDOF_E_UNSUPPORTED, "FFT length %d is not supported", n);
+}
+
+struct StageRadices { int r1, r2, r3; };
+static StageRadices radices_for(int n) {
+    switch (n) {
+        case 64: return {8, 8, 1};
+        case 128: return {16, 8, 1};
+        case 256: return {16, 16, 1};
+        case 512: return {32, 16, 1};
+        case 1024: return {32, 32, 1};
+        case 2048: return {64, 32, 1};
+        case 4096: return {64, 64, 1};
+        case 8192: return {64, 64, 2};
+    }
+    return {0, 0, 0};
+}
+
+// stage twiddles, forward sign, LineCfg layout, computed in double
+static std::vector<float2> make_twiddles(int n) {
+    StageRadices r = radices_for(n);
+    std::vector<float2> tw;
+    auto add_stage = [&](int R, int NS) {
+        const double M = double(NS) * R;
+        for (int rr = 1; rr < R; ++rr)
+            for (int k = 0; k < NS; ++k) {
+                double a = -2.0 * M_PI * double((long long)rr * k % (long long)M) / M;
+                tw.push_back(make_float2(float(cos(a)), float(sin(a))));
+            }
+    };
+    add_stage(r.r2, r.r1);
+    if (r.r3 > 1) add_stage(r.r3, r.r1 * r.r2);
+    return tw;
+}
+
+// ------------------------------------------------------------------------------------------
+// elementwise kernels
+// ------------------------------------------------------------------------------------------
+__global__ void k_broadcast_probe(const float2* __restrict__ probe, float2* __restrict__ out, long long n_per, int batch) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_per) return;
+    float2 v = probe[i];
+    for (int b = 0; b < batch; ++b) out[b * n_per + i] = v;
+}
+
+// out = in * t(db)    (slice that modulates without propagating, npfuncs.py:38-40)
+__global__ void k_modulate(const float2* __restrict__ in, const float2* __restrict__ db, float2* __restrict__ out,
+                           long long n, float k) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = cmul(in[i], transmission(db[i], k));
+}
+
+// adjoint of k_modulate: grad = -k (Im, Re)(conj(G) psi t), G <- conj(t) G
+__global__ void k_modulate_adj(float2* __restrict__ G, const float2* __restrict__ psi, const float2* __restrict__ db,
+                               float2* __restrict__ grad, long long n, float k) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float2 tr = transmission(db[i], k);
+    const float2 u = cmul(psi[i], tr);
+    const float2 g = G[i];
+    const float2 w = cmulc(u, g);
+    grad[i] = make_float2(-k * w.y, -k * w.x);
+    G[i] = cmulc(g, tr);
+}
+
+// out = in * (re + i im)
+__global__ void k_scale_complex(const float2* __restrict__ in, float2* __restrict__ out, long long n, float re, float im) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = cmul(in[i], make_float2(re, im));
+}
+
+__global__ void k_sum_batch(const float2* __restrict__ in, float2* __restrict__ out, long long n_per, int batch) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_per) return;
+    float sx = 0.f, sy = 0.f;
+    for (int b = 0; b < batch; ++b) { float2 v = in[b * n_per + i]; sx += v.x; sy += v.y; }
+    out[i] = make_float2(sx, sy);
+}
+
+// loss head: partial sums of (|psi| - y)^2 per block (double), G = scale*(2/M)(|psi|-y) psi/|psi|
+constexpr int LOSS_BLOCKS = 1184;   // 148 SMs x 8
+constexpr int LOSS_THREADS = 256;
+__global__ void __launch_bounds__(LOSS_THREADS) k_loss_mag(const float2* __restrict__ psi, const float* __restrict__ target,
+                                                            float2* __restrict__ G, long long n, float gscale,
+                                                            double* __restrict__ partial) {
+    double acc = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float2 v = psi[i];
+        const float mag = sqrtf(v.x * v.x + v.y * v.y);
+        const float d = mag - target[i];
+        acc += double(d) * double(d);
+        if (G != nullptr) {
+            const float s = mag > 0.f ? gscale * d / mag : 0.f;
+            G[i] = make_float2(s * v.x, s * v.y);
+        }
+    }
+    __shared__ double red[LOSS_THREADS / 32];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < LOSS_THREADS / 32; ++w) s += red[w];
+        partial[blockIdx.x] = s;
+    }
+}
+__global__ void k_loss_final(const double* __restrict__ partial, int n_partial, double scale, double* __restrict__ out) {
+    // single warp, fixed order -> deterministic
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n_partial; i += 32) acc += partial[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) *out = acc * scale;
+}
+
+// [B,Y,X,Z] planes -> [Z,B,Y,X,2]: per (b,y) a [X][Z] -> [Z][X] tile transpose through smem
+__global__ void k_pack_db(const float* __restrict__ delta, const float* __restrict__ beta, float2* __restrict__ db,
+                          int n_rows /*B*Y*/, int nx, int nz) {
+    __shared__ float td[32][33], tb[32][33];
+    const int row = blockIdx.z;
+    const int x0 = blockIdx.x * 32, z0 = blockIdx.y * 32;
+    const long long in_base = (long long)row * nx * nz;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int x = x0 + i, z = z0 + threadIdx.x;
+        if (x < nx && z < nz) {
+            td[i][threadIdx.x] = delta[in_base + (long long)x * nz + z];
+            tb[i][threadIdx.x] = beta[in_base + (long long)x * nz + z];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int z = z0 + i, x = x0 + threadIdx.x;
+        if (x < nx && z < nz)
+            db[((long long)z * n_rows + row) * nx + x] = make_float2(td[threadIdx.x][i], tb[threadIdx.x][i]);
+    }
+}
+__global__ void k_unpack_db(const float2* __restrict__ db, float* __restrict__ delta, float* __restrict__ beta,
+                            int n_rows, int nx, int nz) {
+    __shared__ float td[32][33], tb[32][33];
+    const int row = blockIdx.z;
+    const int x0 = blockIdx.x * 32, z0 = blockIdx.y * 32;
+    const long long out_base = (long long)row * nx * nz;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int z = z0 + i, x = x0 + threadIdx.x;
+        if (x < nx && z < nz) {
+            const float2 v = db[((long long)z * n_rows + row) * nx + x];
+            td[i][threadIdx.x] = v.x;
+            tb[i][threadIdx.x] = v.y;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int x = x0 + i, z = z0 + threadIdx.x;
+        if (x < nx && z < nz) {
+            delta[out_base + (long long)x * nz + z] = td[threadIdx.x][i];
+            beta[out_base + (long long)x * nz + z] = tb[threadIdx.x][i];
+        }
+    }
+}
+
+// ptychography windows (ptychography.py:62-76): zero outside the object
+__global__ void k_patch_gather(const float2* __restrict__ obj, int oy, int ox, const int* __restrict__ pos, int n_pos,
+                               int py, int px, float2* __restrict__ patches) {
+    // grid: (ceil(px*py/256), n_pos, n_slice)
+    const int z = blockIdx.z, ip = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= py * px) return;
+    const int yy = i / px, xx = i - yy * px;
+    const int y = pos[2 * ip] + yy, x = pos[2 * ip + 1] + xx;
+    float2 v = make_float2(0.f, 0.f);
+    if (y >= 0 && y < oy && x >= 0 && x < ox) v = obj[((long long)z * oy + y) * ox + x];
+    patches[(((long long)z * n_pos + ip) * py + yy) * px + xx] = v;
+}
+__global__ void k_patch_scatter_add(const float2* __restrict__ gpatch, int oy, int ox, const int* __restrict__ pos,
+                                    int n_pos, int py, int px, float2* __restrict__ gobj) {
+    const int z = blockIdx.z, ip = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= py * px) return;
+    const int yy = i / px, xx = i - yy * px;
+    const int y = pos[2 * ip] + yy, x = pos[2 * ip + 1] + xx;
+    if (y >= 0 && y < oy && x >= 0 && x < ox) {
+        const float2 v = gpatch[(((long long)z * n_pos + ip) * py + yy) * px + xx];
+        float* dst = reinterpret_cast<float*>(gobj + ((long long)z * oy + y) * ox + x);
+        atomicAdd(dst, v.x);
+        atomicAdd(dst + 1, v.y);
+    }
+}
+
+// real-space propagator step (propagation.py:85-99): out = conv2d_valid(pad(in * t, edge), kernel)
+constexpr int CNN_MAX_K = 33;
+__constant__ float2 c_cnn_kernel[CNN_MAX_K * CNN_MAX_K];
+template <int TILE>
+__global__ void k_cnn_step(const float2* __restrict__ in, const float2* __restrict__ db, float2* __restrict__ out,
+                           int ny, int nx, int ks, float k_dz, float2 edge) {
+    extern __shared__ float2 tile[];          // (TILE + ks - 1)^2
+    const int pad = (ks - 1) / 2, W = TILE + ks - 1;
+    const int b = blockIdx.z;
+    const int y0 = blockIdx.y * TILE, x0 = blockIdx.x * TILE;
+    const long long fbase = (long long)b * ny * nx;
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < W * W; i += blockDim.x * blockDim.y) {
+        const int ty = i / W, tx = i - ty * W;
+        const int y = y0 + ty - pad, x = x0 + tx - pad;
+        float2 v = edge;
+        if (y >= 0 && y < ny && x >= 0 && x < nx) {
+            const long long o = fbase + (long long)y * nx + x;
+            v = cmul(in[o], transmission(db[o], k_dz));
+        }
+        tile[i] = v;
+    }
+    __syncthreads();
+    const int y = y0 + threadIdx.y, x = x0 + threadIdx.x;
+    if (y >= ny || x >= nx) return;
+    float ax = 0.f, ay = 0.f;
+    // true convolution: out[y,x] = sum_{a,b} K[a,b] * padded[y + 2p - a, x + 2p - b]
+    for (int a = 0; a < ks; ++a)
+        for (int c = 0; c < ks; ++c) {
+            const float2 kk = c_cnn_kernel[a * ks + c];
+            const float2 v = tile[(threadIdx.y + 2 * pad - a) * W + (threadIdx.x + 2 * pad - c)];
+            ax += kk.x * v.x - kk.y * v.y;
+            ay += kk.x * v.y + kk.y * v.x;
+        }
+    out[fbase + (long long)y * nx + x] = make_float2(ax, ay);
+}
+
+static inline unsigned blocks_for(long long n, int threads) { return unsigned((n + threads - 1) / threads); }
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+struct AxisTables {
+    int n = 0;
+    float2* tw = nullptr;      // stage twiddles
+    float2* h = nullptr;       // ifftshift(h)/n, per-slice propagator
+    float2* h_adj = nullptr;   // conj
+    float2* hf = nullptr;      // free-space propagator
+    float2* hf_adj = nullptr;
+};
+
+struct bdof_plan {
+    int ny, nx, batch, n_slice;
+    uint32_t flags;
+    cudaStream_t stream;
+    long long F;               // batch*ny*nx
+    AxisTables ax, ay;
+    bool have_kernel = false, full_kernel = false;
+    float2* H2 = nullptr;      // general 2-D multiplier ifftshift2(H)/(nx ny) and its conjugate
+    float2* H2_adj = nullptr;
+    std::complex<double> phase0{1.0, 0.0}, phasef{1.0, 0.0};
+    double k_dz = 0.0;
+    int free_mode = BDOF_FREE_NONE;
+    float2* tmp = nullptr;     // one field
+    float2* work[2] = {nullptr, nullptr};   // ping-pong fields (no-store forward) / G buffer
+    float2* slabs = nullptr;   // n_slice fields (STORE_SLICES)
+    double* partial = nullptr;
+    std::complex<double> total_phase{1.0, 0.0};
+    bool forward_done = false;
+    // host staging for bdof_forward_host
+    float* e2e_delta = nullptr; float* e2e_beta = nullptr; float2* e2e_db = nullptr;
+    float2* e2e_probe = nullptr; float2* e2e_exit = nullptr;
+};
+
+static int upload(float2** dst, const std::vector<float2>& v) {
+    if (*dst == nullptr) CUDA_TRY(cudaMalloc((void**)dst, v.size() * sizeof(float2)));
+    CUDA_TRY(cudaMemcpy(*dst, v.data(), v.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// centred complex128 factor -> ifftshift, scale, fp32 (and conjugate)
+static void shift_factor(const double* h, int n, double scale, std::vector<float2>& out, std::vector<float2>& out_adj) {
+    out.resize(n); out_adj.resize(n);
+    const int s = n / 2;                            // ifftshift(a)[i] = a[(i + n//2) % n]
+    for (int i = 0; i < n; ++i) {
+        const int src = (i + s) % n;
+        double re = h[2 * src] * scale, im = h[2 * src + 1] * scale;
+        out[i] = make_float2(float(re), float(im));
+        out_adj[i] = make_float2(float(re), float(-im));
+    }
+}
+
+extern "C" int bdof_kernel_factors(double dist_nm, double lmbda_nm, const double* voxel_nm, int ny, int nx,
+                                   double pi_const, double* hy_out, double* hx_out, double* phase0_out) {
+    if (!voxel_nm || !hy_out || !hx_out || !phase0_out || ny < 1 || nx < 1) return fail(BDOF_E_BADARG, "bad argument");
+    // util.py:176-181: u along axis 1 spans +-1/(2 voxel[0]) over nx points (endpoint inclusive),
+    // v along axis 0 spans +-1/(2 voxel[1]) over ny points
+    const double k = 2.0 * pi_const / lmbda_nm;
+    const double u_max = 1.0 / (2.0 * voxel_nm[0]), v_max = 1.0 / (2.0 * voxel_nm[1]);
+    auto fill = [&](double* out, int n, double mx) {
+        for (int i = 0; i < n; ++i) {
+            // numpy.linspace(-mx, mx, n): start + i*step, last point forced to stop
+            double step = (n > 1) ? (2.0 * mx) / double(n - 1) : 0.0;
+            double u = (i == n - 1 && n > 1) ? mx : -mx + double(i) * step;
+            double ph = -pi_const * lmbda_nm * dist_nm * (u * u);
+            out[2 * i] = cos(ph);
+            out[2 * i + 1] = sin(ph);
+        }
+    };
+    fill(hy_out, ny, v_max);
+    fill(hx_out, nx, u_max);
+    phase0_out[0] = cos(k * dist_nm);
+    phase0_out[1] = sin(k * dist_nm);
+    return 0;
+}
+
+extern "C" int bdof_plan_create(bdof_plan** out, int ny, int nx, int batch, int n_slice, uint32_t flags, void* cuda_stream) {
+    if (!out || ny < 1 || nx < 1 || batch < 1 || n_slice < 1) return fail(BDOF_E_BADARG, "bad plan shape");
+    if (!bdof_size_supported(ny) || !bdof_size_supported(nx))
+        return fail(BDOF_E_UNSUPPORTED, "field %dx%d: each side must be a power of two in [64, 8192]", ny, nx);
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    bdof_plan* p = new bdof_plan();
+    p->ny = ny; p->nx = nx; p->batch = batch; p->n_slice = n_slice; p->flags = flags;
+    p->stream = (cudaStream_t)cuda_stream;
+    p->F = (long long)batch * ny * nx;
+    p->ax.n = nx; p->ay.n = ny;
+    int r = 0;
+    do {
+        if ((r = upload(&p->ax.tw, make_twiddles(nx)))) break;
+        if ((r = upload(&p->ay.tw, make_twiddles(ny)))) break;
+        cudaError_t e;
+        if ((e = cudaMalloc((void**)&p->tmp, p->F * sizeof(float2))) != cudaSuccess) { r = fail(int(e), "cudaMalloc tmp: %s", cudaGetErrorString(e)); break; }
+        if ((e = cudaMalloc((void**)&p->work[0], p->F * sizeof(float2))) != cudaSuccess) { r = fail(int(e), "cudaMalloc work: %s", cudaGetErrorString(e)); break; }
+        if (!(flags & BDOF_STORE_SLICES)) {
+            if ((e = cudaMalloc((void**)&p->work[1], p->F * sizeof(float2))) != cudaSuccess) { r = fail(int(e), "cudaMalloc work: %s", cudaGetErrorString(e)); break; }
+        } else {
+            if ((e = cudaMalloc((void**)&p->slabs, (size_t)n_slice * p->F * sizeof(float2))) != cudaSuccess) { r = fail(int(e), "cudaMalloc slice store (%lld bytes): %s", (long long)n_slice * p->F * 8, cudaGetErrorString(e)); break; }
+        }
+        if ((e = cudaMalloc((void**)&p->partial, LOSS_BLOCKS * sizeof(double))) != cudaSuccess) { r = fail(int(e), "cudaMalloc: %s", cudaGetErrorString(e)); break; }
+    } while (0);
+    if (r) { bdof_plan_destroy(p); return r; }
+    *out = p;
+    return 0;
+}
+
+static void free_axis(AxisTables& a) {
+    cudaFree(a.tw); cudaFree(a.h); cudaFree(a.h_adj); cudaFree(a.hf); cudaFree(a.hf_adj);
+}
+extern "C" void bdof_plan_destroy(bdof_plan* p) {
+    if (!p) return;
+    free_axis(p->ax); free_axis(p->ay);
+    cudaFree(p->H2); cudaFree(p->H2_adj);
+    cudaFree(p->tmp); cudaFree(p->work[0]); cudaFree(p->work[1]); cudaFree(p->slabs); cudaFree(p->partial);
+    cudaFree(p->e2e_delta); cudaFree(p->e2e_beta); cudaFree(p->e2e_db); cudaFree(p->e2e_probe); cudaFree(p->e2e_exit);
+    delete p;
+}
+
+extern "C" int bdof_plan_workspace_bytes(const bdof_plan* p, size_t* bytes_out) {
+    if (!p || !bytes_out) return fail(BDOF_E_BADARG, "null");
+    size_t f = size_t(p->F) * sizeof(float2);
+    *bytes_out = f * 2 + ((p->flags & BDOF_STORE_SLICES) ? f * p->n_slice : f);
+    return 0;
+}
+
+extern "C" int bdof_set_kernel(bdof_plan* p, const double* h_hy, const double* h_hx, double phase0_re, double phase0_im, double k_dz) {
+    if (!p || !h_hy || !h_hx) return fail(BDOF_E_BADARG, "null");
+    std::vector<float2> a, b;
+    shift_factor(h_hx, p->nx, 1.0 / p->nx, a, b);
+    BDOF_TRY(upload(&p->ax.h, a)); BDOF_TRY(upload(&p->ax.h_adj, b));
+    shift_factor(h_hy, p->ny, 1.0 / p->ny, a, b);
+    BDOF_TRY(upload(&p->ay.h, a)); BDOF_TRY(upload(&p->ay.h_adj, b));
+    p->phase0 = {phase0_re, phase0_im};
+    p->k_dz = k_dz;
+    p->have_kernel = true; p->full_kernel = false;
+    return 0;
+}
+
+extern "C" int bdof_set_kernel_full(bdof_plan* p, const double* h_H, double k_dz) {
+    if (!p || !h_H) return fail(BDOF_E_BADARG, "null");
+    const int ny = p->ny, nx = p->nx;
+    std::vector<float2> a((size_t)ny * nx), b((size_t)ny * nx);
+    const double sc = 1.0 / (double(nx) * double(ny));
+    for (int y = 0; y < ny; ++y)
+        for (int x = 0; x < nx; ++x) {
+            const size_t src = (size_t)((y + ny / 2) % ny) * nx + (x + nx / 2) % nx;
+            a[(size_t)y * nx + x] = make_float2(float(h_H[2 * src] * sc), float(h_H[2 * src + 1] * sc));
+            b[(size_t)y * nx + x] = make_float2(float(h_H[2 * src] * sc), float(-h_H[2 * src + 1] * sc));
+        }
+    BDOF_TRY(upload(&p->H2, a)); BDOF_TRY(upload(&p->H2_adj, b));
+    p->phase0 = {1.0, 0.0};
+    p->k_dz = k_dz;
+    p->have_kernel = true; p->full_kernel = true;
+    return 0;
+}
+
+extern "C" int bdof_set_free_prop(bdof_plan* p, int mode, const double* h_hy, const double* h_hx, double phase0_re, double phase0_im) {
+    if (!p) return fail(BDOF_E_BADARG, "null");
+    if (mode != BDOF_FREE_NONE && mode != BDOF_FREE_INF && mode != BDOF_FREE_TF) return fail(BDOF_E_BADARG, "bad free-space mode %d", mode);
+    p->phasef = {1.0, 0.0};
+    if (mode == BDOF_FREE_TF) {
+        if (!h_hy || !h_hx) return fail(BDOF_E_BADARG, "free-space factors missing");
+        std::vector<float2> a, b;
+        shift_factor(h_hx, p->nx, 1.0 / p->nx, a, b);
+        BDOF_TRY(upload(&p->ax.hf, a)); BDOF_TRY(upload(&p->ax.hf_adj, b));
+        shift_factor(h_hy, p->ny, 1.0 / p->ny, a, b);
+        BDOF_TRY(upload(&p->ay.hf, a)); BDOF_TRY(upload(&p->ay.hf_adj, b));
+        p->phasef = {phase0_re, phase0_im};
+    }
+    p->free_mode = mode;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// pass helpers
+// ------------------------------------------------------------------------------------------
+static LineParams row_params(const bdof_plan* p, const float2* in, float2* out, const float2* h) {
+    LineParams q{};
+    q.in = in; q.out = out; q.h = h; q.tw = p->ax.tw;
+    q.batch_stride = (long long)p->ny * p->nx; q.db_batch_stride = q.batch_stride;
+    q.lines_per_batch = p->ny; q.elem_stride = 1; q.line_stride = p->nx;
+    q.k_dz = float(p->k_dz);
+    return q;
+}
+static LineParams col_params(const bdof_plan* p, const float2* in, float2* out, const float2* h) {
+    LineParams q{};
+    q.in = in; q.out = out; q.h = h; q.tw = p->ay.tw;
+    q.batch_stride = (long long)p->ny * p->nx; q.db_batch_stride = q.batch_stride;
+    q.lines_per_batch = p->nx; q.elem_stride = p->nx; q.line_stride = 1;
+    q.k_dz = float(p->k_dz);
+    return q;
+}
+static int row_pass(const bdof_plan* p, int variant, const LineParams& q) {
+    return launch_variant(p->nx, variant, q, (long long)p->batch * p->ny, p->stream);
+}
+static int col_pass(const bdof_plan* p, int variant, const LineParams& q) {
+    return launch_variant(p->ny, variant, q, (long long)p->batch * p->nx, p->stream);
+}
+
+// one propagation of slice i: out = P(in * t(db))
+static int propagate_slice(bdof_plan* p, const float2* in, const float2* db, float2* out) {
+    if (!p->full_kernel) {
+        LineParams r = row_params(p, in, p->tmp, p->ax.h);
+        r.db = db;
+        BDOF_TRY(row_pass(p, V_ROW_CONV_T, r));
+        LineParams c = col_params(p, p->tmp, out, p->ay.h);
+        return col_pass(p, V_COL_CONV, c);
+    }
+    // general 2-D H: modulate, FFT_x, (FFT_y * H * IFFT_y), IFFT_x
+    k_modulate<<<blocks_for(p->F, 256), 256, 0, p->stream>>>(in, db, p->tmp, p->F, float(p->k_dz));
+    BDOF_TRY(launch_check("k_modulate"));
+    BDOF_TRY(row_pass(p, V_ROW_FWD, row_params(p, p->tmp, p->tmp, nullptr)));
+    LineParams c = col_params(p, p->tmp, p->tmp, p->H2);
+    BDOF_TRY(col_pass(p, V_COL_CONV2D, c));
+    return row_pass(p, V_ROW_INV, row_params(p, p->tmp, out, nullptr));
+}
+
+// adjoint of propagate_slice: G <- conj(t) P^H G, grad = -k (Im, Re)(conj(P^H G) psi t)
+static int propagate_slice_adj(bdof_plan* p, float2* G, const float2* psi, const float2* db, float2* grad) {
+    if (!p->full_kernel) {
+        LineParams c = col_params(p, G, p->tmp, p->ay.h_adj);
+        BDOF_TRY(col_pass(p, V_COL_CONV, c));
+        LineParams r = row_params(p, p->tmp, G, p->ax.h_adj);
+        r.db = db; r.psi = psi; r.grad = grad;
+        return row_pass(p, V_ROW_CONV_ADJ, r);
+    }
+    BDOF_TRY(row_pass(p, V_ROW_FWD, row_params(p, G, p->tmp, nullptr)));
+    LineParams c = col_params(p, p->tmp, p->tmp, p->H2_adj);
+    BDOF_TRY(col_pass(p, V_COL_CONV2D, c));
+    BDOF_TRY(row_pass(p, V_ROW_INV, row_params(p, p->tmp, G, nullptr)));
+    k_modulate_adj<<<blocks_for(p->F, 256), 256, 0, p->stream>>>(G, psi, db, grad, p->F, float(p->k_dz));
+    return launch_check("k_modulate_adj");
+}
+
+static inline bool slice_propagates(const bdof_plan* p, int i) {
+    return (p->flags & BDOF_PROPAGATE_LAST) ? (p->n_slice > 1) : (i < p->n_slice - 1);
+}
+
+extern "C" int bdof_forward(bdof_plan* p, const float* d_db_f, const float* d_probe_f, float* d_exit_f) {
+    if (!p || !d_db_f || !d_probe_f || !d_exit_f) return fail(BDOF_E_BADARG, "null");
+    if (!p->have_kernel) return fail(BDOF_E_STATE, "bdof_set_kernel has not been called");
+    const float2* d_db = reinterpret_cast<const float2*>(d_db_f);
+    const float2* d_probe = reinterpret_cast<const float2*>(d_probe_f);
+    float2* d_exit = reinterpret_cast<float2*>(d_exit_f);
+    const bool store = p->flags & BDOF_STORE_SLICES;
+    const long long per = (long long)p->ny * p->nx;
+    const int Z = p->n_slice;
+
+    float2* cur = store ? p->slabs : p->work[0];
+    k_broadcast_probe<<<blocks_for(per, 256), 256, 0, p->stream>>>(d_probe, cur, per, p->batch);
+    BDOF_TRY(launch_check("k_broadcast_probe"));
+    std::complex<double> phase{1.0, 0.0};
+    // where the object part of the chain leaves its result
+    float2* obj_out = (p->free_mode == BDOF_FREE_NONE) ? d_exit : (store ? p->work[0] : nullptr);
+    for (int i = 0; i < Z; ++i) {
+        const float2* db_i = d_db + ((p->flags & BDOF_Z_BROADCAST) ? 0 : (long long)i * p->F);
+        const bool last = (i == Z - 1);
+        float2* dst;
+        if (last) dst = obj_out ? obj_out : (cur == p->work[0] ? p->work[1] : p->work[0]);
+        else if (store) dst = p->slabs + (long long)(i + 1) * p->F;
+        else dst = (cur == p->work[0]) ? p->work[1] : p->work[0];
+        if (slice_propagates(p, i)) {
+            BDOF_TRY(propagate_slice(p, cur, db_i, dst));
+            phase *= p->phase0;
+        } else {
+            k_modulate<<<blocks_for(p->F, 256), 256, 0, p->stream>>>(cur, db_i, dst, p->F, float(p->k_dz));
+            BDOF_TRY(launch_check("k_modulate"));
+        }
+        cur = dst;
+    }
+    if (p->free_mode == BDOF_FREE_INF) {
+        // fftshift(fft2(psi)) (npfuncs.py:46)
+        LineParams r = row_params(p, cur, p->tmp, nullptr);
+        r.out_shift = p->nx / 2;
+        BDOF_TRY(row_pass(p, V_ROW_FWD, r));
+        LineParams c = col_params(p, p->tmp, d_exit, nullptr);
+        c.out_shift = p->ny / 2;
+        BDOF_TRY(col_pass(p, V_COL_FWD, c));
+    } else if (p->free_mode == BDOF_FREE_TF) {
+        BDOF_TRY(row_pass(p, V_ROW_CONV, row_params(p, cur, p->tmp, p->ax.hf)));
+        BDOF_TRY(col_pass(p, V_COL_CONV, col_params(p, p->tmp, d_exit, p->ay.hf)));
+        phase *= p->phasef;
+    }
+    p->total_phase = phase;
+    if (std::abs(phase - std::complex<double>(1.0, 0.0)) > 0.0) {
+        k_scale_complex<<<blocks_for(p->F, 256), 256, 0, p->stream>>>(d_exit, d_exit, p->F, float(phase.real()), float(phase.imag()));
+        BDOF_TRY(launch_check("k_scale_complex"));
+    }
+    p->forward_done = true;
+    return 0;
+}
+
+extern "C" int bdof_loss_mag(bdof_plan* p, const float* d_exit, const float* d_target_mag, double loss_scale,
+                             double* d_loss, float* d_grad_exit) {
+    if (!p || !d_exit || !d_target_mag || !d_loss) return fail(BDOF_E_BADARG, "null");
+    const double inv_m = 1.0 / double(p->F);
+    k_loss_mag<<<LOSS_BLOCKS, LOSS_THREADS, 0, p->stream>>>(reinterpret_cast<const float2*>(d_exit), d_target_mag,
+                                                            reinterpret_cast<float2*>(d_grad_exit), p->F,
+                                                            float(2.0 * inv_m * loss_scale), p->partial);
+    BDOF_TRY(launch_check("k_loss_mag"));
+    k_loss_final<<<1, 32, 0, p->stream>>>(p->partial, LOSS_BLOCKS, inv_m * loss_scale, d_loss);
+    return launch_check("k_loss_final");
+}
+
+extern "C" int bdof_adjoint(bdof_plan* p, float* d_db_inout, const float* d_grad_exit, float* d_grad_out, float* d_grad_probe) {
+    if (!p || !d_db_inout || !d_grad_exit) return fail(BDOF_E_BADARG, "null");
+    if (!(p->flags & BDOF_STORE_SLICES)) return fail(BDOF_E_STATE, "plan was created without BDOF_STORE_SLICES");
+    if (!p->forward_done) return fail(BDOF_E_STATE, "bdof_adjoint before bdof_forward");
+    const bool zb = p->flags & BDOF_Z_BROADCAST;
+    if (zb && !d_grad_out) return fail(BDOF_E_BADARG, "BDOF_Z_BROADCAST needs d_grad_out");
+    float2* db = reinterpret_cast<float2*>(d_db_inout);
+    float2* gout = reinterpret_cast<float2*>(d_grad_out);
+    float2* G = p->work[0];
+    const int Z = p->n_slice;
+    // psi_out = c * psi'_out with |c| = 1 (global phase kept out of the fp32 chain): G' = conj(c) G
+    const std::complex<double> c = std::conj(p->total_phase);
+    k_scale_complex<<<blocks_for(p->F, 256), 256, 0, p->stream>>>(reinterpret_cast<const float2*>(d_grad_exit), G, p->F,
+                                                                  float(c.real()), float(c.imag()));
+    BDOF_TRY(launch_check("k_scale_complex"));
+    if (p->free_mode == BDOF_FREE_INF) {
+        // adjoint of fftshift(fft2(.)): unnormalised inverse transform of ifftshift(G)
+        LineParams cc = col_params(p, G, p->tmp, nullptr);
+        cc.in_shift = p->ny / 2;
+        BDOF_TRY(col_pass(p, V_COL_INV, cc));
+        LineParams r = row_params(p, p->tmp, G, nullptr);
+        r.in_shift = p->nx / 2;
+        BDOF_TRY(row_pass(p, V_ROW_INV, r));
+    } else if (p->free_mode == BDOF_FREE_TF) {
+        BDOF_TRY(col_pass(p, V_COL_CONV, col_params(p, G, p->tmp, p->ay.hf_adj)));
+        BDOF_TRY(row_pass(p, V_ROW_CONV, row_params(p, p->tmp, G, p->ax.hf_adj)));
+    }
+    for (int i = Z - 1; i >= 0; --i) {
+        const float2* db_i = db + (zb ? 0 : (long long)i * p->F);
+        float2* grad_i = gout ? gout + (long long)i * p->F : db + (long long)i * p->F;
+        const float2* psi_i = p->slabs + (long long)i * p->F;
+        if (slice_propagates(p, i)) {
+            BDOF_TRY(propagate_slice_adj(p, G, psi_i, db_i, grad_i));
+        } else {
+            k_modulate_adj<<<blocks_for(p->F, 256), 256, 0, p->stream>>>(G, psi_i, db_i, grad_i, p->F, float(p->k_dz));
+            BDOF_TRY(launch_check("k_modulate_adj"));
+        }
+    }
+    if (d_grad_probe) {
+        const long long per = (long long)p->ny * p->nx;
+        k_sum_batch<<<blocks_for(per, 256), 256, 0, p->stream>>>(G, reinterpret_cast<float2*>(d_grad_probe), per, p->batch);
+        BDOF_TRY(launch_check("k_sum_batch"));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// layout conversion, ptychography windows, real-space propagator
+// ------------------------------------------------------------------------------------------
+extern "C" int bdof_pack_db(const float* d_delta, const float* d_beta, float* d_db, int batch, int ny, int nx, int n_slice, void* st) {
+    if (!d_delta || !d_beta || !d_db || batch < 1 || ny < 1 || nx < 1 || n_slice < 1) return fail(BDOF_E_BADARG, "bad argument");
+    const long long rows = (long long)batch * ny;
+    if (rows > 65535LL * 1024) return fail(BDOF_E_UNSUPPORTED, "too many rows");
+    // gridDim.z <= 65535: fold rows
+    for (long long r0 = 0; r0 < rows; r0 += 65535) {
+        const int nr = int(std::min<long long>(65535, rows - r0));
+        dim3 grid((nx + 31) / 32, (n_slice + 31) / 32, nr), block(32, 8);
+        k_pack_db<<<grid, block, 0, (cudaStream_t)st>>>(d_delta + r0 * nx * n_slice, d_beta + r0 * nx * n_slice,
+                                                      reinterpret_cast<float2*>(d_db) + r0 * nx, int(rows), nx, n_slice);
+        BDOF_TRY(launch_check("k_pack_db"));
+    }
+    return 0;
+}
+extern "C" int bdof_unpack_db(const float* d_db, float* d_delta, float* d_beta, int batch, int ny, int nx, int n_slice, void* st) {
+    if (!d_delta || !d_beta || !d_db || batch < 1 || ny < 1 || nx < 1 || n_slice < 1) return fail(BDOF_E_BADARG, "bad argument");
+    const long long rows = (long long)batch * ny;
+    for (long long r0 = 0; r0 < rows; r0 += 65535) {
+        const int nr = int(std::min<long long>(65535, rows - r0));
+        dim3 grid((nx + 31) / 32, (n_slice + 31) / 32, nr), block(32, 8);
+        k_unpack_db<<<grid, block, 0, (cudaStream_t)st>>>(reinterpret_cast<const float2*>(d_db) + r0 * nx,
+                                                        d_delta + r0 * nx * n_slice, d_beta + r0 * nx * n_slice, int(rows), nx, n_slice);
+        BDOF_TRY(launch_check("k_unpack_db"));
+    }
+    return 0;
+}
+
+extern "C" int bdof_patch_gather(const float* d_db_obj, int n_slice, int oy, int ox, const int* d_pos_yx, int n_pos,
+                                 int py, int px, float* d_db_patches, void* st) {
+    if (!d_db_obj || !d_pos_yx || !d_db_patches || n_pos < 1 || n_slice < 1) return fail(BDOF_E_BADARG, "bad argument");
+    if (n_pos > 65535 || n_slice > 65535) return fail(BDOF_E_UNSUPPORTED, "n_pos / n_slice > 65535");
+    dim3 grid((py * px + 255) / 256, n_pos, n_slice);
+    k_patch_gather<<<grid, 256, 0, (cudaStream_t)st>>>(reinterpret_cast<const float2*>(d_db_obj), oy, ox, d_pos_yx, n_pos, py, px,
+                                                     reinterpret_cast<float2*>(d_db_patches));
+    return launch_check("k_patch_gather");
+}
+extern "C" int bdof_patch_scatter_add(const float* d_grad_patches, int n_slice, int oy, int ox, const int* d_pos_yx, int n_pos,
+                                      int py, int px, float* d_grad_obj, void* st) {
+    if (!d_grad_patches || !d_pos_yx || !d_grad_obj || n_pos < 1 || n_slice < 1) return fail(BDOF_E_BADARG, "bad argument");
+    if (n_pos > 65535 || n_slice > 65535) return fail(BDOF_E_UNSUPPORTED, "n_pos / n_slice > 65535");
+    dim3 grid((py * px + 255) / 256, n_pos, n_slice);
+    k_patch_scatter_add<<<grid, 256, 0, (cudaStream_t)st>>>(reinterpret_cast<const float2*>(d_grad_patches), oy, ox, d_pos_yx, n_pos,
+                                                          py, px, reinterpret_cast<float2*>(d_grad_obj));
+    return launch_check("k_patch_scatter_add");
+}
+
+extern "C" int bdof_cnn_forward(const float* d_db, const float* d_probe, float* d_exit, float* d_work, int batch, int ny, int nx,
+                                int n_slice, const double* h_kernel, int ks, double k_dz, void* st_) {
+    if (!d_db || !d_probe || !d_exit || !d_work || !h_kernel) return fail(BDOF_E_BADARG, "null");
+    if (ks < 1 || ks % 2 == 0 || ks > CNN_MAX_K) return fail(BDOF_E_BADARG, "kernel_size must be odd and <= %d", CNN_MAX_K);
+    cudaStream_t st = (cudaStream_t)st_;
+    std::vector<float2> kf((size_t)ks * ks);
+    std::complex<double> ksum = 0.0;
+    for (int i = 0; i < ks * ks; ++i) {
+        kf[i] = make_float2(float(h_kernel[2 * i]), float(h_kernel[2 * i + 1]));
+        ksum += std::complex<double>(h_kernel[2 * i], h_kernel[2 * i + 1]);
+    }
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_cnn_kernel, kf.data(), kf.size() * sizeof(float2), 0, cudaMemcpyHostToDevice, st));
+    const long long per = (long long)ny * nx, F = per * batch;
+    float2* bufs[2] = {reinterpret_cast<float2*>(d_work), reinterpret_cast<float2*>(d_work) + F};
+    k_broadcast_probe<<<blocks_for(per, 256), 256, 0, st>>>(reinterpret_cast<const float2*>(d_probe), bufs[0], per, batch);
+    BDOF_TRY(launch_check("k_broadcast_probe"));
+    constexpr int TILE = 16;
+    const size_t smem = size_t(TILE + ks - 1) * (TILE + ks - 1) * sizeof(float2);
+    dim3 grid((nx + TILE - 1) / TILE, (ny + TILE - 1) / TILE, batch), block(TILE, TILE);
+    std::complex<double> edge = 1.0;
+    int cur = 0;
+    for (int i = 0; i < n_slice; ++i) {
+        float2* dst = (i == n_slice - 1) ? reinterpret_cast<float2*>(d_exit) : bufs[cur ^ 1];
+        k_cnn_step<TILE><<<grid, block, smem, st>>>(bufs[cur], reinterpret_cast<const float2*>(d_db) + (long long)i * F, dst, ny, nx,
+                                                   ks, float(k_dz), make_float2(float(edge.real()), float(edge.imag())));
+        BDOF_TRY(launch_check("k_cnn_step"));
+        edge *= ksum;                         // propagation.py:99
+        cur ^= 1;
+    }
+    return 0;
+}
+
+extern "C" int bdof_forward_host(bdof_plan* p, const float* h_delta, const float* h_beta, const float* h_probe, float* h_exit) {
+    if (!p || !h_delta || !h_beta || !h_probe || !h_exit) return fail(BDOF_E_BADARG, "null");
+    const size_t vol = (size_t)p->F * p->n_slice;
+    const size_t per = (size_t)p->ny * p->nx;
+    if (!p->e2e_delta) {
+        CUDA_TRY(cudaMalloc((void**)&p->e2e_delta, vol * sizeof(float)));
+        CUDA_TRY(cudaMalloc((void**)&p->e2e_beta, vol * sizeof(float)));
+        CUDA_TRY(cudaMalloc((void**)&p->e2e_db, vol * sizeof(float2)));
+        CUDA_TRY(cudaMalloc((void**)&p->e2e_probe, per * sizeof(float2)));
+        CUDA_TRY(cudaMalloc((void**)&p->e2e_exit, (size_t)p->F * sizeof(float2)));
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->e2e_delta, h_delta, vol * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->e2e_beta, h_beta, vol * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->e2e_probe, h_probe, per * sizeof(float2), cudaMemcpyHostToDevice, p->stream));
+    BDOF_TRY(bdof_pack_db(p->e2e_delta, p->e2e_beta, reinterpret_cast<float*>(p->e2e_db), p->batch, p->ny, p->nx, p->n_slice, p->stream));
+    BDOF_TRY(bdof_forward(p, reinterpret_cast<const float*>(p->e2e_db), reinterpret_cast<const float*>(p->e2e_probe),
+                          reinterpret_cast<float*>(p->e2e_exit)));
+    CUDA_TRY(cudaMemcpyAsync(h_exit, p->e2e_exit, (size_t)p->F * sizeof(float2), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}

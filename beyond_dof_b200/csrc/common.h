@@ -1,0 +1,54 @@
+// Shared between bdof.cu (plan, C ABI) and line_inst.cu (one instantiation unit per FFT length).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace bdof {
+
+struct LineParams {
+    const float2* in;        // field in
+    float2* out;             // field out (may alias in)
+    const float2* h;         // frequency-domain multiplier (natural FFT order, 1/N folded in)
+    const float2* tw;        // stage twiddles (LineCfg layout), forward sign
+    const float2* db;        // (delta, beta) slice for PRE_TRANSMIT / POST_ADJ (row mode)
+    float2* grad;            // POST_ADJ: (dL/ddelta, dL/dbeta) out (may alias db)
+    const float2* psi;       // POST_ADJ: stored psi entering the slice
+    long long batch_stride;  // elements between batch items in the field
+    long long db_batch_stride;
+    int lines_per_batch;     // rows per batch item (row mode) or columns (col mode)
+    int elem_stride;         // 1 (row) or nx (col)
+    int line_stride;         // nx (row) or 1 (col)
+    int in_shift;            // circular shift applied to the load index (ifftshift), MODE_INV
+    int out_shift;           // circular shift applied to the store index (fftshift), MODE_FWD
+    float k_dz;              // 2 pi dz / lambda
+};
+
+enum Variant { V_ROW_CONV_T = 0, V_ROW_CONV, V_ROW_CONV_ADJ, V_ROW_FWD, V_ROW_INV, V_COL_CONV, V_COL_FWD, V_COL_INV, V_COL_CONV2D };
+
+// t = exp(i k delta) * exp(-k beta)   (npfuncs.py:38)
+__device__ __forceinline__ float2 transmission(float2 db, float k) {
+    float s, c;
+    sincosf(k * db.x, &s, &c);
+    float m = expf(-k * db.y);
+    return make_float2(m * c, m * s);
+}
+
+}  // namespace bdof
+
+int bdof_fail(int code, const char* fmt, ...);
+int bdof_launch_check(const char* what);
+
+#define BDOF_DECL_LINE(N) int bdof_launch_line_##N(int variant, const bdof::LineParams& p, long long n_lines, cudaStream_t st);
+BDOF_DECL_LINE(64) BDOF_DECL_LINE(128) BDOF_DECL_LINE(256) BDOF_DECL_LINE(512)
+BDOF_DECL_LINE(1024) BDOF_DECL_LINE(2048) BDOF_DECL_LINE(4096) BDOF_DECL_LINE(8192)
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return bdof_fail(int(_e), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+#define BDOF_TRY(expr)            \
+    do {                          \
+        int _r = (expr);          \
+        if (_r != 0) return _r;   \
+    } while (0)

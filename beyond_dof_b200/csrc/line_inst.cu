@@ -1,0 +1,55 @@
+// Instantiation unit for the line kernels of ONE FFT length: compile with -DBDOF_N=<length>.
+#include "../../include/bdof.h"
+#include "common.h"
+#include "linefft.cuh"
+
+using namespace bdof;
+
+#ifndef BDOF_N
+#error "compile with -DBDOF_N=<fft length>"
+#endif
+
+template <int N> struct CfgFor;
+//                                          N    T   R1  R2  R3        row LPC, col LPC
+template <> struct CfgFor<64>   { using C = LineCfg<64, 8, 8, 8, 1>;      static constexpr int RL = 16, CL = 16; };
+template <> struct CfgFor<128>  { using C = LineCfg<128, 8, 16, 8, 1>;    static constexpr int RL = 16, CL = 16; };
+template <> struct CfgFor<256>  { using C = LineCfg<256, 16, 16, 16, 1>;  static constexpr int RL = 8,  CL = 8; };
+template <> struct CfgFor<512>  { using C = LineCfg<512, 16, 32, 16, 1>;  static constexpr int RL = 8,  CL = 8; };
+template <> struct CfgFor<1024> { using C = LineCfg<1024, 32, 32, 32, 1>; static constexpr int RL = 4,  CL = 8; };
+template <> struct CfgFor<2048> { using C = LineCfg<2048, 32, 64, 32, 1>; static constexpr int RL = 4,  CL = 8; };
+template <> struct CfgFor<4096> { using C = LineCfg<4096, 64, 64, 64, 1>; static constexpr int RL = 1,  CL = 4; };
+template <> struct CfgFor<8192> { using C = LineCfg<8192, 128, 64, 64, 2>; static constexpr int RL = 1, CL = 2; };
+
+template <class Cfg, int LPC, bool COL, int MODE, int PRE, int POST>
+static int launch_line(const LineParams& p, long long n_lines, cudaStream_t st) {
+    using SM = LineSmem<Cfg, LPC, COL>;
+    auto kern = line_kernel<Cfg, LPC, COL, MODE, PRE, POST>;
+    static bool attr_done = false;        // per instantiation
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::BYTES)));
+        attr_done = true;
+    }
+    if (n_lines % LPC != 0) return bdof_fail(BDOF_E_UNSUPPORTED, "line count %lld not a multiple of %d", n_lines, LPC);
+    kern<<<unsigned(n_lines / LPC), Cfg::T * LPC, SM::BYTES, st>>>(p);
+    return bdof_launch_check("line_kernel");
+}
+
+#define BDOF_CAT2(a, b) a##b
+#define BDOF_CAT(a, b) BDOF_CAT2(a, b)
+
+int BDOF_CAT(bdof_launch_line_, BDOF_N)(int variant, const LineParams& p, long long n_lines, cudaStream_t st) {
+    using C = typename CfgFor<BDOF_N>::C;
+    constexpr int RL = CfgFor<BDOF_N>::RL, CL = CfgFor<BDOF_N>::CL;
+    switch (variant) {
+        case V_ROW_CONV_T:   return launch_line<C, RL, false, MODE_CONV, PRE_TRANSMIT, POST_NONE>(p, n_lines, st);
+        case V_ROW_CONV:     return launch_line<C, RL, false, MODE_CONV, PRE_NONE, POST_NONE>(p, n_lines, st);
+        case V_ROW_CONV_ADJ: return launch_line<C, RL, false, MODE_CONV, PRE_NONE, POST_ADJ>(p, n_lines, st);
+        case V_ROW_FWD:      return launch_line<C, RL, false, MODE_FWD, PRE_NONE, POST_NONE>(p, n_lines, st);
+        case V_ROW_INV:      return launch_line<C, RL, false, MODE_INV, PRE_NONE, POST_NONE>(p, n_lines, st);
+        case V_COL_CONV:     return launch_line<C, CL, true, MODE_CONV, PRE_NONE, POST_NONE>(p, n_lines, st);
+        case V_COL_FWD:      return launch_line<C, CL, true, MODE_FWD, PRE_NONE, POST_NONE>(p, n_lines, st);
+        case V_COL_INV:      return launch_line<C, CL, true, MODE_INV, PRE_NONE, POST_NONE>(p, n_lines, st);
+        case V_COL_CONV2D:   return launch_line<C, CL, true, MODE_CONV2D, PRE_NONE, POST_NONE>(p, n_lines, st);
+    }
+    return bdof_fail(BDOF_E_BADARG, "bad variant %d", variant);
+}

@@ -1,0 +1,158 @@
+"""Forward models + loss + gradient for the two reconstruction drivers of the reference.
+
+  fullfield_loss_and_grad <- rotate_and_project_batch  tensorflow_recon/fullfield.py:92-116
+                             calculate_loss            cnn_propagator/fullfield.py:93-121
+                             + autodiff gradient       tensorflow_recon/fullfield.py:428-435
+  ptycho_loss_and_grad    <- rotate_and_project        tensorflow_recon/ptychography.py:37-97
+                             calculate_loss            cnn_propagator/ptychography.py:30-81
+                             + autodiff gradient       cnn_propagator/ptychography.py:248
+
+The reference differentiates with TF / autograd; here the gradient is the hand-written adjoint
+of the multislice chain (libbdof), returned as the 2-tuple (g_delta, g_beta) that
+`loss_grad = grad(calculate_loss, [0, 1])` returns in the reference.
+Object rotation (tf.contrib.image.rotate / apply_rotation) is the step before the hot path and
+is not part of this round: theta must be 0.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .capi import lib, check
+from .plan import MultislicePlan, _ptr
+from .propagation import _cached_plan, _device, _to_dev, _probe_c64
+
+
+def total_variation_3d(arr):
+    """cnn_propagator/util.py:61-70 (periodic first differences, L1)."""
+    res = torch.sum(torch.abs(torch.roll(arr, 1, 0) - arr))
+    res = res + torch.sum(torch.abs(torch.roll(arr, 1, 1) - arr))
+    res = res + torch.sum(torch.abs(torch.roll(arr, 1, 2) - arr))
+    return res
+
+
+def _tv_grad(arr):
+    g = torch.zeros_like(arr)
+    for ax in range(3):
+        s = torch.sign(torch.roll(arr, 1, ax) - arr)
+        g += torch.roll(s, -1, ax) - s
+    return g
+
+
+def _check_theta(theta):
+    th = np.atleast_1d(np.asarray(theta.cpu() if isinstance(theta, torch.Tensor) else theta, dtype=np.float64))
+    if np.any(th != 0):
+        raise NotImplementedError('object rotation is not part of the multislice hot path yet: theta must be 0')
+    return th
+
+
+def fullfield_loss_and_grad(obj_delta, obj_beta, theta_batch, prj_batch, probe_real, probe_imag, energy_ev, psize_cm,
+                            free_prop_cm=None, alpha_d=None, alpha_b=None, gamma=0.0, propagate_last=True,
+                            want_grad=True):
+    """loss = mean((|psi_exit| - |prj|)^2) [+ alpha_d |delta|_1 + alpha_b |beta|_1 + gamma TV(delta)]
+    over a minibatch of projection angles; returns (loss, (g_delta, g_beta), exit_wave).
+
+    obj_delta, obj_beta: [Y,X,Z] float32; prj_batch: [B,Y,X] complex or magnitude.
+    propagate_last=True follows the TF driver (fullfield.py:107-109); False the NumPy simulator.
+    """
+    th = _check_theta(theta_batch)
+    B = len(th)
+    dev = _device()
+    od = _to_dev(obj_delta, torch.float32)
+    ob = _to_dev(obj_beta, torch.float32)
+    Y, X, Z = od.shape
+    key = ('ff', (B, Y, X, Z), float(energy_ev), float(psize_cm), free_prop_cm, propagate_last, dev.index)
+    plan = _cached_plan(key, lambda: MultislicePlan(Y, X, B, Z, energy_ev, psize_cm, free_prop_cm=free_prop_cm,
+                                                     propagate_last=propagate_last, store_slices=True))
+    # theta == 0: every batch element sees the unrotated object
+    db = plan.pack(od[None].expand(B, Y, X, Z), ob[None].expand(B, Y, X, Z))
+    probe = _probe_c64(probe_real, probe_imag, (Y, X))
+    exit_wave = plan.forward(db, probe)
+    prj = _to_dev(prj_batch, torch.complex64 if (isinstance(prj_batch, torch.Tensor) and prj_batch.is_complex())
+                  or np.iscomplexobj(prj_batch) else torch.float32)
+    target = prj.abs().to(torch.float32)
+    loss, g_exit = plan.loss_mag(exit_wave, target, want_grad=want_grad)
+    loss = loss.clone()
+    g_d = g_b = None
+    if want_grad:
+        plan.adjoint(db, g_exit)                       # db now holds (dL/ddelta, dL/dbeta) per batch element
+        gd_b, gb_b = plan.unpack(db)
+        g_d, g_b = gd_b.sum(0), gb_b.sum(0)
+    if alpha_d is not None and alpha_d != 0:
+        loss = loss + alpha_d * od.abs().sum()
+        if want_grad:
+            g_d = g_d + alpha_d * torch.sign(od)
+    if alpha_b is not None and alpha_b != 0:
+        loss = loss + alpha_b * ob.abs().sum()
+        if want_grad:
+            g_b = g_b + alpha_b * torch.sign(ob)
+    if gamma:
+        loss = loss + gamma * total_variation_3d(od)
+        if want_grad:
+            g_d = g_d + gamma * _tv_grad(od)
+    return loss, (g_d, g_b), exit_wave
+
+
+def pack_object(obj_delta, obj_beta):
+    """[Y,X,Z] delta/beta -> slice-major interleaved object [Z,Y,X,2] on the current device."""
+    od = _to_dev(obj_delta, torch.float32).contiguous()
+    ob = _to_dev(obj_beta, torch.float32).contiguous()
+    Y, X, Z = od.shape
+    out = torch.empty((Z, Y, X, 2), dtype=torch.float32, device=od.device)
+    check(lib.bdof_pack_db(_ptr(od), _ptr(ob), _ptr(out), 1, Y, X, Z, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out
+
+
+def unpack_object(db_obj):
+    Z, Y, X, _ = db_obj.shape
+    d = torch.empty((Y, X, Z), dtype=torch.float32, device=db_obj.device)
+    b = torch.empty((Y, X, Z), dtype=torch.float32, device=db_obj.device)
+    check(lib.bdof_unpack_db(_ptr(db_obj), _ptr(d), _ptr(b), 1, Y, X, Z, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return d, b
+
+
+def ptycho_loss_and_grad(obj_delta, obj_beta, theta, probe_pos_batch, prj_batch, probe_real, probe_imag, probe_size,
+                         energy_ev, psize_cm, n_dp_batch=None, scale_by_npos=True, n_pos_total=None, want_grad=True,
+                         db_obj=None, grad_obj_out=None):
+    """Ptychography forward model + loss + gradient for one rotation angle (theta = 0).
+
+    probe_pos_batch: integer (y, x) scan positions; the window of size probe_size starts at
+    pos - int(probe_size/2) and is zero-padded outside the object (ptychography.py:45-76).
+    prj_batch: [n_pos, py, px] measured far-field amplitudes (complex or magnitude).
+    loss = mean((|Psi| - |prj|)^2) (* n_pos_total if scale_by_npos, ptychography.py:94).
+    Returns (loss, (g_delta, g_beta)); with db_obj / grad_obj_out (slice-major [Z,Y,X,2]) the
+    object and its gradient stay in the native layout and (loss, grad_obj_out) is returned.
+    """
+    _check_theta(theta)
+    dev = _device()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    native = db_obj is not None
+    if not native:
+        db_obj = pack_object(obj_delta, obj_beta)
+    Z, OY, OX, _ = db_obj.shape
+    py, px = int(probe_size[0]), int(probe_size[1])
+    pos = np.asarray(probe_pos_batch.cpu() if isinstance(probe_pos_batch, torch.Tensor) else probe_pos_batch).astype(np.int64)
+    n = len(pos)
+    half = (np.array([py, px]) / 2).astype('int')                 # ptychography.py:184
+    origin = torch.as_tensor((pos - half[None, :]).astype(np.int32)).to(dev).contiguous()
+    key = ('pty', (n, py, px, Z), float(energy_ev), float(psize_cm), dev.index)
+    plan = _cached_plan(key, lambda: MultislicePlan(py, px, n, Z, energy_ev, psize_cm, free_prop_cm='inf',
+                                                     propagate_last=True, store_slices=True))
+    patches = torch.empty((Z, n, py, px, 2), dtype=torch.float32, device=dev)
+    check(lib.bdof_patch_gather(_ptr(db_obj), Z, OY, OX, _ptr(origin), n, py, px, _ptr(patches), st))
+    probe = _probe_c64(probe_real, probe_imag, (py, px))
+    exit_wave = plan.forward(patches, probe)
+    is_cplx = (isinstance(prj_batch, torch.Tensor) and prj_batch.is_complex()) or np.iscomplexobj(prj_batch)
+    target = _to_dev(prj_batch, torch.complex64 if is_cplx else torch.float32).abs().to(torch.float32)
+    scale = float(n_pos_total if n_pos_total is not None else n) if scale_by_npos else 1.0
+    loss, g_exit = plan.loss_mag(exit_wave, target, want_grad=want_grad, loss_scale=scale)
+    loss = loss.clone()
+    if not want_grad:
+        return loss, None
+    plan.adjoint(patches, g_exit)
+    if grad_obj_out is None:
+        grad_obj_out = torch.zeros_like(db_obj)
+    check(lib.bdof_patch_scatter_add(_ptr(patches), Z, OY, OX, _ptr(origin), n, py, px, _ptr(grad_obj_out), st))
+    if native:
+        return loss, grad_obj_out
+    return loss, unpack_object(grad_obj_out)

@@ -1,0 +1,169 @@
+"""MultislicePlan: the host-side handle of one multislice problem shape on one GPU.
+
+PyTorch is only the array container here (device memory, streams); all arithmetic happens in
+libbdof.so through the C ABI (include/bdof.h).  There is no CPU fallback: constructing a plan
+without a CUDA device raises.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import capi
+from .capi import lib, check
+from .util import PI, kernel_factors, factor_kernel
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _hptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _c128(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.complex128))
+
+
+class MultislicePlan:
+    """Forward / adjoint multislice for a fixed [batch, ny, nx, n_slice] shape.
+
+    Semantics switches:
+      propagate_last=False  NumPy path, last slice only modulates   (npfuncs.py:35-41)
+      propagate_last=True   TF path, every slice propagates          (util.py:464-488)
+      free_prop_cm          None | 'inf' | float (cm)                (npfuncs.py:43-61)
+      h                     optional caller-supplied centred H [ny,nx] (util.py:459-461)
+    """
+
+    def __init__(self, ny, nx, batch, n_slice, energy_ev, psize_cm, free_prop_cm=None, propagate_last=False,
+                 store_slices=False, z_broadcast=False, h=None, pi=PI, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('beyond_dof_b200 needs a CUDA device: the multislice path has no CPU fallback')
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.ny, self.nx, self.batch, self.n_slice = int(ny), int(nx), int(batch), int(n_slice)
+        self.propagate_last = bool(propagate_last)
+        self.store_slices = bool(store_slices)
+        self.z_broadcast = bool(z_broadcast)
+        if np.ndim(psize_cm) == 0:
+            voxel_nm = np.array([psize_cm] * 3, dtype=np.float64) * 1.e7
+        else:
+            voxel_nm = np.array(psize_cm, dtype=np.float64) * 1.e7
+        self.voxel_nm = voxel_nm
+        self.lmbda_nm = 1240. / energy_ev
+        delta_nm = voxel_nm[-1]
+        self.k_dz = 2. * pi * delta_nm / self.lmbda_nm
+        flags = 0
+        if self.propagate_last:
+            flags |= capi.PROPAGATE_LAST
+        if self.store_slices:
+            flags |= capi.STORE_SLICES
+        if self.z_broadcast:
+            flags |= capi.Z_BROADCAST
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            self.stream = torch.cuda.current_stream(self.device)
+            check(lib.bdof_plan_create(ctypes.byref(self._h), self.ny, self.nx, self.batch, self.n_slice, flags,
+                                       ctypes.c_void_p(self.stream.cuda_stream)))
+            grid_shape = [self.ny, self.nx, self.n_slice]
+            fac = None
+            if h is None:
+                fac = kernel_factors(delta_nm, self.lmbda_nm, voxel_nm, grid_shape, pi=pi)
+            else:
+                fac = factor_kernel(h)
+            if fac is not None:
+                p0, hy, hx = fac
+                hy, hx = _c128(hy), _c128(hx)
+                check(lib.bdof_set_kernel(self._h, _hptr(hy), _hptr(hx), p0.real, p0.imag, self.k_dz))
+            else:
+                hh = _c128(h)
+                check(lib.bdof_set_kernel_full(self._h, _hptr(hh), self.k_dz))
+            if free_prop_cm is None:
+                check(lib.bdof_set_free_prop(self._h, capi.FREE_NONE, None, None, 1.0, 0.0))
+            elif isinstance(free_prop_cm, str):
+                if free_prop_cm != 'inf':
+                    raise ValueError("free_prop_cm must be None, 'inf' or a distance in cm")
+                check(lib.bdof_set_free_prop(self._h, capi.FREE_INF, None, None, 1.0, 0.0))
+            else:
+                # npfuncs.py:48-56: the TF/IR choice is computed and then forced to 'TF'
+                p0, hy, hx = kernel_factors(free_prop_cm * 1e7, self.lmbda_nm, voxel_nm, grid_shape, pi=pi)
+                hy, hx = _c128(hy), _c128(hx)
+                check(lib.bdof_set_free_prop(self._h, capi.FREE_TF, _hptr(hy), _hptr(hx), p0.real, p0.imag))
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h is not None and h.value:
+            lib.bdof_plan_destroy(h)
+            self._h = ctypes.c_void_p()
+
+    # ---- layout helpers -----------------------------------------------------------------
+    @property
+    def db_shape(self):
+        return (1 if self.z_broadcast else self.n_slice, self.batch, self.ny, self.nx, 2)
+
+    def pack(self, grid_delta_batch, grid_beta_batch):
+        """[B,Y,X,Z] float32 device tensors -> slice-major interleaved db [Z,B,Y,X,2]."""
+        d = grid_delta_batch.to(self.device, torch.float32).contiguous()
+        b = grid_beta_batch.to(self.device, torch.float32).contiguous()
+        B, Y, X, Z = d.shape
+        db = torch.empty((Z, B, Y, X, 2), dtype=torch.float32, device=self.device)
+        check(lib.bdof_pack_db(_ptr(d), _ptr(b), _ptr(db), B, Y, X, Z, ctypes.c_void_p(self.stream.cuda_stream)))
+        return db
+
+    def unpack(self, db):
+        Z, B, Y, X, _ = db.shape
+        d = torch.empty((B, Y, X, Z), dtype=torch.float32, device=self.device)
+        b = torch.empty((B, Y, X, Z), dtype=torch.float32, device=self.device)
+        check(lib.bdof_unpack_db(_ptr(db), _ptr(d), _ptr(b), B, Y, X, Z, ctypes.c_void_p(self.stream.cuda_stream)))
+        return d, b
+
+    # ---- compute ------------------------------------------------------------------------
+    def forward(self, db, probe, out=None):
+        """db [Z,B,Y,X,2] float32, probe [Y,X] complex64 -> exit wave [B,Y,X] complex64."""
+        assert db.is_cuda and db.dtype == torch.float32 and db.is_contiguous() and tuple(db.shape) == self.db_shape, \
+            'db must be a contiguous float32 CUDA tensor of shape %s' % (self.db_shape,)
+        probe = probe.to(self.device, torch.complex64).contiguous()
+        assert tuple(probe.shape) == (self.ny, self.nx)
+        if out is None:
+            out = torch.empty((self.batch, self.ny, self.nx), dtype=torch.complex64, device=self.device)
+        check(lib.bdof_forward(self._h, _ptr(db), _ptr(probe), _ptr(out)))
+        return out
+
+    def loss_mag(self, exit_wave, target_mag, want_grad=True, loss_scale=1.0):
+        """mean((|psi| - |y|)^2) * loss_scale and G = dL/dRe + i dL/dIm (fullfield.py:115)."""
+        target_mag = target_mag.to(self.device, torch.float32).contiguous()
+        loss = torch.empty((), dtype=torch.float64, device=self.device)
+        g = torch.empty_like(exit_wave) if want_grad else None
+        check(lib.bdof_loss_mag(self._h, _ptr(exit_wave), _ptr(target_mag), float(loss_scale), _ptr(loss),
+                                _ptr(g) if want_grad else None))
+        return loss, g
+
+    def adjoint(self, db, grad_exit, grad_out=None, want_probe_grad=False):
+        """Back-propagate grad_exit.  By default db is overwritten in place with (dL/ddelta, dL/dbeta);
+        pass grad_out [Z,B,Y,X,2] to keep db intact (mandatory with z_broadcast)."""
+        assert self.store_slices, 'plan was created with store_slices=False'
+        grad_exit = grad_exit.to(self.device, torch.complex64).contiguous()
+        gp = torch.empty((self.ny, self.nx), dtype=torch.complex64, device=self.device) if want_probe_grad else None
+        if grad_out is not None:
+            assert grad_out.is_contiguous() and tuple(grad_out.shape) == (self.n_slice, self.batch, self.ny, self.nx, 2)
+        check(lib.bdof_adjoint(self._h, _ptr(db), _ptr(grad_exit), _ptr(grad_out) if grad_out is not None else None,
+                               _ptr(gp) if want_probe_grad else None))
+        res = grad_out if grad_out is not None else db
+        return (res, gp) if want_probe_grad else res
+
+    def forward_host(self, delta_byxz, beta_byxz, probe, out=None):
+        """End-to-end call with HOST float32 arrays in the reference layout [B,Y,X,Z]: H2D copies,
+        layout conversion, the forward chain and the D2H copy of the exit wave all happen inside."""
+        d = np.ascontiguousarray(delta_byxz, dtype=np.float32)
+        b = np.ascontiguousarray(beta_byxz, dtype=np.float32)
+        pr = np.ascontiguousarray(probe, dtype=np.complex64)
+        if out is None:
+            out = np.empty((self.batch, self.ny, self.nx), dtype=np.complex64)
+        assert d.shape == (self.batch, self.ny, self.nx, self.n_slice) and b.shape == d.shape
+        check(lib.bdof_forward_host(self._h, _hptr(d), _hptr(b), _hptr(pr), _hptr(out)))
+        return out
+
+    def workspace_bytes(self):
+        n = ctypes.c_size_t()
+        check(lib.bdof_plan_workspace_bytes(self._h, ctypes.byref(n)))
+        return n.value

@@ -1,0 +1,140 @@
+/*
+ * bdof.h -- C ABI of the B200-native Fresnel multislice engine (libbdof.so).
+ *
+ * The reference (mdw771/beyond_dof) is pure Python and has no FFI: the hot path is reached
+ * through Python functions.  Each entry point below names the reference function whose work
+ * it replaces; beyond_dof_b200/ binds them with ctypes and re-exposes the reference's own
+ * Python signatures (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ *   bdof_kernel_factors      <- get_kernel                tensorflow_recon/util.py:165-185
+ *   bdof_forward             <- multislice_propagate_batch_numpy  tensorflow_recon/npfuncs.py:16-63
+ *                               multislice_propagate_batch        tensorflow_recon/util.py:432-508
+ *                               multislice_propagate              tensorflow_recon/util.py:360-429
+ *   bdof_loss_mag            <- mean((|psi|-|y|)^2)       tensorflow_recon/fullfield.py:115,
+ *                                                          cnn_propagator/fullfield.py:106
+ *   bdof_adjoint             <- autodiff of the above     tensorflow_recon/fullfield.py:428-435,
+ *                                                          cnn_propagator/fullfield.py:329
+ *   bdof_pack_db / unpack    <- grid[:, :, :, i] slicing  tensorflow_recon/npfuncs.py:36-37
+ *   bdof_patch_gather/scatter<- probe-window cut          tensorflow_recon/ptychography.py:62-76
+ *   bdof_cnn_forward         <- multislice_propagate_cnn  cnn_propagator/propagation.py:18-133
+ *   bdof_forward_host        <- the whole call with HOST buffers in the reference layout
+ *
+ * Conventions
+ *   - Every pointer named d_* is DEVICE memory owned by the caller; h_* is HOST memory.
+ *   - Fields are complex64 stored as interleaved (re, im) floats, layout [batch][ny][nx].
+ *   - The object is "db": interleaved (delta, beta) float pairs, slice-major
+ *     [n_slice][batch][ny][nx][2].  bdof_pack_db converts from the reference's [B,Y,X,Z].
+ *   - Return value: 0 = OK, negative = BDOF_E_*, positive = cudaError_t.  A message for the
+ *     last failure on the calling thread is available from bdof_last_error().
+ *   - A plan is bound to one device and one stream and is not re-entrant; all calls are
+ *     stream-asynchronous unless stated.  There is no CPU fallback: without a CUDA device
+ *     every compute entry point fails with a cudaError_t.
+ */
+#ifndef BDOF_H
+#define BDOF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bdof_plan bdof_plan;
+
+enum {
+    BDOF_OK = 0,
+    BDOF_E_BADARG = -1,       /* null pointer / non-positive size */
+    BDOF_E_UNSUPPORTED = -2,  /* field size not a supported FFT length */
+    BDOF_E_STATE = -3,        /* call order (e.g. adjoint before a storing forward) */
+    BDOF_E_NOMEM = -4
+};
+
+/* plan flags */
+enum {
+    BDOF_PROPAGATE_LAST = 1u << 0,  /* TF semantics: every slice propagates (util.py:464-483);
+                                       default = NumPy semantics, last slice only modulates */
+    BDOF_STORE_SLICES   = 1u << 1,  /* keep psi entering every slice for bdof_adjoint */
+    BDOF_Z_BROADCAST    = 1u << 2   /* db holds ONE slice that repeats along z (axially invariant) */
+};
+
+/* free-space step after the object (npfuncs.py:43-61) */
+enum { BDOF_FREE_NONE = 0, BDOF_FREE_INF = 1, BDOF_FREE_TF = 2 };
+
+int  bdof_version(void);
+const char* bdof_last_error(void);
+/* number of kernels launched by this library since load (all plans, this process) */
+unsigned long long bdof_launch_count(void);
+
+/* FFT lengths the line kernels are compiled for; returns 1/0 */
+int  bdof_size_supported(int n);
+
+/* Separable factors of the reference transfer function, float64 on the host:
+ * H[v,u] = phase0 * hy[v] * hx[u], centred, voxel_nm has 3 entries, h*_out are complex128
+ * (interleaved re,im doubles) of length ny / nx. */
+int  bdof_kernel_factors(double dist_nm, double lmbda_nm, const double* voxel_nm, int ny, int nx,
+                         double pi_const, double* hy_out, double* hx_out, double* phase0_out);
+
+int  bdof_plan_create(bdof_plan** out, int ny, int nx, int batch, int n_slice, uint32_t flags,
+                      void* cuda_stream);
+void bdof_plan_destroy(bdof_plan* p);
+
+/* Per-slice propagator.  h_hy/h_hx: centred complex128 factors (host). phase0 (re,im) is the
+ * global phase exp(i k dz) kept out of the fp32 tables and restored analytically.
+ * k_dz = 2*pi*dz/lambda is the transmission constant (npfuncs.py:33). */
+int  bdof_set_kernel(bdof_plan* p, const double* h_hy, const double* h_hx, double phase0_re,
+                     double phase0_im, double k_dz);
+/* General (non-separable) centred H[ny][nx], complex128 on the host (util.py:459-461, h=...). */
+int  bdof_set_kernel_full(bdof_plan* p, const double* h_H, double k_dz);
+/* Free-space step: mode BDOF_FREE_*; factors only for BDOF_FREE_TF. */
+int  bdof_set_free_prop(bdof_plan* p, int mode, const double* h_hy, const double* h_hx,
+                        double phase0_re, double phase0_im);
+
+/* psi_exit[b] = multislice(db[:, b], probe).  d_probe [ny][nx] complex64 shared by the batch. */
+int  bdof_forward(bdof_plan* p, const float* d_db, const float* d_probe, float* d_exit);
+
+/* loss = mean((|exit| - target_mag)^2) over [batch][ny][nx], written to d_loss (one double,
+ * device); d_grad_exit (nullable) receives G = dL/dRe + i dL/dIm. loss_scale multiplies both. */
+int  bdof_loss_mag(bdof_plan* p, const float* d_exit, const float* d_target_mag, double loss_scale,
+                   double* d_loss, float* d_grad_exit);
+
+/* Back-propagate d_grad_exit through the last bdof_forward (plan must have BDOF_STORE_SLICES).
+ * d_db_inout holds (delta,beta) on entry and (dL/ddelta, dL/dbeta) on return, in place.
+ * With BDOF_Z_BROADCAST the gradient is written to d_grad_out [n_slice][batch][ny][nx][2]
+ * instead (required).  d_grad_probe (nullable) [ny][nx] complex64 = sum over batch. */
+int  bdof_adjoint(bdof_plan* p, float* d_db_inout, const float* d_grad_exit, float* d_grad_out,
+                  float* d_grad_probe);
+
+/* layout conversion: reference [B,Y,X,Z] float32 planes <-> slice-major interleaved db */
+int  bdof_pack_db(const float* d_delta_byxz, const float* d_beta_byxz, float* d_db, int batch, int ny,
+                  int nx, int n_slice, void* cuda_stream);
+int  bdof_unpack_db(const float* d_db, float* d_delta_byxz, float* d_beta_byxz, int batch, int ny,
+                    int nx, int n_slice, void* cuda_stream);
+
+/* Ptychography windows.  Object db_obj [n_slice][oy][ox][2]; positions (y0,x0) = window origin
+ * (may be negative / overhang: zero padding as ptychography.py:45-61); output
+ * [n_slice][n_pos][py][px][2].  scatter_add accumulates window gradients back (fp32 atomics). */
+int  bdof_patch_gather(const float* d_db_obj, int n_slice, int oy, int ox, const int* d_pos_yx, int n_pos,
+                       int py, int px, float* d_db_patches, void* cuda_stream);
+int  bdof_patch_scatter_add(const float* d_grad_patches, int n_slice, int oy, int ox, const int* d_pos_yx,
+                            int n_pos, int py, int px, float* d_grad_obj, void* cuda_stream);
+
+/* Real-space propagator of cnn_propagator/propagation.py:18-133: h_kernel is the cropped
+ * kernel_size^2 complex128 kernel (host).  db as above; exit [batch][ny][nx]. */
+int  bdof_cnn_forward(const float* d_db, const float* d_probe, float* d_exit, float* d_work, int batch,
+                      int ny, int nx, int n_slice, const double* h_kernel, int kernel_size, double k_dz,
+                      void* cuda_stream);
+
+/* End-to-end convenience with HOST buffers in the reference layout: copies delta/beta
+ * [B,Y,X,Z] float32 and the probe to the device, packs, runs bdof_forward, copies the exit wave
+ * [B,Y,X] complex64 back and synchronises the stream. */
+int  bdof_forward_host(bdof_plan* p, const float* h_delta_byxz, const float* h_beta_byxz,
+                       const float* h_probe, float* h_exit);
+
+/* kernel-only timing hook: run the per-slice pass pair `reps` times on scratch data */
+int  bdof_plan_workspace_bytes(const bdof_plan* p, size_t* bytes_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDOF_H */

@@ -379,3 +379,39 @@ def random_phantom(shape_byxz, seed=1234, delta_scale=1e-5, beta_scale=1e-6):
     gd = rng.random(shape_byxz, dtype=np.float32) * np.float32(delta_scale)
     gb = rng.random(shape_byxz, dtype=np.float32) * np.float32(beta_scale)
     return gd, gb
+
+
+# ---------------------------------------------------------------------------------------------
+# model-level gradients (hand adjoint + window scatter-add); pinned against torch.autograd
+# ---------------------------------------------------------------------------------------------
+
+def fullfield_loss_and_grad(obj_delta, obj_beta, prj_batch, probe_real, probe_imag, energy_ev, psize_cm,
+                            free_prop_cm=None, propagate_last=True):
+    """Data term of tensorflow_recon/fullfield.py:92-116 at theta = 0 and its gradient w.r.t. the
+    [Y,X,Z] object (sum of the per-batch-element gradients)."""
+    B = len(prj_batch)
+    d = np.broadcast_to(obj_delta, (B,) + obj_delta.shape).astype(np.float64)
+    b = np.broadcast_to(obj_beta, (B,) + obj_beta.shape).astype(np.float64)
+    loss, gd, gb, psi = loss_and_grad(d, b, probe_real, probe_imag, energy_ev, psize_cm, np.abs(prj_batch),
+                                      free_prop_cm=free_prop_cm, propagate_last=propagate_last)
+    return loss, gd.sum(0), gb.sum(0), psi
+
+
+def ptycho_loss_and_grad(obj_delta, obj_beta, probe_pos, prj, probe_real, probe_imag, probe_size, energy_ev,
+                         psize_cm, scale_by_npos=True):
+    """tensorflow_recon/ptychography.py:37-97 at theta = 0 with the gradient w.r.t. the object."""
+    probe_pos = np.asarray(probe_pos).astype(int)
+    wd, pad_arr = ptycho_windows(obj_delta, probe_pos, probe_size)
+    wb, _ = ptycho_windows(obj_beta, probe_pos, probe_size)
+    loss, gd, gb, psi = loss_and_grad(wd.astype(np.float64), wb.astype(np.float64), probe_real, probe_imag,
+                                      energy_ev, psize_cm, np.abs(prj), free_prop_cm='inf', propagate_last=True)
+    scale = len(probe_pos) if scale_by_npos else 1
+    half = (np.array(probe_size) / 2).astype('int')
+    Y, X, Z = obj_delta.shape
+    g_d = np.zeros((Y, X, Z)); g_b = np.zeros((Y, X, Z))
+    for n, pos in enumerate(probe_pos):
+        y0, x0 = int(pos[0]) - half[0], int(pos[1]) - half[1]
+        ys = slice(max(y0, 0), min(y0 + probe_size[0], Y)); xs = slice(max(x0, 0), min(x0 + probe_size[1], X))
+        g_d[ys, xs] += gd[n, ys.start - y0:ys.stop - y0, xs.start - x0:xs.stop - x0]
+        g_b[ys, xs] += gb[n, ys.start - y0:ys.stop - y0, xs.start - x0:xs.stop - x0]
+    return loss * scale, g_d * scale, g_b * scale, psi

@@ -1,0 +1,104 @@
+"""GPU tier: full-field and ptychography forward model + loss + gradient against the oracle
+(rotation = identity: theta = 0), and the real-space 'cnn' propagator against the reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+from oracle import multislice_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def bd():
+    import beyond_dof_b200 as pkg
+    assert torch.cuda.is_available()
+    return pkg
+
+
+def test_fullfield_loss_and_grad(bd):
+    Y, X, Z, B = 64, 64, 8, 3
+    rng = np.random.default_rng(50)
+    od = np.clip(rng.normal(8.7e-7, 1e-7, (Y, X, Z)), 0, None).astype(np.float32) * 100
+    ob = np.clip(rng.normal(5.1e-8, 1e-8, (Y, X, Z)), 0, None).astype(np.float32) * 100
+    gt_d, gt_b = mo.random_phantom((1, Y, X, Z), seed=51, delta_scale=1e-4, beta_scale=1e-5)
+    one, zero = np.ones((Y, X)), np.zeros((Y, X))
+    prj = mo.multislice_propagate_batch(gt_d.astype(np.float64), gt_b.astype(np.float64), one, zero, 5000, 1e-7, free_prop_cm=1e-4)
+    prj_b = np.repeat(prj, B, axis=0)
+    lo, gdo, gbo, _ = mo.fullfield_loss_and_grad(od, ob, prj_b, one, zero, 5000, 1e-7, free_prop_cm=1e-4)
+    loss, (g_d, g_b), ex = bd.fullfield_loss_and_grad(od, ob, np.zeros(B), prj_b, one, zero, 5000, 1e-7, free_prop_cm=1e-4)
+    assert abs(loss.item() - lo) < 1e-5 * abs(lo)
+    assert rel_l2(g_d.cpu().numpy(), gdo) < 1e-4 and rel_l2(g_b.cpu().numpy(), gbo) < 1e-4
+    # regularisers (fullfield.py:389-396)
+    loss2, (g_d2, _), _ = bd.fullfield_loss_and_grad(od, ob, np.zeros(B), prj_b, one, zero, 5000, 1e-7, free_prop_cm=1e-4,
+                                                     alpha_d=1e-3, alpha_b=1e-4, gamma=1e-5)
+    tod = torch.tensor(od, dtype=torch.float64, requires_grad=True)
+    reg = 1e-3 * tod.abs().sum() + 1e-5 * sum((torch.roll(tod, 1, a) - tod).abs().sum() for a in range(3))
+    reg.backward()
+    assert abs((loss2 - loss).item() - (reg.item() + 1e-4 * np.abs(ob).sum())) < 1e-6 * reg.item()
+    assert rel_l2((g_d2 - g_d).cpu().numpy(), tod.grad.numpy()) < 1e-5
+    with pytest.raises(NotImplementedError):
+        bd.fullfield_loss_and_grad(od, ob, np.array([0.3]), prj, one, zero, 5000, 1e-7)
+
+
+def test_ptycho_loss_and_grad_with_padding(bd):
+    Y, X, Z = 96, 112, 6
+    probe_size = (64, 64)
+    od, ob = mo.random_phantom((Y, X, Z), seed=60, delta_scale=3e-4, beta_scale=3e-5)
+    gt_d, gt_b = mo.random_phantom((Y, X, Z), seed=61, delta_scale=3e-4, beta_scale=3e-5)
+    pr, pi = mo.gaussian_probe(probe_size, 6., 6., 0.5)
+    # positions include windows that overhang every edge (zero padding, ptychography.py:45-61)
+    pos = [(0, 0), (10, 100), (95, 111), (48, 56), (40, 40), (90, 5)]
+    _, prj = mo.ptycho_loss(gt_d, gt_b, pos, np.zeros((len(pos),) + probe_size), pr, pi, probe_size, 5000, 1e-7)
+    lo, gdo, gbo, _ = mo.ptycho_loss_and_grad(od, ob, pos, prj, pr, pi, probe_size, 5000, 1e-7)
+    loss, (g_d, g_b) = bd.ptycho_loss_and_grad(od, ob, 0.0, pos, prj, pr, pi, probe_size, 5000, 1e-7)
+    assert abs(loss.item() - lo) < 1e-5 * abs(lo)
+    assert rel_l2(g_d.cpu().numpy(), gdo) < 1e-4 and rel_l2(g_b.cpu().numpy(), gbo) < 1e-4
+    # oracle model head agrees with the literal restatement of the TF loss
+    l2, _ = mo.ptycho_loss(od, ob, pos, prj, pr, pi, probe_size, 5000, 1e-7)
+    assert abs(l2 - lo) < 1e-12 * abs(lo)
+
+
+def test_ptycho_gradient_matches_torch_autograd_small(bd):
+    # independent check of oracle + GPU against torch.autograd through a complex128 torch restatement
+    Y, X, Z = 80, 80, 3
+    probe_size = (64, 64)
+    od, ob = mo.random_phantom((Y, X, Z), seed=62, delta_scale=1e-3, beta_scale=1e-4)
+    pr, pi = mo.gaussian_probe(probe_size, 8., 8., 0.3)
+    pos = [(32, 32), (40, 44), (47, 47)]
+    rng = np.random.default_rng(63)
+    prj = rng.random((3,) + probe_size) * 30
+    tod = torch.tensor(od.astype(np.float64), requires_grad=True); tob = torch.tensor(ob.astype(np.float64), requires_grad=True)
+    h = torch.tensor(np.fft.ifftshift(mo.get_kernel(1.0, 0.248, [1., 1., 1.], [64, 64, Z])))
+    k = 2 * mo.PI_TF / 0.248
+    probe = torch.tensor((pr + 1j * pi).astype(np.complex64).astype(np.complex128))
+    loss_t = 0
+    outs = []
+    for (py, px) in pos:
+        wd = tod[py - 32:py + 32, px - 32:px + 32]; wb = tob[py - 32:py + 32, px - 32:px + 32]
+        psi = probe
+        for i in range(Z):
+            psi = psi * torch.exp(1j * k * wd[..., i]) * torch.exp(-k * wb[..., i])
+            psi = torch.fft.ifft2(torch.fft.fft2(psi) * h)
+        outs.append(torch.fft.fftshift(torch.fft.fft2(psi)))
+    ex = torch.stack(outs)
+    loss_t = torch.mean((ex.abs() - torch.tensor(prj)) ** 2) * len(pos)
+    loss_t.backward()
+    loss, (g_d, g_b) = bd.ptycho_loss_and_grad(od, ob, 0.0, pos, prj, pr, pi, probe_size, 5000, 1e-7)
+    assert abs(loss.item() - loss_t.item()) < 1e-5 * abs(loss_t.item())
+    assert rel_l2(g_d.cpu().numpy(), tod.grad.numpy()) < 1e-4 and rel_l2(g_b.cpu().numpy(), tob.grad.numpy()) < 1e-4
+
+
+def test_cnn_propagator_matches_reference(bd, golden_dir):
+    gold = np.load(os.path.join(golden_dir, 'ref_cnn.npz'))
+    gd, gb = mo.random_phantom((2, 32, 40, 6), seed=21, delta_scale=1e-4, beta_scale=1e-5)
+    for ks in (5, 17):
+        for free in (None, 'inf'):
+            psi = bd.multislice_propagate_cnn(gd, gb, np.ones([32, 40]), np.zeros([32, 40]), 5000, [1e-7] * 3,
+                                              kernel_size=ks, free_prop_cm=free)
+            ref = gold['cnn_ks%d_%s' % (ks, free)]
+            assert rel_l2(np.abs(psi) ** 2, np.abs(ref) ** 2) < 1e-5
+            assert rel_l2(psi, ref) < 1e-5
