@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Benchmark of the multislice hot path (BASELINE.json metric: multislice Gpixel*slice/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config2|headline|config1] [--impl reference]
+
+One "step" = forward multislice + |psi| loss + adjoint gradient over one synthetic field per GPU.
+Default workload (N=1) is BASELINE.json configs[1]: random delta/beta phantom 2048 x 2048 x 256,
+forward + adjoint on one B200.  1 unit = one pixel advanced through one slice (forward + adjoint
+counts the slice once).  With N>1 ranks (torchrun) every rank owns one such field (one projection
+angle of the data-parallel reconstruction, weak scaling) and the object gradient is all-reduced over
+NCCL every step.
+
+Keys of the JSON line: see the contract in the task description; in short
+  value        device-timed whole-job throughput, inputs resident in HBM
+  e2e          the same step through the public API (FullfieldObjective.step) with this step's
+               measured projections copied from pinned host memory and the loss read back
+  roofline     dominant line kernel: algorithmic bytes / in-situ CUDA-event duration vs measured HBM peak
+  cpu_baseline oracle port (NumPy complex128, the reference algorithm) on the host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+WORKLOADS = {
+    # name: (ny, nx, n_slice, description)
+    'config2': (2048, 2048, 256, 'random delta/beta phantom 2048x2048x256, forward + adjoint gradient (BASELINE configs[1])'),
+    'headline': (4096, 4096, 512, 'random delta/beta phantom 4096x4096x512, forward + adjoint gradient (north_star target size)'),
+    'config1': (512, 512, 100, 'zone-plate-sized 512x512x100 field, forward + adjoint gradient (BASELINE configs[0] shape)'),
+    'small': (256, 256, 16, 'tiny functional check'),
+}
+ENERGY_EV, PSIZE_CM = 5000, 1e-7
+# algorithmic bytes per pixel*slice of each pass: complex64 field, fp32 (delta,beta)
+PASS_BYTES = {'row_conv_transmit': 24, 'col_conv': 16, 'row_conv_adjoint': 40}
+STEP_BYTES = 96
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '200',
+                                          '-i', str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+            except Exception:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(smax)), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm (NumPy complex128) on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def _cpu_sample(args):
+    ny, nx, nz, seed = args
+    from oracle import multislice_oracle as mo       # the one place bench.py executes oracle/: the measured CPU baseline
+    gd, gb = mo.random_phantom((1, ny, nx, nz), seed=seed)
+    gd = gd.astype(np.float64); gb = gb.astype(np.float64)
+    one, zero = np.ones((ny, nx)), np.zeros((ny, nx))
+    target = np.full((1, ny, nx), 0.98)
+    t0 = time.perf_counter()
+    mo.loss_and_grad(gd, gb, one, zero, ENERGY_EV, PSIZE_CM, target)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(ny, nx, procs, sample_slices):
+    """forward + adjoint of the oracle on [1, ny, nx, sample_slices], `procs` independent processes
+    (the reference's parallel model is one MPI rank per batch element; NumPy's FFT is single-threaded)."""
+    import multiprocessing as mp
+    work = [(ny, nx, sample_slices, 100 + i) for i in range(procs)]
+    t0 = time.perf_counter()
+    if procs == 1:
+        times = [_cpu_sample(work[0])]
+    else:
+        with mp.get_context('fork').Pool(procs) as pool:
+            times = pool.map(_cpu_sample, work)
+    wall = max(times) if procs > 1 else times[0]
+    units = procs * ny * nx * sample_slices
+    return units / wall / 1e9, wall, time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    ny, nx, nz, desc = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))
+    sample_slices = 4 if ny * nx >= 2048 * 2048 else min(nz, max(4, (2048 * 2048 * 4) // (ny * nx)))
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, wall, _ = cpu_baseline(ny, nx, procs, sample_slices)
+        if i >= args.warmup:
+            vals.append((v, wall))
+    v = float(np.mean([a for a, _ in vals]))
+    ms = float(np.mean([b for _, b in vals])) * 1e3
+    sample = '%d independent processes x forward+adjoint of [1,%d,%d,%d] (NumPy complex128 oracle port of npfuncs.py:16-63 + hand adjoint)' % (procs, ny, nx, sample_slices)
+    line = {
+        'impl': 'reference', 'metric': 'multislice Gpixel*slice/s (forward + adjoint)', 'value': v, 'unit': 'Gpixel*slice/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'c128', 'data': 'synthetic',
+        'config': {'workload': desc, 'ny': ny, 'nx': nx, 'n_slice': nz, 'sample': sample},
+        'cpu_baseline': {'value': v, 'unit': 'Gpixel*slice/s', 'cores': procs, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': 'Gpixel*slice/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from beyond_dof_b200 import capi
+    from beyond_dof_b200.models import FullfieldObjective
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    ny, nx, nz, desc = WORKLOADS[args.workload]
+    B = 1
+    units_per_step = B * ny * nx * nz * world
+
+    # synthetic inputs, created once on the device (value arm) / in pinned host memory (e2e arm)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    db = torch.empty((nz, B, ny, nx, 2), dtype=torch.float32, device=dev)
+    for z0 in range(0, nz, 16):                       # bounded temporaries
+        blk = db[z0:z0 + 16]
+        blk.copy_(torch.rand(blk.shape, device=dev, generator=g))
+        blk[..., 0] *= 1e-5
+        blk[..., 1] *= 1e-6
+    probe = torch.ones((ny, nx), dtype=torch.complex64, device=dev)
+    obj = FullfieldObjective(db, probe, ENERGY_EV, PSIZE_CM)
+    # target: measured magnitudes of a perturbed object (well inside (0, 1]); synthetic
+    target_host = (0.9 + 0.1 * torch.rand((B, ny, nx), generator=torch.Generator().manual_seed(4321 + rank))).pin_memory()
+    target_dev = target_host.to(dev)
+
+    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+
+    def allreduce_grad():
+        # data-parallel exchange (Horovod allreduce in fullfield.py:412; comm.Allreduce in cnn fullfield.py:350):
+        # sum of the object gradient over ranks, in z-buckets
+        if world == 1:
+            return
+        nb = 8
+        step = (nz + nb - 1) // nb
+        for z0 in range(0, nz, step):
+            dist.all_reduce(obj.grad[z0:z0 + step], op=dist.ReduceOp.SUM)
+
+    def step_device():
+        loss = obj.step_device(target_dev)
+        allreduce_grad()
+        return loss
+
+    def step_e2e():
+        loss = obj.step(target_host)
+        allreduce_grad()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident inputs
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = capi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        loss = step_device()
+    ev1.record()
+    barrier()
+    launches = capi.launch_count() - l0
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    value = units_per_step / (ms_step * 1e-3) / 1e9
+
+    # ---- e2e: this step's projections from pinned host memory, loss read back, through the public API
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = units_per_step / (t.item() / args.steps * 1e-3) / 1e9
+    h2d = target_host.numel() * target_host.element_size()
+    d2h = 8
+
+    # ---- per-kernel in-situ timing (one extra, untimed step with CUDA events around every pass)
+    kern = {}
+    roofline = None
+    cpu = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        obj.plan.profile_begin()
+        obj.step_device(target_dev)
+        prof = obj.plan.profile_end()
+        px = B * ny * nx
+        tot = sum(ms for _, ms in prof.values())
+        for name, (cnt, ms) in prof.items():
+            avg_ms = ms / cnt
+            bpp = PASS_BYTES.get(name)
+            kern[name] = {'launches': cnt, 'avg_ms': avg_ms, 'share_of_kernel_time': ms / tot,
+                          'alg_bytes_per_px': bpp, 'achieved_gbs': (px * bpp / (avg_ms * 1e-3) / 1e9) if bpp else None}
+        dom = max(prof.items(), key=lambda kv: kv[1][1])[0]
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+                traffic = json.load(f).get(args.workload, {}).get(dom)
+        except Exception:
+            pass
+        a = kern[dom]['achieved_gbs']
+        roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': a, 'peak': peak, 'unit': 'GB/s', 'frac': a / peak if a else None,
+                    'traffic': traffic, 'peak_source': peak_src,
+                    'whole_step': {'alg_bytes_per_px_slice': STEP_BYTES, 'achieved': value * STEP_BYTES, 'frac': value * STEP_BYTES / peak}}
+        # ---- CPU baseline: oracle port, 1 process (scalar port), bounded sample
+        if not args.no_cpu:
+            ss = 4 if ny * nx >= 2048 * 2048 else min(nz, max(4, (2048 * 2048 * 4) // (ny * nx)))
+            v, wall, _ = cpu_baseline(ny, nx, 1, ss)
+            cpu = {'value': v, 'unit': 'Gpixel*slice/s', 'cores': 1, 'kind': 'port',
+                   'sample': 'forward+adjoint of [1,%d,%d,%d], NumPy complex128 oracle (%.1f s)' % (ny, nx, ss, wall)}
+        line = {
+            'metric': 'multislice Gpixel*slice/s (forward + adjoint)', 'value': value, 'unit': 'Gpixel*slice/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'c64', 'data': 'synthetic',
+            'config': {'workload': desc, 'ny': ny, 'nx': nx, 'n_slice': nz, 'batch_per_gpu': B, 'semantics': 'numpy (last slice modulates only)',
+                       'l2': 'inputs larger than L2 (%.1f GB of delta/beta + %.1f GB slice store per GPU streamed every step)' % (db.numel() * 4 / 1e9, db.numel() * 4 / 1e9),
+                       'parallelism': 'dp%d: one field per GPU, NCCL all-reduce (sum) of the object gradient' % world if world > 1 else 'single GPU'},
+            'e2e': {'value': e2e_value, 'unit': 'Gpixel*slice/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'api': 'beyond_dof_b200.models.FullfieldObjective.step(projection magnitudes in pinned host memory) -> loss'},
+            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'kernels': kern, 'cpu_baseline': cpu,
+            'loss': float(loss.item()),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS))
+    ap.add_argument('--impl', default='bdof', choices=['bdof', 'reference'])
+    ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -18,6 +18,7 @@ SYMBOLS = [
     'bdof_plan_create', 'bdof_plan_destroy', 'bdof_set_kernel', 'bdof_set_kernel_full', 'bdof_set_free_prop',
     'bdof_forward', 'bdof_loss_mag', 'bdof_adjoint', 'bdof_pack_db', 'bdof_unpack_db', 'bdof_patch_gather',
     'bdof_patch_scatter_add', 'bdof_cnn_forward', 'bdof_forward_host', 'bdof_plan_workspace_bytes',
+    'bdof_free_prop', 'bdof_profile_begin', 'bdof_profile_end',
 ]
 
 
@@ -54,6 +55,9 @@ def _load():
     lib.bdof_cnn_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, i32, f64, vp]
     lib.bdof_forward_host.argtypes = [vp, vp, vp, vp, vp]
     lib.bdof_plan_workspace_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
+    lib.bdof_free_prop.argtypes = [vp, vp, vp]
+    lib.bdof_profile_begin.argtypes = [vp]
+    lib.bdof_profile_end.argtypes = [vp, i32, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is ctypes.c_int and name not in ('bdof_version', 'bdof_size_supported'):

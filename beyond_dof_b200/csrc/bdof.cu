@@ -316,6 +316,10 @@ struct bdof_plan {
     double* partial = nullptr;
     std::complex<double> total_phase{1.0, 0.0};
     bool forward_done = false;
+    // in-situ per-variant timing (bdof_profile_*): events around every line-kernel launch
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;      // pairs (start, stop)
+    std::vector<int> prof_variant;
     // host staging for bdof_forward_host
     float* e2e_delta = nullptr; float* e2e_beta = nullptr; float2* e2e_db = nullptr;
     float2* e2e_probe = nullptr; float2* e2e_exit = nullptr;
@@ -479,11 +483,23 @@ static LineParams col_params(const bdof_plan* p, const float2* in, float2* out, 
     q.k_dz = float(p->k_dz);
     return q;
 }
-static int row_pass(const bdof_plan* p, int variant, const LineParams& q) {
-    return launch_variant(p->nx, variant, q, (long long)p->batch * p->ny, p->stream);
+static int timed_launch(bdof_plan* p, int n, int variant, const LineParams& q, long long n_lines) {
+    if (!p->profile) return launch_variant(n, variant, q, n_lines, p->stream);
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a));
+    CUDA_TRY(cudaEventCreate(&b));
+    CUDA_TRY(cudaEventRecord(a, p->stream));
+    int r = launch_variant(n, variant, q, n_lines, p->stream);
+    CUDA_TRY(cudaEventRecord(b, p->stream));
+    p->prof_events.push_back(a); p->prof_events.push_back(b);
+    p->prof_variant.push_back(variant);
+    return r;
 }
-static int col_pass(const bdof_plan* p, int variant, const LineParams& q) {
-    return launch_variant(p->ny, variant, q, (long long)p->batch * p->nx, p->stream);
+static int row_pass(bdof_plan* p, int variant, const LineParams& q) {
+    return timed_launch(p, p->nx, variant, q, (long long)p->batch * p->ny);
+}
+static int col_pass(bdof_plan* p, int variant, const LineParams& q) {
+    return timed_launch(p, p->ny, variant, q, (long long)p->batch * p->nx);
 }
 
 // one propagation of slice i: out = P(in * t(db))
@@ -737,5 +753,54 @@ extern "C" int bdof_forward_host(bdof_plan* p, const float* h_delta, const float
                           reinterpret_cast<float*>(p->e2e_exit)));
     CUDA_TRY(cudaMemcpyAsync(h_exit, p->e2e_exit, (size_t)p->F * sizeof(float2), cudaMemcpyDeviceToHost, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// in-situ kernel timing and the free-space step on its own
+// ------------------------------------------------------------------------------------------
+extern "C" int bdof_profile_begin(bdof_plan* p) {
+    if (!p) return fail(BDOF_E_BADARG, "null");
+    for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
+    p->prof_events.clear(); p->prof_variant.clear();
+    p->profile = true;
+    return 0;
+}
+extern "C" int bdof_profile_end(bdof_plan* p, int n_variants, int* counts, double* ms_total) {
+    if (!p || !counts || !ms_total || n_variants < 1) return fail(BDOF_E_BADARG, "bad argument");
+    p->profile = false;
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    for (int v = 0; v < n_variants; ++v) { counts[v] = 0; ms_total[v] = 0.0; }
+    for (size_t i = 0; i < p->prof_variant.size(); ++i) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, p->prof_events[2 * i], p->prof_events[2 * i + 1]));
+        const int v = p->prof_variant[i];
+        if (v >= 0 && v < n_variants) { counts[v] += 1; ms_total[v] += double(ms); }
+    }
+    for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
+    p->prof_events.clear(); p->prof_variant.clear();
+    return 0;
+}
+
+extern "C" int bdof_free_prop(bdof_plan* p, const float* d_in_f, float* d_out_f) {
+    if (!p || !d_in_f || !d_out_f) return fail(BDOF_E_BADARG, "null");
+    const float2* in = reinterpret_cast<const float2*>(d_in_f);
+    float2* out = reinterpret_cast<float2*>(d_out_f);
+    if (p->free_mode == BDOF_FREE_INF) {
+        LineParams r = row_params(p, in, p->tmp, nullptr);
+        r.out_shift = p->nx / 2;
+        BDOF_TRY(row_pass(p, V_ROW_FWD, r));
+        LineParams c = col_params(p, p->tmp, out, nullptr);
+        c.out_shift = p->ny / 2;
+        return col_pass(p, V_COL_FWD, c);
+    }
+    if (p->free_mode == BDOF_FREE_TF) {
+        BDOF_TRY(row_pass(p, V_ROW_CONV, row_params(p, in, p->tmp, p->ax.hf)));
+        BDOF_TRY(col_pass(p, V_COL_CONV, col_params(p, p->tmp, out, p->ay.hf)));
+        const std::complex<double> c = p->phasef;
+        k_scale_complex<<<blocks_for(p->F, 256), 256, 0, p->stream>>>(out, out, p->F, float(c.real()), float(c.imag()));
+        return launch_check("k_scale_complex");
+    }
+    if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, (size_t)p->F * sizeof(float2), cudaMemcpyDeviceToDevice, p->stream));
     return 0;
 }

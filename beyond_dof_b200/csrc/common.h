@@ -24,10 +24,36 @@ struct LineParams {
 
 enum Variant { V_ROW_CONV_T = 0, V_ROW_CONV, V_ROW_CONV_ADJ, V_ROW_FWD, V_ROW_INV, V_COL_CONV, V_COL_FWD, V_COL_INV, V_COL_CONV2D };
 
+// sin/cos for |x| up to ~1e4 rad: 3-term Cody-Waite reduction by pi/2 and the cephes single-precision
+// minimax polynomials (max error ~1 ulp on the reduced range).  Same arithmetic as the fast path of
+// sincosf(), without its Payne-Hanek slow path (which drags a local-memory frame into every kernel);
+// k*delta per slice is O(1e-4..1) rad for every physical configuration.
+__device__ __forceinline__ void sincos_fast(float x, float* s, float* c) {
+    const float q = rintf(x * 0.636619772367581343f);
+    float r = fmaf(q, -1.57079601287841796875f, x);
+    r = fmaf(q, -3.1391647326017846353e-7f, r);
+    r = fmaf(q, -5.3903025299577647655e-15f, r);
+    const int iq = __float2int_rn(q);
+    const float r2 = r * r;
+    float sp = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+    sp = fmaf(sp, r2, -1.6666654611e-1f);
+    sp = fmaf(sp * r2, r, r);
+    float cp = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    cp = fmaf(cp, r2, 4.166664568298827e-2f);
+    cp = fmaf(cp, r2, -0.5f);
+    cp = fmaf(cp, r2, 1.0f);
+    float ss = (iq & 1) ? cp : sp;
+    float cc = (iq & 1) ? sp : cp;
+    if (iq & 2) ss = -ss;
+    if ((iq + 1) & 2) cc = -cc;
+    *s = ss;
+    *c = cc;
+}
+
 // t = exp(i k delta) * exp(-k beta)   (npfuncs.py:38)
 __device__ __forceinline__ float2 transmission(float2 db, float k) {
     float s, c;
-    sincosf(k * db.x, &s, &c);
+    sincos_fast(k * db.x, &s, &c);
     float m = expf(-k * db.y);
     return make_float2(m * c, m * s);
 }
@@ -44,7 +70,7 @@ BDOF_DECL_LINE(1024) BDOF_DECL_LINE(2048) BDOF_DECL_LINE(4096) BDOF_DECL_LINE(81
 #define CUDA_TRY(expr)                                                                        \
     do {                                                                                      \
         cudaError_t _e = (expr);                                                              \
-        if (_e != cudaSuccess)                                                                \
+        if (_e != cudaSuccess && (cudaGetLastError(), true))   /* clear the sticky last-error */ \
             return bdof_fail(int(_e), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 #define BDOF_TRY(expr)            \

@@ -20,17 +20,35 @@ template <> struct CfgFor<2048> { using C = LineCfg<2048, 32, 64, 32, 1>; static
 template <> struct CfgFor<4096> { using C = LineCfg<4096, 64, 64, 64, 1>; static constexpr int RL = 1,  CL = 4; };
 template <> struct CfgFor<8192> { using C = LineCfg<8192, 128, 64, 64, 2>; static constexpr int RL = 1, CL = 2; };
 
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// persistent launch: one CTA per resident slot, each looping over tiles of LPC lines
 template <class Cfg, int LPC, bool COL, int MODE, int PRE, int POST>
 static int launch_line(const LineParams& p, long long n_lines, cudaStream_t st) {
-    using SM = LineSmem<Cfg, LPC, COL>;
+    using SM = LineSmem<Cfg, LPC, COL, MODE>;
     auto kern = line_kernel<Cfg, LPC, COL, MODE, PRE, POST>;
-    static bool attr_done = false;        // per instantiation
-    if (!attr_done) {
+    static int ctas_per_sm = 0;           // per instantiation
+    if (ctas_per_sm == 0) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::BYTES)));
-        attr_done = true;
+        int occ = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::T * LPC, SM::BYTES));
+        if (occ < 1) return bdof_fail(BDOF_E_UNSUPPORTED, "line kernel does not fit on an SM (%zu bytes smem)", SM::BYTES);
+        ctas_per_sm = occ;
     }
     if (n_lines % LPC != 0) return bdof_fail(BDOF_E_UNSUPPORTED, "line count %lld not a multiple of %d", n_lines, LPC);
-    kern<<<unsigned(n_lines / LPC), Cfg::T * LPC, SM::BYTES, st>>>(p);
+    const long long n_tiles = n_lines / LPC;
+    const long long slots = (long long)ctas_per_sm * sm_count();
+    const unsigned grid = unsigned(n_tiles < slots ? n_tiles : slots);
+    kern<<<grid, Cfg::T * LPC, SM::BYTES, st>>>(p, int(n_tiles));
     return bdof_launch_check("line_kernel");
 }
 

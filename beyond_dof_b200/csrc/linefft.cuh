@@ -1,11 +1,16 @@
 // Line kernels: one pass of the separable Fresnel step over a bundle of lines of the field.
 //
-// A "line" is a row (contiguous) or a column (stride nx) of one batch element.  A CTA holds
-// LPC lines entirely on chip: every thread keeps E = N/T elements of one line in registers
-// (element t + T*q in register q), the Stockham stages run as in-register radix-R butterflies
-// (regfft.cuh) and the inter-stage exchanges go through padded shared memory.  One kernel does
+// A "line" is a row (contiguous) or a column (stride nx) of one batch element.  A persistent CTA
+// loops over tiles of LPC lines; a tile lives entirely on chip: every thread keeps E = N/T elements
+// of one line in registers (element t + T*q in register q), the Stockham stages run as in-register
+// radix-R butterflies (regfft.cuh, packed FFMA2/FADD2 math) and the inter-stage exchanges go through
+// padded shared memory.  The stage twiddles and the frequency-domain multiplier h are staged once per
+// CTA in shared memory.  One kernel does
 //     load [x transmission exp(k(i delta - beta))] -> FFT -> x h -> IFFT -> [adjoint epilogue] -> store
 // so a pass is exactly one HBM read and one HBM write of the field (plus delta/beta once).
+//
+// Only the forward transform is instantiated: IFFT(z) = conj(FFT(conj(z))), and the two transforms
+// of a convolution run through the same code in a two-trip loop (halves the instruction footprint).
 #pragma once
 #include "regfft.cuh"
 #include "common.h"
@@ -32,12 +37,17 @@ struct LineCfg {
     static constexpr int TW_TOTAL = TW2 + TW3;
 };
 
-template <class Cfg, int LPC, bool COL>
+template <class Cfg, int LPC, bool COL, int MODE>
 struct LineSmem {
     // line stride in float2: banks of the LPC interleaved lines must not collide in col mode
     static constexpr int ADJ = COL ? ((((16 / LPC) - Cfg::PADDED) % 16) + 16) % 16 : 0;
     static constexpr int STRIDE = Cfg::PADDED + ADJ;
-    static constexpr size_t BYTES = size_t(STRIDE) * LPC * sizeof(float2);
+    static constexpr int TW_ELEMS = (Cfg::TW_TOTAL + 1) & ~1;
+    // h is staged in shared memory unless that would overflow the 227 KB CTA limit (8192-long columns)
+    static constexpr bool H_IN_SMEM = (MODE == MODE_CONV) &&
+        size_t(TW_ELEMS + Cfg::N + STRIDE * LPC) * sizeof(float2) <= 227 * 1024;
+    static constexpr int H_ELEMS = H_IN_SMEM ? Cfg::N : 0;
+    static constexpr size_t BYTES = size_t(TW_ELEMS + H_ELEMS + STRIDE * LPC) * sizeof(float2);
 };
 
 template <class Cfg, int LPC, bool COL>
@@ -47,14 +57,14 @@ __device__ __forceinline__ void line_sync() {
 }
 
 // butterflies of radix R on the register file: E/R independent butterflies per thread
-template <class Cfg, int R, bool INV>
+template <class Cfg, int R>
 __device__ __forceinline__ void reg_butterflies(float2 (&v)[Cfg::E]) {
     constexpr int E = Cfg::E, M = E / R;
     static_for<M>([&](auto MM) {
         constexpr int m = decltype(MM)::value;
         float2 a[R];
         static_for<R>([&](auto RR) { constexpr int r = decltype(RR)::value; a[r] = v[m + r * M]; });
-        RegFFT<R, INV>::run(a);
+        RegFFT<R, false>::run(a);
         static_for<R>([&](auto RR) { constexpr int r = decltype(RR)::value; v[m + r * M] = a[r]; });
     });
 }
@@ -80,159 +90,176 @@ __device__ __forceinline__ void exchange(float2 (&v)[Cfg::E], int t, float2* sm)
     });
 }
 
-template <class Cfg>
-__device__ __forceinline__ void exchange_read(float2 (&v)[Cfg::E], int t, const float2* sm) {
-    constexpr int E = Cfg::E, T = Cfg::T, R1 = Cfg::R1;
-    if constexpr (T % R1 == 0) {
-        const int base = t + t / R1;
-        static_for<E>([&](auto Q) { constexpr int q = decltype(Q)::value; v[q] = sm[base + q * (T + T / R1)]; });
-    } else {
-        static_for<E>([&](auto Q) {
-            constexpr int q = decltype(Q)::value;
-            const int i = t + T * q;
-            v[q] = sm[i + i / R1];
-        });
-    }
-}
-
-// multiply by the stage twiddles W_{NS*R}^{r*k}, k = j mod NS, table row r-1 at tw[(r-1)*NS + k]
-template <class Cfg, int R, int NS, bool INV>
-__device__ __forceinline__ void stage_twiddle(float2 (&v)[Cfg::E], int t, const float2* __restrict__ tw) {
-    constexpr int E = Cfg::E, T = Cfg::T, M = E / R;
-    static_for<M>([&](auto MM) {
-        constexpr int m = decltype(MM)::value;
-        const int k = (t + T * m) % NS;
-        static_for<R - 1>([&](auto RR) {
-            constexpr int r = decltype(RR)::value + 1;
-            const float2 w = __ldg(tw + (r - 1) * NS + k);
-            v[m + r * M] = INV ? cmulc(v[m + r * M], w) : cmul(v[m + r * M], w);
-        });
+// read element t + T*q back and multiply by the next stage's twiddle W_{NS*R}^{r*k}, k = j mod NS
+// (table row r-1 at tw[(r-1)*NS + k], r = q / (E/R), j = t + T*(q mod E/R))
+template <class Cfg, int R, int NS>
+__device__ __forceinline__ void exchange_read_twiddle(float2 (&v)[Cfg::E], int t, const float2* sm, const float2* tw) {
+    constexpr int E = Cfg::E, T = Cfg::T, R1 = Cfg::R1, M = E / R;
+    static_for<E>([&](auto Q) {
+        constexpr int q = decltype(Q)::value;
+        constexpr int m = q % M, r = q / M;
+        int idx;
+        if constexpr (T % R1 == 0) idx = (t + t / R1) + q * (T + T / R1);
+        else { const int i = t + T * q; idx = i + i / R1; }
+        const float2 x = sm[idx];
+        if constexpr (r == 0) v[q] = x;
+        else {
+            const int k = (t + T * m) % NS;
+            v[q] = cmul(x, tw[(r - 1) * NS + k]);
+        }
     });
 }
 
-// full length-N transform of the line held in v (natural order in and out)
-template <class Cfg, int LPC, bool COL, bool INV>
-__device__ __forceinline__ void line_fft(float2 (&v)[Cfg::E], int t, float2* sm, const float2* __restrict__ tw) {
+// forward length-N transform of the line held in v (natural order in and out)
+template <class Cfg, int LPC, bool COL>
+__device__ __forceinline__ void line_fft(float2 (&v)[Cfg::E], int t, float2* sm, const float2* tw) {
     constexpr int R1 = Cfg::R1, R2 = Cfg::R2, R3 = Cfg::R3;
-    reg_butterflies<Cfg, R1, INV>(v);
+    reg_butterflies<Cfg, R1>(v);
     line_sync<Cfg, LPC, COL>();                 // previous readers of the exchange buffer are done
     exchange<Cfg, R1, 1>(v, t, sm);
     line_sync<Cfg, LPC, COL>();
-    exchange_read<Cfg>(v, t, sm);
-    stage_twiddle<Cfg, R2, R1, INV>(v, t, tw);
-    reg_butterflies<Cfg, R2, INV>(v);
+    exchange_read_twiddle<Cfg, R2, R1>(v, t, sm, tw);
+    reg_butterflies<Cfg, R2>(v);
     if constexpr (R3 > 1) {
         line_sync<Cfg, LPC, COL>();
         exchange<Cfg, R2, R1>(v, t, sm);
         line_sync<Cfg, LPC, COL>();
-        exchange_read<Cfg>(v, t, sm);
-        stage_twiddle<Cfg, R3, R1 * R2, INV>(v, t, tw + Cfg::TW2);
-        reg_butterflies<Cfg, R3, INV>(v);
-    }
-}
-
-// Element accessor for one line: element e of the line lives at ptr[e * stride].  In row mode the
-// stride is the compile-time constant 1 so every access is base + immediate; in column mode the
-// pointer is stepped by a uniform stride so no per-element 64-bit address is kept live.
-template <bool COL, int T, int E, class F>
-__device__ __forceinline__ void for_each_elem(long long first_off, long long step, F&& f) {
-    if constexpr (!COL) {
-        static_for<E>([&](auto Q) { constexpr int q = decltype(Q)::value; f(Q, first_off + T * q); });
-    } else {
-        long long off = first_off;
-        static_for<E>([&](auto Q) { f(Q, off); off += step; });
+        exchange_read_twiddle<Cfg, R3, R1 * R2>(v, t, sm, tw + Cfg::TW2);
+        reg_butterflies<Cfg, R3>(v);
     }
 }
 
 template <class Cfg, int LPC, bool COL, int MODE, int PRE, int POST>
-__global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p) {
+__global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, const int n_tiles) {
     constexpr int N = Cfg::N, T = Cfg::T, E = Cfg::E;
-    using SM = LineSmem<Cfg, LPC, COL>;
+    using SM = LineSmem<Cfg, LPC, COL, MODE>;
+    constexpr int CH = (E < 16) ? E : 16;          // prologue / epilogue load batch
     extern __shared__ float2 smem[];
+    float2* s_tw = smem;
+    float2* s_h = smem + SM::TW_ELEMS;
+    float2* s_x = s_h + SM::H_ELEMS;
 
     const int tid = threadIdx.x;
+    for (int i = tid; i < Cfg::TW_TOTAL; i += T * LPC) s_tw[i] = p.tw[i];
+    if constexpr (SM::H_IN_SMEM)
+        for (int i = tid; i < N; i += T * LPC) s_h[i] = p.h[i];
+    __syncthreads();
+
     int l, t;
     if constexpr (COL) { l = tid % LPC; t = tid / LPC; }
     else               { l = tid / T;   t = tid % T; }
-    const long long line = (long long)blockIdx.x * LPC + l;
-    const int b = int(line / p.lines_per_batch);
-    const int li = int(line - (long long)b * p.lines_per_batch);
-    const long long base = (long long)b * p.batch_stride + (long long)li * p.line_stride;
-    // offset of element t and the step between this thread's consecutive elements (t + T*q)
-    const long long first = COL ? (long long)t * p.elem_stride : (long long)t;
-    const long long step = COL ? (long long)T * p.elem_stride : (long long)T;
-    float2* sm = smem + l * SM::STRIDE;
+    float2* sm = s_x + l * SM::STRIDE;
+    const long long estride = COL ? (long long)p.elem_stride : 1LL;
+    const long long step = (long long)T * estride;
 
-    float2 v[E];
-    // ---- load (element t + T*q -> register q)
-    {
-        const float2* __restrict__ src = p.in + base;
-        if constexpr (MODE == MODE_INV) {
-            // circular input shift (ifftshift), far-field adjoint only
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long line = (long long)tile * LPC + l;
+        const int b = int(line / p.lines_per_batch);
+        const int li = int(line - (long long)b * p.lines_per_batch);
+        const long long base = (long long)b * p.batch_stride + (long long)li * p.line_stride + (long long)t * estride;
+
+        float2 v[E];
+        // ---- load (element t + T*q -> register q)
+        {
+            const float2* __restrict__ src = p.in + base;
+            if constexpr (MODE == MODE_INV) {
+                // conj + circular input shift (ifftshift), far-field adjoint only
+                const float2* __restrict__ src0 = p.in + (base - (long long)t * estride);
+                static_for<E>([&](auto Q) {
+                    constexpr int q = decltype(Q)::value;
+                    int e = t + T * q + p.in_shift;
+                    if (e >= N) e -= N;
+                    v[q] = conjf2(src0[(long long)e * estride]);
+                });
+            } else if constexpr (!COL) {
+                static_for<E>([&](auto Q) { constexpr int q = decltype(Q)::value; v[q] = src[T * q]; });
+            } else {
+                const float2* ptr = src;
+                static_for<E>([&](auto Q) { v[decltype(Q)::value] = *ptr; ptr += step; });
+            }
+        }
+        if constexpr (PRE == PRE_TRANSMIT) {
+            static_assert(PRE == PRE_NONE || !COL, "transmission is fused into the row pass");
+            const float2* __restrict__ dbp = p.db + (long long)b * p.db_batch_stride + (long long)li * p.line_stride + t;
+            static_for<E / CH>([&](auto C) {
+                constexpr int c = decltype(C)::value;
+                float2 d[CH];
+                static_for<CH>([&](auto I) { constexpr int i = decltype(I)::value; d[i] = dbp[T * (c * CH + i)]; });
+                static_for<CH>([&](auto I) {
+                    constexpr int i = decltype(I)::value;
+                    v[c * CH + i] = cmul(v[c * CH + i], transmission(d[i], p.k_dz));
+                });
+            });
+        }
+        // ---- transform(s)
+        if constexpr (MODE == MODE_FWD || MODE == MODE_INV) {
+            line_fft<Cfg, LPC, COL>(v, t, sm, s_tw);
+        } else {
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                line_fft<Cfg, LPC, COL>(v, t, sm, s_tw);
+                if (pass == 0) {
+                    // v <- conj(v * h): the second trip then computes conj(IFFT(v h))
+                    if constexpr (MODE == MODE_CONV) {
+                        const float2* hs = SM::H_IN_SMEM ? s_h : p.h;
+                        static_for<E>([&](auto Q) {
+                            constexpr int q = decltype(Q)::value;
+                            v[q] = cmul_conj(v[q], hs[t + T * q]);
+                        });
+                    } else {
+                        // general 2-D multiplier H[ky][kx] (column pass): this line is column li
+                        const float2* hp = p.h + li + (long long)t * estride;
+                        static_for<E>([&](auto Q) {
+                            constexpr int q = decltype(Q)::value;
+                            v[q] = cmul_conj(v[q], __ldg(hp));
+                            hp += step;
+                        });
+                    }
+                }
+            }
+        }
+        // ---- store.  Except for MODE_FWD the register file holds the CONJUGATE of the result.
+        float2* __restrict__ dst = p.out + base;
+        if constexpr (POST == POST_ADJ) {
+            // G_u = conj(v) is the gradient w.r.t. u_i = psi_i t_i.  SURVEY.md 7.1:
+            //   dL/ddelta = -k Im(conj(G_u) u),  dL/dbeta = -k Re(conj(G_u) u),  G_i = conj(t) G_u
+            const long long dbase = (long long)b * p.db_batch_stride + (long long)li * p.line_stride + t;
+            const float2* __restrict__ dbp = p.db + dbase;
+            const float2* __restrict__ psip = p.psi + base;
+            float2* __restrict__ gp = p.grad + dbase;
+            static_for<E / CH>([&](auto C) {
+                constexpr int c = decltype(C)::value;
+                float2 d[CH], ps[CH];
+                static_for<CH>([&](auto I) {
+                    constexpr int i = decltype(I)::value;
+                    d[i] = dbp[T * (c * CH + i)];
+                    ps[i] = psip[T * (c * CH + i)];
+                });
+                static_for<CH>([&](auto I) {
+                    constexpr int i = decltype(I)::value;
+                    constexpr int q = c * CH + i;
+                    const float2 tr = transmission(d[i], p.k_dz);
+                    const float2 u = cmul(ps[i], tr);
+                    const float2 w = cmul(u, v[q]);              // u * conj(G_u) = u * v
+                    gp[T * q] = make_float2(-p.k_dz * w.y, -p.k_dz * w.x);
+                    dst[T * q] = cmul_conj(v[q], tr);           // conj(v) conj(t) = G_u conj(t)
+                });
+            });
+        } else if constexpr (MODE == MODE_FWD) {
+            // circular output shift (fftshift), far field only
+            float2* __restrict__ dst0 = p.out + (base - (long long)t * estride);
             static_for<E>([&](auto Q) {
                 constexpr int q = decltype(Q)::value;
-                int e = t + T * q + p.in_shift;
+                int e = t + T * q + p.out_shift;
                 if (e >= N) e -= N;
-                v[q] = src[(long long)e * p.elem_stride];
+                dst0[(long long)e * estride] = v[q];
             });
+        } else if constexpr (!COL) {
+            static_for<E>([&](auto Q) { constexpr int q = decltype(Q)::value; dst[T * q] = conjf2(v[q]); });
         } else {
-            for_each_elem<COL, T, E>(first, step, [&](auto Q, long long off) { v[decltype(Q)::value] = src[off]; });
+            float2* ptr = dst;
+            static_for<E>([&](auto Q) { *ptr = conjf2(v[decltype(Q)::value]); ptr += step; });
         }
-    }
-    if constexpr (PRE == PRE_TRANSMIT) {
-        const float2* __restrict__ dbp = p.db + (long long)b * p.db_batch_stride + (long long)li * p.line_stride;
-        for_each_elem<COL, T, E>(first, step, [&](auto Q, long long off) {
-            constexpr int q = decltype(Q)::value;
-            v[q] = cmul(v[q], transmission(dbp[off], p.k_dz));
-        });
-    }
-    // ---- transform
-    if constexpr (MODE != MODE_INV) line_fft<Cfg, LPC, COL, false>(v, t, sm, p.tw);
-    if constexpr (MODE == MODE_CONV) {
-        const float2* __restrict__ hp = p.h + t;
-        static_for<E>([&](auto Q) {
-            constexpr int q = decltype(Q)::value;
-            v[q] = cmul(v[q], __ldg(hp + T * q));
-        });
-    }
-    if constexpr (MODE == MODE_CONV2D) {
-        // general 2-D multiplier H[ky][kx] (column pass): this line is column li
-        const float2* __restrict__ hp = p.h + li;
-        for_each_elem<true, T, E>(first, step, [&](auto Q, long long off) {
-            constexpr int q = decltype(Q)::value;
-            v[q] = cmul(v[q], __ldg(hp + off));
-        });
-    }
-    if constexpr (MODE != MODE_FWD) line_fft<Cfg, LPC, COL, true>(v, t, sm, p.tw);
-    // ---- store
-    float2* __restrict__ dst = p.out + base;
-    if constexpr (POST == POST_ADJ) {
-        // v = G_u (gradient w.r.t. u_i = psi_i t_i).  SURVEY.md 7.1:
-        //   dL/ddelta = -k Im(conj(G_u) u),  dL/dbeta = -k Re(conj(G_u) u),  G_i = conj(t) G_u
-        const long long dbase = (long long)b * p.db_batch_stride + (long long)li * p.line_stride;
-        const float2* __restrict__ dbp = p.db + dbase;
-        const float2* __restrict__ psip = p.psi + base;
-        float2* __restrict__ gp = p.grad + dbase;
-        for_each_elem<COL, T, E>(first, step, [&](auto Q, long long off) {
-            constexpr int q = decltype(Q)::value;
-            const float2 d = dbp[off];
-            const float2 ps = psip[off];
-            const float2 tr = transmission(d, p.k_dz);
-            const float2 u = cmul(ps, tr);
-            const float2 w = cmulc(u, v[q]);            // u * conj(G_u)
-            gp[off] = make_float2(-p.k_dz * w.y, -p.k_dz * w.x);
-            dst[off] = cmulc(v[q], tr);                 // G_u * conj(t)
-        });
-    } else if constexpr (MODE == MODE_FWD) {
-        // circular output shift (fftshift), far field only
-        static_for<E>([&](auto Q) {
-            constexpr int q = decltype(Q)::value;
-            int e = t + T * q + p.out_shift;
-            if (e >= N) e -= N;
-            dst[(long long)e * p.elem_stride] = v[q];
-        });
-    } else {
-        for_each_elem<COL, T, E>(first, step, [&](auto Q, long long off) { dst[off] = v[decltype(Q)::value]; });
     }
 }
 

@@ -54,15 +54,34 @@ __device__ __forceinline__ void static_for(F&& f) {
 }
 
 // ---------------------------------------------------------------- complex helpers
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex values are float2 in an aligned register pair.  Arithmetic uses the sm_100 packed FP32
+// instructions (add/mul/fma .f32x2 -> SASS FADD2/FMUL2/FFMA2): one issue slot per complex add, two per
+// complex multiply.  ptxas folds the (re,im) swap, per-half negation and scalar broadcast of the
+// operands below into operand modifiers (R.F32x2.LO_HI.NP, R.F32, immediates), so multiplying by
+// +-i or by a compile-time twiddle needs no extra instructions or registers.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float x, float y) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ float2 upk(u64 r) { float2 c; asm("mov.b64 {%0,%1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(r)); return c; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return upk(add2(pk(a.x, a.y), pk(b.x, b.y))); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return upk(sub2(pk(a.x, a.y), pk(b.x, b.y))); }
+// a * b
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+    return upk(fma2(pk(-a.y, a.x), pk(b.y, b.y), mul2(pk(a.x, a.y), pk(b.x, b.x))));
 }
 // a * conj(b)
 __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
-    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+    return upk(fma2(pk(a.y, -a.x), pk(b.y, b.y), mul2(pk(a.x, a.y), pk(b.x, b.x))));
 }
+// conj(a * b)
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {
+    return upk(fma2(pk(-a.y, -a.x), pk(b.y, b.y), mul2(pk(a.x, -a.y), pk(b.x, b.x))));
+}
+__device__ __forceinline__ float2 conjf2(float2 a) { return make_float2(a.x, -a.y); }
 // forward: a * (-i); inverse: a * (+i)
 template <bool INV>
 __device__ __forceinline__ float2 mul_mi(float2 a) {
@@ -79,7 +98,7 @@ __device__ __forceinline__ float2 mul_tw(float2 a) {
     else if constexpr (w.c == -1.0 && w.s == 0.0) return make_float2(-a.x, -a.y);
     else if constexpr (w.c == 0.0 && w.s == 1.0) return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
     else if constexpr (w.c == 0.0 && w.s == -1.0) return INV ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
-    else return make_float2(a.x * c + a.y * s, a.y * c - a.x * s);
+    else return upk(fma2(pk(a.y, -a.x), pk(s, s), mul2(pk(a.x, a.y), pk(c, c))));   // (xc + ys, yc - xs)
 }
 
 // ---------------------------------------------------------------- butterflies

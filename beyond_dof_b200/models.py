@@ -156,3 +156,39 @@ def ptycho_loss_and_grad(obj_delta, obj_beta, theta, probe_pos_batch, prj_batch,
     if native:
         return loss, grad_obj_out
     return loss, unpack_object(grad_obj_out)
+
+
+class FullfieldObjective:
+    """One full-field reconstruction step with the object resident on the GPU in the native
+    slice-major layout -- what the optimisation loop of reconstruct_fullfield calls every minibatch
+    (tensorflow_recon/fullfield.py:497-556: feed the projection batch, get loss + gradient).
+
+    db_obj: [Z,B,Y,X,2] float32 CUDA tensor (delta, beta) of the (rotated) object per batch element.
+    step(prj_mag_host) copies this step's measured projection magnitudes host->device, runs
+    forward + loss + adjoint into self.grad and returns the loss as a Python float (one D2H read).
+    """
+
+    def __init__(self, db_obj, probe, energy_ev, psize_cm, free_prop_cm=None, propagate_last=False):
+        Z, B, Y, X, _ = db_obj.shape
+        self.plan = MultislicePlan(Y, X, B, Z, energy_ev, psize_cm, free_prop_cm=free_prop_cm,
+                                   propagate_last=propagate_last, store_slices=True, device=db_obj.device)
+        self.db = db_obj
+        self.probe = probe.to(db_obj.device, torch.complex64).contiguous()
+        self.grad = torch.empty_like(db_obj)
+        self.target = torch.empty((B, Y, X), dtype=torch.float32, device=db_obj.device)
+        self.exit = torch.empty((B, Y, X), dtype=torch.complex64, device=db_obj.device)
+        self.loss_host = torch.empty((), dtype=torch.float64).pin_memory()
+
+    def step_device(self, target_dev):
+        """forward + loss + adjoint with the target already on the device; returns the device loss."""
+        self.plan.forward(self.db, self.probe, out=self.exit)
+        loss, g = self.plan.loss_mag(self.exit, target_dev)
+        self.plan.adjoint(self.db, g, grad_out=self.grad)
+        return loss
+
+    def step(self, prj_mag_host):
+        self.target.copy_(prj_mag_host, non_blocking=True)
+        loss = self.step_device(self.target)
+        self.loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.loss_host)

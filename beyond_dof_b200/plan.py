@@ -163,6 +163,28 @@ class MultislicePlan:
         check(lib.bdof_forward_host(self._h, _hptr(d), _hptr(b), _hptr(pr), _hptr(out)))
         return out
 
+    VARIANT_NAMES = ['row_conv_transmit', 'row_conv', 'row_conv_adjoint', 'row_fft', 'row_ifft', 'col_conv', 'col_fft',
+                     'col_ifft', 'col_conv_2d']
+
+    def free_prop(self, field, out=None):
+        """The plan's free-space step on its own: [B,Y,X] complex64 -> [B,Y,X]."""
+        field = field.to(self.device, torch.complex64).contiguous()
+        if out is None:
+            out = torch.empty_like(field)
+        check(lib.bdof_free_prop(self._h, _ptr(field), _ptr(out)))
+        return out
+
+    def profile_begin(self):
+        check(lib.bdof_profile_begin(self._h))
+
+    def profile_end(self):
+        """-> {variant name: (launches, total ms)} for the launches since profile_begin()."""
+        n = len(self.VARIANT_NAMES)
+        counts = (ctypes.c_int * n)()
+        ms = (ctypes.c_double * n)()
+        check(lib.bdof_profile_end(self._h, n, counts, ms))
+        return {self.VARIANT_NAMES[i]: (int(counts[i]), float(ms[i])) for i in range(n) if counts[i]}
+
     def workspace_bytes(self):
         n = ctypes.c_size_t()
         check(lib.bdof_plan_workspace_bytes(self._h, ctypes.byref(n)))

@@ -131,8 +131,18 @@ int  bdof_cnn_forward(const float* d_db, const float* d_probe, float* d_exit, fl
 int  bdof_forward_host(bdof_plan* p, const float* h_delta_byxz, const float* h_beta_byxz,
                        const float* h_probe, float* h_exit);
 
-/* kernel-only timing hook: run the per-slice pass pair `reps` times on scratch data */
+/* The free-space step of the plan on its own (npfuncs.py:43-61): out = free_prop(in), [batch][ny][nx]. */
+int  bdof_free_prop(bdof_plan* p, const float* d_in, float* d_out);
+
+/* Bytes of device memory the plan owns (work fields + slice store). */
 int  bdof_plan_workspace_bytes(const bdof_plan* p, size_t* bytes_out);
+
+/* In-situ timing: between begin and end every line-kernel launch of this plan is bracketed by CUDA
+ * events on the plan's stream; end() synchronises and returns, per pass variant (0 row fwd with
+ * transmission, 1 row conv, 2 row adjoint, 3 row FFT, 4 row IFFT, 5 col conv, 6 col FFT, 7 col IFFT,
+ * 8 col conv with 2-D H), the launch count and the summed device time in ms. */
+int  bdof_profile_begin(bdof_plan* p);
+int  bdof_profile_end(bdof_plan* p, int n_variants, int* counts, double* ms_total);
 
 #ifdef __cplusplus
 }

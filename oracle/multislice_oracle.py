@@ -97,8 +97,9 @@ def multislice_forward(grid_delta_batch, grid_beta_batch, probe_real, probe_imag
                            except the n_slice == 1 special case which only modulates)
     return_slices: also return psi entering every slice (for the adjoint).
     """
-    grid_delta_batch = np.asarray(grid_delta_batch)
-    grid_beta_batch = np.asarray(grid_beta_batch)
+    # float64 always: a float32 array times the Python complex 1j*k would stay complex64 in NumPy 2
+    grid_delta_batch = np.asarray(grid_delta_batch, dtype=np.float64)
+    grid_beta_batch = np.asarray(grid_beta_batch, dtype=np.float64)
     if obj_batch_shape is None:
         obj_batch_shape = grid_delta_batch.shape
     batch = obj_batch_shape[0]
@@ -171,8 +172,8 @@ def multislice_adjoint(grid_delta_batch, grid_beta_batch, slices, grad_exit, ene
     Returns (grad_delta, grad_beta, grad_probe) with grad_* in [B,Y,X,Z] and
     grad_probe = G at the entrance plane summed over the batch (the probe is shared).
     """
-    grid_delta_batch = np.asarray(grid_delta_batch)
-    grid_beta_batch = np.asarray(grid_beta_batch)
+    grid_delta_batch = np.asarray(grid_delta_batch, dtype=np.float64)
+    grid_beta_batch = np.asarray(grid_beta_batch, dtype=np.float64)
     batch, ny, nx, n_slice = grid_delta_batch.shape
     voxel_nm = np.array([psize_cm] * 3) * 1.e7
     lmbda_nm = 1240. / energy_ev
@@ -248,8 +249,8 @@ def multislice_propagate_cnn(grid_delta, grid_beta, probe_real, probe_imag, ener
     replaced by an equivalent explicit shift-and-add; arithmetic order differs only in the
     summation order of the kernel taps)."""
     assert kernel_size % 2 == 1, 'kernel_size must be an odd number.'
-    grid_delta = np.asarray(grid_delta)
-    grid_beta = np.asarray(grid_beta)
+    grid_delta = np.asarray(grid_delta, dtype=np.float64)
+    grid_beta = np.asarray(grid_beta, dtype=np.float64)
     n_batch, shape_y, shape_x, n_slice = grid_delta.shape
     lmbda_nm = 1240. / energy_ev
     voxel_nm = np.array(psize_cm) * 1.e7

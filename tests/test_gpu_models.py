@@ -24,7 +24,7 @@ def test_fullfield_loss_and_grad(bd):
     rng = np.random.default_rng(50)
     od = np.clip(rng.normal(8.7e-7, 1e-7, (Y, X, Z)), 0, None).astype(np.float32) * 100
     ob = np.clip(rng.normal(5.1e-8, 1e-8, (Y, X, Z)), 0, None).astype(np.float32) * 100
-    gt_d, gt_b = mo.random_phantom((1, Y, X, Z), seed=51, delta_scale=1e-4, beta_scale=1e-5)
+    gt_d, gt_b = mo.random_phantom((1, Y, X, Z), seed=51, delta_scale=2e-3, beta_scale=4e-3)   # strong contrast: O(1) misfit
     one, zero = np.ones((Y, X)), np.zeros((Y, X))
     prj = mo.multislice_propagate_batch(gt_d.astype(np.float64), gt_b.astype(np.float64), one, zero, 5000, 1e-7, free_prop_cm=1e-4)
     prj_b = np.repeat(prj, B, axis=0)
@@ -48,7 +48,7 @@ def test_ptycho_loss_and_grad_with_padding(bd):
     Y, X, Z = 96, 112, 6
     probe_size = (64, 64)
     od, ob = mo.random_phantom((Y, X, Z), seed=60, delta_scale=3e-4, beta_scale=3e-5)
-    gt_d, gt_b = mo.random_phantom((Y, X, Z), seed=61, delta_scale=3e-4, beta_scale=3e-5)
+    gt_d, gt_b = mo.random_phantom((Y, X, Z), seed=61, delta_scale=5e-3, beta_scale=5e-3)          # strong contrast: O(1) misfit
     pr, pi = mo.gaussian_probe(probe_size, 6., 6., 0.5)
     # positions include windows that overhang every edge (zero padding, ptychography.py:45-61)
     pos = [(0, 0), (10, 100), (95, 111), (48, 56), (40, 40), (90, 5)]
