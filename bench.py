@@ -178,6 +178,9 @@ def run_gpu(args):
         dist.init_process_group('nccl', device_id=dev)
     ny, nx, nz, desc = WORKLOADS[args.workload]
     B = 1
+    if args.shape:
+        B, ny, nx, nz = (int(v) for v in args.shape.split(','))
+        desc = 'custom shape %s' % args.shape
     units_per_step = B * ny * nx * nz * world
 
     # synthetic inputs, created once on the device (value arm) / in pinned host memory (e2e arm)
@@ -189,7 +192,7 @@ def run_gpu(args):
         blk[..., 0] *= 1e-5
         blk[..., 1] *= 1e-6
     probe = torch.ones((ny, nx), dtype=torch.complex64, device=dev)
-    obj = FullfieldObjective(db, probe, ENERGY_EV, PSIZE_CM)
+    obj = FullfieldObjective(db, probe, ENERGY_EV, PSIZE_CM, in_place=args.in_place)
     # target: measured magnitudes of a perturbed object (well inside (0, 1]); synthetic
     target_host = (0.9 + 0.1 * torch.rand((B, ny, nx), generator=torch.Generator().manual_seed(4321 + rank))).pin_memory()
     target_dev = target_host.to(dev)
@@ -320,6 +323,8 @@ def main():
     ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='bdof', choices=['bdof', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
+    ap.add_argument('--shape', default=None, help='experiment: B,NY,NX,NZ overrides the workload shape')
+    ap.add_argument('--in-place', action='store_true', help='adjoint overwrites delta/beta with the gradient (needed for the 4096^2x512 size)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

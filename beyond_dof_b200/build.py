@@ -15,7 +15,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(CSRC, '_obj')
-LIB = os.path.join(HERE, 'libbdof.so')
+ALT = int(os.environ.get('BDOF_ALT', '0'))          # experimental FFT factorizations (csrc/line_inst.cu)
+LIB = os.path.join(HERE, 'libbdof.so' if ALT == 0 else 'libbdof_alt%d.so' % ALT)
+if ALT:
+    OBJ = os.path.join(CSRC, '_obj_alt%d' % ALT)
 SIZES = [64, 128, 256, 512, 1024, 2048, 4096, 8192]
 NVCC_FLAGS = ['-O3', '-std=c++17', '--expt-relaxed-constexpr', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-lineinfo', '-Xcompiler', '-fPIC', '-Xptxas', '-v']
@@ -39,7 +42,7 @@ def _sources_mtime():
 
 def _compile(args):
     src, obj, defs, log = args
-    cmd = [_nvcc()] + NVCC_FLAGS + defs + ['-c', src, '-o', obj]
+    cmd = [_nvcc()] + NVCC_FLAGS + defs + (['-DBDOF_ALT=%d' % ALT] if ALT in (1, 2) else []) + (['-DBDOF_PHASE_TIMING'] if ALT == 9 else []) + (['-DBDOF_NO_STAGGER'] if ALT in (3, 5) else []) + (['-DBDOF_NO_ROWPF'] if ALT in (4, 5) else []) + ['-c', src, '-o', obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     with open(log, 'w') as f:
         f.write(' '.join(cmd) + '\n' + r.stdout + r.stderr)

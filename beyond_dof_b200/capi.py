@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libbdof.so')
+LIB_PATH = os.path.join(_HERE, os.environ.get('BDOF_LIB', 'libbdof.so'))
 
 # plan flags / modes (mirror include/bdof.h)
 PROPAGATE_LAST = 1 << 0
@@ -18,7 +18,7 @@ SYMBOLS = [
     'bdof_plan_create', 'bdof_plan_destroy', 'bdof_set_kernel', 'bdof_set_kernel_full', 'bdof_set_free_prop',
     'bdof_forward', 'bdof_loss_mag', 'bdof_adjoint', 'bdof_pack_db', 'bdof_unpack_db', 'bdof_patch_gather',
     'bdof_patch_scatter_add', 'bdof_cnn_forward', 'bdof_forward_host', 'bdof_plan_workspace_bytes',
-    'bdof_free_prop', 'bdof_profile_begin', 'bdof_profile_end',
+    'bdof_free_prop', 'bdof_profile_begin', 'bdof_profile_end', 'bdof_debug_set_buffer',
 ]
 
 
@@ -57,6 +57,7 @@ def _load():
     lib.bdof_plan_workspace_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
     lib.bdof_free_prop.argtypes = [vp, vp, vp]
     lib.bdof_profile_begin.argtypes = [vp]
+    lib.bdof_debug_set_buffer.argtypes = [vp]
     lib.bdof_profile_end.argtypes = [vp, i32, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)

@@ -9,6 +9,7 @@
 #include <complex>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -32,6 +33,11 @@ int bdof_launch_check(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return bdof_fail(int(e), "launch of %s failed: %s", what, cudaGetErrorString(e));
     return 0;
+}
+bool bdof_use_pdl() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("BDOF_PDL"); v = (e && e[0] == '1') ? 1 : 0; }     // measured: no gain on B200, off by default
+    return v == 1;
 }
 #define fail bdof_fail
 #define launch_check bdof_launch_check
@@ -70,7 +76,13 @@ static StageRadices radices_for(int n) {
         case 256: return {16, 16, 1};
         case 512: return {32, 16, 1};
         case 1024: return {32, 32, 1};
+#if !defined(BDOF_ALT) || BDOF_ALT == 0
         case 2048: return {64, 32, 1};
+#elif BDOF_ALT == 1
+        case 2048: return {32, 32, 2};
+#else
+        case 2048: return {16, 16, 8};
+#endif
         case 4096: return {64, 64, 1};
         case 8192: return {64, 64, 2};
     }
@@ -305,6 +317,9 @@ struct bdof_plan {
     long long F;               // batch*ny*nx
     AxisTables ax, ay;
     bool have_kernel = false, full_kernel = false;
+    bool row_prefetch = false; // row passes L2-prefetch their own side inputs at tile start (BDOF_ROW_PREFETCH=1 enables; measured slower)
+    bool l2_prefetch = false;  // column passes prefetch the next row pass's DRAM inputs into L2 (BDOF_L2_PREFETCH=1 enables;
+                               // measured slower on B200 at 2048^2: the prefetch traffic slows the column pass itself)
     float2* H2 = nullptr;      // general 2-D multiplier ifftshift2(H)/(nx ny) and its conjugate
     float2* H2_adj = nullptr;
     std::complex<double> phase0{1.0, 0.0}, phasef{1.0, 0.0};
@@ -378,6 +393,8 @@ extern "C" int bdof_plan_create(bdof_plan** out, int ny, int nx, int batch, int 
     p->stream = (cudaStream_t)cuda_stream;
     p->F = (long long)batch * ny * nx;
     p->ax.n = nx; p->ay.n = ny;
+    if (const char* e = getenv("BDOF_L2_PREFETCH")) p->l2_prefetch = (e[0] != '0');
+    if (const char* e = getenv("BDOF_ROW_PREFETCH")) p->row_prefetch = (e[0] != '0');
     int r = 0;
     do {
         if ((r = upload(&p->ax.tw, make_twiddles(nx)))) break;
@@ -464,6 +481,9 @@ extern "C" int bdof_set_free_prop(bdof_plan* p, int mode, const double* h_hy, co
     return 0;
 }
 
+static long long* g_dbg = nullptr;      // phase-timing buffer for instrumented builds (bdof_debug_set_buffer)
+extern "C" int bdof_debug_set_buffer(void* d_buf) { g_dbg = reinterpret_cast<long long*>(d_buf); return 0; }
+
 // ------------------------------------------------------------------------------------------
 // pass helpers
 // ------------------------------------------------------------------------------------------
@@ -473,6 +493,8 @@ static LineParams row_params(const bdof_plan* p, const float2* in, float2* out, 
     q.batch_stride = (long long)p->ny * p->nx; q.db_batch_stride = q.batch_stride;
     q.lines_per_batch = p->ny; q.elem_stride = 1; q.line_stride = p->nx;
     q.k_dz = float(p->k_dz);
+    q.dbg = g_dbg;
+    q.pf_bytes = p->row_prefetch ? 0 : -1;
     return q;
 }
 static LineParams col_params(const bdof_plan* p, const float2* in, float2* out, const float2* h) {
@@ -481,9 +503,14 @@ static LineParams col_params(const bdof_plan* p, const float2* in, float2* out, 
     q.batch_stride = (long long)p->ny * p->nx; q.db_batch_stride = q.batch_stride;
     q.lines_per_batch = p->nx; q.elem_stride = p->nx; q.line_stride = 1;
     q.k_dz = float(p->k_dz);
+    q.dbg = g_dbg;
+    q.pf_bytes = p->row_prefetch ? 0 : -1;
     return q;
 }
-static int timed_launch(bdof_plan* p, int n, int variant, const LineParams& q, long long n_lines) {
+static int timed_launch(bdof_plan* p, int n, int variant, const LineParams& q0, long long n_lines) {
+    LineParams q = q0;
+    if (g_dbg) q.dbg = g_dbg + (long long)variant * (1 << 17);     // one region per pass variant
+    { static int flags = -1; if (flags < 0) { const char* e = getenv("BDOF_DBG_FLAGS"); flags = e ? atoi(e) : 0; } q.dbg_flags = flags; }
     if (!p->profile) return launch_variant(n, variant, q, n_lines, p->stream);
     cudaEvent_t a, b;
     CUDA_TRY(cudaEventCreate(&a));
@@ -503,12 +530,13 @@ static int col_pass(bdof_plan* p, int variant, const LineParams& q) {
 }
 
 // one propagation of slice i: out = P(in * t(db))
-static int propagate_slice(bdof_plan* p, const float2* in, const float2* db, float2* out) {
+static int propagate_slice(bdof_plan* p, const float2* in, const float2* db, float2* out, const float2* db_next) {
     if (!p->full_kernel) {
         LineParams r = row_params(p, in, p->tmp, p->ax.h);
         r.db = db;
         BDOF_TRY(row_pass(p, V_ROW_CONV_T, r));
         LineParams c = col_params(p, p->tmp, out, p->ay.h);
+        if (db_next != nullptr && p->l2_prefetch) { c.pf0 = db_next; c.pf_bytes = p->F * (long long)sizeof(float2); }
         return col_pass(p, V_COL_CONV, c);
     }
     // general 2-D H: modulate, FFT_x, (FFT_y * H * IFFT_y), IFFT_x
@@ -524,6 +552,7 @@ static int propagate_slice(bdof_plan* p, const float2* in, const float2* db, flo
 static int propagate_slice_adj(bdof_plan* p, float2* G, const float2* psi, const float2* db, float2* grad) {
     if (!p->full_kernel) {
         LineParams c = col_params(p, G, p->tmp, p->ay.h_adj);
+        if (p->l2_prefetch) { c.pf0 = db; c.pf1 = psi; c.pf_bytes = p->F * (long long)sizeof(float2); }
         BDOF_TRY(col_pass(p, V_COL_CONV, c));
         LineParams r = row_params(p, p->tmp, G, p->ax.h_adj);
         r.db = db; r.psi = psi; r.grad = grad;
@@ -565,7 +594,8 @@ extern "C" int bdof_forward(bdof_plan* p, const float* d_db_f, const float* d_pr
         else if (store) dst = p->slabs + (long long)(i + 1) * p->F;
         else dst = (cur == p->work[0]) ? p->work[1] : p->work[0];
         if (slice_propagates(p, i)) {
-            BDOF_TRY(propagate_slice(p, cur, db_i, dst));
+            const float2* db_next = (i + 1 < Z && !(p->flags & BDOF_Z_BROADCAST)) ? d_db + (long long)(i + 1) * p->F : nullptr;
+            BDOF_TRY(propagate_slice(p, cur, db_i, dst, db_next));
             phase *= p->phase0;
         } else {
             k_modulate<<<blocks_for(p->F, 256), 256, 0, p->stream>>>(cur, db_i, dst, p->F, float(p->k_dz));

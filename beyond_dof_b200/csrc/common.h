@@ -20,6 +20,12 @@ struct LineParams {
     int in_shift;            // circular shift applied to the load index (ifftshift), MODE_INV
     int out_shift;           // circular shift applied to the store index (fftshift), MODE_FWD
     float k_dz;              // 2 pi dz / lambda
+    long long* dbg;          // phase-timing buffer (only read when built with -DBDOF_PHASE_TIMING)
+    int dbg_flags;           // ablation switches, instrumented builds only (BDOF_DBG_FLAGS): 1 no stream wait, 2 no stores, 4 no transmission math
+    // L2 prefetch of what the NEXT kernel streams from DRAM (issued by this kernel's CTAs at start)
+    const void* pf0;         // nullable
+    const void* pf1;         // nullable
+    long long pf_bytes;      // bytes per prefetched array (multiple of 16)
 };
 
 enum Variant { V_ROW_CONV_T = 0, V_ROW_CONV, V_ROW_CONV_ADJ, V_ROW_FWD, V_ROW_INV, V_COL_CONV, V_COL_FWD, V_COL_INV, V_COL_CONV2D };
@@ -58,10 +64,37 @@ __device__ __forceinline__ float2 transmission(float2 db, float k) {
     return make_float2(m * c, m * s);
 }
 
+// Same function for |k delta| <= pi/4 and |k beta| <= 0.5 (every X-ray configuration: k*delta per slice
+// is O(1e-4..1e-1)): no range reduction, no quadrant selects, exp by a degree-7 Taylor polynomial
+// (truncation 0.5^8/8! = 1e-7).  Callers pick it with a warp-uniform vote and fall back to transmission().
+__device__ __forceinline__ float2 transmission_small(float2 db, float k) {
+    const float x = k * db.x, y = -k * db.y;
+    const float x2 = x * x;
+    float sp = fmaf(x2, -1.9515295891e-4f, 8.3321608736e-3f);
+    sp = fmaf(sp, x2, -1.6666654611e-1f);
+    sp = fmaf(sp * x2, x, x);
+    float cp = fmaf(x2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    cp = fmaf(cp, x2, 4.166664568298827e-2f);
+    cp = fmaf(cp, x2, -0.5f);
+    cp = fmaf(cp, x2, 1.0f);
+    float m = fmaf(y, 1.98412698e-4f, 1.38888889e-3f);
+    m = fmaf(m, y, 8.33333333e-3f);
+    m = fmaf(m, y, 4.16666667e-2f);
+    m = fmaf(m, y, 1.66666667e-1f);
+    m = fmaf(m, y, 0.5f);
+    m = fmaf(m, y, 1.0f);
+    m = fmaf(m, y, 1.0f);
+    return make_float2(m * cp, m * sp);
+}
+__device__ __forceinline__ bool transmission_is_small(float2 db, float k) {
+    return fabsf(k * db.x) <= 0.78539816f && fabsf(k * db.y) <= 0.5f;
+}
+
 }  // namespace bdof
 
 int bdof_fail(int code, const char* fmt, ...);
 int bdof_launch_check(const char* what);
+bool bdof_use_pdl();      // programmatic dependent launch of the line kernels (BDOF_PDL=0 disables)
 
 #define BDOF_DECL_LINE(N) int bdof_launch_line_##N(int variant, const bdof::LineParams& p, long long n_lines, cudaStream_t st);
 BDOF_DECL_LINE(64) BDOF_DECL_LINE(128) BDOF_DECL_LINE(256) BDOF_DECL_LINE(512)

@@ -15,9 +15,15 @@ template <> struct CfgFor<64>   { using C = LineCfg<64, 8, 8, 8, 1>;      static
 template <> struct CfgFor<128>  { using C = LineCfg<128, 8, 16, 8, 1>;    static constexpr int RL = 16, CL = 16; };
 template <> struct CfgFor<256>  { using C = LineCfg<256, 16, 16, 16, 1>;  static constexpr int RL = 8,  CL = 8; };
 template <> struct CfgFor<512>  { using C = LineCfg<512, 16, 32, 16, 1>;  static constexpr int RL = 8,  CL = 8; };
-template <> struct CfgFor<1024> { using C = LineCfg<1024, 32, 32, 32, 1>; static constexpr int RL = 4,  CL = 8; };
-template <> struct CfgFor<2048> { using C = LineCfg<2048, 32, 64, 32, 1>; static constexpr int RL = 4,  CL = 8; };
-template <> struct CfgFor<4096> { using C = LineCfg<4096, 64, 64, 64, 1>; static constexpr int RL = 1,  CL = 4; };
+template <> struct CfgFor<1024> { using C = LineCfg<1024, 32, 32, 32, 1>; static constexpr int RL = 8,  CL = 8; };
+#if !defined(BDOF_ALT) || BDOF_ALT == 0
+template <> struct CfgFor<2048> { using C = LineCfg<2048, 32, 64, 32, 1>; static constexpr int RL = 8,  CL = 8; };
+#elif BDOF_ALT == 1     // experiment: 32 elements/thread, three stages
+template <> struct CfgFor<2048> { using C = LineCfg<2048, 64, 32, 32, 2>; static constexpr int RL = 4,  CL = 8; };
+#elif BDOF_ALT == 2     // experiment: 16 elements/thread, three stages
+template <> struct CfgFor<2048> { using C = LineCfg<2048, 128, 16, 16, 8>; static constexpr int RL = 2,  CL = 8; };
+#endif
+template <> struct CfgFor<4096> { using C = LineCfg<4096, 64, 64, 64, 1>; static constexpr int RL = 4,  CL = 4; };
 template <> struct CfgFor<8192> { using C = LineCfg<8192, 128, 64, 64, 2>; static constexpr int RL = 1, CL = 2; };
 
 static int sm_count() {
@@ -34,7 +40,8 @@ static int sm_count() {
 // persistent launch: one CTA per resident slot, each looping over tiles of LPC lines
 template <class Cfg, int LPC, bool COL, int MODE, int PRE, int POST>
 static int launch_line(const LineParams& p, long long n_lines, cudaStream_t st) {
-    using SM = LineSmem<Cfg, LPC, COL, MODE>;
+    constexpr int NSTREAM = (PRE == PRE_TRANSMIT) ? 1 : (POST == POST_ADJ ? 2 : 0);
+    using SM = LineSmem<Cfg, LPC, COL, MODE, NSTREAM>;
     auto kern = line_kernel<Cfg, LPC, COL, MODE, PRE, POST>;
     static int ctas_per_sm = 0;           // per instantiation
     if (ctas_per_sm == 0) {

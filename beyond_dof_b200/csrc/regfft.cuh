@@ -133,25 +133,25 @@ template <int R, bool INV> struct RegFFT {
     static constexpr int A = (R == 8) ? 2 : 4;
     static constexpr int B = R / A;
     static __device__ __forceinline__ void run(float2 (&v)[R]) {
-        static_for<B>([&](auto N2) {
+        static_for<B>([&](auto N2) __attribute__((always_inline)) {
             constexpr int n2 = decltype(N2)::value;
             float2 t[A];
-            static_for<A>([&](auto N1) { constexpr int n1 = decltype(N1)::value; t[n1] = v[B * n1 + n2]; });
+            static_for<A>([&](auto N1) __attribute__((always_inline)) { constexpr int n1 = decltype(N1)::value; t[n1] = v[B * n1 + n2]; });
             RegFFT<A, INV>::run(t);
-            static_for<A>([&](auto K1) {
+            static_for<A>([&](auto K1) __attribute__((always_inline)) {
                 constexpr int k1 = decltype(K1)::value;
                 v[B * k1 + n2] = mul_tw<(n2 * k1) % R, R, INV>(t[k1]);
             });
         });
         float2 out[R];
-        static_for<A>([&](auto K1) {
+        static_for<A>([&](auto K1) __attribute__((always_inline)) {
             constexpr int k1 = decltype(K1)::value;
             float2 u[B];
-            static_for<B>([&](auto N2) { constexpr int n2 = decltype(N2)::value; u[n2] = v[B * k1 + n2]; });
+            static_for<B>([&](auto N2) __attribute__((always_inline)) { constexpr int n2 = decltype(N2)::value; u[n2] = v[B * k1 + n2]; });
             RegFFT<B, INV>::run(u);
-            static_for<B>([&](auto K2) { constexpr int k2 = decltype(K2)::value; out[k1 + A * k2] = u[k2]; });
+            static_for<B>([&](auto K2) __attribute__((always_inline)) { constexpr int k2 = decltype(K2)::value; out[k1 + A * k2] = u[k2]; });
         });
-        static_for<R>([&](auto I) { constexpr int i = decltype(I)::value; v[i] = out[i]; });
+        static_for<R>([&](auto I) __attribute__((always_inline)) { constexpr int i = decltype(I)::value; v[i] = out[i]; });
     }
 };
 

@@ -168,13 +168,15 @@ class FullfieldObjective:
     forward + loss + adjoint into self.grad and returns the loss as a Python float (one D2H read).
     """
 
-    def __init__(self, db_obj, probe, energy_ev, psize_cm, free_prop_cm=None, propagate_last=False):
+    def __init__(self, db_obj, probe, energy_ev, psize_cm, free_prop_cm=None, propagate_last=False, in_place=False):
         Z, B, Y, X, _ = db_obj.shape
         self.plan = MultislicePlan(Y, X, B, Z, energy_ev, psize_cm, free_prop_cm=free_prop_cm,
                                    propagate_last=propagate_last, store_slices=True, device=db_obj.device)
         self.db = db_obj
         self.probe = probe.to(db_obj.device, torch.complex64).contiguous()
-        self.grad = torch.empty_like(db_obj)
+        # in_place: the adjoint overwrites db_obj with the gradient (halves the footprint: 4096^2 x 512 fits in 180 GB)
+        self.in_place = in_place
+        self.grad = db_obj if in_place else torch.empty_like(db_obj)
         self.target = torch.empty((B, Y, X), dtype=torch.float32, device=db_obj.device)
         self.exit = torch.empty((B, Y, X), dtype=torch.complex64, device=db_obj.device)
         self.loss_host = torch.empty((), dtype=torch.float64).pin_memory()
@@ -183,7 +185,7 @@ class FullfieldObjective:
         """forward + loss + adjoint with the target already on the device; returns the device loss."""
         self.plan.forward(self.db, self.probe, out=self.exit)
         loss, g = self.plan.loss_mag(self.exit, target_dev)
-        self.plan.adjoint(self.db, g, grad_out=self.grad)
+        self.plan.adjoint(self.db, g, grad_out=None if self.in_place else self.grad)
         return loss
 
     def step(self, prj_mag_host):
