@@ -197,27 +197,17 @@ def run_gpu(args):
     target_host = (0.9 + 0.1 * torch.rand((B, ny, nx), generator=torch.Generator().manual_seed(4321 + rank))).pin_memory()
     target_dev = target_host.to(dev)
 
-    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-
-    def allreduce_grad():
+    if world > 1:
         # data-parallel exchange (Horovod allreduce in fullfield.py:412; comm.Allreduce in cnn fullfield.py:350):
-        # sum of the object gradient over ranks, in z-buckets
-        if world == 1:
-            return
-        nb = 8
-        step = (nz + nb - 1) // nb
-        for z0 in range(0, nz, step):
-            dist.all_reduce(obj.grad[z0:z0 + step], op=dist.ReduceOp.SUM)
+        # mean of the object gradient over ranks, reduced in z-buckets on a communication stream while the
+        # adjoint sweep is still producing the remaining slices
+        obj.enable_data_parallel(n_buckets=args.buckets)
 
     def step_device():
-        loss = obj.step_device(target_dev)
-        allreduce_grad()
-        return loss
+        return obj.step_device(target_dev)
 
     def step_e2e():
-        loss = obj.step(target_host)
-        allreduce_grad()
-        return loss
+        return obj.step(target_host)
 
     def barrier():
         if world > 1:
@@ -323,6 +313,7 @@ def main():
     ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='bdof', choices=['bdof', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
+    ap.add_argument('--buckets', type=int, default=8, help='z-buckets of the gradient all-reduce (N > 1)')
     ap.add_argument('--shape', default=None, help='experiment: B,NY,NX,NZ overrides the workload shape')
     ap.add_argument('--in-place', action='store_true', help='adjoint overwrites delta/beta with the gradient (needed for the 4096^2x512 size)')
     args = ap.parse_args()

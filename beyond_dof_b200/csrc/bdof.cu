@@ -331,6 +331,8 @@ struct bdof_plan {
     double* partial = nullptr;
     std::complex<double> total_phase{1.0, 0.0};
     bool forward_done = false;
+    // gradient buckets along z: events recorded by bdof_adjoint when a bucket's gradient is final
+    std::vector<cudaEvent_t> bucket_events;
     // in-situ per-variant timing (bdof_profile_*): events around every line-kernel launch
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;      // pairs (start, stop)
@@ -664,6 +666,7 @@ extern "C" int bdof_adjoint(bdof_plan* p, float* d_db_inout, const float* d_grad
         BDOF_TRY(col_pass(p, V_COL_CONV, col_params(p, G, p->tmp, p->ay.hf_adj)));
         BDOF_TRY(row_pass(p, V_ROW_CONV, row_params(p, p->tmp, G, p->ax.hf_adj)));
     }
+    const int n_buckets = int(p->bucket_events.size());
     for (int i = Z - 1; i >= 0; --i) {
         const float2* db_i = db + (zb ? 0 : (long long)i * p->F);
         float2* grad_i = gout ? gout + (long long)i * p->F : db + (long long)i * p->F;
@@ -673,6 +676,15 @@ extern "C" int bdof_adjoint(bdof_plan* p, float* d_db_inout, const float* d_grad
         } else {
             k_modulate_adj<<<blocks_for(p->F, 256), 256, 0, p->stream>>>(G, psi_i, db_i, grad_i, p->F, float(p->k_dz));
             BDOF_TRY(launch_check("k_modulate_adj"));
+        }
+        if (n_buckets > 0) {
+            // bucket j covers slices [z_lo(j), z_lo(j-1)) counted from the top: it is final once slice z_lo(j) is done
+            const int per = (Z + n_buckets - 1) / n_buckets;
+            const int from_top = Z - 1 - i;
+            if ((from_top + 1) % per == 0 || i == 0) {
+                const int j = from_top / per;
+                if (j < n_buckets) CUDA_TRY(cudaEventRecord(p->bucket_events[j], p->stream));
+            }
         }
     }
     if (d_grad_probe) {
@@ -832,5 +844,26 @@ extern "C" int bdof_free_prop(bdof_plan* p, const float* d_in_f, float* d_out_f)
         return launch_check("k_scale_complex");
     }
     if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, (size_t)p->F * sizeof(float2), cudaMemcpyDeviceToDevice, p->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// single-slice stepping (tiling with halo exchange) and gradient buckets (overlapped all-reduce)
+// ------------------------------------------------------------------------------------------
+extern "C" int bdof_slice_step(bdof_plan* p, const float* d_in, const float* d_db_slice, float* d_out, int propagate) {
+    if (!p || !d_in || !d_db_slice || !d_out) return fail(BDOF_E_BADARG, "null");
+    if (!p->have_kernel) return fail(BDOF_E_STATE, "bdof_set_kernel has not been called");
+    const float2* in = reinterpret_cast<const float2*>(d_in);
+    const float2* db = reinterpret_cast<const float2*>(d_db_slice);
+    float2* out = reinterpret_cast<float2*>(d_out);
+    if (propagate) return propagate_slice(p, in, db, out, nullptr);
+    k_modulate<<<blocks_for(p->F, 256), 256, 0, p->stream>>>(in, db, out, p->F, float(p->k_dz));
+    return launch_check("k_modulate");
+}
+
+extern "C" int bdof_plan_set_bucket_events(bdof_plan* p, int n_buckets, void** cuda_events) {
+    if (!p || n_buckets < 0 || (n_buckets > 0 && !cuda_events)) return fail(BDOF_E_BADARG, "bad argument");
+    p->bucket_events.clear();
+    for (int j = 0; j < n_buckets; ++j) p->bucket_events.push_back(reinterpret_cast<cudaEvent_t>(cuda_events[j]));
     return 0;
 }

@@ -1,0 +1,129 @@
+"""Data-parallel layer of the reconstruction loops: one process per GPU, torch.distributed for the plumbing.
+
+The reference's only parallelism strategy is data parallel: projection angles
+(full field) or (angle, scan position) pairs (ptychography) are sharded over ranks and the object
+gradient is all-reduced every optimiser step:
+
+  dataset .shard(hvd.size(), hvd.rank())                 tensorflow_recon/fullfield.py:221-224
+  hvd.DistributedOptimizer (allreduce-mean)              tensorflow_recon/fullfield.py:412,444
+  each rank takes minibatch_size positions of one angle  cnn_propagator/ptychography.py:292-297
+  comm.Allreduce(this_grads, grads); grads / size        cnn_propagator/fullfield.py:348-351, ptychography.py:302-306
+
+Here the exchange is one NCCL all-reduce of the slice-major object gradient [Z, ..., 2] (fp32), optionally
+issued bucket by bucket along z on a communication stream while the adjoint sweep is still producing
+the remaining slices (a slice's gradient is final once the backward sweep has passed it).
+Everything in this file is host logic: it runs unchanged over gloo on CPU tensors (tests) and over
+NCCL on CUDA tensors (production).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def world():
+    """(rank, world_size) of the default process group, (0, 1) when not initialised
+    (the single-process stand-in the reference ships as pseudo.py:3-33)."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_round_robin(n_items, rank=None, world_size=None):
+    """tf.data .shard(size, rank) semantics (fullfield.py:221-224): every size-th item starting at rank."""
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    return np.arange(rank, n_items, world_size)
+
+
+def shard_contiguous(n_items, rank=None, world_size=None):
+    """Contiguous blocks, as the ptychography driver hands out scan positions of one angle
+    (cnn_propagator/ptychography.py:292-297).  The first n_items % world ranks get one extra item."""
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    base, extra = divmod(n_items, world_size)
+    start = rank * base + min(rank, extra)
+    return np.arange(start, start + base + (1 if rank < extra else 0))
+
+
+def allreduce_gradient(grad, average=True, buckets=None, comm_stream=None):
+    """Sum (or mean) of the object gradient over ranks, in place.
+
+    grad: tensor whose FIRST axis is z (slice-major native layout) or any tensor when buckets is None.
+    buckets: optional [(z_lo, z_hi, event)] from MultislicePlan.set_gradient_buckets(): each bucket is
+    reduced on comm_stream as soon as its event (recorded inside the adjoint sweep) has fired, so the
+    exchange overlaps the rest of the sweep.  Returns the list of async work handles (empty when
+    world_size == 1); call finish_allreduce() before using the gradient.
+    """
+    rank, w = world()
+    if w == 1:
+        return []
+    works = []
+    if buckets is None:
+        works.append(dist.all_reduce(grad, op=dist.ReduceOp.SUM, async_op=True))
+    else:
+        for z_lo, z_hi, ev in buckets:
+            if comm_stream is not None and grad.is_cuda:
+                comm_stream.wait_event(ev)
+                with torch.cuda.stream(comm_stream):
+                    works.append(dist.all_reduce(grad[z_lo:z_hi], op=dist.ReduceOp.SUM, async_op=True))
+            else:
+                works.append(dist.all_reduce(grad[z_lo:z_hi], op=dist.ReduceOp.SUM, async_op=True))
+    if average:
+        works.append(('scale', 1.0 / w))
+    return works
+
+
+def finish_allreduce(grad, works, comm_stream=None):
+    """Wait for the handles returned by allreduce_gradient and apply the 1/world scaling."""
+    scale = None
+    for wk in works:
+        if isinstance(wk, tuple):
+            scale = wk[1]
+        else:
+            wk.wait()
+    if comm_stream is not None and grad.is_cuda:
+        torch.cuda.current_stream().wait_stream(comm_stream)
+    if scale is not None:
+        grad.mul_(scale)
+    return grad
+
+
+def allreduce_scalar(value, average=False):
+    """Sum (mean) of a Python/0-d scalar over ranks, e.g. the per-rank partial loss
+    (cnn_propagator/ptychography.py:338 keeps a per-rank loss table)."""
+    rank, w = world()
+    if w == 1:
+        return float(value)
+    backend = dist.get_backend()
+    dev = torch.device('cuda', torch.cuda.current_device()) if backend == 'nccl' else torch.device('cpu')
+    t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item()) / (w if average else 1)
+
+
+def broadcast_object_(tensor, src=0):
+    """hvd.broadcast_global_variables(0) (fullfield.py:481): every rank starts from rank 0's object."""
+    rank, w = world()
+    if w > 1:
+        dist.broadcast(tensor, src=src)
+    return tensor
+
+
+def data_parallel_step(n_items, local_loss_and_grad, grad_buffer, shard='contiguous', average=True):
+    """One data-parallel loss/gradient evaluation.
+
+    n_items: number of work items of this step (scan positions of one angle, or angles of a minibatch).
+    local_loss_and_grad(indices, grad_buffer) -> local loss: evaluates the model on this rank's items,
+        ACCUMULATING the object gradient into grad_buffer (pre-zeroed here) and returning the sum of the
+        per-item losses (so that sum over ranks = loss over all items).
+    Returns (loss_total, grad_buffer) with the gradient summed (average=False) or averaged over ranks as
+    the reference does (grads / size, cnn_propagator/ptychography.py:306).
+    """
+    idx = shard_contiguous(n_items) if shard == 'contiguous' else shard_round_robin(n_items)
+    grad_buffer.zero_()
+    local = local_loss_and_grad(idx, grad_buffer) if len(idx) else 0.0
+    works = allreduce_gradient(grad_buffer, average=average)
+    finish_allreduce(grad_buffer, works)
+    return allreduce_scalar(float(local)), grad_buffer

@@ -181,11 +181,24 @@ class FullfieldObjective:
         self.exit = torch.empty((B, Y, X), dtype=torch.complex64, device=db_obj.device)
         self.loss_host = torch.empty((), dtype=torch.float64).pin_memory()
 
+    def enable_data_parallel(self, n_buckets=8):
+        """Reduce the object gradient over the ranks of the default process group every step, bucket by
+        bucket along z on a separate stream while the adjoint sweep is still running."""
+        from . import dist as bdist
+        self._dp = bdist
+        self._buckets = self.plan.set_gradient_buckets(n_buckets)
+        self._comm_stream = torch.cuda.Stream(device=self.db.device)
+        return self
+
     def step_device(self, target_dev):
-        """forward + loss + adjoint with the target already on the device; returns the device loss."""
+        """forward + loss + adjoint (+ gradient all-reduce when data parallel) with the target already on
+        the device; returns the device loss of this rank."""
         self.plan.forward(self.db, self.probe, out=self.exit)
         loss, g = self.plan.loss_mag(self.exit, target_dev)
         self.plan.adjoint(self.db, g, grad_out=None if self.in_place else self.grad)
+        if getattr(self, '_dp', None) is not None:
+            works = self._dp.allreduce_gradient(self.grad, average=True, buckets=self._buckets, comm_stream=self._comm_stream)
+            self._dp.finish_allreduce(self.grad, works, comm_stream=self._comm_stream)
         return loss
 
     def step(self, prj_mag_host):

@@ -163,6 +163,33 @@ class MultislicePlan:
         check(lib.bdof_forward_host(self._h, _hptr(d), _hptr(b), _hptr(pr), _hptr(out)))
         return out
 
+    def slice_step(self, field, db_slice, out=None, propagate=True):
+        """One slice: out = P(field * t(db_slice)) (or only the modulation).  field [B,Y,X] complex64,
+        db_slice [B,Y,X,2] float32.  The global phase exp(i k dz) is not applied."""
+        assert field.is_cuda and field.dtype == torch.complex64 and field.is_contiguous()
+        assert db_slice.is_cuda and db_slice.dtype == torch.float32 and db_slice.is_contiguous()
+        if out is None:
+            out = torch.empty_like(field)
+        check(lib.bdof_slice_step(self._h, _ptr(field), _ptr(db_slice), _ptr(out), 1 if propagate else 0))
+        return out
+
+    def set_gradient_buckets(self, n_buckets):
+        """Split z into n_buckets (counted from the last slice); returns [(z_lo, z_hi, event)] in the order
+        the adjoint sweep completes them.  The events are recorded inside bdof_adjoint."""
+        self._bucket_events = [torch.cuda.Event() for _ in range(n_buckets)]
+        for ev in self._bucket_events:
+            ev.record(self.stream)                       # materialise the cudaEvent_t handle
+        arr = (ctypes.c_void_p * max(n_buckets, 1))(*[ctypes.c_void_p(ev.cuda_event) for ev in self._bucket_events])
+        check(lib.bdof_plan_set_bucket_events(self._h, n_buckets, arr))
+        per = (self.n_slice + n_buckets - 1) // n_buckets if n_buckets else 0
+        out = []
+        for j in range(n_buckets):
+            z_hi = self.n_slice - j * per
+            z_lo = max(0, z_hi - per)
+            if z_hi > 0:
+                out.append((z_lo, z_hi, self._bucket_events[j]))
+        return out
+
     VARIANT_NAMES = ['row_conv_transmit', 'row_conv', 'row_conv_adjoint', 'row_fft', 'row_ifft', 'col_conv', 'col_fft',
                      'col_ifft', 'col_conv_2d']
 

@@ -131,6 +131,19 @@ int  bdof_cnn_forward(const float* d_db, const float* d_probe, float* d_exit, fl
 int  bdof_forward_host(bdof_plan* p, const float* h_delta_byxz, const float* h_beta_byxz,
                        const float* h_probe, float* h_exit);
 
+/* One slice of the chain on its own: out = P(in * t(db_slice)) (propagate != 0) or in * t(db_slice).
+ * Used by the tiling scheme, which refreshes tile halos between slices.  d_db_slice is
+ * [batch][ny][nx][2]; in/out [batch][ny][nx] complex64; out must not alias in.  The global phase
+ * exp(i k dz) per propagation is NOT applied (it cancels in every |psi|-based quantity). */
+int  bdof_slice_step(bdof_plan* p, const float* d_in, const float* d_db_slice, float* d_out, int propagate);
+
+/* Gradient buckets for the data-parallel all-reduce (Horovod allreduce, tensorflow_recon/fullfield.py:412):
+ * the z range is split into n_buckets contiguous buckets counted from the last slice; bdof_adjoint
+ * records cuda_events[j] (cudaEvent_t handles owned by the caller) on the plan's stream as soon as
+ * bucket j's gradient is final, so a communication stream can reduce it while the sweep continues.
+ * n_buckets = 0 disables. */
+int  bdof_plan_set_bucket_events(bdof_plan* p, int n_buckets, void** cuda_events);
+
 /* The free-space step of the plan on its own (npfuncs.py:43-61): out = free_prop(in), [batch][ny][nx]. */
 int  bdof_free_prop(bdof_plan* p, const float* d_in, float* d_out);
 
