@@ -1,0 +1,64 @@
+"""Summarise an .ncu-rep (read offline with `ncu -i`) into a small text file for profiles/.
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/out.txt"""
+import csv, re, subprocess, sys
+from collections import defaultdict
+
+KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread', 'launch__occupancy_limit_registers',
+        'launch__occupancy_limit_shared_mem', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
+        'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'lts__t_sector_hit_rate.pct', 'sass__inst_executed_local_loads', 'sass__inst_executed_local_stores', 'smsp__cycles_active.avg']
+
+
+def short(name):
+    m = re.search(r'LineCfg<\(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+)>, \(int\)(\d+), \(bool\)(\d), \(int\)(\d), \(int\)(\d), \(int\)(\d)', name)
+    if not m:
+        return name.split('(')[0]
+    n, t, r1, r2, r3, lpc, col, mode, pre, post = m.groups()
+    kind = ('col' if col == '1' else 'row') + '_' + ['conv', 'fft', 'ifft', 'conv2d'][int(mode)] + ('_transmit' if pre == '1' else '') + ('_adjoint' if post == '1' else '')
+    return 'line_kernel N=%s T=%s radices=%sx%sx%s lines/CTA=%s %s' % (n, t, r1, r2, r3, lpc, kind)
+
+
+def main(rep, out):
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    lines = ['ncu summary of %s (ncu --set full --clock-control none; per-launch values, cold cache, serialised)' % rep, '']
+    seen = set()
+    for i, d in enumerate(data):
+        name = short(d[hdr.index('Kernel Name')])
+        if name in seen:
+            continue
+        seen.add(name)
+        lines.append('== ' + name)
+        for k in KEYS:
+            if k in hdr:
+                lines.append('   %-70s %s %s' % (k, d[hdr.index(k)], units[hdr.index(k)]))
+        # stall reasons from the source page
+        src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-id', '::regex:line_kernel:%d' % (i + 1)], capture_output=True, text=True).stdout
+        srows = list(csv.reader(src.splitlines()))
+        tot = defaultdict(float)
+        for j, r in enumerate(srows):
+            if r and r[0] == 'Address':
+                h2 = r
+                cols = [k for k, h in enumerate(h2) if h.startswith('stall_') and 'Not Issued' not in h]
+                for rr in srows[j + 1:]:
+                    if len(rr) == len(h2):
+                        for k in cols:
+                            try:
+                                tot[h2[k]] += float(rr[k])
+                            except ValueError:
+                                pass
+                break
+        s = sum(tot.values())
+        if s:
+            lines.append('   warp stall samples: ' + ', '.join('%s %.1f%%' % (k[6:], 100 * v / s) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:7]))
+        lines.append('')
+    open(out, 'w').write('\n'.join(lines))
+    print('wrote', out)
+
+
+if __name__ == '__main__':
+    main(sys.argv[1], sys.argv[2])
