@@ -88,6 +88,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// Ampere-style 16-byte asynchronous copies (LDGSTS): column tiles are 32..64-byte row segments, too
+// small for bulk copies without a tensor map
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // bulk prefetch of a global range into L2 (no shared-memory destination, no completion tracking)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
@@ -174,9 +182,13 @@ __device__ __forceinline__ void exchange_read_twiddle(float2 (&v)[Cfg::E], int t
 }
 
 // forward length-N transform of the line held in v (natural order in and out)
-template <class Cfg, int LPC, bool COL>
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+// `after_last_read` runs once all threads sharing the exchange buffer have finished their LAST read of
+// it in this transform: from then on the buffer is free (used to prefetch the next tile into it).
+template <class Cfg, int LPC, bool COL, class Hook = NoHook>
 __device__ __forceinline__ void line_fft(float2 (&v)[Cfg::E], int t, int l, float2* sm, const float2* tw,
-                                         [[maybe_unused]] long long* stamps = nullptr) {
+                                         [[maybe_unused]] long long* stamps = nullptr, Hook after_last_read = Hook()) {
     constexpr int R1 = Cfg::R1, R2 = Cfg::R2, R3 = Cfg::R3;
     reg_butterflies<Cfg, R1>(v);
 #ifdef BDOF_PHASE_TIMING
@@ -187,6 +199,7 @@ __device__ __forceinline__ void line_fft(float2 (&v)[Cfg::E], int t, int l, floa
     exchange<Cfg, R1, 1>(v, t, sm);
     line_sync<Cfg, LPC, COL>(l);
     exchange_read_twiddle<Cfg, R2, R1>(v, t, sm, tw);
+    if constexpr (R3 == 1) after_last_read();
 #ifdef BDOF_PHASE_TIMING
     asm volatile("" ::"f"(v[0].x), "f"(v[Cfg::E - 1].y));
     if (stamps) stamps[1] = clock64();
@@ -197,6 +210,7 @@ __device__ __forceinline__ void line_fft(float2 (&v)[Cfg::E], int t, int l, floa
         exchange<Cfg, R2, R1>(v, t, sm);
         line_sync<Cfg, LPC, COL>(l);
         exchange_read_twiddle<Cfg, R3, R1 * R2>(v, t, sm, tw + Cfg::TW2);
+        after_last_read();
         reg_butterflies<Cfg, R3>(v);
     }
 }
@@ -241,12 +255,27 @@ __global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, c
 #endif
     constexpr bool STAGGER = STAGGER_ON && !COL && (PRE == PRE_TRANSMIT || POST == POST_ADJ) && (LPC % 2 == 0) && (T >= 32) && ((LPC / 2) * (T / 32) % 4 == 0);
     __shared__ volatile int stagger_flag[STAGGER ? LPC / 2 : 1];
+    // Next-tile prefetch of the main input into the exchange buffers (convolution passes only): column
+    // tiles by cp.async 16-byte pieces issued by every thread, rows by one bulk copy per line.
+#ifdef BDOF_NO_ROW_TILE_PREFETCH
+    constexpr bool PF_ROW = false;
+#else
+    constexpr bool PF_ROW = true;
+#endif
+#ifdef BDOF_NO_COL_TILE_PREFETCH
+    constexpr bool PF_COL = false;
+#else
+    constexpr bool PF_COL = true;
+#endif
+    constexpr bool PREFETCH = (MODE == MODE_CONV) && (COL ? (PF_COL && LPC >= 2 && (N * LPC / 2) % (T * LPC) == 0) : (PF_ROW && T >= 32));
+    __shared__ unsigned long long line_bar[(PREFETCH && !COL) ? LPC : 1];
     constexpr unsigned TW_BYTES = Cfg::TW_TOTAL * sizeof(float2);
     constexpr unsigned H_BYTES = SM::H_IN_SMEM ? N * sizeof(float2) : 0;
     static_assert(TW_BYTES % 16 == 0 && H_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
     if (tid == 0) {
         mbar_init(&table_bar, 1);
         for (int i = 0; i < SM::NBARS; ++i) mbar_init(&s_bar[i], 1);
+        if constexpr (PREFETCH && !COL) { for (int i = 0; i < LPC; ++i) mbar_init(&line_bar[i], 1); }
         fence_mbar_init();
     }
     if constexpr (STAGGER) { if (tid < LPC / 2) stagger_flag[tid] = 0; }
@@ -364,7 +393,23 @@ __global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, c
 
         float2 v[E];
         // ---- load (element t + T*q -> register q)
-        {
+        bool loaded = false;
+        if constexpr (PREFETCH) {
+            if (tile_iter > 0) {
+                // this tile was prefetched into the exchange buffers while the previous one finished
+                if constexpr (COL) {
+                    cp_async_wait_all();
+                    __syncthreads();
+                    const float2* sp = s_x + t * LPC + l;                 // staged as [row][LPC]
+                    static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = sp[T * q * LPC]; });
+                } else {
+                    mbar_wait(&line_bar[l], (tile_iter - 1) & 1);
+                    static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = sm[t + T * q]; });
+                }
+                loaded = true;
+            }
+        }
+        if (!loaded) {
             const float2* __restrict__ src = p.in + base;
             if constexpr (MODE == MODE_INV) {
                 // conj + circular input shift (ifftshift), far-field adjoint only
@@ -382,6 +427,42 @@ __global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, c
                 static_for<E>([&](auto Q) __attribute__((always_inline)) { v[decltype(Q)::value] = *ptr; ptr += step; });
             }
         }
+        // issued from inside the second transform, right after its last read of the exchange buffer
+        auto prefetch_next = [&]() __attribute__((always_inline)) {
+            if constexpr (PREFETCH) {
+                const long long nl = line + line_step;
+                if (nl < n_lines) {
+                    line_sync<Cfg, LPC, COL>(l);                          // every reader of the buffer is done
+                    if constexpr (COL) {
+                        const long long tl = nl - l;                      // first column of the next tile
+                        const int bb = int(tl / p.lines_per_batch);
+                        const int c0 = int(tl - (long long)bb * p.lines_per_batch);
+                        constexpr int PPR = LPC / 2;                      // 16-byte pieces per row segment
+                        constexpr int RPI = T * LPC / PPR;                // rows covered per sweep of the CTA
+                        constexpr int NP = N / RPI;                       // pieces per thread
+                        const int r = tid / PPR, j = tid % PPR;
+                        const char* sp = reinterpret_cast<const char*>(p.in + (long long)bb * p.batch_stride + c0) +
+                                         ((long long)r * p.elem_stride) * (long long)sizeof(float2) + j * 16;
+                        char* dp = reinterpret_cast<char*>(s_x) + r * (LPC * (int)sizeof(float2)) + j * 16;
+                        const long long sstep = (long long)RPI * p.elem_stride * (long long)sizeof(float2);
+#pragma unroll 8
+                        for (int m = 0; m < NP; ++m) {
+                            cp_async16(dp, sp);
+                            sp += sstep;
+                            dp += RPI * LPC * (int)sizeof(float2);
+                        }
+                        cp_async_commit();
+                    } else {
+                        if (t == 0) {
+                            const int bb = int(nl / p.lines_per_batch);
+                            const int lli = int(nl - (long long)bb * p.lines_per_batch);
+                            mbar_expect_tx(&line_bar[l], N * (unsigned)sizeof(float2));
+                            bulk_g2s(sm, p.in + (long long)bb * p.batch_stride + (long long)lli * p.line_stride, N * (unsigned)sizeof(float2), &line_bar[l]);
+                        }
+                    }
+                }
+            }
+        };
 #ifndef BDOF_NO_ROWPF
         if constexpr (POST == POST_ADJ) stream_prefetch_l2(line);      // lands in L2 while the transforms run
 #endif
@@ -436,14 +517,16 @@ __global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, c
         } else {
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
+                auto hook = [&]() __attribute__((always_inline)) { if (pass == 1) prefetch_next(); };
 #ifdef BDOF_PHASE_TIMING
                 long long* st = (p.dbg != nullptr && (threadIdx.x & 31) == 0 && tile_iter < 2)
                     ? p.dbg + ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + tile_iter * 12 + 3 + pass * 4 : nullptr;
-                line_fft<Cfg, LPC, COL>(v, t, l, sm, s_tw, st);
+                // ONE call site: a second instantiation would double the instruction footprint
+                line_fft<Cfg, LPC, COL>(v, t, l, sm, s_tw, st, hook);
                 asm volatile("" ::"f"(v[0].x), "f"(v[E - 1].y));
                 if (st) st[2] = clock64();
 #else
-                line_fft<Cfg, LPC, COL>(v, t, l, sm, s_tw);
+                line_fft<Cfg, LPC, COL>(v, t, l, sm, s_tw, nullptr, hook);
 #endif
                 if constexpr (STAGGER && POST == POST_ADJ) {
                     // adjoint row pass: the memory-heavy epilogue is at the END of a tile, so the partner
