@@ -203,6 +203,8 @@ def run_gpu(args):
         # mean of the object gradient over ranks, reduced in z-buckets on a communication stream while the
         # adjoint sweep is still producing the remaining slices
         obj.enable_data_parallel(n_buckets=args.buckets)
+        if args.sm_reserve:
+            capi.check(capi.lib.bdof_set_sm_reserve(args.sm_reserve))
 
     def step_device():
         return obj.step_device(target_dev)
@@ -317,6 +319,7 @@ def main():
     ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='bdof', choices=['bdof', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
+    ap.add_argument('--sm-reserve', type=int, default=0, help='SMs left free for NCCL while the sweep runs (N > 1)')
     ap.add_argument('--buckets', type=int, default=8, help='z-buckets of the gradient all-reduce (N > 1)')
     ap.add_argument('--shape', default=None, help='experiment: B,NY,NX,NZ overrides the workload shape')
     ap.add_argument('--in-place', action='store_true', help='adjoint overwrites delta/beta with the gradient (needed for the 4096^2x512 size)')

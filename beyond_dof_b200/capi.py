@@ -19,7 +19,7 @@ SYMBOLS = [
     'bdof_forward', 'bdof_loss_mag', 'bdof_adjoint', 'bdof_pack_db', 'bdof_unpack_db', 'bdof_patch_gather',
     'bdof_patch_scatter_add', 'bdof_cnn_forward', 'bdof_forward_host', 'bdof_plan_workspace_bytes',
     'bdof_free_prop', 'bdof_profile_begin', 'bdof_profile_end', 'bdof_debug_set_buffer', 'bdof_slice_step',
-    'bdof_plan_set_bucket_events',
+    'bdof_plan_set_bucket_events', 'bdof_set_sm_reserve',
 ]
 
 
@@ -61,6 +61,7 @@ def _load():
     lib.bdof_debug_set_buffer.argtypes = [vp]
     lib.bdof_slice_step.argtypes = [vp, vp, vp, vp, i32]
     lib.bdof_plan_set_bucket_events.argtypes = [vp, i32, vp]
+    lib.bdof_set_sm_reserve.argtypes = [i32]
     lib.bdof_profile_end.argtypes = [vp, i32, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)

@@ -34,6 +34,16 @@ int bdof_launch_check(const char* what) {
     if (e != cudaSuccess) return bdof_fail(int(e), "launch of %s failed: %s", what, cudaGetErrorString(e));
     return 0;
 }
+static int g_sm_reserve = -1;
+int bdof_sm_reserve() {
+    if (g_sm_reserve < 0) { const char* e = getenv("BDOF_SM_RESERVE"); g_sm_reserve = e ? atoi(e) : 0; }
+    return g_sm_reserve;
+}
+extern "C" int bdof_set_sm_reserve(int n_sms) {
+    if (n_sms < 0) return bdof_fail(BDOF_E_BADARG, "negative SM count");
+    g_sm_reserve = n_sms;
+    return 0;
+}
 bool bdof_use_pdl() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("BDOF_PDL"); v = (e && e[0] == '1') ? 1 : 0; }     // measured: no gain on B200, off by default

@@ -94,6 +94,7 @@ __device__ __forceinline__ bool transmission_is_small(float2 db, float k) {
 
 int bdof_fail(int code, const char* fmt, ...);
 int bdof_launch_check(const char* what);
+int bdof_sm_reserve();    // SMs the persistent line kernels leave free (bdof_set_sm_reserve / BDOF_SM_RESERVE)
 bool bdof_use_pdl();      // programmatic dependent launch of the line kernels (BDOF_PDL=0 disables)
 
 #define BDOF_DECL_LINE(N) int bdof_launch_line_##N(int variant, const bdof::LineParams& p, long long n_lines, cudaStream_t st);

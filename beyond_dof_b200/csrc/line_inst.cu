@@ -53,7 +53,8 @@ static int launch_line(const LineParams& p, long long n_lines, cudaStream_t st) 
     }
     if (n_lines % LPC != 0) return bdof_fail(BDOF_E_UNSUPPORTED, "line count %lld not a multiple of %d", n_lines, LPC);
     const long long n_tiles = n_lines / LPC;
-    const long long slots = (long long)ctas_per_sm * sm_count();
+    // leave `bdof_sm_reserve()` SMs free (for NCCL kernels that must run concurrently with the sweep)
+    const long long slots = (long long)ctas_per_sm * (sm_count() > bdof_sm_reserve() ? sm_count() - bdof_sm_reserve() : 1);
     const unsigned grid = unsigned(n_tiles < slots ? n_tiles : slots);
     kern<<<grid, Cfg::T * LPC, SM::BYTES, st>>>(p, int(n_tiles));
     return bdof_launch_check("line_kernel");

@@ -379,6 +379,19 @@ __global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, c
         if (line0 < n_lines)
             for (int c = 0; c < ST::NBUF; ++c) stream_issue(line0, c);
     }
+    // start of row `ln` of the input field (row mode)
+    auto row_ptr = [&](long long ln) __attribute__((always_inline)) {
+        const int bb = int(ln / p.lines_per_batch);
+        const int lli = int(ln - (long long)bb * p.lines_per_batch);
+        return p.in + (long long)bb * p.batch_stride + (long long)lli * p.line_stride;
+    };
+    if constexpr (PREFETCH && !COL) {
+        // the first row of every line slot is fetched the same way as all later ones
+        if (line0 < n_lines && t == 0) {
+            mbar_expect_tx(&line_bar[l], N * (unsigned)sizeof(float2));
+            bulk_g2s(sm, row_ptr(line0), N * (unsigned)sizeof(float2), &line_bar[l]);
+        }
+    }
 
     if constexpr (STAGGER) {
         if (l >= LPC / 2) { while (stagger_flag[l - LPC / 2] == 0) __nanosleep(64); }
@@ -393,19 +406,21 @@ __global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, c
 
         float2 v[E];
         // ---- load (element t + T*q -> register q)
+        constexpr bool ROW_TMA = PREFETCH && !COL;        // every row arrives by bulk copy in the line's exchange buffer
         bool loaded = false;
-        if constexpr (PREFETCH) {
+        if constexpr (ROW_TMA) {
+            mbar_wait(&line_bar[l], tile_iter & 1);
+            if constexpr (PRE != PRE_TRANSMIT) {
+                static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = sm[t + T * q]; });
+            }
+            loaded = true;
+        } else if constexpr (PREFETCH) {
             if (tile_iter > 0) {
-                // this tile was prefetched into the exchange buffers while the previous one finished
-                if constexpr (COL) {
-                    cp_async_wait_all();
-                    __syncthreads();
-                    const float2* sp = s_x + t * LPC + l;                 // staged as [row][LPC]
-                    static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = sp[T * q * LPC]; });
-                } else {
-                    mbar_wait(&line_bar[l], (tile_iter - 1) & 1);
-                    static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = sm[t + T * q]; });
-                }
+                // this column tile was prefetched into the exchange buffers while the previous one finished
+                cp_async_wait_all();
+                __syncthreads();
+                const float2* sp = s_x + t * LPC + l;                 // staged as [row][LPC]
+                static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = sp[T * q * LPC]; });
                 loaded = true;
             }
         }
@@ -431,7 +446,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, c
         auto prefetch_next = [&]() __attribute__((always_inline)) {
             if constexpr (PREFETCH) {
                 const long long nl = line + line_step;
-                if (nl < n_lines) {
+                if (nl < n_lines && (COL || POST != POST_ADJ)) {
                     line_sync<Cfg, LPC, COL>(l);                          // every reader of the buffer is done
                     if constexpr (COL) {
                         const long long tl = nl - l;                      // first column of the next tile
@@ -452,12 +467,11 @@ __global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, c
                             dp += RPI * LPC * (int)sizeof(float2);
                         }
                         cp_async_commit();
-                    } else {
+                    } else if constexpr (POST != POST_ADJ) {
+                        // (the adjoint epilogue still needs the buffer: it prefetches chunk by chunk itself)
                         if (t == 0) {
-                            const int bb = int(nl / p.lines_per_batch);
-                            const int lli = int(nl - (long long)bb * p.lines_per_batch);
                             mbar_expect_tx(&line_bar[l], N * (unsigned)sizeof(float2));
-                            bulk_g2s(sm, p.in + (long long)bb * p.batch_stride + (long long)lli * p.line_stride, N * (unsigned)sizeof(float2), &line_bar[l]);
+                            bulk_g2s(sm, row_ptr(nl), N * (unsigned)sizeof(float2), &line_bar[l]);
                         }
                     }
                 }
@@ -467,40 +481,55 @@ __global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, c
         if constexpr (POST == POST_ADJ) stream_prefetch_l2(line);      // lands in L2 while the transforms run
 #endif
         if constexpr (PRE == PRE_TRANSMIT) {
-#ifndef BDOF_NO_ROWPF
-            if (line + line_step < n_lines) stream_prefetch_l2(line + line_step);
-#endif
-            // delta/beta arrive through the streaming buffers, chunk by chunk
-            static_for<ST::NCH>([&](auto C) __attribute__((always_inline)) {
-                constexpr int c = decltype(C)::value;
-                constexpr int buf = c % ST::NBUF;
-                mbar_wait(&my_bar[buf], (chunk_seq / ST::NBUF) & 1);
-                const float2* sb = my_stage + buf * ST::CHUNK_ELEMS + t;
-                float2 d[ST::CHK];
-                bool small = true;
-                static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) {
-                    constexpr int i = decltype(I)::value;
-                    d[i] = sb[T * i];
-                    small = small && transmission_is_small(d[i], p.k_dz);
-                });
-                if (__all_sync(0xffffffffu, small)) {
+            if constexpr (ROW_TMA) {
+                // ROLLED chunk loop (keeps the instruction footprint small: the 64x unrolled version made
+                // instruction-cache misses the top stall): psi sits in the exchange buffer, delta/beta arrive
+                // through the streaming buffers; u = psi * t is formed in place, then read into registers
+#pragma unroll 1
+                for (int c = 0; c < ST::NCH; ++c) {
+                    const int buf = c % ST::NBUF;
+                    mbar_wait(&my_bar[buf], (chunk_seq / ST::NBUF) & 1);
+                    const float2* sb = my_stage + buf * ST::CHUNK_ELEMS + t;
+                    float2* sx = sm + c * ST::CHUNK_ELEMS + t;
+                    float2 d[ST::CHK];
+                    bool small = true;
                     static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) {
                         constexpr int i = decltype(I)::value;
-                        v[c * ST::CHK + i] = cmul(v[c * ST::CHK + i], transmission_small(d[i], p.k_dz));
+                        d[i] = sb[T * i];
+                        small = small && transmission_is_small(d[i], p.k_dz);
                     });
-                } else {
-                    static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) {
-                        constexpr int i = decltype(I)::value;
-                        v[c * ST::CHK + i] = cmul(v[c * ST::CHK + i], transmission(d[i], p.k_dz));
-                    });
+                    if (__all_sync(0xffffffffu, small)) {
+                        static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) {
+                            constexpr int i = decltype(I)::value;
+                            sx[T * i] = cmul(sx[T * i], transmission_small(d[i], p.k_dz));
+                        });
+                    } else {
+                        static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) {
+                            constexpr int i = decltype(I)::value;
+                            sx[T * i] = cmul(sx[T * i], transmission(d[i], p.k_dz));
+                        });
+                    }
+                    ++chunk_seq;
+                    stream_advance(line, c);
                 }
-                ++chunk_seq;
-                stream_advance(line, c);
-            });
+                // every thread touched only its own elements of the buffer: no barrier needed before reading them
+                static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = sm[t + T * q]; });
+            } else {
+                // short lines (T < 32): fully unrolled register version
+                static_for<ST::NCH>([&](auto C) __attribute__((always_inline)) {
+                    constexpr int c = decltype(C)::value;
+                    constexpr int buf = c % ST::NBUF;
+                    mbar_wait(&my_bar[buf], (chunk_seq / ST::NBUF) & 1);
+                    const float2* sb = my_stage + buf * ST::CHUNK_ELEMS + t;
+                    static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) {
+                        constexpr int i = decltype(I)::value;
+                        v[c * ST::CHK + i] = cmul(v[c * ST::CHK + i], transmission(sb[T * i], p.k_dz));
+                    });
+                    ++chunk_seq;
+                    stream_advance(line, c);
+                });
+            }
         }
-#ifdef BDOF_PHASE_TIMING
-        asm volatile("" ::"f"(v[0].x), "f"(v[E - 1].y), "f"(v[E / 2].x));    // loads (and transmission) have landed
-#endif
         if constexpr (STAGGER && PRE == PRE_TRANSMIT) {
             // forward row pass: release the partner line once my memory-heavy prologue is done
             if (tile_iter == 0 && l < LPC / 2) {
@@ -567,50 +596,68 @@ __global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, c
             //   dL/ddelta = -k Im(conj(G_u) u),  dL/dbeta = -k Re(conj(G_u) u),  G_i = conj(t) G_u
             const long long dbase = (long long)b * p.db_batch_stride + (long long)li * p.line_stride + t;
             float2* __restrict__ gp = p.grad + dbase;
-            static_for<ST::NCH>([&](auto C) __attribute__((always_inline)) {
-                constexpr int c = decltype(C)::value;
-                constexpr int buf = c % ST::NBUF;
-#ifdef BDOF_PHASE_TIMING
-                if (!(p.dbg_flags & 1))
-#endif
-                mbar_wait(&my_bar[buf], (chunk_seq / ST::NBUF) & 1);
-                const float2* sb = my_stage + buf * (2 * ST::CHUNK_ELEMS) + t;
-                float2 d[ST::CHK];
-                bool small = true;
-                static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) {
-                    constexpr int i = decltype(I)::value;
-                    d[i] = sb[T * i];
-                    small = small && transmission_is_small(d[i], p.k_dz);
-                });
-                float2 trs[ST::CHK];
-#ifdef BDOF_PHASE_TIMING
-                if (p.dbg_flags & 4) {
-                    static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) { constexpr int i = decltype(I)::value; trs[i] = d[i]; });
-                } else
-#endif
-                if (__all_sync(0xffffffffu, small)) {
-                    static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) { constexpr int i = decltype(I)::value; trs[i] = transmission_small(d[i], p.k_dz); });
-                } else {
-                    static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) { constexpr int i = decltype(I)::value; trs[i] = transmission(d[i], p.k_dz); });
+            if constexpr (ROW_TMA) {
+                // park conj(G_u) in the (now idle) exchange buffer, then a ROLLED chunk loop streams delta/beta
+                // and psi_i; as soon as chunk c has been consumed its part of the buffer receives chunk c of the
+                // NEXT row (bulk copy), so the next tile's input lands during this epilogue
+                line_sync<Cfg, LPC, COL>(l);
+                static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; sm[t + T * q] = v[q]; });
+                const long long nl = line + line_step;
+                const bool has_next = nl < n_lines;
+                const float2* next_row = has_next ? row_ptr(nl) : nullptr;
+                if (has_next && t == 0) mbar_expect_tx(&line_bar[l], N * (unsigned)sizeof(float2));
+                float2* __restrict__ dstc = dst;
+#pragma unroll 1
+                for (int c = 0; c < ST::NCH; ++c) {
+                    const int buf = c % ST::NBUF;
+                    mbar_wait(&my_bar[buf], (chunk_seq / ST::NBUF) & 1);
+                    const float2* sb = my_stage + buf * (2 * ST::CHUNK_ELEMS) + t;
+                    const float2* sx = sm + c * ST::CHUNK_ELEMS + t;
+                    float2 d[ST::CHK];
+                    bool small = true;
+                    static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) {
+                        constexpr int i = decltype(I)::value;
+                        d[i] = sb[T * i];
+                        small = small && transmission_is_small(d[i], p.k_dz);
+                    });
+                    float2 trs[ST::CHK];
+                    if (__all_sync(0xffffffffu, small)) {
+                        static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) { constexpr int i = decltype(I)::value; trs[i] = transmission_small(d[i], p.k_dz); });
+                    } else {
+                        static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) { constexpr int i = decltype(I)::value; trs[i] = transmission(d[i], p.k_dz); });
+                    }
+                    static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) {
+                        constexpr int i = decltype(I)::value;
+                        const float2 vq = sx[T * i];                        // conj(G_u)
+                        const float2 u = cmul(sb[ST::CHUNK_ELEMS + T * i], trs[i]);
+                        const float2 w = cmul(u, vq);                       // u * conj(G_u)
+                        gp[c * ST::CHUNK_ELEMS + T * i] = make_float2(-p.k_dz * w.y, -p.k_dz * w.x);
+                        dstc[c * ST::CHUNK_ELEMS + T * i] = cmul_conj(vq, trs[i]);   // G_u conj(t)
+                    });
+                    ++chunk_seq;
+                    stream_advance(line, c);                                // (line barrier inside)
+                    if (has_next && t == 0)
+                        bulk_g2s(sm + c * ST::CHUNK_ELEMS, next_row + c * ST::CHUNK_ELEMS, ST::CHUNK_BYTES, &line_bar[l]);
                 }
-                static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) {
-                    constexpr int i = decltype(I)::value;
-                    constexpr int q = c * ST::CHK + i;
-                    const float2 tr = trs[i];
-                    const float2 u = cmul(sb[ST::CHUNK_ELEMS + T * i], tr);
-                    const float2 w = cmul(u, v[q]);              // u * conj(G_u) = u * v
-#ifdef BDOF_PHASE_TIMING
-                    if ((p.dbg_flags & 2) && w.x != 12345.f) return;
-#endif
-                    gp[T * q] = make_float2(-p.k_dz * w.y, -p.k_dz * w.x);
-                    dst[T * q] = cmul_conj(v[q], tr);           // conj(v) conj(t) = G_u conj(t)
+            } else {
+                static_for<ST::NCH>([&](auto C) __attribute__((always_inline)) {
+                    constexpr int c = decltype(C)::value;
+                    constexpr int buf = c % ST::NBUF;
+                    mbar_wait(&my_bar[buf], (chunk_seq / ST::NBUF) & 1);
+                    const float2* sb = my_stage + buf * (2 * ST::CHUNK_ELEMS) + t;
+                    static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) {
+                        constexpr int i = decltype(I)::value;
+                        constexpr int q = c * ST::CHK + i;
+                        const float2 tr = transmission(sb[T * i], p.k_dz);
+                        const float2 u = cmul(sb[ST::CHUNK_ELEMS + T * i], tr);
+                        const float2 w = cmul(u, v[q]);              // u * conj(G_u) = u * v
+                        gp[T * q] = make_float2(-p.k_dz * w.y, -p.k_dz * w.x);
+                        dst[T * q] = cmul_conj(v[q], tr);           // conj(v) conj(t) = G_u conj(t)
+                    });
+                    ++chunk_seq;
+                    stream_advance(line, c);
                 });
-                ++chunk_seq;
-#ifdef BDOF_PHASE_TIMING
-                if (!(p.dbg_flags & 1))
-#endif
-                stream_advance(line, c);
-            });
+            }
         } else if constexpr (MODE == MODE_FWD) {
             // circular output shift (fftshift), far field only
             float2* __restrict__ dst0 = p.out + (base - (long long)t * estride);

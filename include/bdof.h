@@ -154,6 +154,10 @@ int  bdof_plan_workspace_bytes(const bdof_plan* p, size_t* bytes_out);
  * events on the plan's stream; end() synchronises and returns, per pass variant (0 row fwd with
  * transmission, 1 row conv, 2 row adjoint, 3 row FFT, 4 row IFFT, 5 col conv, 6 col FFT, 7 col IFFT,
  * 8 col conv with 2-D H), the launch count and the summed device time in ms. */
+/* Leave n_sms streaming multiprocessors free of the persistent pass kernels (process-wide), so that
+ * communication kernels (NCCL all-reduce of the gradient buckets) can run concurrently with the sweep. */
+int  bdof_set_sm_reserve(int n_sms);
+
 /* Developer hook: device buffer that instrumented builds (-DBDOF_PHASE_TIMING) fill with clock64()
  * phase stamps; ignored by the production build. */
 int  bdof_debug_set_buffer(void* d_buf);
