@@ -49,6 +49,29 @@ bool bdof_use_pdl() {
     if (v < 0) { const char* e = getenv("BDOF_PDL"); v = (e && e[0] == '1') ? 1 : 0; }     // measured: no gain on B200, off by default
     return v == 1;
 }
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int bdof_make_tensor_map(CUtensorMap* out, const void* base, long long rows, long long cols, int box_cols, int box_rows) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+        if (!f || q != cudaDriverEntryPointSuccess) return bdof_fail(BDOF_E_UNSUPPORTED, "cuTensorMapEncodeTiled is not available in this driver");
+        fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+    // complex64 as pairs of fp32: inner dimension 2*cols floats
+    const cuuint64_t gdim[2] = {cuuint64_t(2 * cols), cuuint64_t(rows)};
+    const cuuint64_t gstride[1] = {cuuint64_t(cols) * sizeof(float2)};
+    const cuuint32_t box[2] = {cuuint32_t(2 * box_cols), cuuint32_t(box_rows)};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return bdof_fail(BDOF_E_BADARG, "cuTensorMapEncodeTiled failed (CUresult %d)", int(r));
+    return 0;
+}
 #define fail bdof_fail
 #define launch_check bdof_launch_check
 
@@ -113,6 +136,18 @@ static std::vector<float2> make_twiddles(int n) {
     };
     add_stage(r.r2, r.r1);
     if (r.r3 > 1) add_stage(r.r3, r.r1 * r.r2);
+    return tw;
+}
+// table of the pipelined passes: the same, except that cyclic-shift plans also carry row 0 (all ones)
+static std::vector<float2> make_twiddles_pipe(int n) {
+    if (!pipe_shift(n)) return make_twiddles(n);
+    StageRadices r = radices_for(n);
+    std::vector<float2> tw;
+    for (int rr = 0; rr < r.r2; ++rr)
+        for (int k = 0; k < r.r1; ++k) {
+            double a = -2.0 * M_PI * double((long long)rr * k % n) / double(n);
+            tw.push_back(make_float2(float(cos(a)), float(sin(a))));
+        }
     return tw;
 }
 
@@ -314,6 +349,7 @@ static inline unsigned blocks_for(long long n, int threads) { return unsigned((n
 struct AxisTables {
     int n = 0;
     float2* tw = nullptr;      // stage twiddles
+    float2* tw_pipe = nullptr; // stage twiddles in the layout of the pipelined passes
     float2* h = nullptr;       // ifftshift(h)/n, per-slice propagator
     float2* h_adj = nullptr;   // conj
     float2* hf = nullptr;      // free-space propagator
@@ -411,6 +447,8 @@ extern "C" int bdof_plan_create(bdof_plan** out, int ny, int nx, int batch, int 
     do {
         if ((r = upload(&p->ax.tw, make_twiddles(nx)))) break;
         if ((r = upload(&p->ay.tw, make_twiddles(ny)))) break;
+        if ((r = upload(&p->ax.tw_pipe, make_twiddles_pipe(nx)))) break;
+        if ((r = upload(&p->ay.tw_pipe, make_twiddles_pipe(ny)))) break;
         cudaError_t e;
         if ((e = cudaMalloc((void**)&p->tmp, p->F * sizeof(float2))) != cudaSuccess) { r = fail(int(e), "cudaMalloc tmp: %s", cudaGetErrorString(e)); break; }
         if ((e = cudaMalloc((void**)&p->work[0], p->F * sizeof(float2))) != cudaSuccess) { r = fail(int(e), "cudaMalloc work: %s", cudaGetErrorString(e)); break; }
@@ -427,7 +465,7 @@ extern "C" int bdof_plan_create(bdof_plan** out, int ny, int nx, int batch, int 
 }
 
 static void free_axis(AxisTables& a) {
-    cudaFree(a.tw); cudaFree(a.h); cudaFree(a.h_adj); cudaFree(a.hf); cudaFree(a.hf_adj);
+    cudaFree(a.tw); cudaFree(a.tw_pipe); cudaFree(a.h); cudaFree(a.h_adj); cudaFree(a.hf); cudaFree(a.hf_adj);
 }
 extern "C" void bdof_plan_destroy(bdof_plan* p) {
     if (!p) return;
@@ -521,8 +559,10 @@ static LineParams col_params(const bdof_plan* p, const float2* in, float2* out, 
 }
 static int timed_launch(bdof_plan* p, int n, int variant, const LineParams& q0, long long n_lines) {
     LineParams q = q0;
-    if (g_dbg) q.dbg = g_dbg + (long long)variant * (1 << 17);     // one region per pass variant
+    const int pv = (variant == V_COL_CONV_PIPE) ? int(V_COL_CONV) : variant;    // reported under the pass it implements
+    if (g_dbg) q.dbg = g_dbg + (long long)pv * (1 << 17);     // one region per pass variant
     { static int flags = -1; if (flags < 0) { const char* e = getenv("BDOF_DBG_FLAGS"); flags = e ? atoi(e) : 0; } q.dbg_flags = flags; }
+    { static int tune = -1; if (tune < 0) { const char* e = getenv("BDOF_TUNE"); tune = e ? atoi(e) : 0; } q.tune = tune; }
     if (!p->profile) return launch_variant(n, variant, q, n_lines, p->stream);
     cudaEvent_t a, b;
     CUDA_TRY(cudaEventCreate(&a));
@@ -531,13 +571,23 @@ static int timed_launch(bdof_plan* p, int n, int variant, const LineParams& q0, 
     int r = launch_variant(n, variant, q, n_lines, p->stream);
     CUDA_TRY(cudaEventRecord(b, p->stream));
     p->prof_events.push_back(a); p->prof_events.push_back(b);
-    p->prof_variant.push_back(variant);
+    p->prof_variant.push_back(pv);
     return r;
 }
 static int row_pass(bdof_plan* p, int variant, const LineParams& q) {
     return timed_launch(p, p->nx, variant, q, (long long)p->batch * p->ny);
 }
+static bool use_pipe() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("BDOF_PIPE"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
 static int col_pass(bdof_plan* p, int variant, const LineParams& q) {
+    if (variant == V_COL_CONV && use_pipe() && pipe_parts(p->ny) > 0) {
+        LineParams q2 = q;
+        q2.tw = p->ay.tw_pipe;
+        return timed_launch(p, p->ny, V_COL_CONV_PIPE, q2, (long long)p->batch * p->nx);
+    }
     return timed_launch(p, p->ny, variant, q, (long long)p->batch * p->nx);
 }
 

@@ -1,5 +1,6 @@
 // Shared between bdof.cu (plan, C ABI) and line_inst.cu (one instantiation unit per FFT length).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace bdof {
@@ -26,9 +27,17 @@ struct LineParams {
     const void* pf0;         // nullable
     const void* pf1;         // nullable
     long long pf_bytes;      // bytes per prefetched array (multiple of 16)
+    int tune;                // runtime switches (BDOF_TUNE): 1 L2-prefetch the next tile's main input at tile start,
+                             // 2 L2-prefetch the next line's delta/beta (forward row pass)
 };
 
-enum Variant { V_ROW_CONV_T = 0, V_ROW_CONV, V_ROW_CONV_ADJ, V_ROW_FWD, V_ROW_INV, V_COL_CONV, V_COL_FWD, V_COL_INV, V_COL_CONV2D };
+enum Variant { V_ROW_CONV_T = 0, V_ROW_CONV, V_ROW_CONV_ADJ, V_ROW_FWD, V_ROW_INV, V_COL_CONV, V_COL_FWD, V_COL_INV, V_COL_CONV2D,
+               V_COL_CONV_PIPE, V_COUNT };
+
+// Pipelined passes (pipefft.cuh): number of parts of the stage exchange per FFT length, 0 = not available.
+// Lengths with T == R1 (4096) use the cyclic-shift scheme and a twiddle table that includes the all-ones row 0.
+constexpr int pipe_parts(int n) { return n == 2048 ? 2 : (n == 4096 ? 4 : (n <= 1024 ? 1 : 0)); }
+constexpr bool pipe_shift(int n) { return n == 4096; }
 
 // sin/cos for |x| up to ~1e4 rad: 3-term Cody-Waite reduction by pi/2 and the cephes single-precision
 // minimax polynomials (max error ~1 ulp on the reduced range).  Same arithmetic as the fast path of
@@ -93,6 +102,9 @@ __device__ __forceinline__ bool transmission_is_small(float2 db, float k) {
 }  // namespace bdof
 
 int bdof_fail(int code, const char* fmt, ...);
+// TMA descriptor of a row-major complex64 matrix [rows][cols] for boxes of box_cols x box_rows elements
+// (cuTensorMapEncodeTiled through the runtime's driver entry point; no link against libcuda)
+int bdof_make_tensor_map(CUtensorMap* out, const void* base, long long rows, long long cols, int box_cols, int box_rows);
 int bdof_launch_check(const char* what);
 int bdof_sm_reserve();    // SMs the persistent line kernels leave free (bdof_set_sm_reserve / BDOF_SM_RESERVE)
 bool bdof_use_pdl();      // programmatic dependent launch of the line kernels (BDOF_PDL=0 disables)

@@ -2,6 +2,7 @@
 #include "../../include/bdof.h"
 #include "common.h"
 #include "linefft.cuh"
+#include "pipefft.cuh"
 
 using namespace bdof;
 
@@ -60,6 +61,31 @@ static int launch_line(const LineParams& p, long long n_lines, cudaStream_t st) 
     return bdof_launch_check("line_kernel");
 }
 
+// pipelined column convolution (pipefft.cuh)
+template <class Cfg, int LPC, int P>
+static int launch_pipe_col(const LineParams& p, long long n_lines, cudaStream_t st) {
+    if constexpr (P == 0) {
+        return bdof_fail(BDOF_E_UNSUPPORTED, "no pipelined pass for this FFT length");
+    } else {
+        using SM = PipeSmem<PipeCfg<Cfg, P>, LPC, true>;
+        auto kern = pipe_col_conv_kernel<Cfg, LPC, P>;
+        static bool ready = false;
+        if (!ready) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::BYTES)));
+            ready = true;
+        }
+        if (n_lines % LPC != 0) return bdof_fail(BDOF_E_UNSUPPORTED, "line count %lld not a multiple of %d", n_lines, LPC);
+        const long long n_tiles = n_lines / LPC;
+        const long long slots = sm_count() > bdof_sm_reserve() ? sm_count() - bdof_sm_reserve() : 1;
+        const unsigned grid = unsigned(n_tiles < slots ? n_tiles : slots);
+        // the field as a matrix [batch * N rows][lines_per_batch columns]; a tile lands in boxes of LPC columns
+        alignas(64) CUtensorMap tm;
+        BDOF_TRY(bdof_make_tensor_map(&tm, p.in, (n_lines / p.lines_per_batch) * (long long)Cfg::N, p.lines_per_batch, LPC, SM::BOXR));
+        kern<<<grid, Cfg::T * LPC, SM::BYTES, st>>>(p, int(n_tiles), tm);
+        return bdof_launch_check("pipe_col_conv_kernel");
+    }
+}
+
 #define BDOF_CAT2(a, b) a##b
 #define BDOF_CAT(a, b) BDOF_CAT2(a, b)
 
@@ -76,6 +102,7 @@ int BDOF_CAT(bdof_launch_line_, BDOF_N)(int variant, const LineParams& p, long l
         case V_COL_FWD:      return launch_line<C, CL, true, MODE_FWD, PRE_NONE, POST_NONE>(p, n_lines, st);
         case V_COL_INV:      return launch_line<C, CL, true, MODE_INV, PRE_NONE, POST_NONE>(p, n_lines, st);
         case V_COL_CONV2D:   return launch_line<C, CL, true, MODE_CONV2D, PRE_NONE, POST_NONE>(p, n_lines, st);
+        case V_COL_CONV_PIPE: return launch_pipe_col<C, CL, pipe_parts(BDOF_N)>(p, n_lines, st);
     }
     return bdof_fail(BDOF_E_BADARG, "bad variant %d", variant);
 }

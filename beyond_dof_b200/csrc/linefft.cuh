@@ -338,9 +338,9 @@ __global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, c
         }
     };
     // pull the side-input rows (delta/beta [, psi_i]) of line `ln` from DRAM into L2 ahead of their use
-    auto stream_prefetch_l2 = [&](long long ln) __attribute__((always_inline)) {
+    auto stream_prefetch_l2 = [&](long long ln, bool enabled) __attribute__((always_inline)) {
         if constexpr (NSTREAM > 0) {
-            if (t == 0 && p.pf_bytes >= 0) {
+            if (t == 0 && enabled) {
                 const int bb = int(ln / p.lines_per_batch);
                 const int lli = int(ln - (long long)bb * p.lines_per_batch);
                 const long long drow = (long long)bb * p.db_batch_stride + (long long)lli * p.line_stride;
@@ -442,6 +442,32 @@ __global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, c
                 static_for<E>([&](auto Q) __attribute__((always_inline)) { v[decltype(Q)::value] = *ptr; ptr += step; });
             }
         }
+        // pull the NEXT tile's main input from DRAM into L2 while this tile is transformed (the cp.async /
+        // bulk copies that fetch it at the end of this tile then hit L2)
+        if constexpr (MODE == MODE_CONV) {
+            const long long nl = line + line_step;
+            if ((p.tune & 1) && nl < n_lines) {
+                if constexpr (COL) {
+                    const long long tl = nl - l;
+                    const int bb = int(tl / p.lines_per_batch);
+                    const int c0 = int(tl - (long long)bb * p.lines_per_batch);
+                    const float2* sp = p.in + (long long)bb * p.batch_stride + c0;
+#pragma unroll 4
+                    for (int r = tid; r < N; r += T * LPC)
+                        bulk_prefetch_l2(sp + (long long)r * p.elem_stride, LPC * (unsigned)sizeof(float2));
+                } else {
+                    if (t == 0) {
+                        constexpr unsigned ROW_BYTES = N * sizeof(float2);
+                        constexpr unsigned PF = ROW_BYTES < 16384 ? ROW_BYTES : 16384;
+                        const char* rp = reinterpret_cast<const char*>(row_ptr(nl));
+                        for (unsigned o = 0; o < ROW_BYTES; o += PF) bulk_prefetch_l2(rp + o, PF);
+                    }
+                }
+            }
+            if constexpr (PRE == PRE_TRANSMIT) {
+                if (nl < n_lines) stream_prefetch_l2(nl, (p.tune & 2) != 0);
+            }
+        }
         // issued from inside the second transform, right after its last read of the exchange buffer
         auto prefetch_next = [&]() __attribute__((always_inline)) {
             if constexpr (PREFETCH) {
@@ -478,7 +504,10 @@ __global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, c
             }
         };
 #ifndef BDOF_NO_ROWPF
-        if constexpr (POST == POST_ADJ) stream_prefetch_l2(line);      // lands in L2 while the transforms run
+        if constexpr (POST == POST_ADJ) {
+            stream_prefetch_l2(line, p.pf_bytes >= 0);      // lands in L2 while the transforms run
+            if (line + line_step < n_lines) stream_prefetch_l2(line + line_step, (p.tune & 4) != 0);
+        }
 #endif
         if constexpr (PRE == PRE_TRANSMIT) {
             if constexpr (ROW_TMA) {
