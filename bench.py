@@ -40,7 +40,9 @@ WORKLOADS = {
 }
 ENERGY_EV, PSIZE_CM = 5000, 1e-7
 # algorithmic bytes per pixel*slice of each pass: complex64 field, fp32 (delta,beta)
-PASS_BYTES = {'row_conv_transmit': 24, 'col_conv': 16, 'row_conv_adjoint': 40}
+PASS_BYTES = {'row_conv_transmit': 24, 'col_conv': 16, 'row_conv_adjoint': 40,
+              # sweep kernels: one slice per launch; contract figures of SURVEY 8d (two-pass model): forward 40, adjoint 56
+              'sweep_forward': 40, 'sweep_adjoint': 56}
 STEP_BYTES = 96
 
 

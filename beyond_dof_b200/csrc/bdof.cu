@@ -3,6 +3,7 @@
 #include "../../include/bdof.h"
 #include "common.h"
 #include "regfft.cuh"
+#include "sweepfft.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -99,6 +100,19 @@ static int launch_variant(int n, int variant, const LineParams& p, long long n_l
         case 8192: return bdof_launch_line_8192(variant, p, n_lines, st);
     }
     return bdof_fail(BDOF_E_UNSUPPORTED, "FFT length %d is not supported", n);
+}
+
+static int launch_sweep_n(int n, int col, int adj, const SweepParams& p, long long rows, int cols, cudaStream_t st) {
+    switch (n) {
+        case 64:   return bdof_launch_sweep_64(col, adj, p, rows, cols, st);
+        case 128:  return bdof_launch_sweep_128(col, adj, p, rows, cols, st);
+        case 256:  return bdof_launch_sweep_256(col, adj, p, rows, cols, st);
+        case 512:  return bdof_launch_sweep_512(col, adj, p, rows, cols, st);
+        case 1024: return bdof_launch_sweep_1024(col, adj, p, rows, cols, st);
+        case 2048: return bdof_launch_sweep_2048(col, adj, p, rows, cols, st);
+        case 4096: return bdof_launch_sweep_4096(col, adj, p, rows, cols, st);
+    }
+    return bdof_fail(BDOF_E_UNSUPPORTED, "no sweep kernel for FFT length %d", n);
 }
 
 struct StageRadices { int r1, r2, r3; };
@@ -591,6 +605,35 @@ static int col_pass(bdof_plan* p, int variant, const LineParams& q) {
     return timed_launch(p, p->ny, variant, q, (long long)p->batch * p->nx);
 }
 
+// ------------------------------------------------------------------------------------------
+// sweep kernels: one launch per slice and direction (sweepfft.cuh)
+// ------------------------------------------------------------------------------------------
+static bool use_sweep(const bdof_plan* p) {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("BDOF_SWEEP"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1 && !p->full_kernel && p->n_slice >= 2 && pipe_parts(p->nx) > 0 && pipe_parts(p->ny) > 0;
+}
+// kernel of slice i: x kernel (rows) for even i, y kernel (columns) for odd i
+static int sweep_launch(bdof_plan* p, int i, bool adj, SweepParams q) {
+    const bool col = (i & 1) != 0;
+    const int n = col ? p->ny : p->nx;
+    q.tw = col ? p->ay.tw_pipe : p->ax.tw_pipe;
+    q.h = col ? (adj ? p->ay.h_adj : p->ay.h) : (adj ? p->ax.h_adj : p->ax.h);
+    q.k_dz = float(p->k_dz);
+    q.dbg = g_dbg;
+    const long long rows = (long long)p->batch * p->ny;
+    if (!p->profile) return launch_sweep_n(n, col, adj, q, rows, p->nx, p->stream);
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a));
+    CUDA_TRY(cudaEventCreate(&b));
+    CUDA_TRY(cudaEventRecord(a, p->stream));
+    int r = launch_sweep_n(n, col, adj, q, rows, p->nx, p->stream);
+    CUDA_TRY(cudaEventRecord(b, p->stream));
+    p->prof_events.push_back(a); p->prof_events.push_back(b);
+    p->prof_variant.push_back(adj ? V_SWEEP_ADJ : V_SWEEP_FWD);
+    return r;
+}
+
 // one propagation of slice i: out = P(in * t(db))
 static int propagate_slice(bdof_plan* p, const float2* in, const float2* db, float2* out, const float2* db_next) {
     if (!p->full_kernel) {
@@ -646,9 +689,33 @@ extern "C" int bdof_forward(bdof_plan* p, const float* d_db_f, const float* d_pr
     k_broadcast_probe<<<blocks_for(per, 256), 256, 0, p->stream>>>(d_probe, cur, per, p->batch);
     BDOF_TRY(launch_check("k_broadcast_probe"));
     std::complex<double> phase{1.0, 0.0};
+    if (use_sweep(p)) {
+        // slice i runs as ONE kernel along axis a(i) (x for even i, y for odd i): second half of the propagation
+        // of slice i-1, modulation by slice i, first half of the propagation of slice i
+        float2* obj_out = (p->free_mode == BDOF_FREE_NONE) ? d_exit : p->work[0];
+        if (!store && obj_out == cur) obj_out = p->work[1];
+        float2* A = p->tmp;
+        for (int i = 0; i < Z; ++i) {
+            const bool prop = slice_propagates(p, i);
+            SweepParams q{};
+            q.in = (i == 0) ? cur : A;
+            q.out = prop ? A : obj_out;
+            q.db = d_db + ((p->flags & BDOF_Z_BROADCAST) ? 0 : (long long)i * p->F);
+            q.slab = (store && i > 0) ? p->slabs + (long long)i * p->F : nullptr;
+            q.conv1 = (i > 0); q.conv2 = prop; q.store_slab = (store && i > 0); q.store_out = 1;
+            BDOF_TRY(sweep_launch(p, i, false, q));
+            if (prop) phase *= p->phase0;
+        }
+        cur = obj_out;
+        if (slice_propagates(p, Z - 1)) {
+            // TF semantics: the last slice propagates too -> its second half along the other axis
+            if (Z & 1) BDOF_TRY(col_pass(p, V_COL_CONV, col_params(p, A, obj_out, p->ay.h)));
+            else       BDOF_TRY(row_pass(p, V_ROW_CONV, row_params(p, A, obj_out, p->ax.h)));
+        }
+    }
     // where the object part of the chain leaves its result
     float2* obj_out = (p->free_mode == BDOF_FREE_NONE) ? d_exit : (store ? p->work[0] : nullptr);
-    for (int i = 0; i < Z; ++i) {
+    for (int i = 0; i < Z && !use_sweep(p); ++i) {
         const float2* db_i = d_db + ((p->flags & BDOF_Z_BROADCAST) ? 0 : (long long)i * p->F);
         const bool last = (i == Z - 1);
         float2* dst;
@@ -727,7 +794,34 @@ extern "C" int bdof_adjoint(bdof_plan* p, float* d_db_inout, const float* d_grad
         BDOF_TRY(row_pass(p, V_ROW_CONV, row_params(p, p->tmp, G, p->ax.hf_adj)));
     }
     const int n_buckets = int(p->bucket_events.size());
-    for (int i = Z - 1; i >= 0; --i) {
+    const bool sweep = use_sweep(p);
+    if (sweep) {
+        if (slice_propagates(p, Z - 1)) {
+            // adjoint of the trailing half propagation (TF semantics), into the work field the sweep runs on
+            if (Z & 1) BDOF_TRY(col_pass(p, V_COL_CONV, col_params(p, G, p->tmp, p->ay.h_adj)));
+            else       BDOF_TRY(row_pass(p, V_ROW_CONV, row_params(p, G, p->tmp, p->ax.h_adj)));
+            G = p->tmp;
+        }
+    }
+    for (int i = Z - 1; i >= 0 && sweep; --i) {
+        SweepParams q{};
+        q.in = G; q.out = G;
+        q.db = db + (zb ? 0 : (long long)i * p->F);
+        q.grad = gout ? gout + (long long)i * p->F : db + (long long)i * p->F;
+        q.slab = p->slabs + (long long)i * p->F;
+        q.conv1 = slice_propagates(p, i); q.conv2 = (i > 0);
+        q.store_out = (i > 0 || d_grad_probe != nullptr);
+        BDOF_TRY(sweep_launch(p, i, true, q));
+        if (n_buckets > 0) {
+            const int per = (Z + n_buckets - 1) / n_buckets;
+            const int from_top = Z - 1 - i;
+            if ((from_top + 1) % per == 0 || i == 0) {
+                const int j = from_top / per;
+                if (j < n_buckets) CUDA_TRY(cudaEventRecord(p->bucket_events[j], p->stream));
+            }
+        }
+    }
+    for (int i = Z - 1; i >= 0 && !sweep; --i) {
         const float2* db_i = db + (zb ? 0 : (long long)i * p->F);
         float2* grad_i = gout ? gout + (long long)i * p->F : db + (long long)i * p->F;
         const float2* psi_i = p->slabs + (long long)i * p->F;

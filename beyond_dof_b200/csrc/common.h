@@ -32,7 +32,7 @@ struct LineParams {
 };
 
 enum Variant { V_ROW_CONV_T = 0, V_ROW_CONV, V_ROW_CONV_ADJ, V_ROW_FWD, V_ROW_INV, V_COL_CONV, V_COL_FWD, V_COL_INV, V_COL_CONV2D,
-               V_COL_CONV_PIPE, V_COUNT };
+               V_COL_CONV_PIPE, V_SWEEP_FWD, V_SWEEP_ADJ, V_COUNT };
 
 // Pipelined passes (pipefft.cuh): number of parts of the stage exchange per FFT length, 0 = not available.
 // Lengths with T == R1 (4096) use the cyclic-shift scheme and a twiddle table that includes the all-ones row 0.
@@ -109,7 +109,11 @@ int bdof_launch_check(const char* what);
 int bdof_sm_reserve();    // SMs the persistent line kernels leave free (bdof_set_sm_reserve / BDOF_SM_RESERVE)
 bool bdof_use_pdl();      // programmatic dependent launch of the line kernels (BDOF_PDL=0 disables)
 
-#define BDOF_DECL_LINE(N) int bdof_launch_line_##N(int variant, const bdof::LineParams& p, long long n_lines, cudaStream_t st);
+namespace bdof { struct SweepParams; }
+// sweep kernels (sweepfft.cuh): col = 0 x kernel (rows), 1 y kernel (columns); adj = 0 forward, 1 adjoint;
+// the field is [rows][cols] complex64 row-major with rows = batch * ny
+#define BDOF_DECL_LINE(N) int bdof_launch_line_##N(int variant, const bdof::LineParams& p, long long n_lines, cudaStream_t st); \
+    int bdof_launch_sweep_##N(int col, int adj, const bdof::SweepParams& p, long long rows, int cols, cudaStream_t st);
 BDOF_DECL_LINE(64) BDOF_DECL_LINE(128) BDOF_DECL_LINE(256) BDOF_DECL_LINE(512)
 BDOF_DECL_LINE(1024) BDOF_DECL_LINE(2048) BDOF_DECL_LINE(4096) BDOF_DECL_LINE(8192)
 

@@ -1,8 +1,10 @@
 // Instantiation unit for the line kernels of ONE FFT length: compile with -DBDOF_N=<length>.
 #include "../../include/bdof.h"
 #include "common.h"
+#include <cstring>
 #include "linefft.cuh"
 #include "pipefft.cuh"
+#include "sweepfft.cuh"
 
 using namespace bdof;
 
@@ -79,10 +81,46 @@ static int launch_pipe_col(const LineParams& p, long long n_lines, cudaStream_t 
         const long long slots = sm_count() > bdof_sm_reserve() ? sm_count() - bdof_sm_reserve() : 1;
         const unsigned grid = unsigned(n_tiles < slots ? n_tiles : slots);
         // the field as a matrix [batch * N rows][lines_per_batch columns]; a tile lands in boxes of LPC columns
-        alignas(64) CUtensorMap tm;
+        alignas(64) CUtensorMap tm, tmo;
         BDOF_TRY(bdof_make_tensor_map(&tm, p.in, (n_lines / p.lines_per_batch) * (long long)Cfg::N, p.lines_per_batch, LPC, SM::BOXR));
-        kern<<<grid, Cfg::T * LPC, SM::BYTES, st>>>(p, int(n_tiles), tm);
+        BDOF_TRY(bdof_make_tensor_map(&tmo, p.out, (n_lines / p.lines_per_batch) * (long long)Cfg::N, p.lines_per_batch, LPC, SM::BOXR));
+        kern<<<grid, Cfg::T * LPC, SM::BYTES, st>>>(p, int(n_tiles), tm, tmo);
         return bdof_launch_check("pipe_col_conv_kernel");
+    }
+}
+
+// sweep kernels (sweepfft.cuh): one kernel per slice and direction
+template <class Cfg, int LPC, int P, bool COL, bool ADJ>
+static int launch_sweep(const SweepParams& p0, long long rows, int cols, cudaStream_t st) {
+    if constexpr (P == 0) {
+        return bdof_fail(BDOF_E_UNSUPPORTED, "no sweep kernel for this FFT length");
+    } else {
+        using SM = PipeSmem<PipeCfg<Cfg, P>, LPC, COL>;
+        auto kern = sweep_kernel<Cfg, LPC, P, COL, ADJ>;
+        static bool ready = false;
+        if (!ready) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::BYTES)));
+            ready = true;
+        }
+        SweepParams p = p0;
+        const long long n_lines = COL ? (rows / Cfg::N) * (long long)cols : rows;
+        if (n_lines % LPC != 0) return bdof_fail(BDOF_E_UNSUPPORTED, "line count %lld not a multiple of %d", n_lines, LPC);
+        p.n_tiles = int(n_lines / LPC);
+        p.lines_per_batch = cols;
+        const long long slots = sm_count() > bdof_sm_reserve() ? sm_count() - bdof_sm_reserve() : 1;
+        const unsigned grid = unsigned(p.n_tiles < slots ? p.n_tiles : slots);
+        alignas(64) CUtensorMap tm_in, tm_out, tm_db, tm_grad;
+        if constexpr (COL) {
+            BDOF_TRY(bdof_make_tensor_map(&tm_in, p.in, rows, cols, LPC, SM::BOXR));
+            BDOF_TRY(bdof_make_tensor_map(&tm_out, p.out ? p.out : p.in, rows, cols, LPC, SM::BOXR));
+            BDOF_TRY(bdof_make_tensor_map(&tm_db, p.db, rows, cols, LPC, SM::BOXR));
+            BDOF_TRY(bdof_make_tensor_map(&tm_grad, p.grad ? (const void*)p.grad : (const void*)p.db, rows, cols, LPC, SM::BOXR));
+        } else {
+            memset(&tm_in, 0, sizeof(tm_in)); memset(&tm_out, 0, sizeof(tm_out));
+            memset(&tm_db, 0, sizeof(tm_db)); memset(&tm_grad, 0, sizeof(tm_grad));
+        }
+        kern<<<grid, Cfg::T * LPC, SM::BYTES, st>>>(p, tm_in, tm_out, tm_db, tm_grad);
+        return bdof_launch_check("sweep_kernel");
     }
 }
 
@@ -105,4 +143,11 @@ int BDOF_CAT(bdof_launch_line_, BDOF_N)(int variant, const LineParams& p, long l
         case V_COL_CONV_PIPE: return launch_pipe_col<C, CL, pipe_parts(BDOF_N)>(p, n_lines, st);
     }
     return bdof_fail(BDOF_E_BADARG, "bad variant %d", variant);
+}
+
+int BDOF_CAT(bdof_launch_sweep_, BDOF_N)(int col, int adj, const SweepParams& p, long long rows, int cols, cudaStream_t st) {
+    using C = typename CfgFor<BDOF_N>::C;
+    constexpr int RL = CfgFor<BDOF_N>::RL, CL = CfgFor<BDOF_N>::CL, PP = pipe_parts(BDOF_N);
+    if (col) return adj ? launch_sweep<C, CL, PP, true, true>(p, rows, cols, st) : launch_sweep<C, CL, PP, true, false>(p, rows, cols, st);
+    return adj ? launch_sweep<C, RL, PP, false, true>(p, rows, cols, st) : launch_sweep<C, RL, PP, false, false>(p, rows, cols, st);
 }

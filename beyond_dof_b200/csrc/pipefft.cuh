@@ -59,6 +59,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* t
                  : "memory");
 }
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, const void* src_smem) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(c0), "r"(c1),
+                 "r"(smem_u32(src_smem))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 template <class PC>
 struct ShiftState {
     int a;                     // block of this thread, t / RB
@@ -134,7 +142,8 @@ __device__ __forceinline__ void pipe_fft(float2 (&v)[PC::E], int t, int l, float
 // Column convolution pass: out[:, c] = IFFT(h * FFT(in[:, c])) for LPC adjacent columns per tile.
 template <class Cfg, int LPC, int P>
 __global__ void __launch_bounds__(Cfg::T* LPC) pipe_col_conv_kernel(const LineParams p, const int n_tiles,
-                                                                    const __grid_constant__ CUtensorMap tm_in) {
+                                                                    const __grid_constant__ CUtensorMap tm_in,
+                                                                    const __grid_constant__ CUtensorMap tm_out) {
     using PC = PipeCfg<Cfg, P>;
     using SM = PipeSmem<PC, LPC, true>;
     constexpr int N = Cfg::N, T = Cfg::T, E = Cfg::E;
@@ -177,8 +186,6 @@ __global__ void __launch_bounds__(Cfg::T* LPC) pipe_col_conv_kernel(const LinePa
     }
     const int l = tid % LPC, t = tid / LPC;
     float2* sm = s_x + l * SM::STRIDE;
-    const long long estride = (long long)p.elem_stride;
-    const long long step = (long long)T * estride;
     ShiftState<PC> st;
     shift_init<PC>(st, t);
 
@@ -193,28 +200,52 @@ __global__ void __launch_bounds__(Cfg::T* LPC) pipe_col_conv_kernel(const LinePa
 #else
 #define PIPE_STAMP(slot) do { } while (0)
 #endif
+    // Results leave through the landing buffer too: when tile k+1 has landed, every thread SWAPS its
+    // finished elements of tile k with its new elements of tile k+1 (same addresses), and one thread
+    // sends the buffer to global memory with tensor copies (TMA store) that drain while tile k+1 is
+    // transformed.  The load of tile k+2 is issued once those copies have read the buffer.
+    float2 v[E];
+    auto store_issue = [&](long long done_tile) __attribute__((always_inline)) {
+        fence_proxy_async();                          // my generic-proxy writes -> visible to the TMA
+        __syncthreads();
+        if (tid == 0) {
+            const long long tl = done_tile * LPC;
+            const int bb = int(tl / p.lines_per_batch);
+            const int c0 = int(tl - (long long)bb * p.lines_per_batch);
+#pragma unroll 1
+            for (int j = 0; j < SM::NBOX; ++j)
+                tma_store_2d(&tm_out, 2 * c0, bb * N + j * SM::BOXR, s_land + j * SM::BOXR * LPC);
+            bulk_commit_group();
+        }
+    };
     for (; tile < n_tiles; tile += gridDim.x) {
         ++tile_iter;
         PIPE_STAMP(0);
-        const long long line = tile * LPC + l;
-        const int b = int(line / p.lines_per_batch);
-        const int li = int(line - (long long)b * p.lines_per_batch);
-        const long long base = (long long)b * p.batch_stride + (long long)li + (long long)t * estride;
-
-        float2 v[E];
         mbar_wait(&land_bar, tile_iter & 1);          // the whole tile has landed
         PIPE_STAMP(1);
         {
-            const float2* sp = s_land + t * LPC + l;
-            static_for<E>([&](auto Q) __attribute__((always_inline)) {
-                constexpr int q = decltype(Q)::value;
-                v[q] = sp[T * q * LPC];
-                if constexpr (PC::SHIFT && (q % P) != 0) v[q] = cmul(v[q], st.cmod[q % P]);
-            });
+            float2* sp = s_land + t * LPC + l;
+            if (tile_iter == 0) {
+                static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = sp[T * q * LPC]; });
+            } else {
+                static_for<E>([&](auto Q) __attribute__((always_inline)) {
+                    constexpr int q = decltype(Q)::value;
+                    const float2 in = sp[T * q * LPC];
+                    sp[T * q * LPC] = v[q];
+                    v[q] = in;
+                });
+            }
+            if constexpr (PC::SHIFT) {
+                static_for<E>([&](auto Q) __attribute__((always_inline)) {
+                    constexpr int q = decltype(Q)::value;
+                    if constexpr ((q % P) != 0) v[q] = cmul(v[q], st.cmod[q % P]);
+                });
+            }
         }
-        __syncthreads();                              // everybody holds its elements: the buffer is free
+        if (tile_iter > 0) store_issue(tile - gridDim.x);
+        else __syncthreads();                         // everybody holds its elements: the buffer is free
         PIPE_STAMP(2);
-        if (tile + gridDim.x < n_tiles) land_issue(tile + gridDim.x);
+        if (tile_iter == 0 && tile + gridDim.x < n_tiles) land_issue(tile + gridDim.x);
         PIPE_STAMP(3);
         if (!tables_ready) { mbar_wait(&table_bar, 0); tables_ready = true; }
 #pragma unroll 1
@@ -225,6 +256,11 @@ __global__ void __launch_bounds__(Cfg::T* LPC) pipe_col_conv_kernel(const LinePa
                     constexpr int q = decltype(Q)::value;
                     v[q] = cmul_conj(v[q], s_h[t + T * q]);
                 });
+                // by now the store of the previous tile has long read the buffer: fetch the next tile
+                if (tile_iter > 0 && tile + gridDim.x < n_tiles) {
+                    if (tid == 0) bulk_wait_group_read0();
+                    land_issue(tile + gridDim.x);
+                }
             }
 #ifdef BDOF_PHASE_TIMING
             asm volatile("" ::"f"(v[0].x), "f"(v[E - 1].y));
@@ -232,14 +268,22 @@ __global__ void __launch_bounds__(Cfg::T* LPC) pipe_col_conv_kernel(const LinePa
 #endif
         }
         // the registers hold the conjugate of the result (times the shift modulation)
-        float2* ptr = p.out + base;
         static_for<E>([&](auto Q) __attribute__((always_inline)) {
             constexpr int q = decltype(Q)::value;
-            if constexpr (PC::SHIFT && (q % P) != 0) *ptr = cmul_conj(v[q], st.cmod[q % P]);
-            else *ptr = conjf2(v[q]);
-            ptr += step;
+            if constexpr (PC::SHIFT && (q % P) != 0) v[q] = cmul_conj(v[q], st.cmod[q % P]);
+            else v[q] = conjf2(v[q]);
         });
         PIPE_STAMP(6);
+    }
+    // drain: the last tile of this CTA
+    if (tile_iter >= 0) {
+        const long long last = tile - gridDim.x;
+        if (tid == 0) bulk_wait_group_read0();        // (a previous store may still be reading the buffer)
+        __syncthreads();
+        float2* sp = s_land + t * LPC + l;
+        static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; sp[T * q * LPC] = v[q]; });
+        store_issue(last);
+        if (tid == 0) bulk_wait_group_read0();
     }
 }
 

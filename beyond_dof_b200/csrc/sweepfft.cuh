@@ -1,0 +1,255 @@
+// Sweep kernels: ONE kernel per slice and direction.
+//
+// The propagator is separable and the two 1-D convolutions commute, so consecutive slices alternate the
+// axis order: slice i is propagated as C_{a(i+1)} C_{a(i)} with a(i) = x for even i, y for odd i.  The
+// kernel of slice i then works along ONE axis a(i):
+//
+//   forward   A_{i-1} --C_a--> psi_i --[store psi_i]--> x t_i(delta,beta) --C_a--> A_i
+//   adjoint   B_i --C_a^H--> G_u --[G = conj(t_i) G_u, grad_i = -k (Im,Re)(psi_i conj(G))]--> --C_a^H--> B_{i-1}
+//
+// i.e. two convolutions (four transforms) per load/store of the field, and every side array (delta/beta,
+// the stored psi_i, the gradient) is touched in the MIDDLE of the kernel, where its DRAM latency hides
+// behind the first convolution.  A tile is LPC lines (rows for the x kernels, adjacent columns for the y
+// kernels) held in registers; all loads are asynchronous (TMA) into one tile-sized landing buffer L that
+// is reused in turn for the tile itself, delta/beta, the stored psi and -- y kernels -- as the staging
+// area of the strided stores (TMA tensor stores; results are SWAPPED into L against the next tile).
+// Stage exchanges run in parts through a small buffer (pipefft.cuh).
+#pragma once
+#include "pipefft.cuh"
+
+namespace bdof {
+
+struct SweepParams {
+    const float2* in;        // field in  (row-major [batch][ny][nx]); x kernels only, y kernels use tensor maps
+    float2* out;             // field out (may alias in)
+    const float2* db;        // (delta, beta) of this slice, row-major
+    float2* grad;            // adjoint: gradient of this slice, row-major (may alias db)
+    float2* slab;            // psi entering this slice in TILE layout (forward: written, adjoint: read)
+    const float2* h;         // multiplier of this axis (forward) or its conjugate (adjoint), 1/N folded in
+    const float2* tw;        // stage twiddles, pipelined layout
+    int n_tiles;
+    int lines_per_batch;     // columns per batch item (y kernels)
+    int conv1, conv2;        // run the first / second convolution
+    int store_slab;          // forward: write psi_i to the slab
+    int store_out;           // write the final field
+    float k_dz;
+    long long* dbg;
+};
+
+enum { LAND_IN = 0, LAND_DB = 1, LAND_SLAB = 2 };
+
+template <class Cfg, int LPC, int P, bool COL, bool ADJ>
+__global__ void __launch_bounds__(Cfg::T* LPC)
+    sweep_kernel(const SweepParams p, const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+                 const __grid_constant__ CUtensorMap tm_db, const __grid_constant__ CUtensorMap tm_grad) {
+    using PC = PipeCfg<Cfg, P>;
+    using SM = PipeSmem<PC, LPC, COL>;
+    constexpr int N = Cfg::N, T = Cfg::T, E = Cfg::E;
+    constexpr unsigned TILE_BYTES = unsigned(SM::LAND_ELEMS * sizeof(float2));
+    extern __shared__ __align__(128) float2 smem_sweep[];
+    float2* s_tw = smem_sweep;
+    float2* s_h = smem_sweep + SM::TW_ELEMS;
+    float2* s_x = s_h + SM::H_ELEMS;
+    float2* L = smem_sweep + SM::LAND_OFF;
+    __shared__ unsigned long long table_bar, land_bar;
+
+    const int tid = threadIdx.x;
+    constexpr unsigned TW_BYTES = PC::TW_ELEMS * sizeof(float2);
+    constexpr unsigned H_BYTES = N * sizeof(float2);
+    if (tid == 0) {
+        mbar_init(&table_bar, 1);
+        mbar_init(&land_bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    // ---- asynchronous landing of one tile-sized array into L (one thread talks to the TMA)
+    auto land = [&](int what, long long tile) __attribute__((always_inline)) {
+        if (tid == 0) {
+            mbar_expect_tx(&land_bar, TILE_BYTES);
+            if (COL && what != LAND_SLAB) {
+                const long long tl = tile * LPC;              // first column of the tile
+                const int bb = int(tl / p.lines_per_batch);
+                const int c0 = int(tl - (long long)bb * p.lines_per_batch);
+                const CUtensorMap* tm = (what == LAND_IN) ? &tm_in : &tm_db;
+#pragma unroll 1
+                for (int j = 0; j < SM::NBOX; ++j) tma_load_2d(L + j * SM::BOXR * LPC, tm, 2 * c0, bb * N + j * SM::BOXR, &land_bar);
+            } else {
+                // contiguous tile: rows of a row-major array (x kernels) or a slab tile
+                const float2* src = (what == LAND_IN ? p.in : (what == LAND_DB ? p.db : p.slab)) + tile * (long long)(N * LPC);
+#pragma unroll 1
+                for (int j = 0; j < LPC; ++j) bulk_g2s(L + j * N, src + j * N, N * (unsigned)sizeof(float2), &land_bar);
+            }
+        }
+    };
+    unsigned land_seq = 0;
+    auto land_wait = [&]() __attribute__((always_inline)) { mbar_wait(&land_bar, land_seq & 1); ++land_seq; };
+
+    long long tile = blockIdx.x;
+    if (tile < p.n_tiles) land(LAND_IN, tile);
+    if (tid == 0) {
+        mbar_expect_tx(&table_bar, TW_BYTES + H_BYTES);
+        bulk_g2s(s_tw, p.tw, TW_BYTES, &table_bar);
+        bulk_g2s(s_h, p.h, H_BYTES, &table_bar);
+    }
+    int l, t;
+    if constexpr (COL) { l = tid % LPC; t = tid / LPC; }
+    else               { l = tid / T;   t = tid % T; }
+    float2* sm = s_x + l * SM::STRIDE;
+    // my elements e = t + T q live at Lme[q * LQ] in every tile-layout array
+    float2* Lme = COL ? (L + t * LPC + l) : (L + l * N + t);
+    constexpr int LQ = COL ? T * LPC : T;
+    ShiftState<PC> st;
+    shift_init<PC>(st, t);
+
+    // y kernels: strided stores leave through L by tensor copies
+    auto tma_store_tile = [&](const CUtensorMap* tm, long long done_tile) __attribute__((always_inline)) {
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            const long long tl = done_tile * LPC;
+            const int bb = int(tl / p.lines_per_batch);
+            const int c0 = int(tl - (long long)bb * p.lines_per_batch);
+#pragma unroll 1
+            for (int j = 0; j < SM::NBOX; ++j) tma_store_2d(tm, 2 * c0, bb * N + j * SM::BOXR, L + j * SM::BOXR * LPC);
+            bulk_commit_group();
+        }
+    };
+
+    float2 v[E];
+    bool pending = false;               // y kernels: the previous tile's result still sits in registers
+    bool tables_ready = false;
+    const float kdz = p.k_dz;
+    for (; tile < p.n_tiles; tile += gridDim.x) {
+        const long long tile_off = tile * (long long)(N * LPC);
+        const bool has_next = tile + gridDim.x < p.n_tiles;
+        land_wait();                    // this tile's field has landed
+        if (COL && pending) {
+            static_for<E>([&](auto Q) __attribute__((always_inline)) {
+                constexpr int q = decltype(Q)::value;
+                const float2 x = Lme[q * LQ];
+                Lme[q * LQ] = v[q];
+                v[q] = x;
+            });
+            tma_store_tile(&tm_out, tile - gridDim.x);
+            pending = false;
+        } else {
+            static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = Lme[q * LQ]; });
+            __syncthreads();            // everybody holds its elements: L is free
+        }
+        bool db_issued = false;
+        if constexpr (!COL) { land(LAND_DB, tile); db_issued = true; }
+        if (!tables_ready) { mbar_wait(&table_bar, 0); tables_ready = true; }
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            if (half == 1) {
+                // ------------------------------------------------ middle: the pointwise part of the slice
+                land_wait();            // delta/beta of this tile
+                // t = exp(k(i delta - beta)) in place (rolled: keeps the instruction footprint small)
+#pragma unroll 1
+                for (int q0 = 0; q0 < E; q0 += 4) {
+                    float2 d[4];
+                    bool small = true;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { d[i] = Lme[(q0 + i) * LQ]; small = small && transmission_is_small(d[i], kdz); }
+                    if (__all_sync(0xffffffffu, small)) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) Lme[(q0 + i) * LQ] = transmission_small(d[i], kdz);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) Lme[(q0 + i) * LQ] = transmission(d[i], kdz);
+                    }
+                }
+                if constexpr (!ADJ) {
+                    if (p.store_slab) {
+                        float2* sp = p.slab + tile_off + (Lme - L);
+                        static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; sp[q * LQ] = v[q]; });
+                    }
+                    static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = cmul(v[q], Lme[q * LQ]); });
+                    __syncthreads();    // L is free again
+                    if (has_next) land(LAND_IN, tile + gridDim.x);
+                } else {
+                    // G = G_u conj(t)
+                    static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = cmulc(v[q], Lme[q * LQ]); });
+                    __syncthreads();
+                    land(LAND_SLAB, tile);
+                    land_wait();        // psi_i
+                    // grad = -k (Im, Re)(psi conj(G))
+                    if constexpr (COL) {
+                        static_for<E>([&](auto Q) __attribute__((always_inline)) {
+                            constexpr int q = decltype(Q)::value;
+                            const float2 w = cmulc(Lme[q * LQ], v[q]);
+                            Lme[q * LQ] = make_float2(-kdz * w.y, -kdz * w.x);
+                        });
+                        tma_store_tile(&tm_grad, tile);
+                        if (tid == 0) bulk_wait_group_read0();
+                        __syncthreads();
+                    } else {
+                        float2* gp = p.grad + tile_off + (Lme - L);
+                        static_for<E>([&](auto Q) __attribute__((always_inline)) {
+                            constexpr int q = decltype(Q)::value;
+                            const float2 w = cmulc(Lme[q * LQ], v[q]);
+                            gp[q * LQ] = make_float2(-kdz * w.y, -kdz * w.x);
+                        });
+                        __syncthreads();
+                    }
+                    if (has_next) land(LAND_IN, tile + gridDim.x);
+                }
+            }
+            const bool conv = (half == 0) ? (p.conv1 != 0) : (p.conv2 != 0);
+            if (conv) {
+                if constexpr (PC::SHIFT) {
+                    static_for<E>([&](auto Q) __attribute__((always_inline)) {
+                        constexpr int q = decltype(Q)::value;
+                        if constexpr ((q % P) != 0) v[q] = cmul(v[q], st.cmod[q % P]);
+                    });
+                }
+#pragma unroll 1
+                for (int pass = 0; pass < 2; ++pass) {
+                    pipe_fft<PC, LPC, COL>(v, t, l, sm, s_tw, st);
+                    if (pass == 0) {
+                        static_for<E>([&](auto Q) __attribute__((always_inline)) {
+                            constexpr int q = decltype(Q)::value;
+                            v[q] = cmul_conj(v[q], s_h[t + T * q]);
+                        });
+                        if (COL && half == 0 && !db_issued) {
+                            // the tensor store of the previous tile has read L by now: fetch delta/beta
+                            if (tid == 0) bulk_wait_group_read0();
+                            land(LAND_DB, tile);
+                            db_issued = true;
+                        }
+                    }
+                }
+                // registers hold the conjugate of the result (times the shift modulation)
+                static_for<E>([&](auto Q) __attribute__((always_inline)) {
+                    constexpr int q = decltype(Q)::value;
+                    if constexpr (PC::SHIFT && (q % P) != 0) v[q] = cmul_conj(v[q], st.cmod[q % P]);
+                    else v[q] = conjf2(v[q]);
+                });
+            } else if (COL && half == 0 && !db_issued) {
+                if (tid == 0) bulk_wait_group_read0();
+                land(LAND_DB, tile);
+                db_issued = true;
+            }
+        }
+        // ---- result
+        if (p.store_out) {
+            if constexpr (COL) {
+                pending = true;
+            } else {
+                float2* op = p.out + tile_off + (Lme - L);
+                static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; op[q * LQ] = v[q]; });
+            }
+        }
+    }
+    if (COL && pending) {
+        // drain: the last tile of this CTA (L is free: no landing is outstanding)
+        if (tid == 0) bulk_wait_group_read0();
+        __syncthreads();
+        static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; Lme[q * LQ] = v[q]; });
+        tma_store_tile(&tm_out, tile - gridDim.x);
+    }
+    if (COL && tid == 0) bulk_wait_group_read0();
+}
+
+}  // namespace bdof
