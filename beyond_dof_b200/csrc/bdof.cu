@@ -47,7 +47,7 @@ extern "C" int bdof_set_sm_reserve(int n_sms) {
 }
 bool bdof_use_pdl() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("BDOF_PDL"); v = (e && e[0] == '1') ? 1 : 0; }     // measured: no gain on B200, off by default
+    if (v < 0) { const char* e = getenv("BDOF_PDL"); v = (e && e[0] == '0') ? 0 : 1; }     // sweep kernels: +2..14 % (prologue overlaps the previous kernel's tail)
     return v == 1;
 }
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -377,6 +377,8 @@ struct bdof_plan {
     long long F;               // batch*ny*nx
     AxisTables ax, ay;
     bool have_kernel = false, full_kernel = false;
+    bool sweep = true;         // one kernel per slice and direction (sweepfft.cuh); BDOF_SWEEP=0 at plan creation selects the
+                               // per-pass kernels (row pass + column pass per slice) instead
     bool row_prefetch = false; // row passes L2-prefetch their own side inputs at tile start (BDOF_ROW_PREFETCH=1 enables; measured slower)
     bool l2_prefetch = false;  // column passes prefetch the next row pass's DRAM inputs into L2 (BDOF_L2_PREFETCH=1 enables;
                                // measured slower on B200 at 2048^2: the prefetch traffic slows the column pass itself)
@@ -455,6 +457,7 @@ extern "C" int bdof_plan_create(bdof_plan** out, int ny, int nx, int batch, int 
     p->stream = (cudaStream_t)cuda_stream;
     p->F = (long long)batch * ny * nx;
     p->ax.n = nx; p->ay.n = ny;
+    if (const char* e = getenv("BDOF_SWEEP")) p->sweep = (e[0] != '0');
     if (const char* e = getenv("BDOF_L2_PREFETCH")) p->l2_prefetch = (e[0] != '0');
     if (const char* e = getenv("BDOF_ROW_PREFETCH")) p->row_prefetch = (e[0] != '0');
     int r = 0;
@@ -609,9 +612,7 @@ static int col_pass(bdof_plan* p, int variant, const LineParams& q) {
 // sweep kernels: one launch per slice and direction (sweepfft.cuh)
 // ------------------------------------------------------------------------------------------
 static bool use_sweep(const bdof_plan* p) {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("BDOF_SWEEP"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v == 1 && !p->full_kernel && p->n_slice >= 2 && pipe_parts(p->nx) > 0 && pipe_parts(p->ny) > 0;
+    return p->sweep && !p->full_kernel && p->n_slice >= 2 && pipe_parts(p->nx) > 0 && pipe_parts(p->ny) > 0;
 }
 // kernel of slice i: x kernel (rows) for even i, y kernel (columns) for odd i
 static int sweep_launch(bdof_plan* p, int i, bool adj, SweepParams q) {
@@ -620,7 +621,7 @@ static int sweep_launch(bdof_plan* p, int i, bool adj, SweepParams q) {
     q.tw = col ? p->ay.tw_pipe : p->ax.tw_pipe;
     q.h = col ? (adj ? p->ay.h_adj : p->ay.h) : (adj ? p->ax.h_adj : p->ax.h);
     q.k_dz = float(p->k_dz);
-    q.dbg = g_dbg;
+    q.dbg = g_dbg ? g_dbg + (long long)((col ? 2 : 0) + (adj ? 1 : 0)) * (1 << 17) : nullptr;
     const long long rows = (long long)p->batch * p->ny;
     if (!p->profile) return launch_sweep_n(n, col, adj, q, rows, p->nx, p->stream);
     cudaEvent_t a, b;

@@ -95,6 +95,19 @@ __device__ __forceinline__ float2 transmission_small(float2 db, float k) {
     m = fmaf(m, y, 1.0f);
     return make_float2(m * cp, m * sp);
 }
+// |k delta| <= 2^-4 and |k beta| <= 2^-6 (one thin slice of any X-ray object): truncation errors
+// x^7/5040 = 7e-13 (sin), x^6/720 = 8e-11 (cos), y^4/24 = 2.5e-9 (exp) are below fp32 resolution
+__device__ __forceinline__ float2 transmission_tiny(float2 db, float k) {
+    const float x = k * db.x, y = -k * db.y;
+    const float x2 = x * x;
+    const float sp = fmaf(fmaf(x2, 8.33333333e-3f, -1.66666667e-1f) * x2, x, x);
+    const float cp = fmaf(fmaf(x2, 4.16666667e-2f, -0.5f), x2, 1.0f);
+    const float m = fmaf(fmaf(fmaf(y, 1.66666667e-1f, 0.5f), y, 1.0f), y, 1.0f);
+    return make_float2(m * cp, m * sp);
+}
+__device__ __forceinline__ bool transmission_is_tiny(float2 db, float k) {
+    return fabsf(k * db.x) <= 0.0625f && fabsf(k * db.y) <= 0.015625f;
+}
 __device__ __forceinline__ bool transmission_is_small(float2 db, float k) {
     return fabsf(k * db.x) <= 0.78539816f && fabsf(k * db.y) <= 0.5f;
 }

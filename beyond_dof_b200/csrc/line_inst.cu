@@ -119,7 +119,17 @@ static int launch_sweep(const SweepParams& p0, long long rows, int cols, cudaStr
             memset(&tm_in, 0, sizeof(tm_in)); memset(&tm_out, 0, sizeof(tm_out));
             memset(&tm_db, 0, sizeof(tm_db)); memset(&tm_grad, 0, sizeof(tm_grad));
         }
-        kern<<<grid, Cfg::T * LPC, SM::BYTES, st>>>(p, tm_in, tm_out, tm_db, tm_grad);
+        if (bdof_use_pdl()) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::T * LPC); cfg.dynamicSmemBytes = SM::BYTES; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p, tm_in, tm_out, tm_db, tm_grad));
+        } else {
+            kern<<<grid, Cfg::T * LPC, SM::BYTES, st>>>(p, tm_in, tm_out, tm_db, tm_grad);
+        }
         return bdof_launch_check("sweep_kernel");
     }
 }

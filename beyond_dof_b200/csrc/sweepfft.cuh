@@ -86,12 +86,16 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
     auto land_wait = [&]() __attribute__((always_inline)) { mbar_wait(&land_bar, land_seq & 1); ++land_seq; };
 
     long long tile = blockIdx.x;
-    if (tile < p.n_tiles) land(LAND_IN, tile);
     if (tid == 0) {
         mbar_expect_tx(&table_bar, TW_BYTES + H_BYTES);
         bulk_g2s(s_tw, p.tw, TW_BYTES, &table_bar);
         bulk_g2s(s_h, p.h, H_BYTES, &table_bar);
     }
+    // Programmatic dependent launch: everything above touches only constant tables, so it may overlap the
+    // tail of the previous kernel of the stream; from here on we read what that kernel wrote.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tile < p.n_tiles) land(LAND_IN, tile);
     int l, t;
     if constexpr (COL) { l = tid % LPC; t = tid / LPC; }
     else               { l = tid / T;   t = tid % T; }
@@ -116,6 +120,16 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
         }
     };
 
+#ifdef BDOF_PHASE_TIMING
+    int tile_iter = -1;
+#define SWEEP_STAMP(slot)                                                                         \
+    do {                                                                                          \
+        if (p.dbg != nullptr && (threadIdx.x & 31) == 0 && tile_iter < 2)                         \
+            p.dbg[((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + tile_iter * 16 + (slot)] = clock64(); \
+    } while (0)
+#else
+#define SWEEP_STAMP(slot) do { } while (0)
+#endif
     float2 v[E];
     bool pending = false;               // y kernels: the previous tile's result still sits in registers
     bool tables_ready = false;
@@ -123,7 +137,12 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
     for (; tile < p.n_tiles; tile += gridDim.x) {
         const long long tile_off = tile * (long long)(N * LPC);
         const bool has_next = tile + gridDim.x < p.n_tiles;
+#ifdef BDOF_PHASE_TIMING
+        ++tile_iter;
+#endif
+        SWEEP_STAMP(0);
         land_wait();                    // this tile's field has landed
+        SWEEP_STAMP(1);
         if (COL && pending) {
             static_for<E>([&](auto Q) __attribute__((always_inline)) {
                 constexpr int q = decltype(Q)::value;
@@ -137,22 +156,42 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
             static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = Lme[q * LQ]; });
             __syncthreads();            // everybody holds its elements: L is free
         }
-        bool db_issued = false;
-        if constexpr (!COL) { land(LAND_DB, tile); db_issued = true; }
+        SWEEP_STAMP(2);
+        // y kernels: L is still being read by a tensor store here; the next landing is issued from inside the
+        // following convolution (or right away if there is none), once that store has drained
+        int deferred = -1;
+        if constexpr (!COL) land(LAND_DB, tile);
+        else deferred = LAND_DB;
+        auto deferred_landing = [&]() __attribute__((always_inline)) {
+            if (COL && deferred >= 0) {
+                if (tid == 0) bulk_wait_group_read0();
+                land(deferred, deferred == LAND_DB ? tile : tile + gridDim.x);
+                deferred = -1;
+            }
+        };
         if (!tables_ready) { mbar_wait(&table_bar, 0); tables_ready = true; }
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             if (half == 1) {
                 // ------------------------------------------------ middle: the pointwise part of the slice
+                SWEEP_STAMP(3);
                 land_wait();            // delta/beta of this tile
+                SWEEP_STAMP(4);
                 // t = exp(k(i delta - beta)) in place (rolled: keeps the instruction footprint small)
 #pragma unroll 1
                 for (int q0 = 0; q0 < E; q0 += 4) {
                     float2 d[4];
-                    bool small = true;
+                    bool tiny = true, small = true;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { d[i] = Lme[(q0 + i) * LQ]; small = small && transmission_is_small(d[i], kdz); }
-                    if (__all_sync(0xffffffffu, small)) {
+                    for (int i = 0; i < 4; ++i) {
+                        d[i] = Lme[(q0 + i) * LQ];
+                        tiny = tiny && transmission_is_tiny(d[i], kdz);
+                        small = small && transmission_is_small(d[i], kdz);
+                    }
+                    if (__all_sync(0xffffffffu, tiny)) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) Lme[(q0 + i) * LQ] = transmission_tiny(d[i], kdz);
+                    } else if (__all_sync(0xffffffffu, small)) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) Lme[(q0 + i) * LQ] = transmission_small(d[i], kdz);
                     } else {
@@ -160,6 +199,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                         for (int i = 0; i < 4; ++i) Lme[(q0 + i) * LQ] = transmission(d[i], kdz);
                     }
                 }
+                SWEEP_STAMP(5);
                 if constexpr (!ADJ) {
                     if (p.store_slab) {
                         float2* sp = p.slab + tile_off + (Lme - L);
@@ -173,7 +213,9 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                     static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = cmulc(v[q], Lme[q * LQ]); });
                     __syncthreads();
                     land(LAND_SLAB, tile);
+                    SWEEP_STAMP(6);
                     land_wait();        // psi_i
+                    SWEEP_STAMP(7);
                     // grad = -k (Im, Re)(psi conj(G))
                     if constexpr (COL) {
                         static_for<E>([&](auto Q) __attribute__((always_inline)) {
@@ -182,8 +224,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                             Lme[q * LQ] = make_float2(-kdz * w.y, -kdz * w.x);
                         });
                         tma_store_tile(&tm_grad, tile);
-                        if (tid == 0) bulk_wait_group_read0();
-                        __syncthreads();
+                        if (has_next) deferred = LAND_IN;
                     } else {
                         float2* gp = p.grad + tile_off + (Lme - L);
                         static_for<E>([&](auto Q) __attribute__((always_inline)) {
@@ -192,10 +233,11 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                             gp[q * LQ] = make_float2(-kdz * w.y, -kdz * w.x);
                         });
                         __syncthreads();
+                        if (has_next) land(LAND_IN, tile + gridDim.x);
                     }
-                    if (has_next) land(LAND_IN, tile + gridDim.x);
                 }
             }
+            if (half == 1) SWEEP_STAMP(8);
             const bool conv = (half == 0) ? (p.conv1 != 0) : (p.conv2 != 0);
             if (conv) {
                 if constexpr (PC::SHIFT) {
@@ -212,12 +254,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                             constexpr int q = decltype(Q)::value;
                             v[q] = cmul_conj(v[q], s_h[t + T * q]);
                         });
-                        if (COL && half == 0 && !db_issued) {
-                            // the tensor store of the previous tile has read L by now: fetch delta/beta
-                            if (tid == 0) bulk_wait_group_read0();
-                            land(LAND_DB, tile);
-                            db_issued = true;
-                        }
+                        deferred_landing();
                     }
                 }
                 // registers hold the conjugate of the result (times the shift modulation)
@@ -226,13 +263,15 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                     if constexpr (PC::SHIFT && (q % P) != 0) v[q] = cmul_conj(v[q], st.cmod[q % P]);
                     else v[q] = conjf2(v[q]);
                 });
-            } else if (COL && half == 0 && !db_issued) {
-                if (tid == 0) bulk_wait_group_read0();
-                land(LAND_DB, tile);
-                db_issued = true;
+            } else {
+                deferred_landing();
             }
         }
         // ---- result
+#ifdef BDOF_PHASE_TIMING
+        asm volatile("" ::"f"(v[0].x), "f"(v[E - 1].y));
+#endif
+        SWEEP_STAMP(9);
         if (p.store_out) {
             if constexpr (COL) {
                 pending = true;
@@ -241,6 +280,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                 static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; op[q * LQ] = v[q]; });
             }
         }
+        SWEEP_STAMP(10);
     }
     if (COL && pending) {
         // drain: the last tile of this CTA (L is free: no landing is outstanding)

@@ -322,3 +322,79 @@ def test_pack_unpack_roundtrip_ragged(bd):
         assert torch.equal(db[..., 0], d.permute(3, 0, 1, 2)) and torch.equal(db[..., 1], b.permute(3, 0, 1, 2))
         d2, b2 = plan.unpack(db)
         assert torch.equal(d, d2) and torch.equal(b, b2)
+
+
+# ---------------------------------------------------------------------------------------------
+# sweep kernels (one kernel per slice and direction) vs the per-pass kernels and vs the oracle
+# ---------------------------------------------------------------------------------------------
+def _run_plan(shape, gd, gb, pr, pi, target, sweep, propagate_last=False, free=None):
+    from beyond_dof_b200.plan import MultislicePlan
+    B, Y, X, Z = shape
+    old = os.environ.get('BDOF_SWEEP')
+    os.environ['BDOF_SWEEP'] = '1' if sweep else '0'           # read when the plan is created
+    try:
+        plan = MultislicePlan(Y, X, B, Z, 5000, 1e-7, free_prop_cm=free, propagate_last=propagate_last, store_slices=True)
+    finally:
+        if old is None:
+            del os.environ['BDOF_SWEEP']
+        else:
+            os.environ['BDOF_SWEEP'] = old
+    db = plan.pack(torch.as_tensor(gd).cuda(), torch.as_tensor(gb).cuda())
+    probe = torch.as_tensor((np.asarray(pr) + 1j * np.asarray(pi)).astype(np.complex64)).cuda()
+    l0 = plan_launches()
+    psi = plan.forward(db, probe)
+    loss, g = plan.loss_mag(psi, torch.as_tensor(target.astype(np.float32)).cuda())
+    gout = torch.empty_like(db)
+    _, gp = plan.adjoint(db, g, grad_out=gout, want_probe_grad=True)
+    torch.cuda.synchronize()
+    n_launch = plan_launches() - l0
+    g_d, g_b = plan.unpack(gout)
+    return psi.cpu().numpy(), g_d.cpu().numpy(), g_b.cpu().numpy(), gp.cpu().numpy(), n_launch
+
+
+def plan_launches():
+    from beyond_dof_b200 import capi
+    return capi.launch_count()
+
+
+@pytest.mark.parametrize('shape', [(2, 64, 128, 5), (1, 256, 64, 4), (3, 128, 512, 2), (1, 1024, 2048, 3), (1, 2048, 1024, 4)])
+@pytest.mark.parametrize('propagate_last', [False, True])
+def test_sweep_kernels_match_per_pass_kernels(bd, shape, propagate_last):
+    gd, gb = mo.random_phantom(shape, seed=51, delta_scale=4e-4, beta_scale=4e-5)
+    pr, pi = mo.gaussian_probe(shape[1:3], max(shape[1:3]) / 2., max(shape[1:3]) / 3., 0.5)   # nowhere near zero amplitude
+    rng = np.random.default_rng(52)
+    target = rng.random(shape[:3]) + 0.5
+    a = _run_plan(shape, gd, gb, pr, pi, target, True, propagate_last)
+    b = _run_plan(shape, gd, gb, pr, pi, target, False, propagate_last)
+    assert a[4] < b[4]                                        # fewer launches: one kernel per slice and direction
+    assert rel_l2(a[0], b[0]) < 2e-6                          # same arithmetic up to the order of the two 1-D passes
+    assert rel_l2(a[1], b[1]) < 2e-5 and rel_l2(a[2], b[2]) < 2e-5 and rel_l2(a[3], b[3]) < 2e-5
+
+
+@pytest.mark.parametrize('shape', [(1, 4096, 1024, 4), (1, 1024, 4096, 3), (2, 2048, 512, 5)])
+def test_sweep_kernels_long_lines_match_oracle(bd, shape):
+    # 4096-long lines use the cyclic-shift stage exchange (pipefft.cuh) in both kernel orientations
+    gd, gb = mo.random_phantom(shape, seed=53, delta_scale=4e-4, beta_scale=4e-5)
+    pr, pi = mo.gaussian_probe(shape[1:3], max(shape[1:3]) / 2., max(shape[1:3]) / 3., 0.5)
+    rng = np.random.default_rng(54)
+    target = rng.random(shape[:3]) + 0.5
+    lo, gdo, gbo, psio = mo.loss_and_grad(gd.astype(np.float64), gb.astype(np.float64), pr, pi, 5000, 1e-7, target)
+    psi, g_d, g_b, _, _ = _run_plan(shape, gd, gb, pr, pi, target, True)
+    assert intensity_err(psi, psio) < TOL_INTENSITY
+    assert rel_l2(g_d, gdo) < TOL_GRAD and rel_l2(g_b, gbo) < TOL_GRAD
+
+
+def test_transmission_paths_agree(bd):
+    # the sweep kernels pick a truncated-series transmission when a whole warp's |k delta|, |k beta| are tiny,
+    # the cephes polynomials when they are small and the range-reduced general path otherwise: all three
+    # against the oracle, strong objects included (k delta up to ~40 rad)
+    shape = (1, 128, 128, 4)
+    one, zero = np.ones(shape[1:3]), np.zeros(shape[1:3])
+    rng = np.random.default_rng(55)
+    target = rng.random(shape[:3]) + 0.5
+    for ds, bs in [(1e-5, 1e-6), (4e-3, 1e-3), (1.5, 2e-2)]:
+        gd, gb = mo.random_phantom(shape, seed=56, delta_scale=ds, beta_scale=bs)
+        lo, gdo, gbo, psio = mo.loss_and_grad(gd.astype(np.float64), gb.astype(np.float64), one, zero, 5000, 1e-7, target)
+        psi, g_d, g_b, _, _ = _run_plan(shape, gd, gb, one, zero, target, True)
+        assert intensity_err(psi, psio) < TOL_INTENSITY
+        assert rel_l2(g_d, gdo) < TOL_GRAD and rel_l2(g_b, gbo) < TOL_GRAD

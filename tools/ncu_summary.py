@@ -15,6 +15,11 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 def short(name):
     m = re.search(r'LineCfg<\(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+)>, \(int\)(\d+), \(bool\)(\d), \(int\)(\d), \(int\)(\d), \(int\)(\d)', name)
     if not m:
+        m2 = re.search(r'(sweep_kernel|pipe_col_conv_kernel)<bdof::LineCfg<\(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+)>, \(int\)(\d+), \(int\)(\d+)(?:, \(bool\)(\d), \(bool\)(\d))?', name)
+        if m2:
+            k, n, t, r1, r2, r3, lpc, parts, col, adj = m2.groups()
+            kind = k if col is None else 'sweep_kernel %s %s' % ('y (columns)' if col == '1' else 'x (rows)', 'adjoint' if adj == '1' else 'forward')
+            return '%s N=%s T=%s radices=%sx%s lines/CTA=%s exchange parts=%s' % (kind, n, t, r1, r2, lpc, parts)
         return name.split('(')[0]
     n, t, r1, r2, r3, lpc, col, mode, pre, post = m.groups()
     kind = ('col' if col == '1' else 'row') + '_' + ['conv', 'fft', 'ifft', 'conv2d'][int(mode)] + ('_transmit' if pre == '1' else '') + ('_adjoint' if post == '1' else '')
@@ -37,7 +42,7 @@ def main(rep, out):
             if k in hdr:
                 lines.append('   %-70s %s %s' % (k, d[hdr.index(k)], units[hdr.index(k)]))
         # stall reasons from the source page
-        src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-id', '::regex:line_kernel:%d' % (i + 1)], capture_output=True, text=True).stdout
+        src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-id', '::regex:kernel:%d' % (i + 1)], capture_output=True, text=True).stdout
         srows = list(csv.reader(src.splitlines()))
         tot = defaultdict(float)
         for j, r in enumerate(srows):
