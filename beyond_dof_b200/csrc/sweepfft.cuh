@@ -32,6 +32,7 @@ struct SweepParams {
     int conv1, conv2;        // run the first / second convolution
     int store_slab;          // forward: write psi_i to the slab
     int store_out;           // write the final field
+    int slab_prefetch;       // adjoint: L2-prefetch the slab tile at tile start
     float k_dz;
     long long* dbg;
 };
@@ -80,6 +81,14 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
 #pragma unroll 1
                 for (int j = 0; j < LPC; ++j) bulk_g2s(L + j * N, src + j * N, N * (unsigned)sizeof(float2), &land_bar);
             }
+        }
+    };
+    // adjoint: pull the stored psi of this tile into L2 while the first convolution runs (it lands in L later)
+    auto slab_prefetch = [&](long long tile) __attribute__((always_inline)) {
+        if (tid == 0 && p.slab_prefetch) {
+            const char* src = reinterpret_cast<const char*>(p.slab + tile * (long long)(N * LPC));
+#pragma unroll 1
+            for (int j = 0; j < LPC; ++j) bulk_prefetch_l2(src + (size_t)j * N * sizeof(float2), N * (unsigned)sizeof(float2));
         }
     };
     unsigned land_seq = 0;
@@ -162,10 +171,12 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
         int deferred = -1;
         if constexpr (!COL) land(LAND_DB, tile);
         else deferred = LAND_DB;
+        if constexpr (ADJ && !COL) slab_prefetch(tile);
         auto deferred_landing = [&]() __attribute__((always_inline)) {
             if (COL && deferred >= 0) {
                 if (tid == 0) bulk_wait_group_read0();
                 land(deferred, deferred == LAND_DB ? tile : tile + gridDim.x);
+                if (ADJ && deferred == LAND_DB) slab_prefetch(tile);
                 deferred = -1;
             }
         };
@@ -177,7 +188,8 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                 SWEEP_STAMP(3);
                 land_wait();            // delta/beta of this tile
                 SWEEP_STAMP(4);
-                // t = exp(k(i delta - beta)) in place (rolled: keeps the instruction footprint small)
+                // t = exp(k(i delta - beta)) in place.  ROLLED on purpose: a straight-line version (64 x 20 instructions)
+                // pushed the kernel past the instruction cache and cost ~10k cycles on the first tile of every launch
 #pragma unroll 1
                 for (int q0 = 0; q0 < E; q0 += 4) {
                     float2 d[4];
@@ -209,6 +221,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                     __syncthreads();    // L is free again
                     if (has_next) land(LAND_IN, tile + gridDim.x);
                 } else {
+                    // G = G_u conj(t)
                     // G = G_u conj(t)
                     static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = cmulc(v[q], Lme[q * LQ]); });
                     __syncthreads();
