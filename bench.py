@@ -46,6 +46,20 @@ PASS_BYTES = {'row_conv_transmit': 24, 'col_conv': 16, 'row_conv_adjoint': 40,
 STEP_BYTES = 96
 
 
+def auto_sm_reserve(B, ny, nx, n_sm=148, max_reserve=24):
+    """largest number of SMs (<= max_reserve) that can be left to NCCL without adding a round of tiles to the
+    sweep kernels (8 lines per tile up to 2048-long lines, 4 for 4096)"""
+    def rounds(lines, length, ctas):
+        lpc = 4 if length >= 4096 else (8 if length >= 256 else 16)
+        tiles = B * lines // lpc
+        return -(-tiles // ctas)
+    best = 0
+    for r in range(0, max_reserve + 1):
+        if rounds(ny, nx, n_sm - r) == rounds(ny, nx, n_sm) and rounds(nx, ny, n_sm - r) == rounds(nx, ny, n_sm):
+            best = r
+    return best
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -176,14 +190,20 @@ def run_gpu(args):
         raise RuntimeError('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
-    if world > 1:
-        import datetime
-        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=90))
     ny, nx, nz, desc = WORKLOADS[args.workload]
     B = 1
     if args.shape:
         B, ny, nx, nz = (int(v) for v in args.shape.split(','))
         desc = 'custom shape %s' % args.shape
+    sm_reserve = 0
+    if world > 1:
+        import datetime
+        # The sweep kernels are persistent (one CTA per SM, all of its shared memory and registers), so the NCCL kernels
+        # that reduce the gradient buckets take SMs away from them while both run.  Measured on 2 B200 (2048^2x256, 8.6 GB
+        # gradient, 14 ms all-reduce at NVLink line rate vs 13.7 ms of adjoint sweep): reserving SMs for NCCL and capping
+        # its grid (NCCL_MAX_CTAS) lost more than it saved (tools/exp11.sh, exp12.sh); the default leaves both alone.
+        sm_reserve = max(0, args.sm_reserve)
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=90))
     units_per_step = B * ny * nx * nz * world
 
     # synthetic inputs, created once on the device (value arm) / in pinned host memory (e2e arm)
@@ -205,8 +225,32 @@ def run_gpu(args):
         # mean of the object gradient over ranks, reduced in z-buckets on a communication stream while the
         # adjoint sweep is still producing the remaining slices
         obj.enable_data_parallel(n_buckets=args.buckets)
-        if args.sm_reserve:
-            capi.check(capi.lib.bdof_set_sm_reserve(args.sm_reserve))
+        if sm_reserve:
+            capi.check(capi.lib.bdof_set_sm_reserve(sm_reserve))
+
+    if world > 1 and args.diag:
+        # diagnostics: the plain all-reduce of the whole gradient, and the step without any exchange
+        for _ in range(2):
+            dist.all_reduce(obj.grad, op=dist.ReduceOp.AVG)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            dist.all_reduce(obj.grad, op=dist.ReduceOp.AVG)
+        torch.cuda.synchronize()
+        t_ar = (time.perf_counter() - t0) / 3
+        dp_state = obj._dp
+        obj._dp = None
+        for _ in range(2):
+            obj.step_device(target_dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            obj.step_device(target_dev)
+        torch.cuda.synchronize()
+        t_step = (time.perf_counter() - t0) / 3
+        obj._dp = dp_state
+        print('[diag rank %d] all-reduce of %.2f GB alone: %.2f ms; step without exchange: %.2f ms' %
+              (rank, obj.grad.numel() * 4 / 1e9, t_ar * 1e3, t_step * 1e3), file=sys.stderr, flush=True)
 
     def step_device():
         return obj.step_device(target_dev)
@@ -300,7 +344,8 @@ def run_gpu(args):
             'vs_baseline': None, 'dtype': 'c64', 'data': 'synthetic',
             'config': {'workload': desc, 'ny': ny, 'nx': nx, 'n_slice': nz, 'batch_per_gpu': B, 'semantics': 'numpy (last slice modulates only)',
                        'l2': 'inputs larger than L2 (%.1f GB of delta/beta + %.1f GB slice store per GPU streamed every step)' % (db.numel() * 4 / 1e9, db.numel() * 4 / 1e9),
-                       'parallelism': 'dp%d: one field per GPU, NCCL all-reduce (sum) of the object gradient' % world if world > 1 else 'single GPU'},
+                       'parallelism': ('dp%d: one field per GPU, NCCL all-reduce (mean) of the object gradient in %d z-buckets overlapped with the adjoint sweep, %d SMs left to NCCL'
+                                       % (world, args.buckets, sm_reserve)) if world > 1 else 'single GPU'},
             'e2e': {'value': e2e_value, 'unit': 'Gpixel*slice/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'api': 'beyond_dof_b200.models.FullfieldObjective.step(projection magnitudes in pinned host memory) -> loss'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'kernels': kern, 'cpu_baseline': cpu,
@@ -324,6 +369,7 @@ def main():
     ap.add_argument('--sm-reserve', type=int, default=0, help='SMs left free for NCCL while the sweep runs (N > 1)')
     ap.add_argument('--buckets', type=int, default=8, help='z-buckets of the gradient all-reduce (N > 1)')
     ap.add_argument('--shape', default=None, help='experiment: B,NY,NX,NZ overrides the workload shape')
+    ap.add_argument('--diag', action='store_true', help='N > 1: print the plain all-reduce time and the step time without exchange')
     ap.add_argument('--in-place', action='store_true', help='adjoint overwrites delta/beta with the gradient (needed for the 4096^2x512 size)')
     args = ap.parse_args()
     if args.impl == 'reference':

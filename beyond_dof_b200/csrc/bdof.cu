@@ -622,6 +622,7 @@ static int sweep_launch(bdof_plan* p, int i, bool adj, SweepParams q) {
     q.h = col ? (adj ? p->ay.h_adj : p->ay.h) : (adj ? p->ax.h_adj : p->ax.h);
     q.k_dz = float(p->k_dz);
     { static int pf = -1; if (pf < 0) { const char* e = getenv("BDOF_SLAB_PREFETCH"); pf = (e && e[0] == '0') ? 0 : 1; } q.slab_prefetch = pf; }
+    { static int sg = -1; if (sg < 0) { const char* e = getenv("BDOF_STAGGER_NS"); sg = e ? atoi(e) : 0; } q.stagger_ns = sg; }
     q.dbg = g_dbg ? g_dbg + (long long)((col ? 2 : 0) + (adj ? 1 : 0)) * (1 << 17) : nullptr;
     const long long rows = (long long)p->batch * p->ny;
     if (!p->profile) return launch_sweep_n(n, col, adj, q, rows, p->nx, p->stream);

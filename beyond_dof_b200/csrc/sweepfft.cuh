@@ -33,6 +33,8 @@ struct SweepParams {
     int store_slab;          // forward: write psi_i to the slab
     int store_out;           // write the final field
     int slab_prefetch;       // adjoint: L2-prefetch the slab tile at tile start
+    int stagger_ns;          // x kernels: the upper half of the lines starts every convolution this much later, so that
+                             // its stage exchanges (shared-memory pipe) overlap the other half's butterflies (FP pipe)
     float k_dz;
     long long* dbg;
 };
@@ -253,6 +255,9 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
             if (half == 1) SWEEP_STAMP(8);
             const bool conv = (half == 0) ? (p.conv1 != 0) : (p.conv2 != 0);
             if (conv) {
+                if constexpr (!COL && LPC >= 2) {
+                    if (p.stagger_ns > 0 && l >= LPC / 2) __nanosleep(p.stagger_ns);
+                }
                 if constexpr (PC::SHIFT) {
                     static_for<E>([&](auto Q) __attribute__((always_inline)) {
                         constexpr int q = decltype(Q)::value;

@@ -60,17 +60,20 @@ def allreduce_gradient(grad, average=True, buckets=None, comm_stream=None):
     if w == 1:
         return []
     works = []
+    # NCCL averages inside the collective (no extra pass over the gradient); gloo only sums
+    fused_avg = average and grad.is_cuda and dist.get_backend() == 'nccl'
+    op = dist.ReduceOp.AVG if fused_avg else dist.ReduceOp.SUM
     if buckets is None:
-        works.append(dist.all_reduce(grad, op=dist.ReduceOp.SUM, async_op=True))
+        works.append(dist.all_reduce(grad, op=op, async_op=True))
     else:
         for z_lo, z_hi, ev in buckets:
             if comm_stream is not None and grad.is_cuda:
                 comm_stream.wait_event(ev)
                 with torch.cuda.stream(comm_stream):
-                    works.append(dist.all_reduce(grad[z_lo:z_hi], op=dist.ReduceOp.SUM, async_op=True))
+                    works.append(dist.all_reduce(grad[z_lo:z_hi], op=op, async_op=True))
             else:
-                works.append(dist.all_reduce(grad[z_lo:z_hi], op=dist.ReduceOp.SUM, async_op=True))
-    if average:
+                works.append(dist.all_reduce(grad[z_lo:z_hi], op=op, async_op=True))
+    if average and not fused_avg:
         works.append(('scale', 1.0 / w))
     return works
 
