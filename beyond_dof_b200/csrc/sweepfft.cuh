@@ -29,6 +29,8 @@ struct SweepParams {
     const float2* tw;        // stage twiddles, pipelined layout
     int n_tiles;
     int lines_per_batch;     // columns per batch item (y kernels)
+    int lines_per_cta;       // x kernels with whole-warp lines: CTA c owns rows [c * lines_per_cta, ...) and walks them in
+    long long total_lines;   //   tiles of LPC rows, the last one partial (0: tiles dealt round-robin as in the y kernels)
     int conv1, conv2;        // run the first / second convolution
     int store_slab;          // forward: write psi_i to the slab
     int store_out;           // write the final field
@@ -57,6 +59,18 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
     __shared__ unsigned long long table_bar, land_bar;
 
     const int tid = threadIdx.x;
+#ifdef BDOF_PHASE_TIMING
+#define SWEEP_GSTAMP(slot)                                                                        \
+    do {                                                                                          \
+        if (p.dbg != nullptr && (threadIdx.x & 31) == 0) {                                        \
+            unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));          \
+            p.dbg[((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + (slot)] = (long long)gt; \
+        }                                                                                         \
+    } while (0)
+#else
+#define SWEEP_GSTAMP(slot) do { } while (0)
+#endif
+    SWEEP_GSTAMP(27);
     constexpr unsigned TW_BYTES = PC::TW_ELEMS * sizeof(float2);
     constexpr unsigned H_BYTES = N * sizeof(float2);
     if (tid == 0) {
@@ -67,8 +81,24 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
     __syncthreads();
 
     // ---- asynchronous landing of one tile-sized array into L (one thread talks to the TMA)
+    // x kernels: `tile` is the first row of the tile and the CTA owns the contiguous row range [.., row_end)
+    constexpr bool RANGES = !COL && T >= 32;
+    const long long row_end = RANGES ? ((long long)(blockIdx.x + 1) * p.lines_per_cta < p.total_lines
+                                            ? (long long)(blockIdx.x + 1) * p.lines_per_cta : p.total_lines) : 0;
+    auto tile_lines = [&](long long tile) __attribute__((always_inline)) {
+        if constexpr (RANGES) return int(row_end - tile < LPC ? row_end - tile : LPC);
+        else return LPC;
+    };
     auto land = [&](int what, long long tile) __attribute__((always_inline)) {
         if (tid == 0) {
+            if constexpr (RANGES) {
+                const int nl = tile_lines(tile);
+                mbar_expect_tx(&land_bar, unsigned(nl) * N * (unsigned)sizeof(float2));
+                const float2* src = (what == LAND_IN ? p.in : (what == LAND_DB ? p.db : p.slab)) + tile * (long long)N;
+#pragma unroll 1
+                for (int j = 0; j < nl; ++j) bulk_g2s(L + j * N, src + j * N, N * (unsigned)sizeof(float2), &land_bar);
+                return;
+            }
             mbar_expect_tx(&land_bar, TILE_BYTES);
             if (COL && what != LAND_SLAB) {
                 const long long tl = tile * LPC;              // first column of the tile
@@ -88,15 +118,18 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
     // adjoint: pull the stored psi of this tile into L2 while the first convolution runs (it lands in L later)
     auto slab_prefetch = [&](long long tile) __attribute__((always_inline)) {
         if (tid == 0 && p.slab_prefetch) {
-            const char* src = reinterpret_cast<const char*>(p.slab + tile * (long long)(N * LPC));
+            const char* src = reinterpret_cast<const char*>(p.slab + tile * (long long)(RANGES ? N : N * LPC));
+            const int nl = tile_lines(tile);
 #pragma unroll 1
-            for (int j = 0; j < LPC; ++j) bulk_prefetch_l2(src + (size_t)j * N * sizeof(float2), N * (unsigned)sizeof(float2));
+            for (int j = 0; j < nl; ++j) bulk_prefetch_l2(src + (size_t)j * N * sizeof(float2), N * (unsigned)sizeof(float2));
         }
     };
     unsigned land_seq = 0;
     auto land_wait = [&]() __attribute__((always_inline)) { mbar_wait(&land_bar, land_seq & 1); ++land_seq; };
 
-    long long tile = blockIdx.x;
+    long long tile = RANGES ? (long long)blockIdx.x * p.lines_per_cta : (long long)blockIdx.x;
+    const long long tile_end = RANGES ? row_end : (long long)p.n_tiles;
+    const long long tile_step = RANGES ? (long long)LPC : (long long)gridDim.x;
     if (tid == 0) {
         mbar_expect_tx(&table_bar, TW_BYTES + H_BYTES);
         bulk_g2s(s_tw, p.tw, TW_BYTES, &table_bar);
@@ -105,8 +138,10 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
     // Programmatic dependent launch: everything above touches only constant tables, so it may overlap the
     // tail of the previous kernel of the stream; from here on we read what that kernel wrote.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    SWEEP_GSTAMP(28);
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (tile < p.n_tiles) land(LAND_IN, tile);
+    SWEEP_GSTAMP(29);
+    if (tile < tile_end) land(LAND_IN, tile);
     int l, t;
     if constexpr (COL) { l = tid % LPC; t = tid / LPC; }
     else               { l = tid / T;   t = tid % T; }
@@ -145,9 +180,10 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
     bool pending = false;               // y kernels: the previous tile's result still sits in registers
     bool tables_ready = false;
     const float kdz = p.k_dz;
-    for (; tile < p.n_tiles; tile += gridDim.x) {
-        const long long tile_off = tile * (long long)(N * LPC);
-        const bool has_next = tile + gridDim.x < p.n_tiles;
+    for (; tile < tile_end; tile += tile_step) {
+        const long long tile_off = tile * (long long)(RANGES ? N : N * LPC);
+        const bool has_next = tile + tile_step < tile_end;
+        const bool active = !RANGES || l < tile_lines(tile);      // partial last tile of an x kernel: whole warps sit out
 #ifdef BDOF_PHASE_TIMING
         ++tile_iter;
 #endif
@@ -164,7 +200,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
             tma_store_tile(&tm_out, tile - gridDim.x);
             pending = false;
         } else {
-            static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = Lme[q * LQ]; });
+            if (active) static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = Lme[q * LQ]; });
             __syncthreads();            // everybody holds its elements: L is free
         }
         SWEEP_STAMP(2);
@@ -177,7 +213,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
         auto deferred_landing = [&]() __attribute__((always_inline)) {
             if (COL && deferred >= 0) {
                 if (tid == 0) bulk_wait_group_read0();
-                land(deferred, deferred == LAND_DB ? tile : tile + gridDim.x);
+                land(deferred, deferred == LAND_DB ? tile : tile + tile_step);
                 if (ADJ && deferred == LAND_DB) slab_prefetch(tile);
                 deferred = -1;
             }
@@ -193,7 +229,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                 // t = exp(k(i delta - beta)) in place.  ROLLED on purpose: a straight-line version (64 x 20 instructions)
                 // pushed the kernel past the instruction cache and cost ~10k cycles on the first tile of every launch
 #pragma unroll 1
-                for (int q0 = 0; q0 < E; q0 += 4) {
+                for (int q0 = 0; q0 < (active ? E : 0); q0 += 4) {
                     float2 d[4];
                     bool tiny = true, small = true;
 #pragma unroll
@@ -215,17 +251,17 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                 }
                 SWEEP_STAMP(5);
                 if constexpr (!ADJ) {
-                    if (p.store_slab) {
+                    if (p.store_slab && active) {
                         float2* sp = p.slab + tile_off + (Lme - L);
                         static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; sp[q * LQ] = v[q]; });
                     }
-                    static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = cmul(v[q], Lme[q * LQ]); });
+                    if (active) static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = cmul(v[q], Lme[q * LQ]); });
                     __syncthreads();    // L is free again
-                    if (has_next) land(LAND_IN, tile + gridDim.x);
+                    if (has_next) land(LAND_IN, tile + tile_step);
                 } else {
                     // G = G_u conj(t)
                     // G = G_u conj(t)
-                    static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = cmulc(v[q], Lme[q * LQ]); });
+                    if (active) static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = cmulc(v[q], Lme[q * LQ]); });
                     __syncthreads();
                     land(LAND_SLAB, tile);
                     SWEEP_STAMP(6);
@@ -242,19 +278,19 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                         if (has_next) deferred = LAND_IN;
                     } else {
                         float2* gp = p.grad + tile_off + (Lme - L);
-                        static_for<E>([&](auto Q) __attribute__((always_inline)) {
+                        if (active) static_for<E>([&](auto Q) __attribute__((always_inline)) {
                             constexpr int q = decltype(Q)::value;
                             const float2 w = cmulc(Lme[q * LQ], v[q]);
                             gp[q * LQ] = make_float2(-kdz * w.y, -kdz * w.x);
                         });
                         __syncthreads();
-                        if (has_next) land(LAND_IN, tile + gridDim.x);
+                        if (has_next) land(LAND_IN, tile + tile_step);
                     }
                 }
             }
             if (half == 1) SWEEP_STAMP(8);
             const bool conv = (half == 0) ? (p.conv1 != 0) : (p.conv2 != 0);
-            if (conv) {
+            if (conv && active) {
                 if constexpr (!COL && LPC >= 2) {
                     if (p.stagger_ns > 0 && l >= LPC / 2) __nanosleep(p.stagger_ns);
                 }
@@ -281,7 +317,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                     if constexpr (PC::SHIFT && (q % P) != 0) v[q] = cmul_conj(v[q], st.cmod[q % P]);
                     else v[q] = conjf2(v[q]);
                 });
-            } else {
+            } else if (!conv) {
                 deferred_landing();
             }
         }
@@ -295,7 +331,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                 pending = true;
             } else {
                 float2* op = p.out + tile_off + (Lme - L);
-                static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; op[q * LQ] = v[q]; });
+                if (active) static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; op[q * LQ] = v[q]; });
             }
         }
         SWEEP_STAMP(10);
@@ -308,6 +344,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
         tma_store_tile(&tm_out, tile - gridDim.x);
     }
     if (COL && tid == 0) bulk_wait_group_read0();
+    SWEEP_GSTAMP(30);
 }
 
 }  // namespace bdof

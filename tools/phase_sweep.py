@@ -27,6 +27,7 @@ plan.adjoint(db, g, grad_out=gout)
 torch.cuda.synchronize()
 b = buf.cpu().numpy().reshape(4, -1, 32)
 names = ['start', 'landed', 'read/swap', 'conv1', 'db-wait', 'transmit', 'mid-a', 'slab-wait', 'mid-b', 'conv2', 'stored']
+gbase = min(b[k][b[k][:, 27] != 0][:, 27].min() for k in range(4) if (b[k][:, 27] != 0).any())
 for k, kn in enumerate(['x forward', 'x adjoint', 'y forward', 'y adjoint']):
     r = b[k]
     r = r[r[:, 0] != 0]
@@ -46,3 +47,10 @@ for k, kn in enumerate(['x forward', 'x adjoint', 'y forward', 'y adjoint']):
             out.append('%s %.0f' % (names[c], np.mean(cur - prev)))
             prev = cur
         print('  tile %d (%d warps): total %.0f | ' % (ti, ok.sum(), np.mean(st[:, 10] - st[:, 0])) + ' | '.join(out))
+
+    # kernel-level timeline from %globaltimer (ns): entry, after prologue, after griddepcontrol.wait, exit
+    g = r[:, 27:31].astype(np.float64)
+    t0 = gbase
+    print('  kernel timeline (us, relative to the first recorded CTA entry of any sweep kernel; forward records slices 4 (x) and 5 (y), adjoint 1 (y) and 0 (x): entry %.1f..%.1f | prologue done %.1f..%.1f | dependency wait done %.1f..%.1f | exit %.1f..%.1f'
+          % tuple(x / 1e3 for x in ((g[:, 0] - t0).min(), (g[:, 0] - t0).max(), (g[:, 1] - t0).min(), (g[:, 1] - t0).max(),
+                                   (g[:, 2] - t0).min(), (g[:, 2] - t0).max(), (g[:, 3] - t0).min(), (g[:, 3] - t0).max())))
