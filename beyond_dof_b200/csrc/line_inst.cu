@@ -71,14 +71,17 @@ static int launch_pipe_col(const LineParams& p, long long n_lines, cudaStream_t 
     } else {
         using SM = PipeSmem<PipeCfg<Cfg, P>, LPC, true>;
         auto kern = pipe_col_conv_kernel<Cfg, LPC, P>;
-        static bool ready = false;
-        if (!ready) {
+        static int ctas_per_sm = 0;
+        if (ctas_per_sm == 0) {
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::BYTES)));
-            ready = true;
+            int occ = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::T * LPC, SM::BYTES));
+            if (occ < 1) return bdof_fail(BDOF_E_UNSUPPORTED, "column pass does not fit on an SM (%zu bytes smem)", SM::BYTES);
+            ctas_per_sm = occ > 8 ? 8 : occ;
         }
         if (n_lines % LPC != 0) return bdof_fail(BDOF_E_UNSUPPORTED, "line count %lld not a multiple of %d", n_lines, LPC);
         const long long n_tiles = n_lines / LPC;
-        const long long slots = sm_count() > bdof_sm_reserve() ? sm_count() - bdof_sm_reserve() : 1;
+        const long long slots = (long long)ctas_per_sm * (sm_count() > bdof_sm_reserve() ? sm_count() - bdof_sm_reserve() : 1);
         const unsigned grid = unsigned(n_tiles < slots ? n_tiles : slots);
         // the field as a matrix [batch * N rows][lines_per_batch columns]; a tile lands in boxes of LPC columns
         alignas(64) CUtensorMap tm, tmo;
@@ -97,17 +100,20 @@ static int launch_sweep(const SweepParams& p0, long long rows, int cols, cudaStr
     } else {
         using SM = PipeSmem<PipeCfg<Cfg, P>, LPC, COL>;
         auto kern = sweep_kernel<Cfg, LPC, P, COL, ADJ>;
-        static bool ready = false;
-        if (!ready) {
+        static int ctas_per_sm = 0;           // per instantiation: short lines leave room for several CTAs per SM
+        if (ctas_per_sm == 0) {
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::BYTES)));
-            ready = true;
+            int occ = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::T * LPC, SM::BYTES));
+            if (occ < 1) return bdof_fail(BDOF_E_UNSUPPORTED, "sweep kernel does not fit on an SM (%zu bytes smem)", SM::BYTES);
+            ctas_per_sm = occ > 8 ? 8 : occ;
         }
         SweepParams p = p0;
         const long long n_lines = COL ? (rows / Cfg::N) * (long long)cols : rows;
         if (n_lines % LPC != 0) return bdof_fail(BDOF_E_UNSUPPORTED, "line count %lld not a multiple of %d", n_lines, LPC);
         p.n_tiles = int(n_lines / LPC);
         p.lines_per_batch = cols;
-        const long long slots = sm_count() > bdof_sm_reserve() ? sm_count() - bdof_sm_reserve() : 1;
+        const long long slots = (long long)ctas_per_sm * (sm_count() > bdof_sm_reserve() ? sm_count() - bdof_sm_reserve() : 1);
         const unsigned grid = unsigned(p.n_tiles < slots ? p.n_tiles : slots);
         // x kernels whose lines are whole warps: contiguous row ranges per CTA, last tile partial (2048 rows on 148 SMs:
         // 14 rows per CTA = a tile of 8 and a tile of 6 instead of two rounds of 8 with a quarter of the SMs idle)
