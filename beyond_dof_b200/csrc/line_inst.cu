@@ -18,7 +18,7 @@ template <> struct CfgFor<64>   { using C = LineCfg<64, 8, 8, 8, 1>;      static
 template <> struct CfgFor<128>  { using C = LineCfg<128, 8, 16, 8, 1>;    static constexpr int RL = 16, CL = 16; };
 template <> struct CfgFor<256>  { using C = LineCfg<256, 16, 16, 16, 1>;  static constexpr int RL = 8,  CL = 8; };
 template <> struct CfgFor<512>  { using C = LineCfg<512, 16, 32, 16, 1>;  static constexpr int RL = 8,  CL = 8; };
-template <> struct CfgFor<1024> { using C = LineCfg<1024, 32, 32, 32, 1>; static constexpr int RL = 8,  CL = 8; };
+template <> struct CfgFor<1024> { using C = LineCfg<1024, 32, 32, 32, 1>; static constexpr int RL = 4,  CL = 4; };
 #if !defined(BDOF_ALT) || BDOF_ALT == 0
 template <> struct CfgFor<2048> { using C = LineCfg<2048, 32, 64, 32, 1>; static constexpr int RL = 8,  CL = 8; };
 #elif BDOF_ALT == 1     // experiment: 32 elements/thread, three stages
