@@ -17,6 +17,10 @@ _LAZY = {
     'MultislicePlan': 'plan',
     'fullfield_loss_and_grad': 'models',
     'ptycho_loss_and_grad': 'models',
+    'TomographyObjective': 'models',
+    'apply_rotation': 'rotation',
+    'rotation_table': 'rotation',
+    'adam_step': 'rotation',
     'get_kernel': 'util',
     'gen_mesh': 'util',
 }
@@ -26,6 +30,6 @@ def __getattr__(name):
     if name in _LAZY:
         mod = importlib.import_module('.' + _LAZY[name], __name__)
         return getattr(mod, name)
-    if name in ('capi', 'plan', 'propagation', 'models', 'util', 'build', 'dist'):
+    if name in ('capi', 'plan', 'propagation', 'models', 'util', 'build', 'dist', 'rotation', 'tiling'):
         return importlib.import_module('.' + name, __name__)
     raise AttributeError(name)

@@ -19,7 +19,7 @@ SYMBOLS = [
     'bdof_forward', 'bdof_loss_mag', 'bdof_adjoint', 'bdof_pack_db', 'bdof_unpack_db', 'bdof_patch_gather',
     'bdof_patch_scatter_add', 'bdof_cnn_forward', 'bdof_forward_host', 'bdof_plan_workspace_bytes',
     'bdof_free_prop', 'bdof_profile_begin', 'bdof_profile_end', 'bdof_debug_set_buffer', 'bdof_slice_step',
-    'bdof_plan_set_bucket_events', 'bdof_set_sm_reserve',
+    'bdof_plan_set_bucket_events', 'bdof_set_sm_reserve', 'bdof_rotate_gather', 'bdof_rotate_scatter_add', 'bdof_adam_step',
 ]
 
 
@@ -63,6 +63,10 @@ def _load():
     lib.bdof_plan_set_bucket_events.argtypes = [vp, i32, vp]
     lib.bdof_set_sm_reserve.argtypes = [i32]
     lib.bdof_profile_end.argtypes = [vp, i32, vp, vp]
+    i64 = ctypes.c_longlong
+    lib.bdof_rotate_gather.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp]
+    lib.bdof_rotate_scatter_add.argtypes = [vp, i64, vp, vp, i32, i32, i32, vp]
+    lib.bdof_adam_step.argtypes = [vp, vp, vp, vp, i64, i32, f64, f64, f64, f64, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is ctypes.c_int and name not in ('bdof_version', 'bdof_size_supported'):

@@ -956,6 +956,72 @@ extern "C" int bdof_forward_host(bdof_plan* p, const float* h_delta, const float
 }
 
 // ------------------------------------------------------------------------------------------
+// the steps either side of the hot path (cnn_propagator drivers)
+// ------------------------------------------------------------------------------------------
+// obj_rot[z][y][x] = obj[z_old(z,x)][y][x_old(z,x)]   (apply_rotation, cnn_propagator/util.py:374-402; the table is the
+// reference's nearest-neighbour lookup of one angle re-ordered slice-major: lookup[z][x] = (x_old, z_old))
+__global__ void k_rotate_gather(const float2* __restrict__ obj, const int2* __restrict__ lookup, float2* __restrict__ out,
+                                long long out_slice_stride, int ny, int nx, int nz) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, z = blockIdx.z;
+    if (x >= nx) return;
+    const int2 src = lookup[(long long)z * nx + x];
+    out[(long long)z * out_slice_stride + (long long)y * nx + x] = obj[((long long)src.y * ny + y) * nx + src.x];
+}
+// transpose of the gather (what autograd does to the fancy index): grad_obj[z_old][y][x_old] += grad_rot[z][y][x]
+__global__ void k_rotate_scatter_add(const float2* __restrict__ grot, long long slice_stride, const int2* __restrict__ lookup,
+                                     float2* __restrict__ gobj, int ny, int nx, int nz) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, z = blockIdx.z;
+    if (x >= nx) return;
+    const int2 src = lookup[(long long)z * nx + x];
+    const float2 g = grot[(long long)z * slice_stride + (long long)y * nx + x];
+    float* dst = reinterpret_cast<float*>(gobj + ((long long)src.y * ny + y) * nx + src.x);
+    atomicAdd(dst, g.x);
+    atomicAdd(dst + 1, g.y);
+}
+extern "C" int bdof_rotate_gather(const float* d_obj_db, const int32_t* d_lookup_zx, float* d_out_db, long long out_slice_stride_px,
+                                  int ny, int nx, int nz, void* st) {
+    if (!d_obj_db || !d_lookup_zx || !d_out_db || ny < 1 || nx < 1 || nz < 1) return fail(BDOF_E_BADARG, "bad argument");
+    if (ny > 65535 || nz > 65535) return fail(BDOF_E_UNSUPPORTED, "ny / nz > 65535");
+    dim3 grid((nx + 127) / 128, ny, nz);
+    k_rotate_gather<<<grid, 128, 0, (cudaStream_t)st>>>(reinterpret_cast<const float2*>(d_obj_db), reinterpret_cast<const int2*>(d_lookup_zx),
+                                                      reinterpret_cast<float2*>(d_out_db), out_slice_stride_px, ny, nx, nz);
+    return launch_check("k_rotate_gather");
+}
+extern "C" int bdof_rotate_scatter_add(const float* d_grad_rot_db, long long slice_stride_px, const int32_t* d_lookup_zx,
+                                       float* d_grad_obj_db, int ny, int nx, int nz, void* st) {
+    if (!d_grad_rot_db || !d_lookup_zx || !d_grad_obj_db || ny < 1 || nx < 1 || nz < 1) return fail(BDOF_E_BADARG, "bad argument");
+    if (ny > 65535 || nz > 65535) return fail(BDOF_E_UNSUPPORTED, "ny / nz > 65535");
+    dim3 grid((nx + 127) / 128, ny, nz);
+    k_rotate_scatter_add<<<grid, 128, 0, (cudaStream_t)st>>>(reinterpret_cast<const float2*>(d_grad_rot_db), slice_stride_px,
+                                                           reinterpret_cast<const int2*>(d_lookup_zx),
+                                                           reinterpret_cast<float2*>(d_grad_obj_db), ny, nx, nz);
+    return launch_check("k_rotate_scatter_add");
+}
+
+// Adam (apply_gradient_adam, cnn_propagator/util.py:280-291): one fused pass over x, g, m, v
+__global__ void k_adam(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                       float b1, float b2, float omb1, float omb2, float inv_c1, float inv_c2, float step, float eps) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float mi = omb1 * gi + b1 * m[i];          // 1 - b formed in double on the host (1.f - 0.999f is 1.3e-5 off)
+        const float vi = omb2 * (gi * gi) + b2 * v[i];
+        m[i] = mi;
+        v[i] = vi;
+        x[i] = x[i] - step * (mi * inv_c1) / (sqrtf(vi * inv_c2) + eps);
+    }
+}
+extern "C" int bdof_adam_step(float* d_x, const float* d_g, float* d_m, float* d_v, long long n, int i_batch, double step_size,
+                              double b1, double b2, double eps, void* st) {
+    if (!d_x || !d_g || !d_m || !d_v || n < 1 || i_batch < 0) return fail(BDOF_E_BADARG, "bad argument");
+    const double c1 = 1.0 - std::pow(b1, i_batch + 1), c2 = 1.0 - std::pow(b2, i_batch + 1);
+    k_adam<<<LOSS_BLOCKS, 256, 0, (cudaStream_t)st>>>(d_x, d_g, d_m, d_v, n, float(b1), float(b2), float(1.0 - b1), float(1.0 - b2), float(1.0 / c1), float(1.0 / c2),
+                                                    float(step_size), float(eps));
+    return launch_check("k_adam");
+}
+
+// ------------------------------------------------------------------------------------------
 // in-situ kernel timing and the free-space step on its own
 // ------------------------------------------------------------------------------------------
 extern "C" int bdof_profile_begin(bdof_plan* p) {

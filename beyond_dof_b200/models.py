@@ -10,8 +10,10 @@
 The reference differentiates with TF / autograd; here the gradient is the hand-written adjoint
 of the multislice chain (libbdof), returned as the 2-tuple (g_delta, g_beta) that
 `loss_grad = grad(calculate_loss, [0, 1])` returns in the reference.
-Object rotation (tf.contrib.image.rotate / apply_rotation) is the step before the hot path and
-is not part of this round: theta must be 0.
+Object rotation follows the cnn_propagator drivers: the nearest-neighbour lookup of save_rotation_lookup /
+apply_rotation (cnn_propagator/util.py:295-402), applied on the GPU to the native slice-major
+object, and its transpose for the gradient.  (tf.contrib.image.rotate of the TF driver is not reproduced.)
+The ptychography model still requires theta = 0.
 """
 import ctypes
 
@@ -21,6 +23,7 @@ import torch
 from .capi import lib, check
 from .plan import MultislicePlan, _ptr
 from .propagation import _cached_plan, _device, _to_dev, _probe_c64
+from . import rotation as _rot
 
 
 def total_variation_3d(arr):
@@ -55,7 +58,7 @@ def fullfield_loss_and_grad(obj_delta, obj_beta, theta_batch, prj_batch, probe_r
     obj_delta, obj_beta: [Y,X,Z] float32; prj_batch: [B,Y,X] complex or magnitude.
     propagate_last=True follows the TF driver (fullfield.py:107-109); False the NumPy simulator.
     """
-    th = _check_theta(theta_batch)
+    th = np.atleast_1d(np.asarray(theta_batch.cpu() if isinstance(theta_batch, torch.Tensor) else theta_batch, dtype=np.float64))
     B = len(th)
     dev = _device()
     od = _to_dev(obj_delta, torch.float32)
@@ -64,8 +67,12 @@ def fullfield_loss_and_grad(obj_delta, obj_beta, theta_batch, prj_batch, probe_r
     key = ('ff', (B, Y, X, Z), float(energy_ev), float(psize_cm), free_prop_cm, propagate_last, dev.index)
     plan = _cached_plan(key, lambda: MultislicePlan(Y, X, B, Z, energy_ev, psize_cm, free_prop_cm=free_prop_cm,
                                                      propagate_last=propagate_last, store_slices=True))
-    # theta == 0: every batch element sees the unrotated object
-    db = plan.pack(od[None].expand(B, Y, X, Z), ob[None].expand(B, Y, X, Z))
+    # every batch element sees the object rotated by its angle (apply_rotation, cnn_propagator/fullfield.py:95-100)
+    obj_db = pack_object(od, ob)
+    db = torch.empty((Z, B, Y, X, 2), dtype=torch.float32, device=dev)
+    tabs = [_rot.device_table([Y, X, Z], t, dev) for t in th]
+    for b in range(B):
+        _rot.rotate_db(obj_db, tabs[b], out=db[:, b])
     probe = _probe_c64(probe_real, probe_imag, (Y, X))
     exit_wave = plan.forward(db, probe)
     prj = _to_dev(prj_batch, torch.complex64 if (isinstance(prj_batch, torch.Tensor) and prj_batch.is_complex())
@@ -75,9 +82,11 @@ def fullfield_loss_and_grad(obj_delta, obj_beta, theta_batch, prj_batch, probe_r
     loss = loss.clone()
     g_d = g_b = None
     if want_grad:
-        plan.adjoint(db, g_exit)                       # db now holds (dL/ddelta, dL/dbeta) per batch element
-        gd_b, gb_b = plan.unpack(db)
-        g_d, g_b = gd_b.sum(0), gb_b.sum(0)
+        plan.adjoint(db, g_exit)                       # db now holds (dL/ddelta, dL/dbeta) per ROTATED batch element
+        g_obj = torch.zeros_like(obj_db)
+        for b in range(B):
+            _rot.rotate_db_adjoint(db[:, b], tabs[b], g_obj)
+        g_d, g_b = unpack_object(g_obj)
     if alpha_d is not None and alpha_d != 0:
         loss = loss + alpha_d * od.abs().sum()
         if want_grad:
@@ -204,6 +213,66 @@ class FullfieldObjective:
     def step(self, prj_mag_host):
         self.target.copy_(prj_mag_host, non_blocking=True)
         loss = self.step_device(self.target)
+        self.loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.loss_host)
+
+
+
+class TomographyObjective:
+    """One optimiser step of the full-field reconstruction loop (cnn_propagator/fullfield.py:300-360) with the object
+    resident on the GPU in the native layout: rotate the object to every angle of the minibatch, multislice forward,
+    loss, adjoint, back-rotate and accumulate the gradient, all-reduce over the data-parallel ranks, Adam.
+
+    db_obj: [Z,Y,X,2] float32 CUDA tensor (delta, beta), updated in place by step().
+    """
+
+    def __init__(self, db_obj, probe, energy_ev, psize_cm, minibatch_size, free_prop_cm=None, propagate_last=True,
+                 step_size=1e-7):
+        Z, Y, X, _ = db_obj.shape
+        self.shape = (Y, X, Z)
+        self.B = int(minibatch_size)
+        self.plan = MultislicePlan(Y, X, self.B, Z, energy_ev, psize_cm, free_prop_cm=free_prop_cm,
+                                   propagate_last=propagate_last, store_slices=True, device=db_obj.device)
+        self.obj = db_obj
+        self.probe = probe.to(db_obj.device, torch.complex64).contiguous()
+        self.db = torch.empty((Z, self.B, Y, X, 2), dtype=torch.float32, device=db_obj.device)
+        self.grad = torch.zeros_like(db_obj)
+        self.m = torch.zeros_like(db_obj)
+        self.v = torch.zeros_like(db_obj)
+        self.target = torch.empty((self.B, Y, X), dtype=torch.float32, device=db_obj.device)
+        self.exit = torch.empty((self.B, Y, X), dtype=torch.complex64, device=db_obj.device)
+        self.loss_host = torch.empty((), dtype=torch.float64).pin_memory()
+        self.step_size = float(step_size)
+        self.i_batch = 0
+        self._dp = None
+
+    def enable_data_parallel(self):
+        from . import dist as bdist
+        self._dp = bdist
+        return self
+
+    def loss_and_grad(self, theta_batch, target_dev):
+        dev = self.obj.device
+        tabs = [_rot.device_table(self.shape, float(t), dev) for t in theta_batch]
+        for b in range(self.B):
+            _rot.rotate_db(self.obj, tabs[b], out=self.db[:, b])
+        self.plan.forward(self.db, self.probe, out=self.exit)
+        loss, g = self.plan.loss_mag(self.exit, target_dev)
+        self.plan.adjoint(self.db, g)
+        self.grad.zero_()
+        for b in range(self.B):
+            _rot.rotate_db_adjoint(self.db[:, b], tabs[b], self.grad)
+        if self._dp is not None:
+            self._dp.finish_allreduce(self.grad, self._dp.allreduce_gradient(self.grad, average=True))
+        return loss
+
+    def step(self, theta_batch, prj_mag_host):
+        """prj_mag_host: [B,Y,X] float32 (pinned host or device); returns this rank's data-fidelity loss."""
+        self.target.copy_(prj_mag_host, non_blocking=True)
+        loss = self.loss_and_grad(theta_batch, self.target)
+        _rot.adam_step(self.obj, self.grad, self.i_batch, self.m, self.v, step_size=self.step_size)
+        self.i_batch += 1
         self.loss_host.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(self.loss_host)

@@ -1,0 +1,113 @@
+"""Object rotation and the optimiser step: the stages either side of the multislice hot path in the
+cnn_propagator drivers.
+
+  rotation_table      <- save_rotation_lookup   cnn_propagator/util.py:295-336 (one angle)
+  apply_rotation      <- apply_rotation         cnn_propagator/util.py:374-402
+  rotate_db / rotate_db_adjoint                 the same on the native slice-major object (CUDA gather / scatter-add)
+  adam_step           <- apply_gradient_adam    cnn_propagator/util.py:280-291
+
+The lookup table is host logic (a few KB per angle) and is built here exactly as the reference builds
+it; applying it to the object and back-projecting the gradient are CUDA kernels of libbdof.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .capi import lib, check
+from .plan import _ptr
+
+
+def rotation_table(array_size, theta):
+    """Nearest-neighbour source pixel (x_old, z_old), clipped to the array, of every rotated pixel (x, z) --
+    flattened with z fastest -- for a rotation by theta about axis 0 around floor(size / 2)
+    (save_rotation_lookup, util.py:295-336).  array_size = [Y, X, Z]; returns int64 [X * Z, 2]."""
+    if array_size[1] != array_size[2]:
+        # the reference drivers only build tables for [dim_y, dim_x, dim_x] (fullfield.py:213); its reshape of the
+        # tiled coordinate vector (util.py:305-307) is not a rotation otherwise
+        if theta == 0:
+            x = np.repeat(np.arange(array_size[1]), array_size[2])
+            return np.stack([x, np.tile(np.arange(array_size[2]), array_size[1])], axis=1)      # identity
+        raise ValueError('rotation needs a square (x, z) cross-section, got X=%d, Z=%d' % (array_size[1], array_size[2]))
+    cy, cx, cz = (np.floor(v / 2) for v in array_size)
+    x = np.repeat(np.arange(array_size[1]), array_size[2]) - cx          # util.py:305-307, 314
+    z = np.tile(np.arange(array_size[2]), array_size[1]) - cz            # util.py:303, 315
+    coord_new = np.stack([x, z]).astype(np.float32)                      # util.py:318
+    m_rot = np.array([[np.cos(theta), -np.sin(theta)],
+                      [np.sin(theta), np.cos(theta)]])
+    coord_old = np.matmul(m_rot, coord_new)
+    x_old = np.clip(np.round(coord_old[0] + cx).astype(int), 0, array_size[1] - 1)
+    z_old = np.clip(np.round(coord_old[1] + cz).astype(int), 0, array_size[2] - 1)
+    return np.stack([x_old, z_old], axis=1)
+
+
+_tables = {}
+
+
+def device_table(array_size, theta, device, coord_old=None):
+    """The table of one angle on the device, re-ordered slice-major: int32 [Z, X, 2] = (x_old, z_old) of pixel (z, x)."""
+    key = (tuple(int(v) for v in array_size), float(theta), str(device)) if coord_old is None else None
+    if key is not None and key in _tables:
+        return _tables[key]
+    tab = rotation_table(array_size, theta) if coord_old is None else np.asarray(coord_old)
+    X, Z = int(array_size[1]), int(array_size[2])
+    t = torch.as_tensor(np.ascontiguousarray(tab.reshape(X, Z, 2).transpose(1, 0, 2)).astype(np.int32)).to(device)
+    if key is not None:
+        if len(_tables) > 512:
+            _tables.clear()
+        _tables[key] = t
+    return t
+
+
+def rotate_db(db_obj, table_zx, out=None):
+    """db_obj [Z, Y, X, 2] float32 (CUDA) -> rotated object, same layout.  `out` may be a [Z, Y, X, 2] view with a
+    larger slice stride (one batch element of a plan's [Z, B, Y, X, 2] object)."""
+    Z, Y, X, _ = db_obj.shape
+    if out is None:
+        out = torch.empty_like(db_obj)
+    assert out.shape == db_obj.shape and out.stride()[1:] == (X * 2, 2, 1) and out.stride(0) % 2 == 0
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib.bdof_rotate_gather(_ptr(db_obj), _ptr(table_zx), _ptr(out), out.stride(0) // 2, Y, X, Z, st))
+    return out
+
+
+def rotate_db_adjoint(grad_rot, table_zx, grad_obj):
+    """grad_obj [Z, Y, X, 2] += transpose-of-rotation(grad_rot); grad_rot may be a strided batch-element view."""
+    Z, Y, X, _ = grad_obj.shape
+    assert grad_rot.shape == grad_obj.shape and grad_rot.stride()[1:] == (X * 2, 2, 1) and grad_obj.is_contiguous()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib.bdof_rotate_scatter_add(_ptr(grad_rot), grad_rot.stride(0) // 2, _ptr(table_zx), _ptr(grad_obj), Y, X, Z, st))
+    return grad_obj
+
+
+def apply_rotation(obj, coord_old, src_folder=None):
+    """Drop-in for cnn_propagator/util.py:374 -- obj [Y, X, Z, C] (NumPy or torch), coord_old the [X*Z, 2] table of one
+    angle (read_origin_coords / rotation_table); src_folder is accepted and ignored (the reference re-reads its
+    coordinate vectors from there).  Runs on the GPU for C == 2 float32 objects; returns the container kind it was given."""
+    is_np = not isinstance(obj, torch.Tensor)
+    t = torch.as_tensor(np.ascontiguousarray(obj)) if is_np else obj
+    if t.shape[-1] != 2:
+        c1 = torch.as_tensor(np.asarray(coord_old)[:, 0].reshape(t.shape[1], t.shape[2]))
+        c2 = torch.as_tensor(np.asarray(coord_old)[:, 1].reshape(t.shape[1], t.shape[2]))
+        out = t[:, c1, c2]
+        return out.numpy() if is_np else out
+    dev = torch.device('cuda', torch.cuda.current_device())
+    Y, X, Z, _ = t.shape
+    db = t.to(dev, torch.float32).permute(2, 0, 1, 3).contiguous()
+    rot = rotate_db(db, device_table([Y, X, Z], None, dev, coord_old=coord_old))
+    out = rot.permute(1, 2, 0, 3).contiguous()
+    return out.cpu().numpy().astype(obj.dtype) if is_np else out.to(obj.dtype)
+
+
+def adam_step(x, g, i_batch, m=None, v=None, step_size=0.001, b1=0.9, b2=0.999, eps=1e-8):
+    """apply_gradient_adam (util.py:280-291) on float32 CUDA tensors, IN PLACE on x, m, v; returns (x, m, v).
+    m, v = None start from zero moments (the first minibatch of the reference)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and g.shape == x.shape
+    if m is None or v is None:
+        m = torch.zeros_like(x)
+        v = torch.zeros_like(x)
+    g = g.to(torch.float32).contiguous()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib.bdof_adam_step(_ptr(x), _ptr(g), _ptr(m), _ptr(v), x.numel(), int(i_batch), float(step_size), float(b1),
+                             float(b2), float(eps), st))
+    return x, m, v

@@ -17,6 +17,8 @@
  *   bdof_pack_db / unpack    <- grid[:, :, :, i] slicing  tensorflow_recon/npfuncs.py:36-37
  *   bdof_patch_gather/scatter<- probe-window cut          tensorflow_recon/ptychography.py:62-76
  *   bdof_cnn_forward         <- multislice_propagate_cnn  cnn_propagator/propagation.py:18-133
+ *   bdof_rotate_gather/scatter<- apply_rotation          cnn_propagator/util.py:374-402
+ *   bdof_adam_step           <- apply_gradient_adam       cnn_propagator/util.py:280-291
  *   bdof_forward_host        <- the whole call with HOST buffers in the reference layout
  *
  * Conventions
@@ -124,6 +126,21 @@ int  bdof_patch_scatter_add(const float* d_grad_patches, int n_slice, int oy, in
 int  bdof_cnn_forward(const float* d_db, const float* d_probe, float* d_exit, float* d_work, int batch,
                       int ny, int nx, int n_slice, const double* h_kernel, int kernel_size, double k_dz,
                       void* cuda_stream);
+
+/* nearest-neighbour rotation of the object about the y axis, in the (x, z) plane, and its transpose
+ * (apply_rotation and the autograd of its fancy index, cnn_propagator/util.py:374-402).  d_obj_db [nz][ny][nx][2];
+ * d_lookup_zx [nz][nx][2] int32 = (x_old, z_old) per rotated pixel: the reference's table of one angle
+ * (save_rotation_lookup, util.py:295-336; beyond_dof_b200/rotation.py builds it) in slice-major order.  Slice z of the
+ * rotated array starts out_slice_stride_px pixels after slice z-1, so it can be a batch element of a plan's db. */
+int  bdof_rotate_gather(const float* d_obj_db, const int32_t* d_lookup_zx, float* d_out_db, long long out_slice_stride_px,
+                        int ny, int nx, int nz, void* cuda_stream);
+int  bdof_rotate_scatter_add(const float* d_grad_rot_db, long long slice_stride_px, const int32_t* d_lookup_zx,
+                             float* d_grad_obj_db, int ny, int nx, int nz, void* cuda_stream);
+
+/* Adam update of apply_gradient_adam (cnn_propagator/util.py:280-291), fused over x, g, m, v (fp32, n values):
+ * m = (1-b1) g + b1 m; v = (1-b2) g^2 + b2 v; x -= step * (m / (1-b1^(i+1))) / (sqrt(v / (1-b2^(i+1))) + eps). */
+int  bdof_adam_step(float* d_x, const float* d_g, float* d_m, float* d_v, long long n, int i_batch, double step_size,
+                    double b1, double b2, double eps, void* cuda_stream);
 
 /* End-to-end convenience with HOST buffers in the reference layout: copies delta/beta
  * [B,Y,X,Z] float32 and the probe to the device, packs, runs bdof_forward, copies the exit wave

@@ -111,9 +111,53 @@ np.savez_compressed(out, **res)
 '''
 
 
+CHILD_ROT = r'''
+import sys, types, os, tempfile
+import numpy as np
+from unittest.mock import MagicMock
+for m in ("tensorflow", "dxchange", "h5py", "matplotlib", "matplotlib.pyplot", "tqdm"):
+    sys.modules[m] = MagicMock()
+ag = types.ModuleType("autograd"); ag.numpy = np; ag.grad = lambda *a, **k: None
+sys.modules.update({"autograd": ag, "autograd.numpy": np, "autograd.numpy.random": np.random})
+np.int = int                                   # util.py:327 uses the alias NumPy removed in 1.24
+sys.path.insert(0, sys.argv[1] + "/cnn_propagator")
+import util
+out = sys.argv[2]
+res = {}
+os.chdir(tempfile.mkdtemp())
+# 8f-1: rotation tables and their application (save_rotation_lookup / apply_rotation, util.py:295-402)
+for tag, size, n_theta in (("a", [6, 16, 16], 7), ("b", [3, 12, 12], 5)):
+    coords = util.save_rotation_lookup(size, n_theta, dest_folder="lk_" + tag)
+    res["rot_%s_size" % tag] = np.array(size)
+    res["rot_%s_coords" % tag] = np.stack(coords).astype(np.int32)
+    rng = np.random.default_rng(61)
+    obj = rng.standard_normal(size + [2])
+    res["rot_%s_obj" % tag] = obj
+    res["rot_%s_out" % tag] = np.stack([util.apply_rotation(obj, util.read_origin_coords("lk_" + tag, i), "lk_" + tag)
+                                        for i in range(n_theta)])
+# 8f-2: Adam (apply_gradient_adam, util.py:280-291), three consecutive updates
+rng = np.random.default_rng(62)
+x = rng.standard_normal((2, 5, 4, 3)) * 1e-6
+m = v = None
+xs = []
+for i in range(3):
+    g = rng.standard_normal(x.shape) * 1e-3
+    res["adam_g%d" % i] = g
+    if i == 0:
+        res["adam_x0"] = x
+        # the reference's first call trips over np.zeros_like(None) (util.py:285); it is only ever called with
+        # m, v = None on the first minibatch, where zero moments are what was meant
+        m = np.zeros_like(x); v = np.zeros_like(x)
+    x, m, v = util.apply_gradient_adam(x, g, i, m, v, step_size=1e-7)
+    xs.append(x)
+res["adam_x"] = np.stack(xs); res["adam_m"] = m; res["adam_v"] = v
+np.savez_compressed(out, **res)
+'''
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    for name, code in (('ref_fft.npz', CHILD_FFT), ('ref_cnn.npz', CHILD_CNN)):
+    for name, code in (('ref_fft.npz', CHILD_FFT), ('ref_cnn.npz', CHILD_CNN), ('ref_rot.npz', CHILD_ROT)):
         path = os.path.join(OUT, name)
         subprocess.run([sys.executable, '-c', code, REF, path, ROOT], check=True)
         print('wrote', path, os.path.getsize(path), 'bytes')

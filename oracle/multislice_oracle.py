@@ -416,3 +416,79 @@ def ptycho_loss_and_grad(obj_delta, obj_beta, probe_pos, prj, probe_real, probe_
         g_d[ys, xs] += gd[n, ys.start - y0:ys.stop - y0, xs.start - x0:xs.stop - x0]
         g_b[ys, xs] += gb[n, ys.start - y0:ys.stop - y0, xs.start - x0:xs.stop - x0]
     return loss * scale, g_d * scale, g_b * scale, psi
+
+
+# ---------------------------------------------------------------------------------------------
+# the steps either side of the hot path in the cnn_propagator drivers
+# ---------------------------------------------------------------------------------------------
+def rotation_lookup(array_size, theta):
+    """Nearest-neighbour rotation table of ONE angle about axis 0, in the (axis 1, axis 2) plane
+    (cnn_propagator/util.py:295-336, save_rotation_lookup): for every rotated pixel (x, z), flattened with z
+    fastest, the clipped source pixel (x_old, z_old).  array_size = [Y, X, Z]."""
+    image_center = [np.floor(x / 2) for x in array_size]
+    coord1 = np.arange(array_size[1])
+    coord2 = np.arange(array_size[2])
+    coord2_vec = np.tile(coord2, array_size[1])                                           # util.py:303
+    coord1_vec = np.tile(coord1, array_size[2])
+    coord1_vec = np.reshape(coord1_vec, [array_size[1], array_size[2]])
+    coord1_vec = np.reshape(np.transpose(coord1_vec), [-1])                               # util.py:305-307
+    coord1_vec = coord1_vec - image_center[1]
+    coord2_vec = coord2_vec - image_center[2]
+    coord_new = np.stack([coord1_vec, coord2_vec]).astype(np.float32)                     # util.py:318
+    m_rot = np.array([[np.cos(theta), -np.sin(theta)],
+                      [np.sin(theta), np.cos(theta)]])
+    coord_old = np.matmul(m_rot, coord_new)
+    coord1_old = np.round(coord_old[0, :] + image_center[1]).astype(int)
+    coord2_old = np.round(coord_old[1, :] + image_center[2]).astype(int)
+    coord1_old = np.clip(coord1_old, 0, array_size[1] - 1)
+    coord2_old = np.clip(coord2_old, 0, array_size[2] - 1)
+    return np.stack([coord1_old, coord2_old], axis=1)                                     # util.py:333
+
+
+def apply_rotation(obj, coord_old):
+    """obj_rot[y, x, z, c] = obj[y, x_old(x, z), z_old(x, z), c]   (cnn_propagator/util.py:374-402)."""
+    s = obj.shape
+    c1 = coord_old[:, 0].reshape(s[1], s[2])
+    c2 = coord_old[:, 1].reshape(s[1], s[2])
+    return obj[:, c1, c2, ...]
+
+
+def apply_rotation_adjoint(grad_rot, coord_old):
+    """Transpose of apply_rotation (what autograd does to the fancy index): scatter-add into the source pixels."""
+    s = grad_rot.shape
+    c1 = coord_old[:, 0].reshape(s[1], s[2])
+    c2 = coord_old[:, 1].reshape(s[1], s[2])
+    out = np.zeros_like(grad_rot)
+    np.add.at(out, (slice(None), c1, c2), grad_rot)
+    return out
+
+
+def apply_gradient_adam(x, g, i_batch, m=None, v=None, step_size=0.001, b1=0.9, b2=0.999, eps=1e-8):
+    """cnn_propagator/util.py:280-291 (first call: zero moments)."""
+    g = np.array(g)
+    if m is None or v is None:
+        m = np.zeros_like(x)
+        v = np.zeros_like(x)
+    m = (1 - b1) * g + b1 * m
+    v = (1 - b2) * (g ** 2) + b2 * v
+    mhat = m / (1 - b1 ** (i_batch + 1))
+    vhat = v / (1 - b2 ** (i_batch + 1))
+    x = x - step_size * mhat / (np.sqrt(vhat) + eps)
+    return x, m, v
+
+
+def tomo_loss_and_grad(obj_delta, obj_beta, theta_batch, prj_batch, probe_real, probe_imag, energy_ev, psize_cm,
+                       free_prop_cm=None, propagate_last=False):
+    """Rotate (nearest-neighbour table) -> multislice -> mean((|psi| - |prj|)^2) over the minibatch, and its
+    gradient w.r.t. the UNROTATED object (calculate_loss of cnn_propagator/fullfield.py:93-107 with the FFT
+    propagator in place of the real-space one)."""
+    Y, X, Z = obj_delta.shape
+    obj = np.stack([obj_delta, obj_beta], axis=3).astype(np.float64)
+    tabs = [rotation_lookup([Y, X, Z], th) for th in theta_batch]
+    rot = np.stack([apply_rotation(obj, t) for t in tabs])                       # [B, Y, X, Z, 2]
+    loss, gd, gb, psi = loss_and_grad(rot[..., 0], rot[..., 1], probe_real, probe_imag, energy_ev, psize_cm,
+                                      prj_batch, free_prop_cm=free_prop_cm, propagate_last=propagate_last)
+    g = np.zeros_like(obj)
+    for b, t in enumerate(tabs):
+        g += apply_rotation_adjoint(np.stack([gd[b], gb[b]], axis=3), t)
+    return loss, g[..., 0], g[..., 1], psi

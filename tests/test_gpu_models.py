@@ -1,5 +1,5 @@
-"""GPU tier: full-field and ptychography forward model + loss + gradient against the oracle
-(rotation = identity: theta = 0), and the real-space 'cnn' propagator against the reference."""
+"""GPU tier: full-field and ptychography forward model + loss + gradient against the oracle, the real-space 'cnn'
+propagator against the reference, and the steps either side of the hot path (rotation, Adam)."""
 import os
 
 import numpy as np
@@ -40,8 +40,9 @@ def test_fullfield_loss_and_grad(bd):
     reg.backward()
     assert abs((loss2 - loss).item() - (reg.item() + 1e-4 * np.abs(ob).sum())) < 1e-6 * reg.item()
     assert rel_l2((g_d2 - g_d).cpu().numpy(), tod.grad.numpy()) < 1e-5
+    # rotation is part of the model now (test_fullfield_loss_and_grad_with_rotation); ptychography still needs theta = 0
     with pytest.raises(NotImplementedError):
-        bd.fullfield_loss_and_grad(od, ob, np.array([0.3]), prj, one, zero, 5000, 1e-7)
+        bd.ptycho_loss_and_grad(od, ob, 0.3, np.array([[32, 32]]), np.ones((1, 64, 64)), one, zero, (64, 64), 5000, 1e-7)
 
 
 def test_ptycho_loss_and_grad_with_padding(bd):
@@ -102,3 +103,88 @@ def test_cnn_propagator_matches_reference(bd, golden_dir):
             ref = gold['cnn_ks%d_%s' % (ks, free)]
             assert rel_l2(np.abs(psi) ** 2, np.abs(ref) ** 2) < 1e-5
             assert rel_l2(psi, ref) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# rotation (nearest-neighbour table of the cnn_propagator drivers), its transpose, Adam
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def gold_rot(golden_dir):
+    return np.load(os.path.join(golden_dir, 'ref_rot.npz'))
+
+
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_apply_rotation_matches_reference_bit_exact(bd, gold_rot, tag):
+    from beyond_dof_b200 import rotation
+    size = [int(v) for v in gold_rot['rot_%s_size' % tag]]
+    coords = gold_rot['rot_%s_coords' % tag]
+    obj = gold_rot['rot_%s_obj' % tag].astype(np.float32)
+    for i, theta in enumerate(np.linspace(0, 2 * np.pi, coords.shape[0])):
+        assert np.array_equal(rotation.rotation_table(size, theta), coords[i])          # host table == save_rotation_lookup
+        out = rotation.apply_rotation(obj, coords[i], 'ignored')
+        assert out.dtype == np.float32 and np.array_equal(out, gold_rot['rot_%s_out' % tag][i].astype(np.float32))
+
+
+def test_rotation_adjoint_matches_oracle_ragged(bd):
+    from beyond_dof_b200 import rotation
+    rng = np.random.default_rng(71)
+    for (Y, X, Z), theta in (((5, 33, 33), 0.3), ((3, 64, 64), 2.1), ((2, 40, 40), 4.0), ((1, 8, 8), 0.0)):
+        g = rng.standard_normal((Y, X, Z, 2)).astype(np.float32)
+        tab = mo.rotation_lookup([Y, X, Z], theta)
+        ref = mo.apply_rotation_adjoint(g.astype(np.float64), tab)
+        dev_tab = rotation.device_table([Y, X, Z], theta, torch.device('cuda'))
+        g_db = torch.as_tensor(g).cuda().permute(2, 0, 1, 3).contiguous()
+        acc = torch.zeros_like(g_db)
+        rotation.rotate_db_adjoint(g_db, dev_tab, acc)
+        assert rel_l2(acc.permute(1, 2, 0, 3).cpu().numpy(), ref) < 1e-6             # fp32 atomics: order-dependent rounding only
+        rot = rotation.rotate_db(g_db, dev_tab)
+        assert np.array_equal(rot.permute(1, 2, 0, 3).cpu().numpy(), mo.apply_rotation(g, tab))
+    # the reference only rotates [dim_y, dim_x, dim_x] objects: other shapes accept the identity only
+    assert np.array_equal(rotation.rotation_table([2, 17, 40], 0.0)[:, 0], np.repeat(np.arange(17), 40))
+    with pytest.raises(ValueError):
+        rotation.rotation_table([2, 17, 40], 0.5)
+
+
+def test_adam_step_matches_reference(bd, gold_rot):
+    from beyond_dof_b200 import rotation
+    x = torch.as_tensor(gold_rot['adam_x0'].astype(np.float32)).cuda()
+    m = v = None
+    for i in range(3):
+        g = torch.as_tensor(gold_rot['adam_g%d' % i].astype(np.float32)).cuda()
+        x, m, v = rotation.adam_step(x, g, i, m, v, step_size=1e-7)
+        assert rel_l2(x.cpu().numpy(), gold_rot['adam_x'][i]) < 2e-6                      # fp32 vs the reference's float64
+    assert rel_l2(m.cpu().numpy(), gold_rot['adam_m']) < 1e-6 and rel_l2(v.cpu().numpy(), gold_rot['adam_v']) < 1e-6
+
+
+def test_fullfield_loss_and_grad_with_rotation(bd):
+    Y, X, Z, B = 64, 64, 64, 3
+    rng = np.random.default_rng(72)
+    od = (rng.random((Y, X, Z)) * 4e-4).astype(np.float32)
+    ob = (rng.random((Y, X, Z)) * 4e-5).astype(np.float32)
+    theta = np.array([0.0, 0.6, 2.5])
+    one, zero = np.ones((Y, X)), np.zeros((Y, X))
+    target = rng.random((B, Y, X)) + 0.5
+    lo, gdo, gbo, psio = mo.tomo_loss_and_grad(od, ob, theta, target, one, zero, 5000, 1e-7, free_prop_cm=None, propagate_last=True)
+    loss, (g_d, g_b), ex = bd.fullfield_loss_and_grad(od, ob, theta, target, one, zero, 5000, 1e-7, propagate_last=True)
+    assert rel_l2(np.abs(ex.cpu().numpy()) ** 2, np.abs(psio) ** 2) < 1e-5
+    assert abs(loss.item() - lo) < 1e-5 * abs(lo)
+    assert rel_l2(g_d.cpu().numpy(), gdo) < 1e-4 and rel_l2(g_b.cpu().numpy(), gbo) < 1e-4
+
+
+def test_tomography_objective_descends(bd):
+    # a few Adam steps of the full loop (rotate -> multislice -> loss -> adjoint -> back-rotate -> Adam) reduce the loss
+    from beyond_dof_b200.models import TomographyObjective, pack_object
+    Y = X = Z = 64
+    rng = np.random.default_rng(73)
+    gt_d = (rng.random((Y, X, Z)) * 2e-3).astype(np.float32)
+    gt_b = (rng.random((Y, X, Z)) * 2e-4).astype(np.float32)
+    theta = np.linspace(0, np.pi, 4)
+    one, zero = np.ones((Y, X)), np.zeros((Y, X))
+    obj = np.stack([gt_d, gt_b], axis=3).astype(np.float64)
+    rot = np.stack([mo.apply_rotation(obj, mo.rotation_lookup([Y, X, Z], t)) for t in theta])
+    prj = np.abs(mo.multislice_propagate_batch(rot[..., 0], rot[..., 1], one, zero, 5000, 1e-7)).astype(np.float32)
+    start = pack_object(np.zeros_like(gt_d), np.zeros_like(gt_b))
+    probe = torch.ones((Y, X), dtype=torch.complex64, device='cuda')
+    tomo = TomographyObjective(start, probe, 5000, 1e-7, minibatch_size=4, step_size=2e-5)
+    losses = [tomo.step(theta, torch.as_tensor(prj)) for _ in range(12)]
+    assert losses[-1] < 0.5 * losses[0]

@@ -176,3 +176,44 @@ def test_ptycho_windows_and_loss_shapes():
     assert np.array_equal(wins[1], obj[1:9, 3:11])
     assert np.all(wins[0][:4, :, :] == 0) and np.all(wins[0][:, :4, :] == 0)
     assert np.array_equal(wins[0][4:, 4:], obj[:4, :4])
+
+
+# ---------------------------------------------------------------------------------------------
+# rotation tables, their application and Adam, pinned by the reference's own functions
+# (oracle/gen_golden.py CHILD_ROT runs cnn_propagator/util.py unmodified)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def gold_rot(golden_dir):
+    return np.load(os.path.join(golden_dir, 'ref_rot.npz'))
+
+
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_rotation_lookup_and_apply_match_reference(gold_rot, tag):
+    size = [int(v) for v in gold_rot['rot_%s_size' % tag]]
+    coords = gold_rot['rot_%s_coords' % tag]
+    n_theta = coords.shape[0]
+    obj = gold_rot['rot_%s_obj' % tag]
+    for i, theta in enumerate(np.linspace(0, 2 * np.pi, n_theta)):        # util.py:321
+        tab = mo.rotation_lookup(size, theta)
+        assert np.array_equal(tab, coords[i])
+        assert np.array_equal(mo.apply_rotation(obj, tab), gold_rot['rot_%s_out' % tag][i])
+
+
+def test_rotation_adjoint_is_the_transpose():
+    rng = np.random.default_rng(3)
+    size = [4, 10, 10]
+    tab = mo.rotation_lookup(size, 0.7)
+    a = rng.standard_normal(size + [2])
+    b = rng.standard_normal(size + [2])
+    lhs = np.sum(mo.apply_rotation(a, tab) * b)
+    rhs = np.sum(a * mo.apply_rotation_adjoint(b, tab))
+    assert abs(lhs - rhs) < 1e-12 * max(1.0, abs(lhs))
+
+
+def test_adam_matches_reference(gold_rot):
+    x = gold_rot['adam_x0']
+    m = v = None
+    for i in range(3):
+        x, m, v = mo.apply_gradient_adam(x, gold_rot['adam_g%d' % i], i, m, v, step_size=1e-7)
+        assert np.array_equal(x, gold_rot['adam_x'][i])
+    assert np.array_equal(m, gold_rot['adam_m']) and np.array_equal(v, gold_rot['adam_v'])
