@@ -19,7 +19,7 @@ SYMBOLS = [
     'bdof_forward', 'bdof_loss_mag', 'bdof_adjoint', 'bdof_pack_db', 'bdof_unpack_db', 'bdof_patch_gather',
     'bdof_patch_scatter_add', 'bdof_cnn_forward', 'bdof_forward_host', 'bdof_plan_workspace_bytes',
     'bdof_free_prop', 'bdof_profile_begin', 'bdof_profile_end', 'bdof_debug_set_buffer', 'bdof_slice_step',
-    'bdof_plan_set_bucket_events', 'bdof_set_sm_reserve', 'bdof_rotate_gather', 'bdof_rotate_scatter_add', 'bdof_adam_step',
+    'bdof_plan_set_bucket_events', 'bdof_set_sm_reserve', 'bdof_rotate_gather', 'bdof_rotate_scatter_add', 'bdof_rotate_adjoint_csr', 'bdof_adam_step',
 ]
 
 
@@ -66,6 +66,7 @@ def _load():
     i64 = ctypes.c_longlong
     lib.bdof_rotate_gather.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp]
     lib.bdof_rotate_scatter_add.argtypes = [vp, i64, vp, vp, i32, i32, i32, vp]
+    lib.bdof_rotate_adjoint_csr.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, vp]
     lib.bdof_adam_step.argtypes = [vp, vp, vp, vp, i64, i32, f64, f64, f64, f64, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)

@@ -228,8 +228,11 @@ class TomographyObjective:
     """
 
     def __init__(self, db_obj, probe, energy_ev, psize_cm, minibatch_size, free_prop_cm=None, propagate_last=True,
-                 step_size=1e-7):
+                 step_size=1e-7, deterministic=False):
         Z, Y, X, _ = db_obj.shape
+        # back-rotation of the gradient: fp32 atomic scatter-add (default, faster) or a gather over inverse lists
+        # (bit-reproducible run to run)
+        self.deterministic = bool(deterministic)
         self.shape = (Y, X, Z)
         self.B = int(minibatch_size)
         self.plan = MultislicePlan(Y, X, self.B, Z, energy_ev, psize_cm, free_prop_cm=free_prop_cm,
@@ -252,6 +255,15 @@ class TomographyObjective:
         self._dp = bdist
         return self
 
+    def prepare(self, thetas):
+        """Build the rotation tables of all angles up front (the reference writes them to disk once and reads them
+        back, save_rotation_lookup / read_all_origin_coords, cnn_propagator/fullfield.py:209-215)."""
+        for t in thetas:
+            tab = _rot.device_table(self.shape, float(t), self.obj.device)
+            if self.deterministic:
+                _rot.device_inverse(tab)
+        return self
+
     def loss_and_grad(self, theta_batch, target_dev):
         dev = self.obj.device
         tabs = [_rot.device_table(self.shape, float(t), dev) for t in theta_batch]
@@ -262,7 +274,7 @@ class TomographyObjective:
         self.plan.adjoint(self.db, g)
         self.grad.zero_()
         for b in range(self.B):
-            _rot.rotate_db_adjoint(self.db[:, b], tabs[b], self.grad)
+            _rot.rotate_db_adjoint(self.db[:, b], tabs[b], self.grad, atomic=not self.deterministic)
         if self._dp is not None:
             self._dp.finish_allreduce(self.grad, self._dp.allreduce_gradient(self.grad, average=True))
         return loss

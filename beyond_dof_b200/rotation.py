@@ -59,6 +59,31 @@ def device_table(array_size, theta, device, coord_old=None):
     return t
 
 
+_inverse = {}
+
+
+def device_inverse(table_zx):
+    """CSR lists of the transpose: for every source pixel (z0, x0) the rotated pixels (z * X + x) that read from it.
+    Host logic (one argsort per angle, cached by table); returns (offsets int32 [Z*X + 1], dest int32 [Z*X]) on the device."""
+    key = table_zx.data_ptr()
+    hit = _inverse.get(key)
+    if hit is not None and hit[0] is table_zx:
+        return hit[1], hit[2]
+    Z, X, _ = table_zx.shape
+    t = table_zx.cpu().numpy().astype(np.int64)
+    src = (t[..., 1] * X + t[..., 0]).reshape(-1)                 # source cell z_old * X + x_old of rotated pixel z * X + x
+    order = np.argsort(src, kind='stable')
+    counts = np.bincount(src, minlength=Z * X)
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    dev = table_zx.device
+    off_d = torch.as_tensor(offsets).to(dev)
+    dest_d = torch.as_tensor(order.astype(np.int32)).to(dev)
+    if len(_inverse) > 512:
+        _inverse.clear()
+    _inverse[key] = (table_zx, off_d, dest_d)
+    return off_d, dest_d
+
+
 def rotate_db(db_obj, table_zx, out=None):
     """db_obj [Z, Y, X, 2] float32 (CUDA) -> rotated object, same layout.  `out` may be a [Z, Y, X, 2] view with a
     larger slice stride (one batch element of a plan's [Z, B, Y, X, 2] object)."""
@@ -71,12 +96,17 @@ def rotate_db(db_obj, table_zx, out=None):
     return out
 
 
-def rotate_db_adjoint(grad_rot, table_zx, grad_obj):
-    """grad_obj [Z, Y, X, 2] += transpose-of-rotation(grad_rot); grad_rot may be a strided batch-element view."""
+def rotate_db_adjoint(grad_rot, table_zx, grad_obj, atomic=False):
+    """grad_obj [Z, Y, X, 2] += transpose-of-rotation(grad_rot); grad_rot may be a strided batch-element view.
+    Default: deterministic gather over the inverse lists of the table; atomic=True: fp32 atomic scatter-add."""
     Z, Y, X, _ = grad_obj.shape
     assert grad_rot.shape == grad_obj.shape and grad_rot.stride()[1:] == (X * 2, 2, 1) and grad_obj.is_contiguous()
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    check(lib.bdof_rotate_scatter_add(_ptr(grad_rot), grad_rot.stride(0) // 2, _ptr(table_zx), _ptr(grad_obj), Y, X, Z, st))
+    if atomic:
+        check(lib.bdof_rotate_scatter_add(_ptr(grad_rot), grad_rot.stride(0) // 2, _ptr(table_zx), _ptr(grad_obj), Y, X, Z, st))
+    else:
+        off, dest = device_inverse(table_zx)
+        check(lib.bdof_rotate_adjoint_csr(_ptr(grad_rot), grad_rot.stride(0) // 2, _ptr(off), _ptr(dest), _ptr(grad_obj), Y, X, Z, st))
     return grad_obj
 
 

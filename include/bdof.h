@@ -137,6 +137,11 @@ int  bdof_rotate_gather(const float* d_obj_db, const int32_t* d_lookup_zx, float
 int  bdof_rotate_scatter_add(const float* d_grad_rot_db, long long slice_stride_px, const int32_t* d_lookup_zx,
                              float* d_grad_obj_db, int ny, int nx, int nz, void* cuda_stream);
 
+/* The same transpose as a deterministic gather: d_offsets [nz*nx + 1] and d_dest [nz*nx] are the CSR lists of the rotated
+ * pixels (z*nx + x) that read from each source pixel (z0*nx + x0); d_grad_obj_db is accumulated into (+=), no atomics. */
+int  bdof_rotate_adjoint_csr(const float* d_grad_rot_db, long long slice_stride_px, const int32_t* d_offsets,
+                             const int32_t* d_dest, float* d_grad_obj_db, int ny, int nx, int nz, void* cuda_stream);
+
 /* Adam update of apply_gradient_adam (cnn_propagator/util.py:280-291), fused over x, g, m, v (fp32, n values):
  * m = (1-b1) g + b1 m; v = (1-b2) g^2 + b2 v; x -= step * (m / (1-b1^(i+1))) / (sqrt(v / (1-b2^(i+1))) + eps). */
 int  bdof_adam_step(float* d_x, const float* d_g, float* d_m, float* d_v, long long n, int i_batch, double step_size,

@@ -134,9 +134,11 @@ def test_rotation_adjoint_matches_oracle_ragged(bd):
         ref = mo.apply_rotation_adjoint(g.astype(np.float64), tab)
         dev_tab = rotation.device_table([Y, X, Z], theta, torch.device('cuda'))
         g_db = torch.as_tensor(g).cuda().permute(2, 0, 1, 3).contiguous()
-        acc = torch.zeros_like(g_db)
-        rotation.rotate_db_adjoint(g_db, dev_tab, acc)
-        assert rel_l2(acc.permute(1, 2, 0, 3).cpu().numpy(), ref) < 1e-6             # fp32 atomics: order-dependent rounding only
+        for atomic in (False, True):                                                # inverse-list gather / atomic scatter-add
+            acc = torch.zeros_like(g_db)
+            rotation.rotate_db_adjoint(g_db, dev_tab, acc, atomic=atomic)
+            rotation.rotate_db_adjoint(g_db, dev_tab, acc, atomic=atomic)          # accumulates
+            assert rel_l2(acc.permute(1, 2, 0, 3).cpu().numpy(), 2 * ref) < 1e-6
         rot = rotation.rotate_db(g_db, dev_tab)
         assert np.array_equal(rot.permute(1, 2, 0, 3).cpu().numpy(), mo.apply_rotation(g, tab))
     # the reference only rotates [dim_y, dim_x, dim_x] objects: other shapes accept the identity only
