@@ -21,6 +21,9 @@ _LAZY = {
     'apply_rotation': 'rotation',
     'rotation_table': 'rotation',
     'adam_step': 'rotation',
+    'finite_support': 'rotation',
+    'ptycho_position_losses': 'models',
+    'dynamic_dropping': 'models',
     'get_kernel': 'util',
     'gen_mesh': 'util',
 }

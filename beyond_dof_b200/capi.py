@@ -20,6 +20,7 @@ SYMBOLS = [
     'bdof_patch_scatter_add', 'bdof_cnn_forward', 'bdof_forward_host', 'bdof_plan_workspace_bytes',
     'bdof_free_prop', 'bdof_profile_begin', 'bdof_profile_end', 'bdof_debug_set_buffer', 'bdof_slice_step',
     'bdof_plan_set_bucket_events', 'bdof_set_sm_reserve', 'bdof_rotate_gather', 'bdof_rotate_scatter_add', 'bdof_rotate_adjoint_csr', 'bdof_adam_step',
+    'bdof_finite_support',
 ]
 
 
@@ -68,6 +69,7 @@ def _load():
     lib.bdof_rotate_scatter_add.argtypes = [vp, i64, vp, vp, i32, i32, i32, vp]
     lib.bdof_rotate_adjoint_csr.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, vp]
     lib.bdof_adam_step.argtypes = [vp, vp, vp, vp, i64, i32, f64, f64, f64, f64, vp]
+    lib.bdof_finite_support.argtypes = [vp, vp, i64, f64, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is ctypes.c_int and name not in ('bdof_version', 'bdof_size_supported'):

@@ -84,8 +84,17 @@ extern "C" unsigned long long bdof_launch_count(void) { return g_launches.load()
 // line-kernel dispatch: one translation unit per FFT length (line_inst.cu, -DBDOF_N=...)
 // ------------------------------------------------------------------------------------------
 extern "C" int bdof_size_supported(int n) {
+    // 1: power-of-two lengths with register-resident kernels (and sweep kernels up to 4096); 2: mixed-radix passes
     switch (n) { case 64: case 128: case 256: case 512: case 1024: case 2048: case 4096: case 8192: return 1; }
-    return 0;
+    return bdof_generic_supported(n) ? 2 : 0;
+}
+static std::vector<float2> make_full_twiddles(int n) {
+    std::vector<float2> tw(n);
+    for (int k = 0; k < n; ++k) {
+        const double a = -2.0 * M_PI * double(k) / double(n);
+        tw[k] = make_float2(float(cos(a)), float(sin(a)));
+    }
+    return tw;
 }
 
 static int launch_variant(int n, int variant, const LineParams& p, long long n_lines, cudaStream_t st) {
@@ -377,6 +386,7 @@ struct bdof_plan {
     long long F;               // batch*ny*nx
     AxisTables ax, ay;
     bool have_kernel = false, full_kernel = false;
+    bool generic = false;      // a side is not one of the power-of-two lengths: every pass runs the mixed-radix kernel (genericfft.cu)
     bool sweep = true;         // one kernel per slice and direction (sweepfft.cuh); BDOF_SWEEP=0 at plan creation selects the
                                // per-pass kernels (row pass + column pass per slice) instead
     bool row_prefetch = false; // row passes L2-prefetch their own side inputs at tile start (BDOF_ROW_PREFETCH=1 enables; measured slower)
@@ -449,7 +459,7 @@ extern "C" int bdof_kernel_factors(double dist_nm, double lmbda_nm, const double
 extern "C" int bdof_plan_create(bdof_plan** out, int ny, int nx, int batch, int n_slice, uint32_t flags, void* cuda_stream) {
     if (!out || ny < 1 || nx < 1 || batch < 1 || n_slice < 1) return fail(BDOF_E_BADARG, "bad plan shape");
     if (!bdof_size_supported(ny) || !bdof_size_supported(nx))
-        return fail(BDOF_E_UNSUPPORTED, "field %dx%d: each side must be a power of two in [64, 8192]", ny, nx);
+        return fail(BDOF_E_UNSUPPORTED, "field %dx%d: each side must be a power of two in [64, 8192] or 2^a 3^b 5^c 7^d <= 2048", ny, nx);
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     bdof_plan* p = new bdof_plan();
@@ -457,15 +467,21 @@ extern "C" int bdof_plan_create(bdof_plan** out, int ny, int nx, int batch, int 
     p->stream = (cudaStream_t)cuda_stream;
     p->F = (long long)batch * ny * nx;
     p->ax.n = nx; p->ay.n = ny;
+    p->generic = bdof_size_supported(ny) != 1 || bdof_size_supported(nx) != 1;
     if (const char* e = getenv("BDOF_SWEEP")) p->sweep = (e[0] != '0');
     if (const char* e = getenv("BDOF_L2_PREFETCH")) p->l2_prefetch = (e[0] != '0');
     if (const char* e = getenv("BDOF_ROW_PREFETCH")) p->row_prefetch = (e[0] != '0');
     int r = 0;
     do {
-        if ((r = upload(&p->ax.tw, make_twiddles(nx)))) break;
-        if ((r = upload(&p->ay.tw, make_twiddles(ny)))) break;
-        if ((r = upload(&p->ax.tw_pipe, make_twiddles_pipe(nx)))) break;
-        if ((r = upload(&p->ay.tw_pipe, make_twiddles_pipe(ny)))) break;
+        if (p->generic) {
+            if ((r = upload(&p->ax.tw, make_full_twiddles(nx)))) break;
+            if ((r = upload(&p->ay.tw, make_full_twiddles(ny)))) break;
+        } else {
+            if ((r = upload(&p->ax.tw, make_twiddles(nx)))) break;
+            if ((r = upload(&p->ay.tw, make_twiddles(ny)))) break;
+            if ((r = upload(&p->ax.tw_pipe, make_twiddles_pipe(nx)))) break;
+            if ((r = upload(&p->ay.tw_pipe, make_twiddles_pipe(ny)))) break;
+        }
         cudaError_t e;
         if ((e = cudaMalloc((void**)&p->tmp, p->F * sizeof(float2))) != cudaSuccess) { r = fail(int(e), "cudaMalloc tmp: %s", cudaGetErrorString(e)); break; }
         if ((e = cudaMalloc((void**)&p->work[0], p->F * sizeof(float2))) != cudaSuccess) { r = fail(int(e), "cudaMalloc work: %s", cudaGetErrorString(e)); break; }
@@ -580,12 +596,13 @@ static int timed_launch(bdof_plan* p, int n, int variant, const LineParams& q0, 
     if (g_dbg) q.dbg = g_dbg + (long long)pv * (1 << 17);     // one region per pass variant
     { static int flags = -1; if (flags < 0) { const char* e = getenv("BDOF_DBG_FLAGS"); flags = e ? atoi(e) : 0; } q.dbg_flags = flags; }
     { static int tune = -1; if (tune < 0) { const char* e = getenv("BDOF_TUNE"); tune = e ? atoi(e) : 0; } q.tune = tune; }
-    if (!p->profile) return launch_variant(n, variant, q, n_lines, p->stream);
+    auto launch = [&]() { return p->generic ? bdof_launch_line_generic(n, variant, q, n_lines, p->stream) : launch_variant(n, variant, q, n_lines, p->stream); };
+    if (!p->profile) return launch();
     cudaEvent_t a, b;
     CUDA_TRY(cudaEventCreate(&a));
     CUDA_TRY(cudaEventCreate(&b));
     CUDA_TRY(cudaEventRecord(a, p->stream));
-    int r = launch_variant(n, variant, q, n_lines, p->stream);
+    int r = launch();
     CUDA_TRY(cudaEventRecord(b, p->stream));
     p->prof_events.push_back(a); p->prof_events.push_back(b);
     p->prof_variant.push_back(pv);
@@ -600,7 +617,7 @@ static bool use_pipe() {
     return v == 1;
 }
 static int col_pass(bdof_plan* p, int variant, const LineParams& q) {
-    if (variant == V_COL_CONV && use_pipe() && pipe_parts(p->ny) > 0) {
+    if (variant == V_COL_CONV && !p->generic && use_pipe() && pipe_parts(p->ny) > 0) {
         LineParams q2 = q;
         q2.tw = p->ay.tw_pipe;
         return timed_launch(p, p->ny, V_COL_CONV_PIPE, q2, (long long)p->batch * p->nx);
@@ -612,7 +629,7 @@ static int col_pass(bdof_plan* p, int variant, const LineParams& q) {
 // sweep kernels: one launch per slice and direction (sweepfft.cuh)
 // ------------------------------------------------------------------------------------------
 static bool use_sweep(const bdof_plan* p) {
-    return p->sweep && !p->full_kernel && p->n_slice >= 2 && pipe_parts(p->nx) > 0 && pipe_parts(p->ny) > 0;
+    return p->sweep && !p->generic && !p->full_kernel && p->n_slice >= 2 && pipe_parts(p->nx) > 0 && pipe_parts(p->ny) > 0;
 }
 // kernel of slice i: x kernel (rows) for even i, y kernel (columns) for odd i
 static int sweep_launch(bdof_plan* p, int i, bool adj, SweepParams q) {
@@ -1049,6 +1066,26 @@ extern "C" int bdof_adam_step(float* d_x, const float* d_g, float* d_m, float* d
     k_adam<<<LOSS_BLOCKS, 256, 0, (cudaStream_t)st>>>(d_x, d_g, d_m, d_v, n, float(b1), float(b2), float(1.0 - b1), float(1.0 - b2), float(1.0 / c1), float(1.0 / c2),
                                                     float(step_size), float(eps));
     return launch_check("k_adam");
+}
+
+// finite support + non-negativity + shrink-wrap (cnn_propagator/fullfield.py:359-368): x <- clip(x * mask, 0, inf) on both
+// channels of the interleaved object; shrink_threshold >= 0 also updates mask <- mask * (delta > threshold)
+__global__ void k_finite_support(float2* __restrict__ x, float* __restrict__ mask, long long npx, float shrink_threshold) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+        float2 v = x[i];
+        if (mask != nullptr) {
+            const float mk = mask[i];
+            v.x *= mk; v.y *= mk;
+        }
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f);
+        x[i] = v;
+        if (mask != nullptr && shrink_threshold >= 0.f) mask[i] = mask[i] * (v.x > shrink_threshold ? 1.f : 0.f);
+    }
+}
+extern "C" int bdof_finite_support(float* d_x_db, float* d_mask, long long n_px, double shrink_threshold, void* st) {
+    if (!d_x_db || n_px < 1) return fail(BDOF_E_BADARG, "bad argument");
+    k_finite_support<<<LOSS_BLOCKS, 256, 0, (cudaStream_t)st>>>(reinterpret_cast<float2*>(d_x_db), d_mask, n_px, float(shrink_threshold));
+    return launch_check("k_finite_support");
 }
 
 // ------------------------------------------------------------------------------------------

@@ -130,6 +130,10 @@ namespace bdof { struct SweepParams; }
 BDOF_DECL_LINE(64) BDOF_DECL_LINE(128) BDOF_DECL_LINE(256) BDOF_DECL_LINE(512)
 BDOF_DECL_LINE(1024) BDOF_DECL_LINE(2048) BDOF_DECL_LINE(4096) BDOF_DECL_LINE(8192)
 
+// mixed-radix passes for the other lengths (genericfft.cu): 2^a 3^b 5^c 7^d <= 2048, p.tw = full table W_N^k
+int bdof_generic_supported(int n);
+int bdof_launch_line_generic(int n, int variant, const bdof::LineParams& p, long long n_lines, cudaStream_t st);
+
 #define CUDA_TRY(expr)                                                                        \
     do {                                                                                      \
         cudaError_t _e = (expr);                                                              \

@@ -13,7 +13,7 @@ of the multislice chain (libbdof), returned as the 2-tuple (g_delta, g_beta) tha
 Object rotation follows the cnn_propagator drivers: the nearest-neighbour lookup of save_rotation_lookup /
 apply_rotation (cnn_propagator/util.py:295-402), applied on the GPU to the native slice-major
 object, and its transpose for the gradient.  (tf.contrib.image.rotate of the TF driver is not reproduced.)
-The ptychography model still requires theta = 0.
+The ptychography model rotates the same way (calculate_loss, cnn_propagator/ptychography.py:30-34).
 """
 import ctypes
 
@@ -42,11 +42,11 @@ def _tv_grad(arr):
     return g
 
 
-def _check_theta(theta):
+def _scalar_theta(theta):
     th = np.atleast_1d(np.asarray(theta.cpu() if isinstance(theta, torch.Tensor) else theta, dtype=np.float64))
-    if np.any(th != 0):
-        raise NotImplementedError('object rotation is not part of the multislice hot path yet: theta must be 0')
-    return th
+    if th.size != 1:
+        raise ValueError('the ptychography model evaluates one rotation angle per call (ptychography.py:292-297)')
+    return float(th[0])
 
 
 def fullfield_loss_and_grad(obj_delta, obj_beta, theta_batch, prj_batch, probe_real, probe_imag, energy_ev, psize_cm,
@@ -123,7 +123,8 @@ def unpack_object(db_obj):
 def ptycho_loss_and_grad(obj_delta, obj_beta, theta, probe_pos_batch, prj_batch, probe_real, probe_imag, probe_size,
                          energy_ev, psize_cm, n_dp_batch=None, scale_by_npos=True, n_pos_total=None, want_grad=True,
                          db_obj=None, grad_obj_out=None):
-    """Ptychography forward model + loss + gradient for one rotation angle (theta = 0).
+    """Ptychography forward model + loss + gradient for one rotation angle theta (radians; the object is rotated with the
+    reference's nearest-neighbour table first, cnn_propagator/ptychography.py:32-34, and the gradient rotated back).
 
     probe_pos_batch: integer (y, x) scan positions; the window of size probe_size starts at
     pos - int(probe_size/2) and is zero-padded outside the object (ptychography.py:45-76).
@@ -132,13 +133,17 @@ def ptycho_loss_and_grad(obj_delta, obj_beta, theta, probe_pos_batch, prj_batch,
     Returns (loss, (g_delta, g_beta)); with db_obj / grad_obj_out (slice-major [Z,Y,X,2]) the
     object and its gradient stay in the native layout and (loss, grad_obj_out) is returned.
     """
-    _check_theta(theta)
+    th = _scalar_theta(theta)
     dev = _device()
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     native = db_obj is not None
     if not native:
         db_obj = pack_object(obj_delta, obj_beta)
     Z, OY, OX, _ = db_obj.shape
+    tab = None
+    if th != 0.0:
+        tab = _rot.device_table([OY, OX, Z], th, dev)
+        db_obj = _rot.rotate_db(db_obj, tab)
     py, px = int(probe_size[0]), int(probe_size[1])
     pos = np.asarray(probe_pos_batch.cpu() if isinstance(probe_pos_batch, torch.Tensor) else probe_pos_batch).astype(np.int64)
     n = len(pos)
@@ -161,10 +166,59 @@ def ptycho_loss_and_grad(obj_delta, obj_beta, theta, probe_pos_batch, prj_batch,
     plan.adjoint(patches, g_exit)
     if grad_obj_out is None:
         grad_obj_out = torch.zeros_like(db_obj)
-    check(lib.bdof_patch_scatter_add(_ptr(patches), Z, OY, OX, _ptr(origin), n, py, px, _ptr(grad_obj_out), st))
+    if tab is None:
+        check(lib.bdof_patch_scatter_add(_ptr(patches), Z, OY, OX, _ptr(origin), n, py, px, _ptr(grad_obj_out), st))
+    else:
+        g_rot = torch.zeros_like(db_obj)
+        check(lib.bdof_patch_scatter_add(_ptr(patches), Z, OY, OX, _ptr(origin), n, py, px, _ptr(g_rot), st))
+        _rot.rotate_db_adjoint(g_rot, tab, grad_obj_out)
     if native:
         return loss, grad_obj_out
     return loss, unpack_object(grad_obj_out)
+
+
+def ptycho_position_losses(obj_delta, obj_beta, theta, probe_pos, prj, probe_real, probe_imag, probe_size, energy_ev,
+                           psize_cm, n_dp_batch=256, db_obj=None):
+    """Loss of every scan position on its own, mean((|Psi_j| - |prj_j|)^2) -- the loss table of the reference's "dynamic
+    dropping" pass (cnn_propagator/ptychography.py:323-342, one calculate_loss call per position there; batched here)."""
+    pos = np.asarray(probe_pos.cpu() if isinstance(probe_pos, torch.Tensor) else probe_pos).astype(np.int64)
+    if db_obj is None:
+        db_obj = pack_object(obj_delta, obj_beta)
+    out = []
+    for s0 in range(0, len(pos), n_dp_batch):
+        sl = slice(s0, min(s0 + n_dp_batch, len(pos)))
+        ex = _ptycho_exit_waves(db_obj, theta, pos[sl], probe_real, probe_imag, probe_size, energy_ev, psize_cm)
+        p = prj[sl]
+        is_cplx = (isinstance(p, torch.Tensor) and p.is_complex()) or np.iscomplexobj(p)
+        target = _to_dev(p, torch.complex64 if is_cplx else torch.float32).abs().to(torch.float32)
+        out.append(((ex.abs() - target) ** 2).mean(dim=(1, 2)))
+    return torch.cat(out)
+
+
+def dynamic_dropping(loss_table, dropping_threshold=8e-5):
+    """Indices of the scan positions to KEEP: the reference drops those whose loss is below the threshold
+    (ptychography.py:340-342; its np.delete result is discarded there, i.e. the shipped code drops nothing)."""
+    lt = loss_table.detach().cpu().numpy() if isinstance(loss_table, torch.Tensor) else np.asarray(loss_table)
+    return np.where(lt >= dropping_threshold)[0]
+
+
+def _ptycho_exit_waves(db_obj, theta, pos, probe_real, probe_imag, probe_size, energy_ev, psize_cm):
+    dev = _device()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    th = _scalar_theta(theta)
+    Z, OY, OX, _ = db_obj.shape
+    if th != 0.0:
+        db_obj = _rot.rotate_db(db_obj, _rot.device_table([OY, OX, Z], th, dev))
+    py, px = int(probe_size[0]), int(probe_size[1])
+    n = len(pos)
+    half = (np.array([py, px]) / 2).astype('int')
+    origin = torch.as_tensor((pos - half[None, :]).astype(np.int32)).to(dev).contiguous()
+    key = ('ptyf', (n, py, px, Z), float(energy_ev), float(psize_cm), dev.index)
+    plan = _cached_plan(key, lambda: MultislicePlan(py, px, n, Z, energy_ev, psize_cm, free_prop_cm='inf',
+                                                     propagate_last=True, store_slices=False))
+    patches = torch.empty((Z, n, py, px, 2), dtype=torch.float32, device=dev)
+    check(lib.bdof_patch_gather(_ptr(db_obj), Z, OY, OX, _ptr(origin), n, py, px, _ptr(patches), st))
+    return plan.forward(patches, _probe_c64(probe_real, probe_imag, (py, px)))
 
 
 class FullfieldObjective:
@@ -228,8 +282,14 @@ class TomographyObjective:
     """
 
     def __init__(self, db_obj, probe, energy_ev, psize_cm, minibatch_size, free_prop_cm=None, propagate_last=True,
-                 step_size=1e-7, deterministic=False):
+                 step_size=1e-7, deterministic=False, mask=None, shrink_threshold=None, alpha_d=None, alpha_b=None, gamma=0.0):
         Z, Y, X, _ = db_obj.shape
+        # finite-support mask [Z,Y,X] float32 (native order), non-negativity and shrink-wrap after every update
+        # (cnn_propagator/fullfield.py:359-368); L1 / TV regularisers of the TF driver (fullfield.py:389-396)
+        self.mask = None if mask is None else mask.to(db_obj.device, torch.float32).contiguous()
+        self.clip = mask is not None or shrink_threshold is not None
+        self.shrink_threshold = shrink_threshold
+        self.alpha_d, self.alpha_b, self.gamma = alpha_d, alpha_b, gamma
         # back-rotation of the gradient: fp32 atomic scatter-add (default, faster) or a gather over inverse lists
         # (bit-reproducible run to run)
         self.deterministic = bool(deterministic)
@@ -277,6 +337,16 @@ class TomographyObjective:
             _rot.rotate_db_adjoint(self.db[:, b], tabs[b], self.grad, atomic=not self.deterministic)
         if self._dp is not None:
             self._dp.finish_allreduce(self.grad, self._dp.allreduce_gradient(self.grad, average=True))
+        # regularisers act on the (replicated) object: added after the exchange, identical on every rank
+        if self.alpha_d:
+            self.grad[..., 0] += self.alpha_d * torch.sign(self.obj[..., 0])
+            loss = loss + self.alpha_d * self.obj[..., 0].abs().sum()
+        if self.alpha_b:
+            self.grad[..., 1] += self.alpha_b * torch.sign(self.obj[..., 1])
+            loss = loss + self.alpha_b * self.obj[..., 1].abs().sum()
+        if self.gamma:
+            self.grad[..., 0] += self.gamma * _tv_grad(self.obj[..., 0])
+            loss = loss + self.gamma * total_variation_3d(self.obj[..., 0])
         return loss
 
     def step(self, theta_batch, prj_mag_host):
@@ -284,6 +354,8 @@ class TomographyObjective:
         self.target.copy_(prj_mag_host, non_blocking=True)
         loss = self.loss_and_grad(theta_batch, self.target)
         _rot.adam_step(self.obj, self.grad, self.i_batch, self.m, self.v, step_size=self.step_size)
+        if self.clip:
+            _rot.finite_support(self.obj, self.mask, self.shrink_threshold)
         self.i_batch += 1
         self.loss_host.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -141,3 +141,16 @@ def adam_step(x, g, i_batch, m=None, v=None, step_size=0.001, b1=0.9, b2=0.999, 
     check(lib.bdof_adam_step(_ptr(x), _ptr(g), _ptr(m), _ptr(v), x.numel(), int(i_batch), float(step_size), float(b1),
                              float(b2), float(eps), st))
     return x, m, v
+
+
+def finite_support(db_obj, mask=None, shrink_threshold=None):
+    """Finite support, non-negativity and shrink-wrap of cnn_propagator/fullfield.py:359-368 on the native object
+    [..., 2] float32 (CUDA), IN PLACE: obj <- clip(obj * mask, 0); with shrink_threshold (the reference: 1e-15) the
+    mask (float32, one value per pixel, same leading shape) is multiplied by (delta > threshold)."""
+    assert db_obj.is_cuda and db_obj.dtype == torch.float32 and db_obj.is_contiguous() and db_obj.shape[-1] == 2
+    if mask is not None:
+        assert mask.is_cuda and mask.dtype == torch.float32 and mask.is_contiguous() and mask.numel() == db_obj.numel() // 2
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib.bdof_finite_support(_ptr(db_obj), None if mask is None else _ptr(mask), db_obj.numel() // 2,
+                                  -1.0 if shrink_threshold is None else float(shrink_threshold), st))
+    return db_obj

@@ -19,6 +19,7 @@
  *   bdof_cnn_forward         <- multislice_propagate_cnn  cnn_propagator/propagation.py:18-133
  *   bdof_rotate_gather/scatter<- apply_rotation          cnn_propagator/util.py:374-402
  *   bdof_adam_step           <- apply_gradient_adam       cnn_propagator/util.py:280-291
+ *   bdof_finite_support      <- mask, clip, shrink-wrap   cnn_propagator/fullfield.py:359-368
  *   bdof_forward_host        <- the whole call with HOST buffers in the reference layout
  *
  * Conventions
@@ -47,7 +48,7 @@ typedef struct bdof_plan bdof_plan;
 enum {
     BDOF_OK = 0,
     BDOF_E_BADARG = -1,       /* null pointer / non-positive size */
-    BDOF_E_UNSUPPORTED = -2,  /* field size not a supported FFT length */
+    BDOF_E_UNSUPPORTED = -2,  /* field size not a supported FFT length (see bdof_size_supported) */
     BDOF_E_STATE = -3,        /* call order (e.g. adjoint before a storing forward) */
     BDOF_E_NOMEM = -4
 };
@@ -68,7 +69,9 @@ const char* bdof_last_error(void);
 /* number of kernels launched by this library since load (all plans, this process) */
 unsigned long long bdof_launch_count(void);
 
-/* FFT lengths the line kernels are compiled for; returns 1/0 */
+/* FFT lengths: 1 = power of two in [64, 8192] (register-resident line kernels; sweep kernels up to 4096),
+ * 2 = any other 2^a 3^b 5^c 7^d <= 2048 (mixed-radix shared-memory passes: the reference's 72 x 72 and 18 x 18
+ * ptychography probes, tensorflow_recon/reconstruct_ptycho.py), 0 = unsupported */
 int  bdof_size_supported(int n);
 
 /* Separable factors of the reference transfer function, float64 on the host:
@@ -146,6 +149,11 @@ int  bdof_rotate_adjoint_csr(const float* d_grad_rot_db, long long slice_stride_
  * m = (1-b1) g + b1 m; v = (1-b2) g^2 + b2 v; x -= step * (m / (1-b1^(i+1))) / (sqrt(v / (1-b2^(i+1))) + eps). */
 int  bdof_adam_step(float* d_x, const float* d_g, float* d_m, float* d_v, long long n, int i_batch, double step_size,
                     double b1, double b2, double eps, void* cuda_stream);
+
+/* finite support, non-negativity and shrink-wrap after every update (cnn_propagator/fullfield.py:359-368):
+ * x <- clip(x * mask, 0, inf) on both channels of the interleaved object d_x_db [n_px][2]; d_mask [n_px] fp32 is nullable
+ * (clip only); shrink_threshold >= 0 also updates mask <- mask * (delta > shrink_threshold) (the reference uses 1e-15). */
+int  bdof_finite_support(float* d_x_db, float* d_mask, long long n_px, double shrink_threshold, void* cuda_stream);
 
 /* End-to-end convenience with HOST buffers in the reference layout: copies delta/beta
  * [B,Y,X,Z] float32 and the probe to the device, packs, runs bdof_forward, copies the exit wave

@@ -33,7 +33,9 @@ def test_version_and_sizes(capi):
     assert capi.lib.bdof_version() >= 100
     for n in (64, 128, 256, 512, 1024, 2048, 4096, 8192):
         assert capi.lib.bdof_size_supported(n) == 1
-    for n in (0, 18, 48, 72, 100, 16384):
+    for n in (18, 48, 72, 100, 45, 1000, 1536):              # mixed-radix passes (genericfft.cu)
+        assert capi.lib.bdof_size_supported(n) == 2
+    for n in (0, 1, 37, 74, 2049, 3072, 16384):
         assert capi.lib.bdof_size_supported(n) == 0
 
 
@@ -67,7 +69,7 @@ def test_python_util_matches_oracle_and_factorisation():
 def test_bad_arguments_are_rejected(capi):
     h = ctypes.c_void_p()
     assert capi.lib.bdof_plan_create(ctypes.byref(h), 0, 64, 1, 1, 0, None) == -1          # BDOF_E_BADARG
-    assert capi.lib.bdof_plan_create(ctypes.byref(h), 72, 64, 1, 1, 0, None) == -2         # BDOF_E_UNSUPPORTED
+    assert capi.lib.bdof_plan_create(ctypes.byref(h), 74, 64, 1, 1, 0, None) == -2         # BDOF_E_UNSUPPORTED
     assert b'power of two' in capi.lib.bdof_last_error()
     assert capi.lib.bdof_forward(None, None, None, None) == -1
 

@@ -40,9 +40,6 @@ def test_fullfield_loss_and_grad(bd):
     reg.backward()
     assert abs((loss2 - loss).item() - (reg.item() + 1e-4 * np.abs(ob).sum())) < 1e-6 * reg.item()
     assert rel_l2((g_d2 - g_d).cpu().numpy(), tod.grad.numpy()) < 1e-5
-    # rotation is part of the model now (test_fullfield_loss_and_grad_with_rotation); ptychography still needs theta = 0
-    with pytest.raises(NotImplementedError):
-        bd.ptycho_loss_and_grad(od, ob, 0.3, np.array([[32, 32]]), np.ones((1, 64, 64)), one, zero, (64, 64), 5000, 1e-7)
 
 
 def test_ptycho_loss_and_grad_with_padding(bd):
@@ -61,6 +58,29 @@ def test_ptycho_loss_and_grad_with_padding(bd):
     # oracle model head agrees with the literal restatement of the TF loss
     l2, _ = mo.ptycho_loss(od, ob, pos, prj, pr, pi, probe_size, 5000, 1e-7)
     assert abs(l2 - lo) < 1e-12 * abs(lo)
+
+
+@pytest.mark.parametrize('probe_size', [(72, 72), (18, 18), (64, 64)])
+def test_ptycho_rotated_object_and_reference_probe_sizes(bd, probe_size):
+    # rotated object (apply_rotation before the window cut, cnn_propagator/ptychography.py:32-34) and the reference's own
+    # probe sizes (72 x 72: reconstruct_ptycho.py; 18 x 18: the 4x down-sampled pass) -> mixed-radix line passes
+    Y, X, Z = 100, 90, 5
+    od, ob = mo.random_phantom((Y, X, Z), seed=64, delta_scale=3e-4, beta_scale=3e-5)
+    gt_d, gt_b = mo.random_phantom((Y, X, Z), seed=65, delta_scale=5e-3, beta_scale=5e-3)
+    pr, pi = mo.gaussian_probe(probe_size, 6., 6., 0.5)
+    pos = [(2, 3), (50, 45), (99, 89), (30, 70), (71, 20)]
+    theta = 0.7
+    tab = mo.rotation_lookup([Y, X, Z], theta)
+
+    def rot(a, b):
+        r = mo.apply_rotation(np.stack([a, b], axis=3).astype(np.float64), tab)
+        return r[..., 0], r[..., 1]
+    _, prj = mo.ptycho_loss(*rot(gt_d, gt_b), pos, np.zeros((len(pos),) + probe_size), pr, pi, probe_size, 5000, 1e-7)
+    lo, gdr, gbr, _ = mo.ptycho_loss_and_grad(*rot(od, ob), pos, prj, pr, pi, probe_size, 5000, 1e-7)
+    go = mo.apply_rotation_adjoint(np.stack([gdr, gbr], axis=3), tab)
+    loss, (g_d, g_b) = bd.ptycho_loss_and_grad(od, ob, theta, pos, prj, pr, pi, probe_size, 5000, 1e-7)
+    assert abs(loss.item() - lo) < 1e-5 * abs(lo)
+    assert rel_l2(g_d.cpu().numpy(), go[..., 0]) < 1e-4 and rel_l2(g_b.cpu().numpy(), go[..., 1]) < 1e-4
 
 
 def test_ptycho_gradient_matches_torch_autograd_small(bd):
@@ -190,3 +210,71 @@ def test_tomography_objective_descends(bd):
     tomo = TomographyObjective(start, probe, 5000, 1e-7, minibatch_size=4, step_size=2e-5)
     losses = [tomo.step(theta, torch.as_tensor(prj)) for _ in range(12)]
     assert losses[-1] < 0.5 * losses[0]
+
+
+def test_finite_support_clip_and_shrink_wrap(bd):
+    # obj <- clip(obj * mask, 0); mask <- mask * (delta > 1e-15)   (cnn_propagator/fullfield.py:359-368)
+    from beyond_dof_b200 import rotation
+    rng = np.random.default_rng(81)
+    obj = (rng.standard_normal((5, 7, 9, 2)) * 1e-5).astype(np.float32)
+    mask = (rng.random((5, 7, 9)) > 0.3).astype(np.float32)
+    x = torch.as_tensor(obj).cuda()
+    m = torch.as_tensor(mask).cuda()
+    rotation.finite_support(x, m, shrink_threshold=1e-15)
+    ref = np.clip(obj * mask[..., None], 0, None)
+    assert np.array_equal(x.cpu().numpy(), ref)
+    assert np.array_equal(m.cpu().numpy(), mask * (ref[..., 0] > 1e-15))
+    y = torch.as_tensor(obj).cuda()
+    rotation.finite_support(y)                       # clip only
+    assert np.array_equal(y.cpu().numpy(), np.clip(obj, 0, None))
+
+
+def test_ptycho_position_losses_and_dynamic_dropping(bd):
+    Y, X, Z = 96, 96, 4
+    probe_size = (72, 72)
+    od, ob = mo.random_phantom((Y, X, Z), seed=82, delta_scale=3e-4, beta_scale=3e-5)
+    pr, pi = mo.gaussian_probe(probe_size, 6., 6., 0.5)
+    pos = [(40, 40), (10, 80), (60, 50), (48, 48)]
+    _, prj = mo.ptycho_loss(od, ob, pos, np.zeros((len(pos),) + probe_size), pr, pi, probe_size, 5000, 1e-7)
+    prj = np.abs(prj)
+    prj[1] *= 1.5                                    # positions 1 and 2 do not fit the data
+    prj[2] += 0.3
+    table = bd.ptycho_position_losses(od, ob, 0.0, pos, prj, pr, pi, probe_size, 5000, 1e-7, n_dp_batch=3)
+    ref = [mo.ptycho_loss(od, ob, [p], prj[j:j + 1], pr, pi, probe_size, 5000, 1e-7, scale_by_npos=False)[0] for j, p in enumerate(pos)]
+    t = table.cpu().numpy()
+    assert np.all(np.abs(t[1:3] - np.array(ref[1:3])) < 1e-4 * np.array(ref[1:3]))
+    assert t[0] < 1e-6 * t[1] and t[3] < 1e-6 * t[1]            # exact fits: only fp32 rounding left
+    assert list(bd.dynamic_dropping(table, dropping_threshold=1e-3 * t[1])) == [1, 2]
+
+
+def test_tomography_objective_regularisers_and_support(bd):
+    # L1 + TV terms (tensorflow_recon/fullfield.py:389-396) and the finite-support mask in the update loop
+    from beyond_dof_b200.models import TomographyObjective, pack_object, unpack_object
+    Y = X = Z = 64
+    rng = np.random.default_rng(83)
+    od = (rng.random((Y, X, Z)) * 4e-4).astype(np.float32)
+    ob = (rng.random((Y, X, Z)) * 4e-5).astype(np.float32)
+    theta = np.array([0.0, 1.1])
+    one, zero = np.ones((Y, X)), np.zeros((Y, X))
+    target = (rng.random((2, Y, X)) + 0.5).astype(np.float32)
+    lo, gdo, gbo, _ = mo.tomo_loss_and_grad(od, ob, theta, target, one, zero, 5000, 1e-7, free_prop_cm=None, propagate_last=True)
+    a_d, a_b, gam = 1e-2, 2e-2, 3e-3
+    tv = sum(np.abs(np.roll(od.astype(np.float64), 1, ax) - od).sum() for ax in range(3))
+    lo_reg = lo + a_d * np.abs(od).sum() + a_b * np.abs(ob).sum() + gam * tv
+    tod = torch.tensor(od.astype(np.float64), requires_grad=True)
+    (a_d * tod.abs().sum() + gam * sum((torch.roll(tod, 1, ax) - tod).abs().sum() for ax in range(3))).backward()
+    probe = torch.ones((Y, X), dtype=torch.complex64, device='cuda')
+    mask = torch.zeros((Z, Y, X), device='cuda'); mask[:, 8:56, 8:56] = 1
+    tomo = TomographyObjective(pack_object(od, ob), probe, 5000, 1e-7, minibatch_size=2, step_size=1e-6, mask=mask,
+                               alpha_d=a_d, alpha_b=a_b, gamma=gam)
+    tgt = torch.as_tensor(target).cuda()
+    loss = tomo.loss_and_grad(theta, tgt)
+    assert abs(float(loss) - lo_reg) < 1e-5 * abs(lo_reg)
+    g_d, g_b = unpack_object(tomo.grad)
+    assert rel_l2(g_d.cpu().numpy(), gdo + tod.grad.numpy()) < 1e-4
+    assert rel_l2(g_b.cpu().numpy(), gbo + a_b * np.sign(ob)) < 1e-4
+    tomo.step(theta, tgt)
+    d, b = unpack_object(tomo.obj)
+    outside = np.ones((Y, X, Z), bool); outside[8:56, 8:56, :] = False
+    assert np.all(d.cpu().numpy()[outside] == 0) and np.all(b.cpu().numpy()[outside] == 0)
+    assert d.min().item() >= 0 and b.min().item() >= 0

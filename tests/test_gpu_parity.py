@@ -154,9 +154,70 @@ def test_forward_torch_containers_and_unbatched(bd):
 
 def test_unsupported_size_fails_loudly(bd):
     from beyond_dof_b200.capi import BdofError
-    z = np.zeros((1, 48, 80, 2), np.float32)
+    z = np.zeros((1, 74, 80, 2), np.float32)                  # 74 = 2 * 37: not a 2^a 3^b 5^c 7^d length
     with pytest.raises(BdofError):
-        bd.multislice_propagate_batch_numpy(z, z, np.ones((48, 80)), np.zeros((48, 80)), 5000, 1e-7, obj_batch_shape=z.shape)
+        bd.multislice_propagate_batch_numpy(z, z, np.ones((74, 80)), np.zeros((74, 80)), 5000, 1e-7, obj_batch_shape=z.shape)
+
+
+# ---------------------------------------------------------------------------------------------
+# mixed-radix passes (genericfft.cu): the reference's 72 x 72 and 18 x 18 probes, ragged and odd sizes
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('shape', [(3, 72, 72, 5), (2, 18, 18, 4), (1, 96, 45, 3), (2, 63, 100, 2), (1, 1000, 24, 2), (1, 64, 72, 3)])
+@pytest.mark.parametrize('propagate_last', [False, True])
+@pytest.mark.parametrize('free', [None, 'inf', 1e-4])
+def test_mixed_radix_forward_and_adjoint_match_oracle(bd, shape, propagate_last, free):
+    gd, gb = mo.random_phantom(shape, seed=61, delta_scale=5e-4, beta_scale=5e-5)
+    pr, pi = mo.gaussian_probe(shape[1:3], 6., 6., 0.5)        # reconstruct_ptycho.py:92-94
+    pr = pr + 0.2
+    rng = np.random.default_rng(62)
+    target = rng.random(shape[:3]) * (np.sqrt(shape[1] * shape[2]) if free == 'inf' else 1.0) + 0.5
+    lo, gdo, gbo, psio = mo.loss_and_grad(gd.astype(np.float64), gb.astype(np.float64), pr, pi, 5000, 1e-7, target,
+                                          free_prop_cm=free, propagate_last=propagate_last)
+    l, g_d, g_b, psi = _gpu_loss_and_grad(bd, gd, gb, pr, pi, 5000, 1e-7, target, free, propagate_last)
+    assert intensity_err(psi, psio) < TOL_INTENSITY
+    assert rel_l2(psi, psio) < 1e-5
+    assert abs(l - lo) < 1e-5 * abs(lo)
+    assert rel_l2(g_d, gdo) < TOL_GRAD and rel_l2(g_b, gbo) < TOL_GRAD
+
+
+def test_mixed_radix_reference_golden_vectors(bd, gold):
+    # outputs of the reference's own multislice_propagate_batch_numpy (oracle/gen_golden.py cases B, C, E)
+    gd, gb = mo.random_phantom((2, 48, 80, 12), seed=11, delta_scale=3e-4, beta_scale=3e-5)
+    pr, pi = mo.gaussian_probe((48, 80), 9., 9., 0.5)
+    psi = bd.multislice_propagate_batch_numpy(gd, gb, pr, pi, 800, 0.67e-7, free_prop_cm=None, obj_batch_shape=gd.shape)
+    assert intensity_err(psi, gold['psi_rand48x80']) < TOL_INTENSITY and rel_l2(psi, gold['psi_rand48x80']) < 1e-5
+    psi = bd.multislice_propagate_batch_numpy(gd, gb, pr, pi, 800, 0.67e-7, free_prop_cm='inf', obj_batch_shape=gd.shape)
+    assert intensity_err(psi, gold['psi_rand48x80_inf']) < TOL_INTENSITY
+    gd, gb = mo.random_phantom((3, 32, 32, 1), seed=13, delta_scale=1e-3, beta_scale=1e-4)
+    psi = bd.multislice_propagate_batch_numpy(gd, gb, np.ones([32, 32]), np.zeros([32, 32]), 5000, 1e-7, obj_batch_shape=gd.shape)
+    assert rel_l2(psi, gold['psi_rand32_1slice']) < 2e-6
+
+
+def test_mixed_radix_general_kernel_and_probe_gradient(bd):
+    from beyond_dof_b200.plan import MultislicePlan
+    shape = (2, 72, 48, 3)
+    gd, gb = mo.random_phantom(shape, seed=63, delta_scale=3e-4, beta_scale=3e-5)
+    one, zero = np.ones(shape[1:3]), np.zeros(shape[1:3])
+    u, v = mo.gen_mesh([0.5, 0.5], shape[1:3])
+    h2 = np.exp(1j * 2 * np.pi / 0.248 * 1.0 * (np.sqrt(1 - 0.248 ** 2 * (u ** 2 + v ** 2)) - 1))
+    psi = bd.multislice_propagate_batch(gd, gb, one, zero, 5000, 1e-7, h=h2, obj_batch_shape=shape)
+    ref = mo.multislice_propagate_batch(gd.astype(np.float64), gb.astype(np.float64), one, zero, 5000, 1e-7, h=h2,
+                                        obj_batch_shape=shape)
+    assert rel_l2(psi, ref) < 1e-5
+    # operator-level adjoint incl. the probe gradient
+    rng = np.random.default_rng(64)
+    G = (rng.standard_normal(shape[:3]) + 1j * rng.standard_normal(shape[:3])).astype(np.complex64)
+    psio, slices = mo.multislice_forward(gd.astype(np.float64), gb.astype(np.float64), one, zero, 5000, 1e-7, return_slices=True)
+    gdo, gbo, gpo = mo.multislice_adjoint(gd.astype(np.float64), gb.astype(np.float64), slices, G.astype(np.complex128), 5000, 1e-7)
+    B, Y, X, Z = shape
+    plan = MultislicePlan(Y, X, B, Z, 5000, 1e-7, store_slices=True)
+    db = plan.pack(torch.as_tensor(gd).cuda(), torch.as_tensor(gb).cuda())
+    plan.forward(db, torch.ones((Y, X), dtype=torch.complex64, device='cuda'))
+    gout = torch.empty_like(db)
+    _, gp = plan.adjoint(db, torch.as_tensor(G).cuda(), grad_out=gout, want_probe_grad=True)
+    g_d, g_b = plan.unpack(gout)
+    assert rel_l2(g_d.cpu().numpy(), gdo) < TOL_GRAD and rel_l2(g_b.cpu().numpy(), gbo) < TOL_GRAD
+    assert rel_l2(gp.cpu().numpy(), gpo) < 1e-5
 
 
 # ---------------------------------------------------------------------------------------------
