@@ -64,11 +64,11 @@ def test_ptycho_loss_and_grad_with_padding(bd):
 def test_ptycho_rotated_object_and_reference_probe_sizes(bd, probe_size):
     # rotated object (apply_rotation before the window cut, cnn_propagator/ptychography.py:32-34) and the reference's own
     # probe sizes (72 x 72: reconstruct_ptycho.py; 18 x 18: the 4x down-sampled pass) -> mixed-radix line passes
-    Y, X, Z = 100, 90, 5
+    Y, X, Z = 100, 40, 40                         # the reference's rotation tables need a square (x, z) cross-section
     od, ob = mo.random_phantom((Y, X, Z), seed=64, delta_scale=3e-4, beta_scale=3e-5)
     gt_d, gt_b = mo.random_phantom((Y, X, Z), seed=65, delta_scale=5e-3, beta_scale=5e-3)
     pr, pi = mo.gaussian_probe(probe_size, 6., 6., 0.5)
-    pos = [(2, 3), (50, 45), (99, 89), (30, 70), (71, 20)]
+    pos = [(2, 3), (50, 20), (99, 39), (30, 35), (71, 12)]
     theta = 0.7
     tab = mo.rotation_lookup([Y, X, Z], theta)
 
