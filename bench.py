@@ -224,7 +224,23 @@ def run_gpu(args):
         # data-parallel exchange (Horovod allreduce in fullfield.py:412; comm.Allreduce in cnn fullfield.py:350):
         # mean of the object gradient over ranks, reduced in z-buckets on a communication stream while the
         # adjoint sweep is still producing the remaining slices
-        obj.enable_data_parallel(n_buckets=args.buckets)
+        # default: copy engines over NVLink peer memory (no communication kernels on the SMs the sweep kernels own);
+        # --exchange nccl = bucketed NCCL all-reduce.  If the peer-memory set-up fails on any rank, all fall back to NCCL.
+        exchange_used = args.exchange
+        if args.exchange == 'ce':
+            ok, why = 1, ''
+            try:
+                obj.enable_data_parallel(n_buckets=args.buckets, exchange='ce')
+            except Exception as ex:               # noqa: BLE001
+                ok, why = 0, '%s: %s' % (type(ex).__name__, ex)
+            t_ok = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+            if int(t_ok.item()) == 0:
+                print('[rank %d] copy-engine exchange unavailable (%s): falling back to NCCL' % (rank, why or 'another rank failed'), file=sys.stderr, flush=True)
+                exchange_used = 'nccl (copy-engine set-up failed)'
+                obj.enable_data_parallel(n_buckets=args.buckets, exchange='nccl')
+        else:
+            obj.enable_data_parallel(n_buckets=args.buckets, exchange='nccl')
         if sm_reserve:
             capi.check(capi.lib.bdof_set_sm_reserve(sm_reserve))
 
@@ -344,8 +360,9 @@ def run_gpu(args):
             'vs_baseline': None, 'dtype': 'c64', 'data': 'synthetic',
             'config': {'workload': desc, 'ny': ny, 'nx': nx, 'n_slice': nz, 'batch_per_gpu': B, 'semantics': 'numpy (last slice modulates only)',
                        'l2': 'inputs larger than L2 (%.1f GB of delta/beta + %.1f GB slice store per GPU streamed every step)' % (db.numel() * 4 / 1e9, db.numel() * 4 / 1e9),
-                       'parallelism': ('dp%d: one field per GPU, NCCL all-reduce (mean) of the object gradient in %d z-buckets overlapped with the adjoint sweep, %d SMs left to NCCL'
-                                       % (world, args.buckets, sm_reserve)) if world > 1 else 'single GPU'},
+                       'parallelism': ('dp%d: one field per GPU; mean of the object gradient (%.1f GB) over ranks every step in %d z-buckets overlapped with the adjoint sweep; exchange: %s'
+                                       % (world, db.numel() * 4 / 1e9, args.buckets,
+                                          'copy engines over NVLink peer memory (push partial shards, owner sums, gather)' if exchange_used == 'ce' else exchange_used)) if world > 1 else 'single GPU'},
             'e2e': {'value': e2e_value, 'unit': 'Gpixel*slice/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'api': 'beyond_dof_b200.models.FullfieldObjective.step(projection magnitudes in pinned host memory) -> loss'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'kernels': kern, 'cpu_baseline': cpu,
@@ -382,7 +399,7 @@ def run_config4(args):
     probe = torch.ones((n, n), dtype=torch.complex64, device=dev)
     tomo = TomographyObjective(obj, probe, ENERGY_EV, PSIZE_CM, minibatch_size=mb, free_prop_cm=1e-4, propagate_last=True, step_size=1e-7)
     if world > 1:
-        tomo.enable_data_parallel()
+        tomo.enable_data_parallel(exchange=args.exchange)
     thetas = np.linspace(0, np.pi, n_theta)
     mine = thetas[rank::world]
     tomo.prepare(mine)
@@ -448,6 +465,7 @@ def main():
     ap.add_argument('--impl', default='bdof', choices=['bdof', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
     ap.add_argument('--sm-reserve', type=int, default=0, help='SMs left free for NCCL while the sweep runs (N > 1)')
+    ap.add_argument('--exchange', default='ce', choices=['ce', 'nccl'], help='N > 1: gradient exchange (copy engines over peer memory, or NCCL all-reduce)')
     ap.add_argument('--buckets', type=int, default=8, help='z-buckets of the gradient all-reduce (N > 1)')
     ap.add_argument('--shape', default=None, help='experiment: B,NY,NX,NZ overrides the workload shape')
     ap.add_argument('--diag', action='store_true', help='N > 1: print the plain all-reduce time and the step time without exchange')

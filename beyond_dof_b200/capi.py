@@ -21,6 +21,8 @@ SYMBOLS = [
     'bdof_free_prop', 'bdof_profile_begin', 'bdof_profile_end', 'bdof_debug_set_buffer', 'bdof_slice_step',
     'bdof_plan_set_bucket_events', 'bdof_set_sm_reserve', 'bdof_rotate_gather', 'bdof_rotate_scatter_add', 'bdof_rotate_adjoint_csr', 'bdof_adam_step',
     'bdof_finite_support',
+    'bdof_dp_create', 'bdof_dp_destroy', 'bdof_dp_handle_bytes', 'bdof_dp_export', 'bdof_dp_connect', 'bdof_dp_grad_ptr',
+    'bdof_dp_bucket', 'bdof_dp_finish',
 ]
 
 
@@ -70,9 +72,19 @@ def _load():
     lib.bdof_rotate_adjoint_csr.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, vp]
     lib.bdof_adam_step.argtypes = [vp, vp, vp, vp, i64, i32, f64, f64, f64, f64, vp]
     lib.bdof_finite_support.argtypes = [vp, vp, i64, f64, vp]
+    sz = ctypes.c_size_t
+    lib.bdof_dp_create.argtypes = [ctypes.POINTER(vp), i32, i32, sz, i32]
+    lib.bdof_dp_destroy.argtypes = [vp]
+    lib.bdof_dp_destroy.restype = None
+    lib.bdof_dp_handle_bytes.argtypes = []
+    lib.bdof_dp_export.argtypes = [vp, vp]
+    lib.bdof_dp_connect.argtypes = [vp, vp]
+    lib.bdof_dp_grad_ptr.argtypes = [vp, ctypes.POINTER(vp)]
+    lib.bdof_dp_bucket.argtypes = [vp, sz, sz, vp]
+    lib.bdof_dp_finish.argtypes = [vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if fn.restype is ctypes.c_int and name not in ('bdof_version', 'bdof_size_supported'):
+        if fn.restype is ctypes.c_int and name not in ('bdof_version', 'bdof_size_supported', 'bdof_dp_handle_bytes'):
             fn.restype = i32
     return lib
 

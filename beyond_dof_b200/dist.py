@@ -12,9 +12,13 @@ gradient is all-reduced every optimiser step:
 Here the exchange is one NCCL all-reduce of the slice-major object gradient [Z, ..., 2] (fp32), optionally
 issued bucket by bucket along z on a communication stream while the adjoint sweep is still producing
 the remaining slices (a slice's gradient is final once the backward sweep has passed it).
-Everything in this file is host logic: it runs unchanged over gloo on CPU tensors (tests) and over
-NCCL on CUDA tensors (production).
+Everything above CopyEngineExchange is host logic: it runs unchanged over gloo on CPU tensors (tests) and over
+NCCL on CUDA tensors.  CopyEngineExchange is the production exchange on one NVLink box: the same mean over ranks, moved
+by the copy engines between peer-mapped buffers (libbdof, csrc/dpexchange.cu) so that no communication kernel competes
+with the persistent sweep kernels for SMs; torch.distributed only carries the 64-byte IPC handles at set-up.
 """
+import ctypes
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -130,3 +134,74 @@ def data_parallel_step(n_items, local_loss_and_grad, grad_buffer, shard='contigu
     works = allreduce_gradient(grad_buffer, average=average)
     finish_allreduce(grad_buffer, works)
     return allreduce_scalar(float(local)), grad_buffer
+
+
+class _DeviceBuffer:
+    """CUDA-array-interface view of memory owned by libbdof (torch.as_tensor wraps it without a copy)."""
+
+    def __init__(self, ptr, n_float32, owner):
+        self.__cuda_array_interface__ = {'shape': (int(n_float32),), 'typestr': '<f4', 'data': (int(ptr), False), 'version': 3,
+                                         'strides': None}
+        self._owner = owner
+
+
+class CopyEngineExchange:
+    """Mean of the object gradient over the ranks of one NVLink box, bucket by bucket, with the copy engines.
+
+    ex = CopyEngineExchange(grad_shape, n_buckets)      # collective: every rank, after init_process_group (any backend)
+    ex.grad                                             # float32 CUDA tensor the adjoint must write its gradient into
+    ex.exchange(buckets)                                # buckets = MultislicePlan.set_gradient_buckets(n): [(z_lo, z_hi, event)]
+                                                        #   (or None: one bucket, ready once the current stream reaches this call)
+    ex.finish()                                         # current stream waits for the averaged gradient
+
+    Replaces hvd.DistributedOptimizer's allreduce (tensorflow_recon/fullfield.py:412) / comm.Allreduce + grads / size
+    (cnn_propagator/fullfield.py:348-351).  Every rank ends with bit-identical values (a shard is summed once, by its owner,
+    in rank order, and broadcast)."""
+
+    def __init__(self, grad_shape, n_buckets=8, group=None, device=None):
+        from .capi import lib, check
+        self._lib, self._check = lib, check
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        n = int(np.prod(grad_shape))
+        self.n_buckets = int(n_buckets)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.bdof_dp_create(ctypes.byref(self._h), self.rank, self.world, n * 4, self.n_buckets))
+            hb = lib.bdof_dp_handle_bytes()
+            mine = ctypes.create_string_buffer(hb)
+            check(lib.bdof_dp_export(self._h, mine))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(mine.raw), group=group)
+            blob = b''.join(handles)
+            assert len(blob) == hb * self.world
+            check(lib.bdof_dp_connect(self._h, ctypes.c_char_p(blob)))
+            ptr = ctypes.c_void_p()
+            check(lib.bdof_dp_grad_ptr(self._h, ctypes.byref(ptr)))
+            self.grad = torch.as_tensor(_DeviceBuffer(ptr.value, n, self), device=self.device).view(*grad_shape)
+        self._ready = torch.cuda.Event()
+        dist.barrier(group=group)             # nobody pushes into a peer that has not opened the handles yet... or freed them
+        self._group = group
+
+    def exchange(self, buckets=None):
+        g = self.grad
+        if buckets is None:
+            self._ready.record(torch.cuda.current_stream(self.device))
+            self._check(self._lib.bdof_dp_bucket(self._h, 0, g.numel() * 4, ctypes.c_void_p(self._ready.cuda_event)))
+            return
+        row = g[0].numel() * 4                 # bytes per z slice
+        for z_lo, z_hi, ev in buckets:
+            self._check(self._lib.bdof_dp_bucket(self._h, z_lo * row, (z_hi - z_lo) * row, ctypes.c_void_p(ev.cuda_event)))
+
+    def finish(self):
+        self._check(self._lib.bdof_dp_finish(self._h, ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return self.grad
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            torch.cuda.synchronize(self.device)
+            if dist.is_initialized():
+                dist.barrier(group=self._group)   # peers may still be copying into / out of my buffers
+            self.grad = None
+            self._lib.bdof_dp_destroy(self._h)
+            self._h = ctypes.c_void_p()

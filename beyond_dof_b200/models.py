@@ -244,13 +244,22 @@ class FullfieldObjective:
         self.exit = torch.empty((B, Y, X), dtype=torch.complex64, device=db_obj.device)
         self.loss_host = torch.empty((), dtype=torch.float64).pin_memory()
 
-    def enable_data_parallel(self, n_buckets=8):
-        """Reduce the object gradient over the ranks of the default process group every step, bucket by
-        bucket along z on a separate stream while the adjoint sweep is still running."""
+    def enable_data_parallel(self, n_buckets=8, exchange='ce'):
+        """Average the object gradient over the ranks of the default process group every step, bucket by
+        bucket along z while the adjoint sweep is still running.  exchange='ce': copy engines over NVLink peer
+        memory (dist.CopyEngineExchange; the gradient then lives in the exchange's exportable buffer);
+        'nccl': NCCL all-reduce on a communication stream."""
         from . import dist as bdist
         self._dp = bdist
         self._buckets = self.plan.set_gradient_buckets(n_buckets)
-        self._comm_stream = torch.cuda.Stream(device=self.db.device)
+        self._ce = None
+        if exchange == 'ce':
+            if self.in_place:
+                raise ValueError('the copy-engine exchange needs the gradient in its own buffer (in_place=False)')
+            self._ce = bdist.CopyEngineExchange(tuple(self.db.shape), n_buckets=len(self._buckets))
+            self.grad = self._ce.grad
+        else:
+            self._comm_stream = torch.cuda.Stream(device=self.db.device)
         return self
 
     def step_device(self, target_dev):
@@ -260,8 +269,12 @@ class FullfieldObjective:
         loss, g = self.plan.loss_mag(self.exit, target_dev)
         self.plan.adjoint(self.db, g, grad_out=None if self.in_place else self.grad)
         if getattr(self, '_dp', None) is not None:
-            works = self._dp.allreduce_gradient(self.grad, average=True, buckets=self._buckets, comm_stream=self._comm_stream)
-            self._dp.finish_allreduce(self.grad, works, comm_stream=self._comm_stream)
+            if self._ce is not None:
+                self._ce.exchange(self._buckets)
+                self._ce.finish()
+            else:
+                works = self._dp.allreduce_gradient(self.grad, average=True, buckets=self._buckets, comm_stream=self._comm_stream)
+                self._dp.finish_allreduce(self.grad, works, comm_stream=self._comm_stream)
         return loss
 
     def step(self, prj_mag_host):
@@ -309,10 +322,15 @@ class TomographyObjective:
         self.step_size = float(step_size)
         self.i_batch = 0
         self._dp = None
+        self._ce = None
 
-    def enable_data_parallel(self):
+    def enable_data_parallel(self, exchange='ce'):
         from . import dist as bdist
         self._dp = bdist
+        self._ce = None
+        if exchange == 'ce':
+            self._ce = bdist.CopyEngineExchange(tuple(self.grad.shape), n_buckets=1)
+            self.grad = self._ce.grad
         return self
 
     def prepare(self, thetas):
@@ -336,7 +354,11 @@ class TomographyObjective:
         for b in range(self.B):
             _rot.rotate_db_adjoint(self.db[:, b], tabs[b], self.grad, atomic=not self.deterministic)
         if self._dp is not None:
-            self._dp.finish_allreduce(self.grad, self._dp.allreduce_gradient(self.grad, average=True))
+            if self._ce is not None:
+                self._ce.exchange(None)
+                self._ce.finish()
+            else:
+                self._dp.finish_allreduce(self.grad, self._dp.allreduce_gradient(self.grad, average=True))
         # regularisers act on the (replicated) object: added after the exchange, identical on every rank
         if self.alpha_d:
             self.grad[..., 0] += self.alpha_d * torch.sign(self.obj[..., 0])

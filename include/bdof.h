@@ -180,6 +180,26 @@ int  bdof_free_prop(bdof_plan* p, const float* d_in, float* d_out);
 /* Bytes of device memory the plan owns (work fields + slice store). */
 int  bdof_plan_workspace_bytes(const bdof_plan* p, size_t* bytes_out);
 
+/* Data-parallel gradient exchange over NVLink peer memory with the copy engines (csrc/dpexchange.cu) -- the all-reduce (mean)
+ * of the object gradient that Horovod / comm.Allreduce perform in the reference (tensorflow_recon/fullfield.py:412,
+ * cnn_propagator/fullfield.py:348-351), without communication kernels on the SMs the sweep kernels own.
+ * One context per rank (one process per GPU).  The context OWNS the gradient buffer (it has to be exportable by CUDA IPC):
+ * the adjoint must write its gradient at bdof_dp_grad_ptr.  Setup: every rank calls bdof_dp_export, the host side
+ * all-gathers the bdof_dp_handle_bytes()-sized handles (any transport) and passes the concatenation [world][handle] to
+ * bdof_dp_connect.  Per step: bdof_dp_bucket for every bucket, in the same order on every rank (offset and size in bytes,
+ * multiples of 16 * world; ready_event = cudaEvent_t recorded once that part of the gradient is final, e.g. the events of
+ * bdof_plan_set_bucket_events), then bdof_dp_finish(stream) which makes `stream` wait for the averaged gradient.
+ * grad_bytes must be a multiple of 16 * world. */
+typedef struct bdof_dp bdof_dp;
+int  bdof_dp_create(bdof_dp** out, int rank, int world, size_t grad_bytes, int n_buckets);
+void bdof_dp_destroy(bdof_dp* c);
+int  bdof_dp_handle_bytes(void);
+int  bdof_dp_export(bdof_dp* c, void* h_handle_out);
+int  bdof_dp_connect(bdof_dp* c, const void* h_all_handles);
+int  bdof_dp_grad_ptr(bdof_dp* c, void** d_grad_out);
+int  bdof_dp_bucket(bdof_dp* c, size_t offset_bytes, size_t n_bytes, void* ready_event);
+int  bdof_dp_finish(bdof_dp* c, void* cuda_stream);
+
 /* In-situ timing: between begin and end every line-kernel launch of this plan is bracketed by CUDA
  * events on the plan's stream; end() synchronises and returns, per pass variant (0 row fwd with
  * transmission, 1 row conv, 2 row adjoint, 3 row FFT, 4 row IFFT, 5 col conv, 6 col FFT, 7 col IFFT,
