@@ -466,7 +466,7 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
     ap.add_argument('--sm-reserve', type=int, default=0, help='SMs left free for NCCL while the sweep runs (N > 1)')
     ap.add_argument('--exchange', default='ce', choices=['ce', 'nccl'], help='N > 1: gradient exchange (copy engines over peer memory, or NCCL all-reduce)')
-    ap.add_argument('--buckets', type=int, default=8, help='z-buckets of the gradient all-reduce (N > 1)')
+    ap.add_argument('--buckets', type=int, default=16, help='z-buckets of the gradient all-reduce (N > 1)')
     ap.add_argument('--shape', default=None, help='experiment: B,NY,NX,NZ overrides the workload shape')
     ap.add_argument('--diag', action='store_true', help='N > 1: print the plain all-reduce time and the step time without exchange')
     ap.add_argument('--in-place', action='store_true', help='adjoint overwrites delta/beta with the gradient (needed for the 4096^2x512 size)')
