@@ -244,13 +244,15 @@ class FullfieldObjective:
         self.exit = torch.empty((B, Y, X), dtype=torch.complex64, device=db_obj.device)
         self.loss_host = torch.empty((), dtype=torch.float64).pin_memory()
 
-    def enable_data_parallel(self, n_buckets=8, exchange='ce'):
+    def enable_data_parallel(self, n_buckets=16, exchange='auto'):
         """Average the object gradient over the ranks of the default process group every step, bucket by
         bucket along z while the adjoint sweep is still running.  exchange='ce': copy engines over NVLink peer
         memory (dist.CopyEngineExchange; the gradient then lives in the exchange's exportable buffer);
-        'nccl': NCCL all-reduce on a communication stream."""
+        'nccl': NCCL all-reduce on a communication stream; 'auto': dist.pick_exchange()."""
         from . import dist as bdist
         self._dp = bdist
+        if exchange == 'auto':
+            exchange = bdist.pick_exchange()
         self._buckets = self.plan.set_gradient_buckets(n_buckets)
         self._ce = None
         if exchange == 'ce':
@@ -324,10 +326,12 @@ class TomographyObjective:
         self._dp = None
         self._ce = None
 
-    def enable_data_parallel(self, exchange='ce'):
+    def enable_data_parallel(self, exchange='auto'):
         from . import dist as bdist
         self._dp = bdist
         self._ce = None
+        if exchange == 'auto':
+            exchange = bdist.pick_exchange()
         if exchange == 'ce':
             self._ce = bdist.CopyEngineExchange(tuple(self.grad.shape), n_buckets=1)
             self.grad = self._ce.grad
