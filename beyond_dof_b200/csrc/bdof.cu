@@ -400,6 +400,8 @@ struct bdof_plan {
     float2* tmp = nullptr;     // one field
     float2* work[2] = {nullptr, nullptr};   // ping-pong fields (no-store forward) / G buffer
     float2* slabs = nullptr;   // n_slice fields (STORE_SLICES)
+    float2* t_stash = nullptr; // caller-owned [n_slice][batch][ny][nx] complex64: the sweep forward leaves t_i there for the adjoint
+    bool stash_valid = false;  // the last forward filled t_stash and nothing has overwritten it since
     double* partial = nullptr;
     std::complex<double> total_phase{1.0, 0.0};
     bool forward_done = false;
@@ -706,6 +708,7 @@ extern "C" int bdof_forward(bdof_plan* p, const float* d_db_f, const float* d_pr
     const int Z = p->n_slice;
 
     float2* cur = store ? p->slabs : p->work[0];
+    p->stash_valid = false;
     k_broadcast_probe<<<blocks_for(per, 256), 256, 0, p->stream>>>(d_probe, cur, per, p->batch);
     BDOF_TRY(launch_check("k_broadcast_probe"));
     std::complex<double> phase{1.0, 0.0};
@@ -723,10 +726,12 @@ extern "C" int bdof_forward(bdof_plan* p, const float* d_db_f, const float* d_pr
             q.db = d_db + ((p->flags & BDOF_Z_BROADCAST) ? 0 : (long long)i * p->F);
             q.slab = (store && i > 0) ? p->slabs + (long long)i * p->F : nullptr;
             q.conv1 = (i > 0); q.conv2 = prop; q.store_slab = (store && i > 0); q.store_out = 1;
+            q.grad = (store && p->t_stash) ? p->t_stash + (long long)i * p->F : nullptr;
             BDOF_TRY(sweep_launch(p, i, false, q));
             if (prop) phase *= p->phase0;
         }
         cur = obj_out;
+        p->stash_valid = store && p->t_stash != nullptr;
         if (slice_propagates(p, Z - 1)) {
             // TF semantics: the last slice propagates too -> its second half along the other axis
             if (Z & 1) BDOF_TRY(col_pass(p, V_COL_CONV, col_params(p, A, obj_out, p->ay.h)));
@@ -827,6 +832,7 @@ extern "C" int bdof_adjoint(bdof_plan* p, float* d_db_inout, const float* d_grad
         SweepParams q{};
         q.in = G; q.out = G;
         q.db = db + (zb ? 0 : (long long)i * p->F);
+        if (p->stash_valid) { q.db = p->t_stash + (long long)i * p->F; q.db_is_t = 1; }
         q.grad = gout ? gout + (long long)i * p->F : db + (long long)i * p->F;
         q.slab = p->slabs + (long long)i * p->F;
         q.conv1 = slice_propagates(p, i); q.conv2 = (i > 0);
@@ -861,6 +867,7 @@ extern "C" int bdof_adjoint(bdof_plan* p, float* d_db_inout, const float* d_grad
             }
         }
     }
+    if (sweep && p->stash_valid && (p->t_stash == (gout ? gout : db))) p->stash_valid = false;      // t has been replaced by the gradient
     if (d_grad_probe) {
         const long long per = (long long)p->ny * p->nx;
         k_sum_batch<<<blocks_for(per, 256), 256, 0, p->stream>>>(G, reinterpret_cast<float2*>(d_grad_probe), per, p->batch);
@@ -1149,6 +1156,13 @@ extern "C" int bdof_slice_step(bdof_plan* p, const float* d_in, const float* d_d
     if (propagate) return propagate_slice(p, in, db, out, nullptr);
     k_modulate<<<blocks_for(p->F, 256), 256, 0, p->stream>>>(in, db, out, p->F, float(p->k_dz));
     return launch_check("k_modulate");
+}
+
+extern "C" int bdof_plan_set_t_stash(bdof_plan* p, float* d_stash) {
+    if (!p) return fail(BDOF_E_BADARG, "null");
+    p->t_stash = reinterpret_cast<float2*>(d_stash);
+    p->stash_valid = false;
+    return 0;
 }
 
 extern "C" int bdof_plan_set_bucket_events(bdof_plan* p, int n_buckets, void** cuda_events) {

@@ -64,6 +64,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int 
                  "r"(smem_u32(src_smem))
                  : "memory");
 }
+// contiguous shared -> global bulk copy (bytes a multiple of 16), tracked by the thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 

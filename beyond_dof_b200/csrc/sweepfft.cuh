@@ -24,6 +24,8 @@ struct SweepParams {
     float2* out;             // field out (may alias in)
     const float2* db;        // (delta, beta) of this slice, row-major
     float2* grad;            // adjoint: gradient of this slice, row-major (may alias db)
+                             // forward: nullable transmission stash -- t_i = exp(k(i delta - beta)) of this slice is written here
+                             // (row-major, may alias db) so that the adjoint kernel of the slice lands t instead of recomputing it
     float2* slab;            // psi entering this slice in TILE layout (forward: written, adjoint: read)
     const float2* h;         // multiplier of this axis (forward) or its conjugate (adjoint), 1/N folded in
     const float2* tw;        // stage twiddles, pipelined layout
@@ -37,6 +39,7 @@ struct SweepParams {
     int slab_prefetch;       // adjoint: L2-prefetch the slab tile at tile start
     int stagger_ns;          // x kernels: the upper half of the lines starts every convolution this much later, so that
                              // its stage exchanges (shared-memory pipe) overlap the other half's butterflies (FP pipe)
+    int db_is_t;             // adjoint: `db` holds the stashed transmission t_i, not (delta, beta)
     float k_dz;
     long long* dbg;
 };
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
         else deferred = LAND_DB;
         if constexpr (ADJ && !COL) slab_prefetch(tile);
         auto deferred_landing = [&]() __attribute__((always_inline)) {
-            if (COL && deferred >= 0) {
+            if ((COL || !ADJ) && deferred >= 0) {
                 if (tid == 0) bulk_wait_group_read0();
                 land(deferred, deferred == LAND_DB ? tile : tile + tile_step);
                 if (ADJ && deferred == LAND_DB) slab_prefetch(tile);
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                 // t = exp(k(i delta - beta)) in place.  ROLLED on purpose: a straight-line version (64 x 20 instructions)
                 // pushed the kernel past the instruction cache and cost ~10k cycles on the first tile of every launch
 #pragma unroll 1
-                for (int q0 = 0; q0 < (active ? E : 0); q0 += 4) {
+                for (int q0 = 0; q0 < ((active && !(ADJ && p.db_is_t)) ? E : 0); q0 += 4) {
                     float2 d[4];
                     bool tiny = true, small = true;
 #pragma unroll
@@ -256,8 +259,27 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                         static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; sp[q * LQ] = v[q]; });
                     }
                     if (active) static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = cmul(v[q], Lme[q * LQ]); });
-                    __syncthreads();    // L is free again
-                    if (has_next) land(LAND_IN, tile + tile_step);
+                    if (p.grad != nullptr) {
+                        // stash t for the adjoint: L leaves by TMA (tensor store for column tiles, bulk rows otherwise); the next
+                        // landing is issued from inside the following convolution once the store has finished reading L
+                        if constexpr (COL) {
+                            tma_store_tile(&tm_grad, tile);
+                        } else {
+                            fence_proxy_async();
+                            __syncthreads();
+                            if (tid == 0) {
+                                const int nl = tile_lines(tile);
+                                float2* dst = p.grad + tile_off;
+#pragma unroll 1
+                                for (int j = 0; j < nl; ++j) bulk_s2g(dst + j * N, L + j * N, N * (unsigned)sizeof(float2));
+                                bulk_commit_group();
+                            }
+                        }
+                        if (has_next) deferred = LAND_IN;
+                    } else {
+                        __syncthreads();    // L is free again
+                        if (has_next) land(LAND_IN, tile + tile_step);
+                    }
                 } else {
                     // G = G_u conj(t)
                     // G = G_u conj(t)
@@ -343,7 +365,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
         static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; Lme[q * LQ] = v[q]; });
         tma_store_tile(&tm_out, tile - gridDim.x);
     }
-    if (COL && tid == 0) bulk_wait_group_read0();
+    if ((COL || !ADJ) && tid == 0) bulk_wait_group_read0();
     SWEEP_GSTAMP(30);
 }
 

@@ -74,6 +74,7 @@ def fullfield_loss_and_grad(obj_delta, obj_beta, theta_batch, prj_batch, probe_r
     for b in range(B):
         _rot.rotate_db(obj_db, tabs[b], out=db[:, b])
     probe = _probe_c64(probe_real, probe_imag, (Y, X))
+    plan.set_t_stash(db if want_grad else None)     # the in-place adjoint finds t_i where it will write the gradient
     exit_wave = plan.forward(db, probe)
     prj = _to_dev(prj_batch, torch.complex64 if (isinstance(prj_batch, torch.Tensor) and prj_batch.is_complex())
                   or np.iscomplexobj(prj_batch) else torch.float32)
@@ -155,6 +156,7 @@ def ptycho_loss_and_grad(obj_delta, obj_beta, theta, probe_pos_batch, prj_batch,
     patches = torch.empty((Z, n, py, px, 2), dtype=torch.float32, device=dev)
     check(lib.bdof_patch_gather(_ptr(db_obj), Z, OY, OX, _ptr(origin), n, py, px, _ptr(patches), st))
     probe = _probe_c64(probe_real, probe_imag, (py, px))
+    plan.set_t_stash(patches if want_grad else None)
     exit_wave = plan.forward(patches, probe)
     is_cplx = (isinstance(prj_batch, torch.Tensor) and prj_batch.is_complex()) or np.iscomplexobj(prj_batch)
     target = _to_dev(prj_batch, torch.complex64 if is_cplx else torch.float32).abs().to(torch.float32)
@@ -243,6 +245,8 @@ class FullfieldObjective:
         self.target = torch.empty((B, Y, X), dtype=torch.float32, device=db_obj.device)
         self.exit = torch.empty((B, Y, X), dtype=torch.complex64, device=db_obj.device)
         self.loss_host = torch.empty((), dtype=torch.float64).pin_memory()
+        # the forward leaves the transmission of every slice where the adjoint will write that slice's gradient
+        self.plan.set_t_stash(self.grad)
 
     def enable_data_parallel(self, n_buckets=16, exchange='auto'):
         """Average the object gradient over the ranks of the default process group every step, bucket by
@@ -260,6 +264,7 @@ class FullfieldObjective:
                 raise ValueError('the copy-engine exchange needs the gradient in its own buffer (in_place=False)')
             self._ce = bdist.CopyEngineExchange(tuple(self.db.shape), n_buckets=len(self._buckets))
             self.grad = self._ce.grad
+            self.plan.set_t_stash(self.grad)
         else:
             self._comm_stream = torch.cuda.Stream(device=self.db.device)
         return self
@@ -315,6 +320,7 @@ class TomographyObjective:
         self.obj = db_obj
         self.probe = probe.to(db_obj.device, torch.complex64).contiguous()
         self.db = torch.empty((Z, self.B, Y, X, 2), dtype=torch.float32, device=db_obj.device)
+        self.plan.set_t_stash(self.db)               # rotated copies: rebuilt every step, overwritten in place by the adjoint
         self.grad = torch.zeros_like(db_obj)
         self.m = torch.zeros_like(db_obj)
         self.v = torch.zeros_like(db_obj)

@@ -173,6 +173,16 @@ class MultislicePlan:
         check(lib.bdof_slice_step(self._h, _ptr(field), _ptr(db_slice), _ptr(out), 1 if propagate else 0))
         return out
 
+    def set_t_stash(self, buf):
+        """buf: float32 CUDA tensor [Z,B,Y,X,2] (or None).  The forward leaves the transmission t_i of every slice there
+        and the next adjoint lands it instead of recomputing exp(k(i delta - beta)).  Pass the tensor the adjoint will write
+        its gradient to (grad_out, or db itself for the in-place adjoint): t then costs no memory."""
+        if buf is not None:
+            assert buf.is_cuda and buf.dtype == torch.float32 and buf.is_contiguous() and \
+                tuple(buf.shape) == (self.n_slice, self.batch, self.ny, self.nx, 2)
+        self._stash = buf
+        check(lib.bdof_plan_set_t_stash(self._h, _ptr(buf) if buf is not None else None))
+
     def set_gradient_buckets(self, n_buckets):
         """Split z into n_buckets (counted from the last slice); returns [(z_lo, z_hi, event)] in the order
         the adjoint sweep completes them.  The events are recorded inside bdof_adjoint."""

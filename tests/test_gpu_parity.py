@@ -460,3 +460,58 @@ def test_transmission_paths_agree(bd):
         psi, g_d, g_b, _, _ = _run_plan(shape, gd, gb, one, zero, target, True)
         assert intensity_err(psi, psio) < TOL_INTENSITY
         assert rel_l2(g_d, gdo) < TOL_GRAD and rel_l2(g_b, gbo) < TOL_GRAD
+
+
+# ---------------------------------------------------------------------------------------------
+# transmission stash: the forward leaves t_i where the adjoint writes the gradient
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('shape', [(2, 64, 128, 5), (1, 256, 64, 4), (3, 128, 512, 3), (1, 1024, 2048, 3), (1, 2048, 1024, 4), (1, 4096, 1024, 2),
+                                   (1, 1024, 4096, 3), (5, 64, 64, 7)])
+@pytest.mark.parametrize('mode', ['grad_out', 'in_place', 'separate'])
+@pytest.mark.parametrize('propagate_last', [False, True])
+def test_transmission_stash_gives_identical_gradients(bd, shape, mode, propagate_last):
+    from beyond_dof_b200.plan import MultislicePlan
+    B, Y, X, Z = shape
+    gd, gb = mo.random_phantom(shape, seed=71, delta_scale=4e-4, beta_scale=4e-5)
+    gd[0, : Y // 2] *= 300.                                   # strong half: general and small transmission paths too
+    pr, pi = mo.gaussian_probe(shape[1:3], max(shape[1:3]) / 2., max(shape[1:3]) / 3., 0.5)
+    probe = torch.as_tensor((pr + 1j * pi).astype(np.complex64)).cuda()
+    target = torch.as_tensor((np.random.default_rng(72).random(shape[:3]) + 0.5).astype(np.float32)).cuda()
+    plan = MultislicePlan(Y, X, B, Z, 5000, 1e-7, propagate_last=propagate_last, store_slices=True)
+    db = plan.pack(torch.as_tensor(gd).cuda(), torch.as_tensor(gb).cuda())
+    keep = db.clone()
+    # reference run: no stash
+    psi0 = plan.forward(db, probe).clone()
+    _, g = plan.loss_mag(psi0, target)
+    g0 = torch.empty_like(db)
+    _, gp0 = plan.adjoint(db, g, grad_out=g0, want_probe_grad=True)
+    for rep in range(2):                                      # twice: the stash is refilled by every forward
+        if mode == 'grad_out':
+            gout = torch.full_like(db, float('nan'))
+            plan.set_t_stash(gout)
+            psi = plan.forward(db, probe)
+            _, gp = plan.adjoint(db, g, grad_out=gout, want_probe_grad=True)
+            assert torch.equal(db, keep)
+        elif mode == 'in_place':
+            work = keep.clone()
+            plan.set_t_stash(work)
+            psi = plan.forward(work, probe)
+            _, gp = plan.adjoint(work, g, want_probe_grad=True)
+            gout = work
+        else:
+            stash = torch.empty_like(db)
+            gout = torch.empty_like(db)
+            plan.set_t_stash(stash)
+            psi = plan.forward(db, probe)
+            _, gp = plan.adjoint(db, g, grad_out=gout, want_probe_grad=True)
+            tz = torch.view_as_complex(stash[Z - 1].contiguous())           # the stash still holds t of the last slice
+            want = torch.exp(torch.complex(-plan.k_dz * keep[Z - 1, ..., 1].double(), plan.k_dz * keep[Z - 1, ..., 0].double()))
+            assert (tz.to(torch.complex128) - want).abs().max().item() < 3e-6
+        assert torch.equal(psi, psi0)
+        # same arithmetic in the same order: equal up to the warp-vote choice of the transmission series
+        assert rel_l2(gout.cpu().numpy(), g0.cpu().numpy()) < 1e-6 and rel_l2(gp.cpu().numpy(), gp0.cpu().numpy()) < 1e-6
+    plan.set_t_stash(None)
+    g1 = torch.empty_like(db)
+    plan.forward(db, probe)
+    plan.adjoint(db, g, grad_out=g1)
+    assert torch.equal(g1, g0)
