@@ -229,11 +229,11 @@ def run_gpu(args):
         from beyond_dof_b200.dist import pick_exchange
         exchange_used = pick_exchange() if args.exchange == 'auto' else args.exchange
         if args.buckets <= 0:
-            args.buckets = 16 if exchange_used == 'ce' else 8        # measured optima (2 x B200)
-        if exchange_used == 'ce':
+            args.buckets = 8 if exchange_used == 'nccl' else 16      # measured optima (2 x B200)
+        if exchange_used in ('ce', 'hybrid'):
             ok, why = 1, ''
             try:
-                obj.enable_data_parallel(n_buckets=args.buckets, exchange='ce')
+                obj.enable_data_parallel(n_buckets=args.buckets, exchange=exchange_used)
             except Exception as ex:               # noqa: BLE001
                 ok, why = 0, '%s: %s' % (type(ex).__name__, ex)
             t_ok = torch.tensor([ok], dtype=torch.int32, device=dev)
@@ -365,7 +365,7 @@ def run_gpu(args):
                        'l2': 'inputs larger than L2 (%.1f GB of delta/beta + %.1f GB slice store per GPU streamed every step)' % (db.numel() * 4 / 1e9, db.numel() * 4 / 1e9),
                        'parallelism': ('dp%d: one field per GPU; mean of the object gradient (%.1f GB) over ranks every step in %d z-buckets overlapped with the adjoint sweep; exchange: %s'
                                        % (world, db.numel() * 4 / 1e9, args.buckets,
-                                          'copy engines over NVLink peer memory (push partial shards, owner sums, gather)' if exchange_used == 'ce' else 'NCCL all-reduce (AVG) on a communication stream' if exchange_used == 'nccl' else exchange_used)) if world > 1 else 'single GPU'},
+                                          'copy engines over NVLink peer memory (push partial shards, owner sums, gather)' if exchange_used == 'ce' else 'NCCL reduce-scatter (AVG) + copy-engine all-gather over NVLink peer memory' if exchange_used == 'hybrid' else 'NCCL all-reduce (AVG) on a communication stream' if exchange_used == 'nccl' else exchange_used)) if world > 1 else 'single GPU'},
             'e2e': {'value': e2e_value, 'unit': 'Gpixel*slice/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'api': 'beyond_dof_b200.models.FullfieldObjective.step(projection magnitudes in pinned host memory) -> loss'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'kernels': kern, 'cpu_baseline': cpu,
@@ -468,7 +468,7 @@ def main():
     ap.add_argument('--impl', default='bdof', choices=['bdof', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
     ap.add_argument('--sm-reserve', type=int, default=0, help='SMs left free for NCCL while the sweep runs (N > 1)')
-    ap.add_argument('--exchange', default='auto', choices=['auto', 'ce', 'nccl'], help='N > 1: gradient exchange (copy engines over peer memory, or NCCL all-reduce)')
+    ap.add_argument('--exchange', default='auto', choices=['auto', 'ce', 'nccl', 'hybrid'], help='N > 1: gradient exchange (copy engines over peer memory, or NCCL all-reduce)')
     ap.add_argument('--buckets', type=int, default=0, help='z-buckets of the gradient all-reduce (N > 1)')
     ap.add_argument('--shape', default=None, help='experiment: B,NY,NX,NZ overrides the workload shape')
     ap.add_argument('--diag', action='store_true', help='N > 1: print the plain all-reduce time and the step time without exchange')

@@ -22,7 +22,7 @@ SYMBOLS = [
     'bdof_plan_set_bucket_events', 'bdof_set_sm_reserve', 'bdof_rotate_gather', 'bdof_rotate_scatter_add', 'bdof_rotate_adjoint_csr', 'bdof_adam_step',
     'bdof_finite_support', 'bdof_plan_set_t_stash',
     'bdof_dp_create', 'bdof_dp_destroy', 'bdof_dp_handle_bytes', 'bdof_dp_export', 'bdof_dp_connect', 'bdof_dp_grad_ptr',
-    'bdof_dp_bucket', 'bdof_dp_finish',
+    'bdof_dp_bucket', 'bdof_dp_gather', 'bdof_dp_finish',
 ]
 
 
@@ -74,7 +74,7 @@ def _load():
     lib.bdof_finite_support.argtypes = [vp, vp, i64, f64, vp]
     lib.bdof_plan_set_t_stash.argtypes = [vp, vp]
     sz = ctypes.c_size_t
-    lib.bdof_dp_create.argtypes = [ctypes.POINTER(vp), i32, i32, sz, i32]
+    lib.bdof_dp_create.argtypes = [ctypes.POINTER(vp), i32, i32, sz, i32, i32]
     lib.bdof_dp_destroy.argtypes = [vp]
     lib.bdof_dp_destroy.restype = None
     lib.bdof_dp_handle_bytes.argtypes = []
@@ -82,6 +82,7 @@ def _load():
     lib.bdof_dp_connect.argtypes = [vp, vp]
     lib.bdof_dp_grad_ptr.argtypes = [vp, ctypes.POINTER(vp)]
     lib.bdof_dp_bucket.argtypes = [vp, sz, sz, vp]
+    lib.bdof_dp_gather.argtypes = [vp, sz, sz, vp]
     lib.bdof_dp_finish.argtypes = [vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)

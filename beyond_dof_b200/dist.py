@@ -143,7 +143,7 @@ def pick_exchange():
     aggregate, exchange alone 36 ms against NCCL's 19 ms), so NCCL (which drives NVLink from SM kernels) is used there."""
     if not (dist.is_available() and dist.is_initialized()):
         return 'nccl'
-    return 'ce' if dist.get_world_size() == 2 else 'nccl'
+    return 'ce' if dist.get_world_size() == 2 else 'nccl'        # 'hybrid' (NCCL reduce-scatter + copy-engine all-gather) is opt-in
 
 
 class _DeviceBuffer:
@@ -168,7 +168,7 @@ class CopyEngineExchange:
     (cnn_propagator/fullfield.py:348-351).  Every rank ends with bit-identical values (a shard is summed once, by its owner,
     in rank order, and broadcast)."""
 
-    def __init__(self, grad_shape, n_buckets=8, group=None, device=None):
+    def __init__(self, grad_shape, n_buckets=8, group=None, device=None, gather_only=False):
         from .capi import lib, check
         self._lib, self._check = lib, check
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
@@ -177,7 +177,7 @@ class CopyEngineExchange:
         self.n_buckets = int(n_buckets)
         self._h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
-            check(lib.bdof_dp_create(ctypes.byref(self._h), self.rank, self.world, n * 4, self.n_buckets))
+            check(lib.bdof_dp_create(ctypes.byref(self._h), self.rank, self.world, n * 4, self.n_buckets, 1 if gather_only else 0))
             hb = lib.bdof_dp_handle_bytes()
             mine = ctypes.create_string_buffer(hb)
             check(lib.bdof_dp_export(self._h, mine))
@@ -202,6 +202,25 @@ class CopyEngineExchange:
         row = g[0].numel() * 4                 # bytes per z slice
         for z_lo, z_hi, ev in buckets:
             self._check(self._lib.bdof_dp_bucket(self._h, z_lo * row, (z_hi - z_lo) * row, ctypes.c_void_p(ev.cuda_event)))
+
+    def reduce_scatter_gather(self, buckets, comm_stream):
+        """Three or more GPUs: per bucket an in-place NCCL reduce-scatter (mean) on comm_stream leaves rank r with shard r of
+        the bucket, which the copy engines then broadcast peer by peer (bdof_dp_gather) -- the SM kernels of NCCL run for
+        half the traffic of an all-reduce and the all-gather half costs no SMs."""
+        g = self.grad
+        row = g[0].numel() * 4
+        if not hasattr(self, '_rs_events'):
+            self._rs_events = [torch.cuda.Event() for _ in range(self.n_buckets)]
+        for j, (z_lo, z_hi, ev) in enumerate(buckets):
+            seg = g[z_lo:z_hi].view(-1)
+            shard = seg.numel() // self.world
+            comm_stream.wait_event(ev)
+            with torch.cuda.stream(comm_stream):
+                wk = dist.reduce_scatter_tensor(seg[self.rank * shard:(self.rank + 1) * shard], seg, op=dist.ReduceOp.AVG,
+                                                group=self._group, async_op=True)
+                wk.wait()
+                self._rs_events[j].record(comm_stream)
+            self._check(self._lib.bdof_dp_gather(self._h, z_lo * row, (z_hi - z_lo) * row, ctypes.c_void_p(self._rs_events[j].cuda_event)))
 
     def finish(self):
         self._check(self._lib.bdof_dp_finish(self._h, ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))

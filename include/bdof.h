@@ -199,13 +199,18 @@ int  bdof_plan_workspace_bytes(const bdof_plan* p, size_t* bytes_out);
  * bdof_plan_set_bucket_events), then bdof_dp_finish(stream) which makes `stream` wait for the averaged gradient.
  * grad_bytes must be a multiple of 16 * world. */
 typedef struct bdof_dp bdof_dp;
-int  bdof_dp_create(bdof_dp** out, int rank, int world, size_t grad_bytes, int n_buckets);
+int  bdof_dp_create(bdof_dp** out, int rank, int world, size_t grad_bytes, int n_buckets, int gather_only);
 void bdof_dp_destroy(bdof_dp* c);
 int  bdof_dp_handle_bytes(void);
 int  bdof_dp_export(bdof_dp* c, void* h_handle_out);
 int  bdof_dp_connect(bdof_dp* c, const void* h_all_handles);
 int  bdof_dp_grad_ptr(bdof_dp* c, void** d_grad_out);
 int  bdof_dp_bucket(bdof_dp* c, size_t offset_bytes, size_t n_bytes, void* ready_event);
+/* gather half only (contexts created with gather_only = 1, no staging area): shard `rank` of the bucket already holds the
+ * reduced values when ready_event fires (in-place NCCL reduce-scatter); it is copied into every peer's gradient, one peer
+ * after the other.  Three or more GPUs: concurrent copy-engine transfers to several peers do not add up, and the
+ * reduce-scatter needs SM kernels anyway, so the exchange is NCCL reduce-scatter + copy-engine all-gather there. */
+int  bdof_dp_gather(bdof_dp* c, size_t offset_bytes, size_t n_bytes, void* ready_event);
 int  bdof_dp_finish(bdof_dp* c, void* cuda_stream);
 
 /* In-situ timing: between begin and end every line-kernel launch of this plan is bracketed by CUDA
