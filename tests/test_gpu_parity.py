@@ -167,10 +167,13 @@ def test_unsupported_size_fails_loudly(bd):
 @pytest.mark.parametrize('free', [None, 'inf', 1e-4])
 def test_mixed_radix_forward_and_adjoint_match_oracle(bd, shape, propagate_last, free):
     gd, gb = mo.random_phantom(shape, seed=61, delta_scale=5e-4, beta_scale=5e-5)
-    sig = max(6., max(shape[1:3]) / 8.)                        # 6 px for the probe-sized cases (reconstruct_ptycho.py:92-94)
-    pr, pi = mo.gaussian_probe(shape[1:3], sig, sig, 0.5)
-    pr = pr + 0.2
+    # Gaussian probe of the ptychography drivers (reconstruct_ptycho.py:92-94) plus a speckle term: a smooth probe on an
+    # elongated field has a far field that is zero to fp32 precision almost everywhere, and psi / |psi| in the loss head is
+    # then noise for ANY complex64 forward model (gradient conditioning)
     rng = np.random.default_rng(62)
+    pr, pi = mo.gaussian_probe(shape[1:3], 6., 6., 0.5)
+    pr = pr + 0.2 + 0.3 * rng.standard_normal(shape[1:3])
+    pi = pi + 0.3 * rng.standard_normal(shape[1:3])
     target = rng.random(shape[:3]) * (np.sqrt(shape[1] * shape[2]) if free == 'inf' else 1.0) + 0.5
     lo, gdo, gbo, psio = mo.loss_and_grad(gd.astype(np.float64), gb.astype(np.float64), pr, pi, 5000, 1e-7, target,
                                           free_prop_cm=free, propagate_last=propagate_last)
