@@ -7,14 +7,16 @@ One "step" = forward multislice + |psi| loss + adjoint gradient over one synthet
 Default workload (N=1) is BASELINE.json configs[1]: random delta/beta phantom 2048 x 2048 x 256,
 forward + adjoint on one B200.  1 unit = one pixel advanced through one slice (forward + adjoint
 counts the slice once).  With N>1 ranks (torchrun) every rank owns one such field (one projection
-angle of the data-parallel reconstruction, weak scaling) and the object gradient is all-reduced over
-NCCL every step.
+angle of the data-parallel reconstruction, weak scaling) and the mean of the object gradient over ranks
+is formed every step, overlapped with the adjoint sweep (--exchange auto: copy engines over NVLink peer
+memory between two GPUs, NCCL all-reduce for three or more).
 
 Keys of the JSON line: see the contract in the task description; in short
   value        device-timed whole-job throughput, inputs resident in HBM
   e2e          the same step through the public API (FullfieldObjective.step) with this step's
                measured projections copied from pinned host memory and the loss read back
-  roofline     dominant line kernel: algorithmic bytes / in-situ CUDA-event duration vs measured HBM peak
+  roofline     dominant kernel (sweep_kernel, forward + adjoint instantiations, launch-weighted): algorithmic
+               bytes / in-situ CUDA-event duration vs measured HBM peak; per direction under "kernels"
   cpu_baseline oracle port (NumPy complex128, the reference algorithm) on the host cores, bounded sample
 """
 import argparse
