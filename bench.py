@@ -323,6 +323,42 @@ def run_gpu(args):
     h2d = target_host.numel() * target_host.element_size()
     d2h = 8
 
+    # ---- e2e with the OBJECT on the host too: the literal drop-in of the cnn_propagator driver's call
+    #      loss_grad(obj_delta, obj_beta, this_ind_batch, this_prj_batch) (cnn_propagator/fullfield.py:329,346) with NumPy arrays in
+    #      and NumPy gradients out -- H2D of delta/beta [Y,X,Z], layout conversion, rotation (theta = 0), forward, loss, adjoint,
+    #      back-rotation, layout conversion, D2H of both gradients.  PCIe-bound by construction; reported beside `e2e`, whose
+    #      object lives on the GPU as the tf.Variables of the TF driver do (tensorflow_recon/fullfield.py:243-303).
+    e2e_host = None
+    if world == 1 and B == 1 and not args.no_host_object and not args.in_place and ny * nx * nz * 8 <= 12e9:
+        try:
+            from beyond_dof_b200 import fullfield_loss_and_grad
+            from beyond_dof_b200.propagation import clear_plan_cache
+            rng = np.random.default_rng(77)
+            od = rng.random((ny, nx, nz), dtype=np.float32); od *= np.float32(1e-5)
+            ob = rng.random((ny, nx, nz), dtype=np.float32); ob *= np.float32(1e-6)
+            prj_np = target_host.numpy()
+            one, zero = np.ones((ny, nx), np.float32), np.zeros((ny, nx), np.float32)
+
+            def host_call():
+                loss_h, (g_d, g_b), _ = fullfield_loss_and_grad(od, ob, np.zeros(1), prj_np, one, zero, ENERGY_EV, PSIZE_CM,
+                                                                 propagate_last=False)
+                return float(loss_h), g_d.cpu().numpy(), g_b.cpu().numpy()
+            host_call()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            host_call()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            e2e_host = {'value': ny * nx * nz / dt / 1e9, 'unit': 'Gpixel*slice/s', 'ms_per_step': dt * 1e3,
+                        'h2d_bytes_per_step': int(od.nbytes + ob.nbytes + prj_np.nbytes), 'd2h_bytes_per_step': int(od.nbytes + ob.nbytes + 8),
+                        'api': 'beyond_dof_b200.fullfield_loss_and_grad(NumPy delta, beta [Y,X,Z], theta, NumPy projections) -> loss, NumPy gradients '
+                               '(pageable host memory, wall clock)'}
+            del od, ob
+            clear_plan_cache()
+            torch.cuda.empty_cache()
+        except Exception as ex:            # noqa: BLE001  (an optional extra must not take the bench line down)
+            e2e_host = {'error': '%s: %s' % (type(ex).__name__, ex)}
+
     # ---- per-kernel in-situ timing (one extra, untimed step with CUDA events around every pass)
     kern = {}
     roofline = None
@@ -380,6 +416,7 @@ def run_gpu(args):
                                           'copy engines over NVLink peer memory (push partial shards, owner sums, gather)' if exchange_used == 'ce' else 'NCCL reduce-scatter (AVG) + copy-engine all-gather over NVLink peer memory' if exchange_used == 'hybrid' else 'NCCL all-reduce (AVG) on a communication stream' if exchange_used == 'nccl' else exchange_used)) if world > 1 else 'single GPU'},
             'e2e': {'value': e2e_value, 'unit': 'Gpixel*slice/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'api': 'beyond_dof_b200.models.FullfieldObjective.step(projection magnitudes in pinned host memory) -> loss'},
+            'e2e_host_object': e2e_host,
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'kernels': kern, 'cpu_baseline': cpu,
             'loss': float(loss.item()),
         }
@@ -479,6 +516,7 @@ def main():
     ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS) + ['config4'])
     ap.add_argument('--impl', default='bdof', choices=['bdof', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
+    ap.add_argument('--no-host-object', action='store_true', help='skip the extra end-to-end leg with delta/beta and the gradients in host memory')
     ap.add_argument('--sm-reserve', type=int, default=0, help='SMs left free for NCCL while the sweep runs (N > 1)')
     ap.add_argument('--exchange', default='auto', choices=['auto', 'ce', 'nccl', 'hybrid'], help='N > 1: gradient exchange (copy engines over peer memory, or NCCL all-reduce)')
     ap.add_argument('--buckets', type=int, default=0, help='z-buckets of the gradient all-reduce (N > 1)')
