@@ -451,7 +451,7 @@ def run_config4(args):
     probe = torch.ones((n, n), dtype=torch.complex64, device=dev)
     tomo = TomographyObjective(obj, probe, ENERGY_EV, PSIZE_CM, minibatch_size=mb, free_prop_cm=1e-4, propagate_last=True, step_size=1e-7)
     if world > 1:
-        tomo.enable_data_parallel(exchange=args.exchange)
+        tomo.enable_data_parallel(exchange='nccl' if args.exchange in ('auto', 'hybrid') else args.exchange)
     thetas = np.linspace(0, np.pi, n_theta)
     mine = thetas[rank::world]
     tomo.prepare(mine)

@@ -345,12 +345,14 @@ class TomographyObjective:
         self._dp = None
         self._ce = None
 
-    def enable_data_parallel(self, exchange='auto'):
+    def enable_data_parallel(self, exchange='nccl'):
+        """exchange: 'nccl' (default: the gradient of one object is small -- 134 MB at 256^3 -- and exchanged after the
+        back-rotation, when no sweep kernel is running; measured 36.2 vs 34.4 Gpx*slice/s on two B200) or 'ce'."""
         from . import dist as bdist
         self._dp = bdist
         self._ce = None
         if exchange == 'auto':
-            exchange = bdist.pick_exchange()
+            exchange = 'nccl'
         if exchange == 'ce':
             self._ce = bdist.CopyEngineExchange(tuple(self.grad.shape), n_buckets=1)
             self.grad = self._ce.grad
