@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
     bool pending = false;               // y kernels: the previous tile's result still sits in registers
     bool tables_ready = false;
     const float kdz = p.k_dz;
+    const float akdz = fabsf(kdz);
     for (; tile < tile_end; tile += tile_step) {
         const long long tile_off = tile * (long long)(RANGES ? N : N * LPC);
         const bool has_next = tile + tile_step < tile_end;
@@ -231,16 +232,35 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                 SWEEP_STAMP(4);
                 // t = exp(k(i delta - beta)) in place.  ROLLED on purpose: a straight-line version (64 x 20 instructions)
                 // pushed the kernel past the instruction cache and cost ~10k cycles on the first tile of every launch
-#pragma unroll 1
-                for (int q0 = 0; q0 < ((active && !(ADJ && p.db_is_t)) ? E : 0); q0 += 4) {
-                    float2 d[4];
-                    bool tiny = true, small = true;
+                const int q_end = (active && !(ADJ && p.db_is_t)) ? E : 0;
+                // software pipeline: the next group's (delta, beta) are loaded while this group is evaluated (its shared-memory
+                // latency hides behind the arithmetic); not in the y kernels of long lines, which have no registers to spare
+                constexpr bool PREF = !COL || N <= 1024;
+                [[maybe_unused]] float2 dn[4];
+                if constexpr (PREF) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        d[i] = Lme[(q0 + i) * LQ];
-                        tiny = tiny && transmission_is_tiny(d[i], kdz);
-                        small = small && transmission_is_small(d[i], kdz);
+                    for (int i = 0; i < 4; ++i) dn[i] = Lme[i * LQ];
+                }
+#pragma unroll 1
+                for (int q0 = 0; q0 < q_end; q0 += 4) {
+                    float2 d[4];
+                    if constexpr (PREF) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) d[i] = dn[i];
+                        if (q0 + 4 < E) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) dn[i] = Lme[(q0 + 4 + i) * LQ];
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) d[i] = Lme[(q0 + i) * LQ];
                     }
+                    // the largest |k delta|, |k beta| of the group pick the series: the same decision as testing every element
+                    // (rounding is monotonic), without the chain of dependent predicate updates
+                    const float md = akdz * fmaxf(fmaxf(fabsf(d[0].x), fabsf(d[1].x)), fmaxf(fabsf(d[2].x), fabsf(d[3].x)));
+                    const float mb = akdz * fmaxf(fmaxf(fabsf(d[0].y), fabsf(d[1].y)), fmaxf(fabsf(d[2].y), fabsf(d[3].y)));
+                    const bool tiny = md <= 0.0625f && mb <= 0.015625f;
+                    const bool small = md <= 0.78539816f && mb <= 0.5f;
                     if (__all_sync(0xffffffffu, tiny)) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) Lme[(q0 + i) * LQ] = transmission_tiny(d[i], kdz);
