@@ -20,7 +20,7 @@ SYMBOLS = [
     'bdof_patch_scatter_add', 'bdof_cnn_forward', 'bdof_forward_host', 'bdof_plan_workspace_bytes',
     'bdof_free_prop', 'bdof_profile_begin', 'bdof_profile_end', 'bdof_debug_set_buffer', 'bdof_slice_step',
     'bdof_plan_set_bucket_events', 'bdof_set_sm_reserve', 'bdof_rotate_gather', 'bdof_rotate_scatter_add', 'bdof_rotate_adjoint_csr', 'bdof_adam_step',
-    'bdof_finite_support', 'bdof_plan_set_t_stash',
+    'bdof_finite_support', 'bdof_plan_set_t_stash', 'bdof_rotate_bilinear', 'bdof_rotate_bilinear_adjoint',
     'bdof_dp_create', 'bdof_dp_destroy', 'bdof_dp_handle_bytes', 'bdof_dp_export', 'bdof_dp_connect', 'bdof_dp_grad_ptr',
     'bdof_dp_bucket', 'bdof_dp_gather', 'bdof_dp_finish',
 ]
@@ -73,6 +73,8 @@ def _load():
     lib.bdof_adam_step.argtypes = [vp, vp, vp, vp, i64, i32, f64, f64, f64, f64, vp]
     lib.bdof_finite_support.argtypes = [vp, vp, i64, f64, vp]
     lib.bdof_plan_set_t_stash.argtypes = [vp, vp]
+    lib.bdof_rotate_bilinear.argtypes = [vp, vp, i64, f64, i32, i32, i32, vp]
+    lib.bdof_rotate_bilinear_adjoint.argtypes = [vp, i64, vp, f64, i32, i32, i32, vp]
     sz = ctypes.c_size_t
     lib.bdof_dp_create.argtypes = [ctypes.POINTER(vp), i32, i32, sz, i32, i32]
     lib.bdof_dp_destroy.argtypes = [vp]

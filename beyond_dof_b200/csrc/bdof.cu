@@ -1054,6 +1054,86 @@ extern "C" int bdof_rotate_scatter_add(const float* d_grad_rot_db, long long sli
     return launch_check("k_rotate_scatter_add");
 }
 
+// Bilinear rotation of the TF drivers: tf.contrib.image.rotate(stack([delta, beta], -1), theta, 'BILINEAR') on [Y, X, Z, 2]
+// (tensorflow_recon/fullfield.py:96, ptychography.py:39), i.e. images of height X and width Z, one per y.  TF semantics
+// (contrib/image: angles_to_projective_transforms + ProjectiveGenerator): output pixel (x_o, z_o) samples the input at
+//   z_i = cos z_o - sin x_o + ((W-1) - (cos (W-1) - sin (H-1))) / 2,   x_i = sin z_o + cos x_o + ((H-1) - (sin (W-1) + cos (H-1))) / 2
+// (W = nz, H = nx) with bilinear weights over floor / floor + 1 and ZERO outside the image.
+struct BilinearTaps { int x0, z0; float wx0, wx1, wz0, wz1; };
+__device__ __forceinline__ BilinearTaps bilinear_taps(int x_o, int z_o, float c, float s, float off_z, float off_x) {
+    const float zi = c * float(z_o) - s * float(x_o) + off_z;
+    const float xi = s * float(z_o) + c * float(x_o) + off_x;
+    const float zf = floorf(zi), xf = floorf(xi);
+    BilinearTaps t;
+    t.x0 = int(xf); t.z0 = int(zf);
+    t.wx1 = xi - xf; t.wx0 = (xf + 1.f) - xi;
+    t.wz1 = zi - zf; t.wz0 = (zf + 1.f) - zi;
+    return t;
+}
+__global__ void k_rotate_bilinear(const float2* __restrict__ obj, float2* __restrict__ out, long long out_slice_stride, int ny, int nx,
+                                  int nz, float c, float s, float off_z, float off_x) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, z = blockIdx.z;
+    if (x >= nx) return;
+    const BilinearTaps t = bilinear_taps(x, z, c, s, off_z, off_x);
+    auto rd = [&](int xi, int zi) {
+        if (xi < 0 || xi >= nx || zi < 0 || zi >= nz) return make_float2(0.f, 0.f);
+        return obj[((long long)zi * ny + y) * nx + xi];
+    };
+    // TF order: interpolate along the width (z) first, then along the height (x)
+    const float2 a0 = rd(t.x0, t.z0), a1 = rd(t.x0, t.z0 + 1), b0 = rd(t.x0 + 1, t.z0), b1 = rd(t.x0 + 1, t.z0 + 1);
+    const float vx0d = t.wz0 * a0.x + t.wz1 * a1.x, vx0b = t.wz0 * a0.y + t.wz1 * a1.y;
+    const float vx1d = t.wz0 * b0.x + t.wz1 * b1.x, vx1b = t.wz0 * b0.y + t.wz1 * b1.y;
+    out[(long long)z * out_slice_stride + (long long)y * nx + x] = make_float2(t.wx0 * vx0d + t.wx1 * vx1d, t.wx0 * vx0b + t.wx1 * vx1b);
+}
+// transpose: every rotated pixel adds its weighted gradient to its (up to) four source pixels
+__global__ void k_rotate_bilinear_adj(const float2* __restrict__ grot, long long slice_stride, float2* __restrict__ gobj, int ny, int nx,
+                                      int nz, float c, float s, float off_z, float off_x) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, z = blockIdx.z;
+    if (x >= nx) return;
+    const BilinearTaps t = bilinear_taps(x, z, c, s, off_z, off_x);
+    const float2 g = grot[(long long)z * slice_stride + (long long)y * nx + x];
+    auto add = [&](int xi, int zi, float w) {
+        if (xi < 0 || xi >= nx || zi < 0 || zi >= nz || w == 0.f) return;
+        float* dst = reinterpret_cast<float*>(gobj + ((long long)zi * ny + y) * nx + xi);
+        atomicAdd(dst, w * g.x);
+        atomicAdd(dst + 1, w * g.y);
+    };
+    add(t.x0, t.z0, t.wx0 * t.wz0);
+    add(t.x0, t.z0 + 1, t.wx0 * t.wz1);
+    add(t.x0 + 1, t.z0, t.wx1 * t.wz0);
+    add(t.x0 + 1, t.z0 + 1, t.wx1 * t.wz1);
+}
+static void bilinear_consts(double theta, int nx, int nz, float* c, float* s, float* off_z, float* off_x) {
+    const double cs = std::cos(theta), sn = std::sin(theta), W = double(nz), H = double(nx);
+    *c = float(cs); *s = float(sn);
+    *off_z = float(((W - 1) - (cs * (W - 1) - sn * (H - 1))) / 2.0);
+    *off_x = float(((H - 1) - (sn * (W - 1) + cs * (H - 1))) / 2.0);
+}
+extern "C" int bdof_rotate_bilinear(const float* d_obj_db, float* d_out_db, long long out_slice_stride_px, double theta, int ny, int nx,
+                                    int nz, void* st) {
+    if (!d_obj_db || !d_out_db || ny < 1 || nx < 1 || nz < 1) return fail(BDOF_E_BADARG, "bad argument");
+    if (ny > 65535 || nz > 65535) return fail(BDOF_E_UNSUPPORTED, "ny / nz > 65535");
+    float c, s, oz, ox;
+    bilinear_consts(theta, nx, nz, &c, &s, &oz, &ox);
+    dim3 grid((nx + 127) / 128, ny, nz);
+    k_rotate_bilinear<<<grid, 128, 0, (cudaStream_t)st>>>(reinterpret_cast<const float2*>(d_obj_db), reinterpret_cast<float2*>(d_out_db),
+                                                        out_slice_stride_px, ny, nx, nz, c, s, oz, ox);
+    return launch_check("k_rotate_bilinear");
+}
+extern "C" int bdof_rotate_bilinear_adjoint(const float* d_grad_rot_db, long long slice_stride_px, float* d_grad_obj_db, double theta, int ny,
+                                            int nx, int nz, void* st) {
+    if (!d_grad_rot_db || !d_grad_obj_db || ny < 1 || nx < 1 || nz < 1) return fail(BDOF_E_BADARG, "bad argument");
+    if (ny > 65535 || nz > 65535) return fail(BDOF_E_UNSUPPORTED, "ny / nz > 65535");
+    float c, s, oz, ox;
+    bilinear_consts(theta, nx, nz, &c, &s, &oz, &ox);
+    dim3 grid((nx + 127) / 128, ny, nz);
+    k_rotate_bilinear_adj<<<grid, 128, 0, (cudaStream_t)st>>>(reinterpret_cast<const float2*>(d_grad_rot_db), slice_stride_px,
+                                                            reinterpret_cast<float2*>(d_grad_obj_db), ny, nx, nz, c, s, oz, ox);
+    return launch_check("k_rotate_bilinear_adj");
+}
+
 // Adam (apply_gradient_adam, cnn_propagator/util.py:280-291): one fused pass over x, g, m, v
 __global__ void k_adam(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
                        float b1, float b2, float omb1, float omb2, float inv_c1, float inv_c2, float step, float eps) {

@@ -51,12 +51,14 @@ def _scalar_theta(theta):
 
 def fullfield_loss_and_grad(obj_delta, obj_beta, theta_batch, prj_batch, probe_real, probe_imag, energy_ev, psize_cm,
                             free_prop_cm=None, alpha_d=None, alpha_b=None, gamma=0.0, propagate_last=True,
-                            want_grad=True):
+                            want_grad=True, rotation='nearest'):
     """loss = mean((|psi_exit| - |prj|)^2) [+ alpha_d |delta|_1 + alpha_b |beta|_1 + gamma TV(delta)]
     over a minibatch of projection angles; returns (loss, (g_delta, g_beta), exit_wave).
 
     obj_delta, obj_beta: [Y,X,Z] float32; prj_batch: [B,Y,X] complex or magnitude.
     propagate_last=True follows the TF driver (fullfield.py:107-109); False the NumPy simulator.
+    rotation: 'nearest' = the lookup tables of the cnn_propagator driver (apply_rotation), 'bilinear' = tf.contrib.image.rotate
+    of the TF driver (fullfield.py:96).
     """
     th = np.atleast_1d(np.asarray(theta_batch.cpu() if isinstance(theta_batch, torch.Tensor) else theta_batch, dtype=np.float64))
     B = len(th)
@@ -70,9 +72,14 @@ def fullfield_loss_and_grad(obj_delta, obj_beta, theta_batch, prj_batch, probe_r
     # every batch element sees the object rotated by its angle (apply_rotation, cnn_propagator/fullfield.py:95-100)
     obj_db = pack_object(od, ob)
     db = torch.empty((Z, B, Y, X, 2), dtype=torch.float32, device=dev)
-    tabs = [_rot.device_table([Y, X, Z], t, dev) for t in th]
+    if rotation not in ('nearest', 'bilinear'):
+        raise ValueError("rotation must be 'nearest' or 'bilinear'")
+    tabs = [_rot.device_table([Y, X, Z], t, dev) for t in th] if rotation == 'nearest' else None
     for b in range(B):
-        _rot.rotate_db(obj_db, tabs[b], out=db[:, b])
+        if tabs is not None:
+            _rot.rotate_db(obj_db, tabs[b], out=db[:, b])
+        else:
+            _rot.rotate_db_bilinear(obj_db, th[b], out=db[:, b])
     probe = _probe_c64(probe_real, probe_imag, (Y, X))
     plan.set_t_stash(db if want_grad else None)     # the in-place adjoint finds t_i where it will write the gradient
     exit_wave = plan.forward(db, probe)
@@ -86,7 +93,10 @@ def fullfield_loss_and_grad(obj_delta, obj_beta, theta_batch, prj_batch, probe_r
         plan.adjoint(db, g_exit)                       # db now holds (dL/ddelta, dL/dbeta) per ROTATED batch element
         g_obj = torch.zeros_like(obj_db)
         for b in range(B):
-            _rot.rotate_db_adjoint(db[:, b], tabs[b], g_obj)
+            if tabs is not None:
+                _rot.rotate_db_adjoint(db[:, b], tabs[b], g_obj)
+            else:
+                _rot.rotate_db_bilinear_adjoint(db[:, b], th[b], g_obj)
         g_d, g_b = unpack_object(g_obj)
     if alpha_d is not None and alpha_d != 0:
         loss = loss + alpha_d * od.abs().sum()
@@ -315,8 +325,12 @@ class TomographyObjective:
     """
 
     def __init__(self, db_obj, probe, energy_ev, psize_cm, minibatch_size, free_prop_cm=None, propagate_last=True,
-                 step_size=1e-7, deterministic=False, mask=None, shrink_threshold=None, alpha_d=None, alpha_b=None, gamma=0.0):
+                 step_size=1e-7, deterministic=False, mask=None, shrink_threshold=None, alpha_d=None, alpha_b=None, gamma=0.0,
+                 rotation='nearest'):
         Z, Y, X, _ = db_obj.shape
+        if rotation not in ('nearest', 'bilinear'):
+            raise ValueError("rotation must be 'nearest' (cnn_propagator tables) or 'bilinear' (tf.contrib.image.rotate)")
+        self.rotation = rotation
         # finite-support mask [Z,Y,X] float32 (native order), non-negativity and shrink-wrap after every update
         # (cnn_propagator/fullfield.py:359-368); L1 / TV regularisers of the TF driver (fullfield.py:389-396)
         self.mask = None if mask is None else mask.to(db_obj.device, torch.float32).contiguous()
@@ -361,7 +375,7 @@ class TomographyObjective:
     def prepare(self, thetas):
         """Build the rotation tables of all angles up front (the reference writes them to disk once and reads them
         back, save_rotation_lookup / read_all_origin_coords, cnn_propagator/fullfield.py:209-215)."""
-        for t in thetas:
+        for t in (thetas if self.rotation == 'nearest' else []):
             tab = _rot.device_table(self.shape, float(t), self.obj.device)
             if self.deterministic:
                 _rot.device_inverse(tab)
@@ -369,15 +383,22 @@ class TomographyObjective:
 
     def loss_and_grad(self, theta_batch, target_dev):
         dev = self.obj.device
-        tabs = [_rot.device_table(self.shape, float(t), dev) for t in theta_batch]
+        nearest = self.rotation == 'nearest'
+        tabs = [_rot.device_table(self.shape, float(t), dev) for t in theta_batch] if nearest else None
         for b in range(self.B):
-            _rot.rotate_db(self.obj, tabs[b], out=self.db[:, b])
+            if nearest:
+                _rot.rotate_db(self.obj, tabs[b], out=self.db[:, b])
+            else:
+                _rot.rotate_db_bilinear(self.obj, float(theta_batch[b]), out=self.db[:, b])
         self.plan.forward(self.db, self.probe, out=self.exit)
         loss, g = self.plan.loss_mag(self.exit, target_dev)
         self.plan.adjoint(self.db, g)
         self.grad.zero_()
         for b in range(self.B):
-            _rot.rotate_db_adjoint(self.db[:, b], tabs[b], self.grad, atomic=not self.deterministic)
+            if nearest:
+                _rot.rotate_db_adjoint(self.db[:, b], tabs[b], self.grad, atomic=not self.deterministic)
+            else:
+                _rot.rotate_db_bilinear_adjoint(self.db[:, b], float(theta_batch[b]), self.grad)
         if self._dp is not None:
             if self._ce is not None:
                 self._ce.exchange(None)

@@ -154,3 +154,25 @@ def finite_support(db_obj, mask=None, shrink_threshold=None):
     check(lib.bdof_finite_support(_ptr(db_obj), None if mask is None else _ptr(mask), db_obj.numel() // 2,
                                   -1.0 if shrink_threshold is None else float(shrink_threshold), st))
     return db_obj
+
+
+def rotate_db_bilinear(db_obj, theta, out=None):
+    """tf.contrib.image.rotate(stack([delta, beta], -1), theta, interpolation='BILINEAR') of the TF drivers
+    (tensorflow_recon/fullfield.py:96, ptychography.py:39) on the native object [Z, Y, X, 2] (CUDA float32): bilinear taps,
+    zero outside, rotation centre ((X-1)/2, (Z-1)/2).  `out` may be a batch-element view of a plan's [Z, B, Y, X, 2] object."""
+    Z, Y, X, _ = db_obj.shape
+    if out is None:
+        out = torch.empty_like(db_obj)
+    assert db_obj.is_contiguous() and out.shape == db_obj.shape and out.stride()[1:] == (X * 2, 2, 1) and out.stride(0) % 2 == 0
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib.bdof_rotate_bilinear(_ptr(db_obj), _ptr(out), out.stride(0) // 2, float(theta), Y, X, Z, st))
+    return out
+
+
+def rotate_db_bilinear_adjoint(grad_rot, theta, grad_obj):
+    """grad_obj [Z, Y, X, 2] += transpose of rotate_db_bilinear applied to grad_rot (what TF's autodiff of the rotation does)."""
+    Z, Y, X, _ = grad_obj.shape
+    assert grad_rot.shape == grad_obj.shape and grad_rot.stride()[1:] == (X * 2, 2, 1) and grad_obj.is_contiguous()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib.bdof_rotate_bilinear_adjoint(_ptr(grad_rot), grad_rot.stride(0) // 2, _ptr(grad_obj), float(theta), Y, X, Z, st))
+    return grad_obj

@@ -18,6 +18,7 @@
  *   bdof_patch_gather/scatter<- probe-window cut          tensorflow_recon/ptychography.py:62-76
  *   bdof_cnn_forward         <- multislice_propagate_cnn  cnn_propagator/propagation.py:18-133
  *   bdof_rotate_gather/scatter<- apply_rotation          cnn_propagator/util.py:374-402
+ *   bdof_rotate_bilinear(+adj)<- tf.contrib.image.rotate  tensorflow_recon/fullfield.py:96, ptychography.py:39
  *   bdof_adam_step           <- apply_gradient_adam       cnn_propagator/util.py:280-291
  *   bdof_finite_support      <- mask, clip, shrink-wrap   cnn_propagator/fullfield.py:359-368
  *   bdof_forward_host        <- the whole call with HOST buffers in the reference layout
@@ -152,6 +153,17 @@ int  bdof_rotate_scatter_add(const float* d_grad_rot_db, long long slice_stride_
  * pixels (z*nx + x) that read from each source pixel (z0*nx + x0); d_grad_obj_db is accumulated into (+=), no atomics. */
 int  bdof_rotate_adjoint_csr(const float* d_grad_rot_db, long long slice_stride_px, const int32_t* d_offsets,
                              const int32_t* d_dest, float* d_grad_obj_db, int ny, int nx, int nz, void* cuda_stream);
+
+/* SURVEY 8f-1, TF drivers: tf.contrib.image.rotate(stack([delta, beta], -1), theta, interpolation='BILINEAR')
+ * (tensorflow_recon/fullfield.py:96, ptychography.py:39) on the native object d_obj_db [nz][ny][nx][2]: rotation by theta
+ * (radians) in the (x, z) plane of every y, about ((nx-1)/2, (nz-1)/2), bilinear taps, zero outside (contrib/image semantics:
+ * angles_to_projective_transforms + ProjectiveGenerator).  The adjoint accumulates (+=) the transpose into d_grad_obj_db with
+ * fp32 atomics.  TensorFlow 1.x cannot run in the build container, so this pair is checked against a restatement only
+ * (parity unpinned by the reference). */
+int  bdof_rotate_bilinear(const float* d_obj_db, float* d_out_db, long long out_slice_stride_px, double theta, int ny, int nx, int nz,
+                          void* cuda_stream);
+int  bdof_rotate_bilinear_adjoint(const float* d_grad_rot_db, long long slice_stride_px, float* d_grad_obj_db, double theta, int ny,
+                                  int nx, int nz, void* cuda_stream);
 
 /* Adam update of apply_gradient_adam (cnn_propagator/util.py:280-291), fused over x, g, m, v (fp32, n values):
  * m = (1-b1) g + b1 m; v = (1-b2) g^2 + b2 v; x -= step * (m / (1-b1^(i+1))) / (sqrt(v / (1-b2^(i+1))) + eps). */

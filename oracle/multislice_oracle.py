@@ -463,6 +463,45 @@ def apply_rotation_adjoint(grad_rot, coord_old):
     return out
 
 
+def _tf_bilinear_taps(shape_yxz, theta):
+    """Source coordinates and weights of tf.contrib.image.rotate(..., 'BILINEAR') on [Y, X, Z, C]: images of height X and
+    width Z (TF 1.x contrib/image: angles_to_projective_transforms, then ProjectiveGenerator::bilinear_interpolation with
+    fill value 0).  TensorFlow cannot run here: restated from the published algorithm, checked against
+    scipy.ndimage.affine_transform(order=1, mode='grid-constant') -- parity unpinned by the reference."""
+    Y, X, Z = shape_yxz
+    H, W = X, Z
+    c, s = np.cos(theta), np.sin(theta)
+    x_off = ((W - 1) - (c * (W - 1) - s * (H - 1))) / 2.0
+    y_off = ((H - 1) - (s * (W - 1) + c * (H - 1))) / 2.0
+    ho, wo = np.meshgrid(np.arange(H, dtype=np.float64), np.arange(W, dtype=np.float64), indexing='ij')
+    wi = c * wo - s * ho + x_off
+    hi = s * wo + c * ho + y_off
+    wf, hf = np.floor(wi), np.floor(hi)
+    taps = []
+    for dh, wh in ((0, hf + 1 - hi), (1, hi - hf)):
+        for dw, ww in ((0, wf + 1 - wi), (1, wi - wf)):
+            h, w = (hf + dh).astype(int), (wf + dw).astype(int)
+            ok = (h >= 0) & (h < H) & (w >= 0) & (w < W)
+            taps.append((np.clip(h, 0, H - 1), np.clip(w, 0, W - 1), wh * ww * ok))
+    return taps
+
+
+def tf_rotate_bilinear(obj, theta):
+    """tf_rotate(obj [Y, X, Z, C], theta, interpolation='BILINEAR')   (tensorflow_recon/fullfield.py:96)."""
+    out = np.zeros(obj.shape, dtype=np.float64)
+    for h, w, wt in _tf_bilinear_taps(obj.shape[:3], theta):
+        out += obj[:, h, w, ...] * wt[None, ..., None]
+    return out
+
+
+def tf_rotate_bilinear_adjoint(grad_rot, theta):
+    """Transpose of tf_rotate_bilinear (what TF's autodiff of the rotation computes)."""
+    out = np.zeros(grad_rot.shape, dtype=np.float64)
+    for h, w, wt in _tf_bilinear_taps(grad_rot.shape[:3], theta):
+        np.add.at(out, (slice(None), h, w), grad_rot * wt[None, ..., None])
+    return out
+
+
 def apply_gradient_adam(x, g, i_batch, m=None, v=None, step_size=0.001, b1=0.9, b2=0.999, eps=1e-8):
     """cnn_propagator/util.py:280-291 (first call: zero moments)."""
     g = np.array(g)
@@ -478,12 +517,20 @@ def apply_gradient_adam(x, g, i_batch, m=None, v=None, step_size=0.001, b1=0.9, 
 
 
 def tomo_loss_and_grad(obj_delta, obj_beta, theta_batch, prj_batch, probe_real, probe_imag, energy_ev, psize_cm,
-                       free_prop_cm=None, propagate_last=False):
+                       free_prop_cm=None, propagate_last=False, rotation='nearest'):
     """Rotate (nearest-neighbour table) -> multislice -> mean((|psi| - |prj|)^2) over the minibatch, and its
     gradient w.r.t. the UNROTATED object (calculate_loss of cnn_propagator/fullfield.py:93-107 with the FFT
     propagator in place of the real-space one)."""
     Y, X, Z = obj_delta.shape
     obj = np.stack([obj_delta, obj_beta], axis=3).astype(np.float64)
+    if rotation == 'bilinear':              # the TF driver (tensorflow_recon/fullfield.py:92-116)
+        rot = np.stack([tf_rotate_bilinear(obj, th) for th in theta_batch])
+        loss, gd, gb, psi = loss_and_grad(rot[..., 0], rot[..., 1], probe_real, probe_imag, energy_ev, psize_cm,
+                                          prj_batch, free_prop_cm=free_prop_cm, propagate_last=propagate_last)
+        g = np.zeros_like(obj)
+        for b, th in enumerate(theta_batch):
+            g += tf_rotate_bilinear_adjoint(np.stack([gd[b], gb[b]], axis=3), th)
+        return loss, g[..., 0], g[..., 1], psi
     tabs = [rotation_lookup([Y, X, Z], th) for th in theta_batch]
     rot = np.stack([apply_rotation(obj, t) for t in tabs])                       # [B, Y, X, Z, 2]
     loss, gd, gb, psi = loss_and_grad(rot[..., 0], rot[..., 1], probe_real, probe_imag, energy_ev, psize_cm,

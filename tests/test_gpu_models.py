@@ -278,3 +278,43 @@ def test_tomography_objective_regularisers_and_support(bd):
     outside = np.ones((Y, X, Z), bool); outside[8:56, 8:56, :] = False
     assert np.all(d.cpu().numpy()[outside] == 0) and np.all(b.cpu().numpy()[outside] == 0)
     assert d.min().item() >= 0 and b.min().item() >= 0
+
+
+@pytest.mark.parametrize('shape,theta', [((5, 24, 24), 0.4), ((3, 20, 36), 2.1), ((2, 33, 17), -1.0), ((4, 16, 16), 0.0)])
+def test_bilinear_rotation_and_transpose_match_restatement(bd, shape, theta):
+    # tf.contrib.image.rotate(..., 'BILINEAR') of the TF drivers (tensorflow_recon/fullfield.py:96): GPU kernels against the
+    # oracle restatement (itself checked against scipy in tests/test_oracle.py; TF 1.x cannot run here)
+    from beyond_dof_b200 import rotation
+    Y, X, Z = shape
+    rng = np.random.default_rng(92)
+    obj = rng.random((Y, X, Z, 2)).astype(np.float32)
+    db = torch.as_tensor(obj).cuda().permute(2, 0, 1, 3).contiguous()                 # [Z, Y, X, 2]
+    batch = torch.zeros((Z, 3, Y, X, 2), device='cuda')
+    rotation.rotate_db_bilinear(db, theta, out=batch[:, 1])                            # strided batch-element view
+    got = batch[:, 1].permute(1, 2, 0, 3).cpu().numpy()
+    ref = mo.tf_rotate_bilinear(obj.astype(np.float64), theta)
+    assert np.abs(got - ref).max() < 2e-5                                             # fp32 coordinates: weights differ by ~1e-6 * size
+    assert float(batch[:, 0].abs().max()) == 0 and float(batch[:, 2].abs().max()) == 0
+    g = rng.standard_normal((Y, X, Z, 2)).astype(np.float32)
+    batch[:, 1] = torch.as_tensor(g).cuda().permute(2, 0, 1, 3)
+    acc = torch.ones((Z, Y, X, 2), device='cuda')
+    rotation.rotate_db_bilinear_adjoint(batch[:, 1], theta, acc)                       # accumulates
+    gref = mo.tf_rotate_bilinear_adjoint(g.astype(np.float64), theta) + 1.0
+    assert np.abs(acc.permute(1, 2, 0, 3).cpu().numpy() - gref).max() < 1e-4
+
+
+def test_fullfield_loss_and_grad_with_bilinear_rotation(bd):
+    Y, X, Z, B = 64, 64, 64, 3
+    rng = np.random.default_rng(93)
+    od = (rng.random((Y, X, Z)) * 4e-4).astype(np.float32)
+    ob = (rng.random((Y, X, Z)) * 4e-5).astype(np.float32)
+    theta = np.array([0.0, 0.6, 2.5])
+    one, zero = np.ones((Y, X)), np.zeros((Y, X))
+    target = rng.random((B, Y, X)) + 0.5
+    lo, gdo, gbo, psio = mo.tomo_loss_and_grad(od, ob, theta, target, one, zero, 5000, 1e-7, free_prop_cm=None, propagate_last=True,
+                                               rotation='bilinear')
+    loss, (g_d, g_b), ex = bd.fullfield_loss_and_grad(od, ob, theta, target, one, zero, 5000, 1e-7, propagate_last=True,
+                                                      rotation='bilinear')
+    assert rel_l2(np.abs(ex.cpu().numpy()) ** 2, np.abs(psio) ** 2) < 1e-5
+    assert abs(loss.item() - lo) < 1e-5 * abs(lo)
+    assert rel_l2(g_d.cpu().numpy(), gdo) < 1e-4 and rel_l2(g_b.cpu().numpy(), gbo) < 1e-4
