@@ -133,7 +133,7 @@ def unpack_object(db_obj):
 
 def ptycho_loss_and_grad(obj_delta, obj_beta, theta, probe_pos_batch, prj_batch, probe_real, probe_imag, probe_size,
                          energy_ev, psize_cm, n_dp_batch=None, scale_by_npos=True, n_pos_total=None, want_grad=True,
-                         db_obj=None, grad_obj_out=None):
+                         db_obj=None, grad_obj_out=None, rotation='nearest'):
     """Ptychography forward model + loss + gradient for one rotation angle theta (radians; the object is rotated with the
     reference's nearest-neighbour table first, cnn_propagator/ptychography.py:32-34, and the gradient rotated back).
 
@@ -152,9 +152,14 @@ def ptycho_loss_and_grad(obj_delta, obj_beta, theta, probe_pos_batch, prj_batch,
         db_obj = pack_object(obj_delta, obj_beta)
     Z, OY, OX, _ = db_obj.shape
     tab = None
-    if th != 0.0:
+    obj_unrot = db_obj
+    if rotation not in ('nearest', 'bilinear'):
+        raise ValueError("rotation must be 'nearest' or 'bilinear'")
+    if th != 0.0 and rotation == 'nearest':
         tab = _rot.device_table([OY, OX, Z], th, dev)
         db_obj = _rot.rotate_db(db_obj, tab)
+    elif th != 0.0:
+        db_obj = _rot.rotate_db_bilinear(db_obj.contiguous(), th)        # tf_rotate(..., 'BILINEAR'), ptychography.py:39
     py, px = int(probe_size[0]), int(probe_size[1])
     pos = np.asarray(probe_pos_batch.cpu() if isinstance(probe_pos_batch, torch.Tensor) else probe_pos_batch).astype(np.int64)
     n = len(pos)
@@ -178,12 +183,15 @@ def ptycho_loss_and_grad(obj_delta, obj_beta, theta, probe_pos_batch, prj_batch,
     plan.adjoint(patches, g_exit)
     if grad_obj_out is None:
         grad_obj_out = torch.zeros_like(db_obj)
-    if tab is None:
+    if db_obj is obj_unrot:
         check(lib.bdof_patch_scatter_add(_ptr(patches), Z, OY, OX, _ptr(origin), n, py, px, _ptr(grad_obj_out), st))
     else:
         g_rot = torch.zeros_like(db_obj)
         check(lib.bdof_patch_scatter_add(_ptr(patches), Z, OY, OX, _ptr(origin), n, py, px, _ptr(g_rot), st))
-        _rot.rotate_db_adjoint(g_rot, tab, grad_obj_out)
+        if tab is not None:
+            _rot.rotate_db_adjoint(g_rot, tab, grad_obj_out)
+        else:
+            _rot.rotate_db_bilinear_adjoint(g_rot, th, grad_obj_out)
     if native:
         return loss, grad_obj_out
     return loss, unpack_object(grad_obj_out)

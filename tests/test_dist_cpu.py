@@ -147,3 +147,21 @@ def test_tile_layout_validation():
     lay = tiling.TileLayout(96, 48, 64, 8, 4)
     assert (lay.ty, lay.tx, lay.interior) == (2, 1, 48)
     assert [len(lay.tiles_of(r)) for r in range(4)] == [1, 1, 0, 0]
+
+
+def _pick(rank, world):
+    from beyond_dof_b200 import dist as bd
+    return bd.pick_exchange()
+
+
+def test_exchange_policy_and_dynamic_dropping():
+    # two ranks: copy engines; anything else: NCCL (measured on B200); no process group: NCCL path (a no-op)
+    from beyond_dof_b200 import dist as bd
+    assert bd.pick_exchange() == 'nccl'
+    assert spawn(_pick, 2) == ['ce', 'ce']
+    assert spawn(_pick, 3) == ['nccl'] * 3
+    # the reference drops the scan positions whose loss is below the threshold (cnn_propagator/ptychography.py:340)
+    from beyond_dof_b200.models import dynamic_dropping
+    table = np.array([1e-3, 2e-5, 8e-5, 7.9e-5, 0.5])
+    assert dynamic_dropping(table).tolist() == [0, 2, 4]
+    assert dynamic_dropping(torch.as_tensor(table), dropping_threshold=1e-2).tolist() == [4]

@@ -318,3 +318,25 @@ def test_fullfield_loss_and_grad_with_bilinear_rotation(bd):
     assert rel_l2(np.abs(ex.cpu().numpy()) ** 2, np.abs(psio) ** 2) < 1e-5
     assert abs(loss.item() - lo) < 1e-5 * abs(lo)
     assert rel_l2(g_d.cpu().numpy(), gdo) < 1e-4 and rel_l2(g_b.cpu().numpy(), gbo) < 1e-4
+
+
+def test_ptycho_with_bilinear_rotation(bd):
+    # TF ptychography driver: tf_rotate(..., 'BILINEAR') before the window cut (tensorflow_recon/ptychography.py:39); the
+    # bilinear rotation has no square-cross-section restriction
+    Y, X, Z = 90, 80, 6
+    probe_size = (64, 64)
+    od, ob = mo.random_phantom((Y, X, Z), seed=94, delta_scale=3e-4, beta_scale=3e-5)
+    gt_d, gt_b = mo.random_phantom((Y, X, Z), seed=95, delta_scale=5e-3, beta_scale=5e-3)
+    pr, pi = mo.gaussian_probe(probe_size, 6., 6., 0.5)
+    pos = [(3, 5), (45, 40), (89, 79), (30, 60)]
+    theta = 0.3
+
+    def rot(a, b):
+        r = mo.tf_rotate_bilinear(np.stack([a, b], axis=3).astype(np.float64), theta)
+        return r[..., 0], r[..., 1]
+    _, prj = mo.ptycho_loss(*rot(gt_d, gt_b), pos, np.zeros((len(pos),) + probe_size), pr, pi, probe_size, 5000, 1e-7)
+    lo, gdr, gbr, _ = mo.ptycho_loss_and_grad(*rot(od, ob), pos, prj, pr, pi, probe_size, 5000, 1e-7)
+    go = mo.tf_rotate_bilinear_adjoint(np.stack([gdr, gbr], axis=3), theta)
+    loss, (g_d, g_b) = bd.ptycho_loss_and_grad(od, ob, theta, pos, prj, pr, pi, probe_size, 5000, 1e-7, rotation='bilinear')
+    assert abs(loss.item() - lo) < 1e-5 * abs(lo)
+    assert rel_l2(g_d.cpu().numpy(), go[..., 0]) < 1e-4 and rel_l2(g_b.cpu().numpy(), go[..., 1]) < 1e-4
