@@ -33,6 +33,6 @@ def __getattr__(name):
     if name in _LAZY:
         mod = importlib.import_module('.' + _LAZY[name], __name__)
         return getattr(mod, name)
-    if name in ('capi', 'plan', 'propagation', 'models', 'util', 'build', 'dist', 'rotation', 'tiling'):
+    if name in ('capi', 'plan', 'propagation', 'models', 'util', 'build', 'dist', 'rotation', 'tiling', 'np_funcs'):
         return importlib.import_module('.' + name, __name__)
     raise AttributeError(name)

@@ -155,9 +155,41 @@ np.savez_compressed(out, **res)
 '''
 
 
+CHILD_NPF = r'''
+import sys, types
+import numpy as np
+from unittest.mock import MagicMock
+for m in ("tensorflow", "dxchange", "h5py", "matplotlib", "matplotlib.pyplot", "tqdm"):
+    sys.modules[m] = MagicMock()
+ag = types.ModuleType("autograd"); ag.numpy = np; ag.grad = lambda *a, **k: None
+pf = types.ModuleType("pyfftw"); pfi = types.ModuleType("pyfftw.interfaces"); pfi.numpy_fft = np.fft; pf.interfaces = pfi
+sys.modules.update({"autograd": ag, "autograd.numpy": np, "autograd.numpy.random": np.random,
+                    "pyfftw": pf, "pyfftw.interfaces": pfi, "pyfftw.interfaces.numpy_fft": np.fft})
+np.int = int
+sys.path.insert(0, sys.argv[1] + "/cnn_propagator")
+import np_funcs                              # cnn_propagator/np_funcs.py:15-65: returns (wavefront, probe_array)
+out = sys.argv[2]
+sys.path.insert(0, sys.argv[3] + "/oracle")
+import multislice_oracle as mo
+res = {}
+gd, gb = mo.random_phantom((2, 32, 40, 5), seed=23, delta_scale=3e-4, beta_scale=3e-5)
+pr, pi = mo.gaussian_probe((32, 40), 7., 7., 0.5)
+for tag, free in (("none", None), ("inf", "inf"), ("free", 2e-6)):
+    wf, pa = np_funcs.multislice_propagate_batch_numpy(gd.astype(np.float64), gb.astype(np.float64), pr, pi, 5000, 1e-7,
+                                                       free_prop_cm=free, obj_batch_shape=gd.shape)
+    res["npf_wavefront_" + tag] = wf
+    if free is None:
+        res["npf_probe_array"] = pa
+np.savez_compressed(out, **res)
+'''
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    for name, code in (('ref_fft.npz', CHILD_FFT), ('ref_cnn.npz', CHILD_CNN), ('ref_rot.npz', CHILD_ROT)):
+    only = sys.argv[1:]
+    for name, code in (('ref_fft.npz', CHILD_FFT), ('ref_cnn.npz', CHILD_CNN), ('ref_rot.npz', CHILD_ROT), ('ref_npfuncs_cnn.npz', CHILD_NPF)):
+        if only and name not in only:
+            continue
         path = os.path.join(OUT, name)
         subprocess.run([sys.executable, '-c', code, REF, path, ROOT], check=True)
         print('wrote', path, os.path.getsize(path), 'bytes')

@@ -141,6 +141,33 @@ def multislice_propagate_batch_numpy(grid_delta_batch, grid_beta_batch, probe_re
                               psize_cm, free_prop_cm, obj_batch_shape, propagate_last=False, pi=PI_TF)
 
 
+def multislice_propagate_batch_numpy_cnn(grid_delta_batch, grid_beta_batch, probe_real, probe_imag, energy_ev, psize_cm,
+                                         free_prop_cm=None, obj_batch_shape=None):
+    """Restatement of cnn_propagator/np_funcs.py:15-65: the same loop with PI = 3.1415927 (np_funcs.py:12), returning
+    (wavefront, probe_array) where probe_array[i] is the field after slice i (np_funcs.py:41), before the free-space step."""
+    gd = np.asarray(grid_delta_batch, dtype=np.float64)
+    gb = np.asarray(grid_beta_batch, dtype=np.float64)
+    if obj_batch_shape is None:
+        obj_batch_shape = gd.shape
+    grid_shape = list(obj_batch_shape[1:])
+    voxel_nm = np.array([psize_cm] * 3) * 1.e7
+    wavefront = np.zeros([obj_batch_shape[0], obj_batch_shape[1], obj_batch_shape[2]], dtype=np.complex64)
+    wavefront += (np.asarray(probe_real) + 1j * np.asarray(probe_imag))
+    wavefront = wavefront.astype(np.complex128)
+    lmbda_nm = 1240. / energy_ev
+    n_slice = obj_batch_shape[-1]
+    h = get_kernel(voxel_nm[-1], lmbda_nm, voxel_nm, grid_shape, pi=PI_CNN)
+    k = 2. * PI_CNN * voxel_nm[-1] / lmbda_nm
+    probe_array = []
+    for i in range(n_slice):
+        wavefront = wavefront * (np.exp(1j * k * gd[:, :, :, i]) * np.exp(-k * gb[:, :, :, i]))
+        if i < n_slice - 1:
+            wavefront = _propagate(wavefront, h)
+        probe_array.append(wavefront)
+    wavefront = _free_prop(wavefront, free_prop_cm, lmbda_nm, voxel_nm, grid_shape, PI_CNN)
+    return wavefront, np.array(probe_array)
+
+
 def multislice_propagate_batch(grid_delta_batch, grid_beta_batch, probe_real, probe_imag, energy_ev,
                                psize_cm, h=None, free_prop_cm=None, obj_batch_shape=None):
     """Restatement of tensorflow_recon/util.py:432-508, type='plane' (TF semantics),

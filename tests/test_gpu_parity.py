@@ -518,3 +518,23 @@ def test_transmission_stash_gives_identical_gradients(bd, shape, mode, propagate
     plan.forward(db, probe)
     plan.adjoint(db, g, grad_out=g1)
     assert torch.equal(g1, g0)
+
+
+def test_np_funcs_variant_returns_probe_array(bd, golden_dir):
+    # drop-in for cnn_propagator/np_funcs.py:15-65 against the reference's own output (mixed-radix 32 x 40 field)
+    from beyond_dof_b200 import np_funcs
+    g = np.load(os.path.join(golden_dir, 'ref_npfuncs_cnn.npz'))
+    gd, gb = mo.random_phantom((2, 32, 40, 5), seed=23, delta_scale=3e-4, beta_scale=3e-5)
+    pr, pi = mo.gaussian_probe((32, 40), 7., 7., 0.5)
+    for tag, free in (('none', None), ('inf', 'inf'), ('free', 2e-6)):
+        wf, pa = np_funcs.multislice_propagate_batch_numpy(gd, gb, pr, pi, 5000, 1e-7, free_prop_cm=free, obj_batch_shape=gd.shape)
+        assert wf.dtype == np.complex64 and pa.shape == (5, 2, 32, 40)
+        assert rel_l2(wf, g['npf_wavefront_' + tag]) < 1e-5 and intensity_err(wf, g['npf_wavefront_' + tag]) < TOL_INTENSITY
+        assert rel_l2(pa, g['npf_probe_array']) < 1e-5
+    # power-of-two field, torch in -> torch out, against the oracle
+    gd, gb = mo.random_phantom((1, 64, 128, 4), seed=24, delta_scale=3e-4, beta_scale=3e-5)
+    one, zero = np.ones((64, 128), np.float32), np.zeros((64, 128), np.float32)
+    wf, pa = np_funcs.multislice_propagate_batch_numpy(torch.as_tensor(gd).cuda(), torch.as_tensor(gb).cuda(), torch.as_tensor(one).cuda(),
+                                                       torch.as_tensor(zero).cuda(), 5000, 1e-7, obj_batch_shape=gd.shape)
+    wo, po = mo.multislice_propagate_batch_numpy_cnn(gd, gb, one, zero, 5000, 1e-7, obj_batch_shape=gd.shape)
+    assert wf.is_cuda and rel_l2(wf.cpu().numpy(), wo) < 1e-5 and rel_l2(pa.cpu().numpy(), po) < 1e-5

@@ -241,3 +241,16 @@ def test_bilinear_rotation_restatement_against_scipy_and_its_transpose():
         rhs = np.sum(obj * mo.tf_rotate_bilinear_adjoint(g, theta))
         assert abs(lhs - rhs) < 1e-10 * max(1.0, abs(lhs))
     assert np.allclose(mo.tf_rotate_bilinear(obj, 0.0), obj)
+
+
+def test_np_funcs_variant_matches_reference(golden_dir):
+    # cnn_propagator/np_funcs.py:15-65 executed unmodified (oracle/gen_golden.py, CHILD_NPF): (wavefront, probe_array)
+    g = np.load(os.path.join(golden_dir, 'ref_npfuncs_cnn.npz'))
+    gd, gb = mo.random_phantom((2, 32, 40, 5), seed=23, delta_scale=3e-4, beta_scale=3e-5)
+    pr, pi = mo.gaussian_probe((32, 40), 7., 7., 0.5)
+    for tag, free in (('none', None), ('inf', 'inf'), ('free', 2e-6)):
+        wf, pa = mo.multislice_propagate_batch_numpy_cnn(gd, gb, pr, pi, 5000, 1e-7, free_prop_cm=free, obj_batch_shape=gd.shape)
+        assert rel_l2(wf, g['npf_wavefront_' + tag]) < 1e-13
+        if free is None:
+            assert pa.shape == (5, 2, 32, 40) and rel_l2(pa, g['npf_probe_array']) < 1e-13
+            assert np.array_equal(pa[-1], wf)
