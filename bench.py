@@ -48,20 +48,6 @@ PASS_BYTES = {'row_conv_transmit': 24, 'col_conv': 16, 'row_conv_adjoint': 40,
 STEP_BYTES = 96
 
 
-def auto_sm_reserve(B, ny, nx, n_sm=148, max_reserve=24):
-    """largest number of SMs (<= max_reserve) that can be left to NCCL without adding a round of tiles to the
-    sweep kernels (8 lines per tile up to 2048-long lines, 4 for 4096)"""
-    def rounds(lines, length, ctas):
-        lpc = 4 if length >= 4096 else (8 if length >= 256 else 16)
-        tiles = B * lines // lpc
-        return -(-tiles // ctas)
-    best = 0
-    for r in range(0, max_reserve + 1):
-        if rounds(ny, nx, n_sm - r) == rounds(ny, nx, n_sm) and rounds(nx, ny, n_sm - r) == rounds(nx, ny, n_sm):
-            best = r
-    return best
-
-
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -179,6 +165,162 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def _make_db(torch, dev, nz, B, ny, nx, seed):
+    """synthetic (delta, beta) in the native slice-major layout, config-2 recipe (delta <= 1e-5, beta <= 1e-6)"""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    db = torch.empty((nz, B, ny, nx, 2), dtype=torch.float32, device=dev)
+    for z0 in range(0, nz, 16):                       # bounded temporaries
+        blk = db[z0:z0 + 16]
+        blk.copy_(torch.rand(blk.shape, device=dev, generator=g))
+        blk[..., 0] *= 1e-5
+        blk[..., 1] *= 1e-6
+    return db
+
+
+def _time_steps(torch, dist, world, dev, fn, steps):
+    """barrier + synchronize, `steps` calls of fn timed by CUDA events on the current stream, max over ranks -> ms per step"""
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    out = None
+    for _ in range(steps):
+        out = fn()
+    ev1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item() / steps, out
+
+
+def _traffic(workload_key):
+    """ncu DRAM bytes per sweep launch (dram__bytes_read.sum + dram__bytes_write.sum, `ncu --set full`), transcribed from the
+    committed summary named in the entry: NOT measured by this run."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            return json.load(f).get(workload_key)
+    except Exception:
+        return None
+
+
+def _sweep_roofline(obj, px, nz, ms_step, value_per_gpu, peak, peak_src, traffic_key):
+    """Roofline record of the dominant kernel family (sweep_kernel: one launch per slice and direction).  Durations come from
+    ONE event pair around the whole forward launch sequence and one around the adjoint's (bdof_plan_last_times), inside a
+    normal step: the launches overlap exactly as in production (programmatic dependent launch), the few small kernels of each
+    call (probe broadcast, phase scale) are counted as sweep time, and forward + adjoint <= ms_per_step by construction."""
+    lt = obj.plan.last_times()
+    (f_ms, f_n), (a_ms, a_n) = lt['forward'], lt['adjoint']
+    n_launch = 2 * nz
+    avg_ms = (f_ms + a_ms) / n_launch
+    alg = px * STEP_BYTES / 2.0                                   # (40 + 56) / 2 bytes per pixel per launch
+    ach = alg / (avg_ms * 1e-3) / 1e9
+    tr = _traffic(traffic_key)
+    return {'bound': 'hbm',
+            'kernel': 'sweep_kernel (forward + adjoint instantiations, %d launches per step)' % n_launch,
+            'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+            'traffic': (tr or {}).get('bytes_per_launch'), 'traffic_source': (tr or {}).get('source'),
+            'alg_bytes_per_launch': alg, 'avg_launch_ms': avg_ms,
+            'forward_ms': f_ms, 'adjoint_ms': a_ms, 'kernel_ms_per_step': f_ms + a_ms, 'ms_per_step': ms_step,
+            'consistent': bool(f_ms + a_ms <= ms_step * 1.02),
+            'by_direction': {'forward': {'alg_bytes_per_px': 40, 'achieved_gbs': px * 40 * nz / (f_ms * 1e-3) / 1e9},
+                             'adjoint': {'alg_bytes_per_px': 56, 'achieved_gbs': px * 56 * nz / (a_ms * 1e-3) / 1e9}},
+            'peak_source': peak_src,
+            'whole_step': {'alg_bytes_per_px_slice': STEP_BYTES, 'achieved_per_gpu': value_per_gpu * STEP_BYTES,
+                           'frac': value_per_gpu * STEP_BYTES / peak}}
+
+
+def cufft_comparison(torch, dev, ny, nx, n_sample, steps=3):
+    """COMPARISON ONLY (north_star: "cuFFT timed only as a comparison"; never on the product path): the reference's unfused
+    TF loop (tensorflow_recon/util.py:464-483: exp, multiply, fft2, fftshift, multiply by H, ifftshift, ifft2) restated op by
+    op on torch (cuFFT + elementwise kernels), complex64, slice-major inputs (kinder than the reference's z-fastest layout),
+    forward only and forward + autograd backward (what the TF driver's minimize() runs), on n_sample slices of this field."""
+    import math
+    k = 2 * math.pi * 1.0 / (1240. / ENERGY_EV)
+    g = torch.Generator(device=dev).manual_seed(5)
+    delta = torch.rand((n_sample, 1, ny, nx), device=dev, generator=g) * 1e-5
+    beta = torch.rand((n_sample, 1, ny, nx), device=dev, generator=g) * 1e-6
+    fy = torch.linspace(-0.5, 0.5, ny, device=dev, dtype=torch.float64)
+    fx = torch.linspace(-0.5, 0.5, nx, device=dev, dtype=torch.float64)
+    lam = 1240. / ENERGY_EV
+    H = torch.exp(-1j * math.pi * lam * 1.0 * (fy[:, None] ** 2 + fx[None, :] ** 2)).to(torch.complex64)       # centred, as get_kernel
+    target = torch.full((1, ny, nx), 0.95, device=dev)
+
+    def forward(d, b):
+        psi = torch.ones((1, ny, nx), dtype=torch.complex64, device=dev)
+        for i in range(n_sample):
+            c = torch.exp(torch.complex(-k * b[i], k * d[i]))
+            psi = psi * c
+            psi = torch.fft.ifft2(torch.fft.ifftshift(torch.fft.fftshift(torch.fft.fft2(psi), dim=(1, 2)) * H, dim=(1, 2)))
+        return psi
+
+    def fwd_only():
+        with torch.no_grad():
+            return forward(delta, beta)
+
+    def fwd_bwd():
+        d = delta.clone().requires_grad_(True)
+        b = beta.clone().requires_grad_(True)
+        loss = ((forward(d, b).abs() - target) ** 2).mean()
+        loss.backward()
+        return loss
+
+    res = {}
+    for name, fn in (('forward', fwd_only), ('forward_backward', fwd_bwd)):
+        try:
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            res[name] = {'value': ny * nx * n_sample / (ms * 1e-3) / 1e9, 'unit': 'Gpixel*slice/s', 'ms': ms}
+        except Exception as ex:            # noqa: BLE001
+            res[name] = {'error': '%s: %s' % (type(ex).__name__, str(ex)[:200])}
+    res['what'] = ('reference TF loop (util.py:464-483) restated on torch.fft/cuFFT, unfused, complex64, [1,%d,%d] x %d slices; '
+                   'comparison only, not on the product path' % (ny, nx, n_sample))
+    del delta, beta
+    torch.cuda.empty_cache()
+    return res
+
+
+def host_object_leg(torch, ny, nx, nz, target_host):
+    """e2e with the OBJECT on the host too: the literal drop-in of the cnn_propagator driver's call
+    loss_grad(obj_delta, obj_beta, this_ind_batch, this_prj_batch) (cnn_propagator/fullfield.py:329,346) with NumPy arrays in
+    and NumPy gradients out.  PCIe-bound by construction; reported beside `e2e`, whose object lives on the GPU as the
+    tf.Variables of the TF driver do (tensorflow_recon/fullfield.py:243-303)."""
+    try:
+        from beyond_dof_b200.models import fullfield_loss_and_grad_host
+        rng = np.random.default_rng(77)
+        od = rng.random((ny, nx, nz), dtype=np.float32); od *= np.float32(1e-5)
+        ob = rng.random((ny, nx, nz), dtype=np.float32); ob *= np.float32(1e-6)
+        prj_np = target_host.numpy()
+        one, zero = np.ones((ny, nx), np.float32), np.zeros((ny, nx), np.float32)
+        g_d, g_b = np.empty_like(od), np.empty_like(ob)
+
+        def host_call():
+            return fullfield_loss_and_grad_host(od, ob, prj_np, one, zero, ENERGY_EV, PSIZE_CM, propagate_last=False,
+                                                out=(g_d, g_b))
+        host_call()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        host_call()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return {'value': ny * nx * nz / dt / 1e9, 'unit': 'Gpixel*slice/s', 'ms_per_step': dt * 1e3,
+                'h2d_bytes_per_step': int(od.nbytes + ob.nbytes + prj_np.nbytes), 'd2h_bytes_per_step': int(od.nbytes + ob.nbytes + 8),
+                'api': 'beyond_dof_b200.models.fullfield_loss_and_grad_host(NumPy delta, beta [Y,X,Z], NumPy projections) -> loss, NumPy '
+                       'gradients (pageable host arrays in and out, chunked through pinned staging; wall clock)'}
+    except Exception as ex:            # noqa: BLE001  (an optional extra must not take the bench line down)
+        return {'error': '%s: %s' % (type(ex).__name__, str(ex)[:300])}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -197,228 +339,126 @@ def run_gpu(args):
     if args.shape:
         B, ny, nx, nz = (int(v) for v in args.shape.split(','))
         desc = 'custom shape %s' % args.shape
-    sm_reserve = 0
     if world > 1:
         import datetime
-        # The sweep kernels are persistent (one CTA per SM, all of its shared memory and registers), so the NCCL kernels
-        # that reduce the gradient buckets take SMs away from them while both run.  Measured on 2 B200 (2048^2x256, 8.6 GB
-        # gradient, 14 ms all-reduce at NVLink line rate vs 13.7 ms of adjoint sweep): reserving SMs for NCCL and capping
-        # its grid (NCCL_MAX_CTAS) lost more than it saved (tools/exp11.sh, exp12.sh); the default leaves both alone.
-        sm_reserve = max(0, args.sm_reserve)
         dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=90))
-    units_per_step = B * ny * nx * nz * world
+    peak, peak_src = measured_peaks()
+    K = max(1, args.fields_per_exchange)
 
-    # synthetic inputs, created once on the device (value arm) / in pinned host memory (e2e arm)
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    db = torch.empty((nz, B, ny, nx, 2), dtype=torch.float32, device=dev)
-    for z0 in range(0, nz, 16):                       # bounded temporaries
-        blk = db[z0:z0 + 16]
-        blk.copy_(torch.rand(blk.shape, device=dev, generator=g))
-        blk[..., 0] *= 1e-5
-        blk[..., 1] *= 1e-6
-    probe = torch.ones((ny, nx), dtype=torch.complex64, device=dev)
-    obj = FullfieldObjective(db, probe, ENERGY_EV, PSIZE_CM, in_place=args.in_place)
-    # target: measured magnitudes of a perturbed object (well inside (0, 1]); synthetic
-    target_host = (0.9 + 0.1 * torch.rand((B, ny, nx), generator=torch.Generator().manual_seed(4321 + rank))).pin_memory()
-    target_dev = target_host.to(dev)
+    def build(ny, nx, nz, B, in_place):
+        db = _make_db(torch, dev, nz, B, ny, nx, 1234 + rank)
+        probe = torch.ones((ny, nx), dtype=torch.complex64, device=dev)
+        obj = FullfieldObjective(db, probe, ENERGY_EV, PSIZE_CM, in_place=in_place)
+        th = (0.9 + 0.1 * torch.rand((B, ny, nx), generator=torch.Generator().manual_seed(4321 + rank))).pin_memory()
+        return obj, th, th.to(dev)
 
+    def measure(obj, target_host, target_dev, ny, nx, nz, B, steps, warmup, traffic_key):
+        """value (device-resident inputs), e2e (public API, pinned host projections in, loss out), roofline"""
+        units = B * ny * nx * nz * world * K
+
+        def step_device():
+            return obj.step_device(target_dev, accumulate=K)
+
+        def step_e2e():
+            return obj.step(target_host, accumulate=K)
+        for _ in range(warmup):
+            step_device()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        l0 = capi.launch_count()
+        ms_step, loss = _time_steps(torch, dist, world, dev, step_device, steps)
+        launches = capi.launch_count() - l0
+        clocks = sampler.stop() if rank == 0 else None
+        value = units / (ms_step * 1e-3) / 1e9
+        roof = _sweep_roofline(obj, B * ny * nx, nz, ms_step / K, value / world, peak, peak_src, traffic_key) if rank == 0 else None
+        for _ in range(max(1, warmup // 2)):
+            step_e2e()
+        ms_e2e, _ = _time_steps(torch, dist, world, dev, step_e2e, steps)
+        e2e = {'value': units / (ms_e2e * 1e-3) / 1e9, 'unit': 'Gpixel*slice/s',
+               'h2d_bytes_per_step': target_host.numel() * target_host.element_size() * K, 'd2h_bytes_per_step': 8,
+               'api': 'beyond_dof_b200.models.FullfieldObjective.step(projection magnitudes in pinned host memory) -> loss'}
+        return {'value': value, 'ms_per_step': ms_step, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
+                'roofline': roof, 'loss': float(loss.item())}
+
+    obj, target_host, target_dev = build(ny, nx, nz, B, args.in_place)
+    exchange_used = None
     if world > 1:
-        # data-parallel exchange (Horovod allreduce in fullfield.py:412; comm.Allreduce in cnn fullfield.py:350):
-        # mean of the object gradient over ranks, reduced in z-buckets on a communication stream while the
-        # adjoint sweep is still producing the remaining slices
-        # default: copy engines over NVLink peer memory (no communication kernels on the SMs the sweep kernels own);
-        # --exchange nccl = bucketed NCCL all-reduce.  If the peer-memory set-up fails on any rank, all fall back to NCCL.
+        # data-parallel exchange (Horovod allreduce in fullfield.py:412; comm.Allreduce in cnn fullfield.py:350): mean of the
+        # object gradient over ranks, z-bucket by z-bucket while the adjoint sweep is still producing the remaining slices
         from beyond_dof_b200.dist import pick_exchange
         exchange_used = pick_exchange() if args.exchange == 'auto' else args.exchange
         if args.buckets <= 0:
             args.buckets = 8 if exchange_used == 'nccl' else 16      # measured optima (2 x B200)
-        if exchange_used in ('ce', 'hybrid'):
-            ok, why = 1, ''
-            try:
-                obj.enable_data_parallel(n_buckets=args.buckets, exchange=exchange_used)
-            except Exception as ex:               # noqa: BLE001
-                ok, why = 0, '%s: %s' % (type(ex).__name__, ex)
-            t_ok = torch.tensor([ok], dtype=torch.int32, device=dev)
-            dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
-            if int(t_ok.item()) == 0:
-                print('[rank %d] copy-engine exchange unavailable (%s): falling back to NCCL' % (rank, why or 'another rank failed'), file=sys.stderr, flush=True)
-                exchange_used = 'nccl (copy-engine set-up failed)'
-                obj.enable_data_parallel(n_buckets=args.buckets, exchange='nccl')
-        else:
-            obj.enable_data_parallel(n_buckets=args.buckets, exchange='nccl')
-        if sm_reserve:
-            capi.check(capi.lib.bdof_set_sm_reserve(sm_reserve))
-
-    if world > 1 and args.diag:
-        # diagnostics: the plain all-reduce of the whole gradient, and the step without any exchange
-        for _ in range(2):
-            dist.all_reduce(obj.grad, op=dist.ReduceOp.AVG)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            dist.all_reduce(obj.grad, op=dist.ReduceOp.AVG)
-        torch.cuda.synchronize()
-        t_ar = (time.perf_counter() - t0) / 3
-        dp_state = obj._dp
-        obj._dp = None
-        for _ in range(2):
-            obj.step_device(target_dev)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            obj.step_device(target_dev)
-        torch.cuda.synchronize()
-        t_step = (time.perf_counter() - t0) / 3
-        obj._dp = dp_state
-        print('[diag rank %d] all-reduce of %.2f GB alone: %.2f ms; step without exchange: %.2f ms' %
-              (rank, obj.grad.numel() * 4 / 1e9, t_ar * 1e3, t_step * 1e3), file=sys.stderr, flush=True)
-
-    def step_device():
-        return obj.step_device(target_dev)
-
-    def step_e2e():
-        return obj.step(target_host)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- value: device-resident inputs
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    l0 = capi.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        loss = step_device()
-    ev1.record()
-    barrier()
-    launches = capi.launch_count() - l0
-    ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = t.item() / args.steps
-    value = units_per_step / (ms_step * 1e-3) / 1e9
-
-    # ---- e2e: this step's projections from pinned host memory, loss read back, through the public API
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step_e2e()
-    ev1.record()
-    barrier()
-    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = units_per_step / (t.item() / args.steps * 1e-3) / 1e9
-    h2d = target_host.numel() * target_host.element_size()
-    d2h = 8
-
-    # ---- e2e with the OBJECT on the host too: the literal drop-in of the cnn_propagator driver's call
-    #      loss_grad(obj_delta, obj_beta, this_ind_batch, this_prj_batch) (cnn_propagator/fullfield.py:329,346) with NumPy arrays in
-    #      and NumPy gradients out -- H2D of delta/beta [Y,X,Z], layout conversion, rotation (theta = 0), forward, loss, adjoint,
-    #      back-rotation, layout conversion, D2H of both gradients.  PCIe-bound by construction; reported beside `e2e`, whose
-    #      object lives on the GPU as the tf.Variables of the TF driver do (tensorflow_recon/fullfield.py:243-303).
-    e2e_host = None
-    if world == 1 and B == 1 and not args.no_host_object and not args.in_place and ny * nx * nz * 8 <= 12e9:
+        ok, why = 1, ''
         try:
-            from beyond_dof_b200 import fullfield_loss_and_grad
-            from beyond_dof_b200.propagation import clear_plan_cache
-            rng = np.random.default_rng(77)
-            od = rng.random((ny, nx, nz), dtype=np.float32); od *= np.float32(1e-5)
-            ob = rng.random((ny, nx, nz), dtype=np.float32); ob *= np.float32(1e-6)
-            prj_np = target_host.numpy()
-            one, zero = np.ones((ny, nx), np.float32), np.zeros((ny, nx), np.float32)
+            obj.enable_data_parallel(n_buckets=args.buckets, exchange=exchange_used, sm_reserve=args.sm_reserve)
+        except Exception as ex:               # noqa: BLE001
+            ok, why = 0, '%s: %s' % (type(ex).__name__, ex)
+        t_ok = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        if int(t_ok.item()) == 0:
+            print('[rank %d] %s exchange unavailable (%s): falling back to NCCL' % (rank, exchange_used, why or 'another rank failed'), file=sys.stderr, flush=True)
+            exchange_used = 'nccl (set-up of the requested exchange failed)'
+            obj.enable_data_parallel(n_buckets=args.buckets, exchange='nccl', sm_reserve=args.sm_reserve)
+        exchange_used = getattr(obj, 'exchange_name', exchange_used)
 
-            def host_call():
-                loss_h, (g_d, g_b), _ = fullfield_loss_and_grad(od, ob, np.zeros(1), prj_np, one, zero, ENERGY_EV, PSIZE_CM,
-                                                                 propagate_last=False)
-                return float(loss_h), g_d.cpu().numpy(), g_b.cpu().numpy()
-            host_call()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            host_call()
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            e2e_host = {'value': ny * nx * nz / dt / 1e9, 'unit': 'Gpixel*slice/s', 'ms_per_step': dt * 1e3,
-                        'h2d_bytes_per_step': int(od.nbytes + ob.nbytes + prj_np.nbytes), 'd2h_bytes_per_step': int(od.nbytes + ob.nbytes + 8),
-                        'api': 'beyond_dof_b200.fullfield_loss_and_grad(NumPy delta, beta [Y,X,Z], theta, NumPy projections) -> loss, NumPy gradients '
-                               '(pageable host memory, wall clock)'}
-            del od, ob
-            clear_plan_cache()
-            torch.cuda.empty_cache()
-        except Exception as ex:            # noqa: BLE001  (an optional extra must not take the bench line down)
-            e2e_host = {'error': '%s: %s' % (type(ex).__name__, ex)}
+    main = measure(obj, target_host, target_dev, ny, nx, nz, B, args.steps, args.warmup, '%dx%d' % (ny, nx))
 
-    # ---- per-kernel in-situ timing (one extra, untimed step with CUDA events around every pass)
-    kern = {}
-    roofline = None
-    cpu = None
-    if rank == 0:
-        peak, peak_src = measured_peaks()
-        dp_state = getattr(obj, '_dp', None)
-        obj._dp = None                       # rank-0-only step: no collective in here
-        obj.plan.profile_begin()
-        obj.step_device(target_dev)
-        prof = obj.plan.profile_end()
-        obj._dp = dp_state
-        px = B * ny * nx
-        tot = sum(ms for _, ms in prof.values())
-        for name, (cnt, ms) in prof.items():
-            avg_ms = ms / cnt
-            bpp = PASS_BYTES.get(name)
-            kern[name] = {'launches': cnt, 'avg_ms': avg_ms, 'share_of_kernel_time': ms / tot,
-                          'alg_bytes_per_px': bpp, 'achieved_gbs': (px * bpp / (avg_ms * 1e-3) / 1e9) if bpp else None}
-        # Dominant kernel = the sweep kernel (csrc/sweepfft.cuh): ONE template whose forward and adjoint instantiations alternate
-        # launch by launch and share the step ~50/50.  Its roofline entry is launch-weighted over both directions: algorithmic bytes
-        # of all its launches / their summed in-situ durations; the per-direction figures stay in "kernels".
-        fam = [n for n in prof if n.startswith('sweep_')] or [max(prof.items(), key=lambda kv: kv[1][1])[0]]
-        fam_bytes = sum(px * PASS_BYTES[n] * prof[n][0] for n in fam if PASS_BYTES.get(n))
-        fam_ms = sum(prof[n][1] for n in fam)
-        fam_launches = sum(prof[n][0] for n in fam)
-        a = fam_bytes / (fam_ms * 1e-3) / 1e9 if fam_ms > 0 else None
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
-                tj = json.load(f).get(args.workload, {})
-            if all(n in tj for n in fam):
-                traffic = sum(tj[n] * prof[n][0] for n in fam) / fam_launches      # ncu DRAM bytes per launch, launch-weighted
-        except Exception:
-            pass
-        roofline = {'bound': 'hbm', 'kernel': 'sweep_kernel (%s; %d launches, %.1f %% of the kernel time of a step)' % (' + '.join(fam), fam_launches, 100 * fam_ms / tot),
-                    'achieved': a, 'peak': peak, 'unit': 'GB/s', 'frac': a / peak if a else None,
-                    'traffic': traffic, 'alg_bytes_per_launch': fam_bytes / fam_launches, 'avg_launch_ms': fam_ms / fam_launches,
-                    'peak_source': peak_src,
-                    'whole_step': {'alg_bytes_per_px_slice': STEP_BYTES, 'achieved': value * STEP_BYTES, 'frac': value * STEP_BYTES / peak}}
-        # ---- CPU baseline: oracle port, 1 process (scalar port), bounded sample
+    extras = {}
+    if rank == 0 and world == 1:
+        if not args.no_host_object and B == 1 and not args.in_place and ny * nx * nz * 8 <= 12e9:
+            extras['e2e_host_object'] = host_object_leg(torch, ny, nx, nz, target_host)
+        if not args.no_cufft:
+            extras['cufft_comparison'] = cufft_comparison(torch, dev, ny, nx, 32 if ny * nx <= 2048 * 2048 else 8)
         if not args.no_cpu:
             ss = 4 if ny * nx >= 2048 * 2048 else min(nz, max(4, (2048 * 2048 * 4) // (ny * nx)))
             v, wall, _ = cpu_baseline(ny, nx, 1, ss)
-            cpu = {'value': v, 'unit': 'Gpixel*slice/s', 'cores': 1, 'kind': 'port',
-                   'sample': 'forward+adjoint of [1,%d,%d,%d], NumPy complex128 oracle (%.1f s)' % (ny, nx, ss, wall)}
+            extras['cpu_baseline'] = {'value': v, 'unit': 'Gpixel*slice/s', 'cores': 1, 'kind': 'port',
+                                      'sample': 'forward+adjoint of [1,%d,%d,%d], NumPy complex128 oracle (%.1f s)' % (ny, nx, ss, wall)}
+    # ---- the north_star target size on the same box, in the same run: 4096^2 x 512, gradient in place (137 GB)
+    headline = None
+    if world == 1 and args.workload == 'config2' and not args.shape and not args.no_headline:
+        hy, hx, hz, hdesc = WORKLOADS['headline']
+        try:
+            free_b, total_b = torch.cuda.mem_get_info()
+            del obj, target_dev
+            torch.cuda.empty_cache()
+            free_b, total_b = torch.cuda.mem_get_info()
+            need = hy * hx * hz * 16 + 3 * hy * hx * 8 + (2 << 30)
+            if free_b < need:
+                headline = {'skipped': 'needs %.0f GB of device memory, %.0f GB free' % (need / 1e9, free_b / 1e9)}
+            else:
+                hobj, hth, htd = build(hy, hx, hz, 1, True)
+                h = measure(hobj, hth, htd, hy, hx, hz, 1, max(2, min(args.steps, 5)), 3, '%dx%d' % (hy, hx))
+                headline = {'workload': hdesc + ', gradient written in place over delta/beta', 'ny': hy, 'nx': hx, 'n_slice': hz,
+                            'value': h['value'], 'unit': 'Gpixel*slice/s', 'ms_per_step': h['ms_per_step'], 'e2e': h['e2e'],
+                            'roofline': h['roofline'], 'gpu_launches': h['gpu_launches'], 'clocks': h['clocks'], 'loss': h['loss'],
+                            'steps': max(2, min(args.steps, 5)), 'warmup': 3}
+                del hobj, htd
+                torch.cuda.empty_cache()
+        except Exception as ex:            # noqa: BLE001
+            headline = {'error': '%s: %s' % (type(ex).__name__, str(ex)[:300])}
+
+    if rank == 0:
+        gb = nz * B * ny * nx * 8 / 1e9
+        if world > 1:
+            par = ('dp%d: %d field(s) per GPU and exchange; mean of the object gradient (%.1f GB) over ranks every step in %d z-buckets '
+                   'overlapped with the adjoint sweep; exchange: %s' % (world, K, gb, args.buckets, exchange_used))
+        else:
+            par = 'single GPU' + ('' if K == 1 else ', %d fields accumulated per step' % K)
         line = {
-            'metric': 'multislice Gpixel*slice/s (forward + adjoint)', 'value': value, 'unit': 'Gpixel*slice/s', 'n_gpus': world,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+            'metric': 'multislice Gpixel*slice/s (forward + adjoint)', 'value': main['value'], 'unit': 'Gpixel*slice/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': main['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'c64', 'data': 'synthetic',
-            'config': {'workload': desc, 'ny': ny, 'nx': nx, 'n_slice': nz, 'batch_per_gpu': B, 'semantics': 'numpy (last slice modulates only)',
-                       'l2': 'inputs larger than L2 (%.1f GB of delta/beta + %.1f GB slice store per GPU streamed every step)' % (db.numel() * 4 / 1e9, db.numel() * 4 / 1e9),
-                       'parallelism': ('dp%d: one field per GPU; mean of the object gradient (%.1f GB) over ranks every step in %d z-buckets overlapped with the adjoint sweep; exchange: %s'
-                                       % (world, db.numel() * 4 / 1e9, args.buckets,
-                                          'copy engines over NVLink peer memory (push partial shards, owner sums, gather)' if exchange_used == 'ce' else 'NCCL reduce-scatter (AVG) + copy-engine all-gather over NVLink peer memory' if exchange_used == 'hybrid' else 'NCCL all-reduce (AVG) on a communication stream' if exchange_used == 'nccl' else exchange_used)) if world > 1 else 'single GPU'},
-            'e2e': {'value': e2e_value, 'unit': 'Gpixel*slice/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'api': 'beyond_dof_b200.models.FullfieldObjective.step(projection magnitudes in pinned host memory) -> loss'},
-            'e2e_host_object': e2e_host,
-            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'kernels': kern, 'cpu_baseline': cpu,
-            'loss': float(loss.item()),
+            'config': {'workload': desc, 'ny': ny, 'nx': nx, 'n_slice': nz, 'batch_per_gpu': B, 'fields_per_exchange': K,
+                       'semantics': 'numpy (last slice modulates only)',
+                       'l2': 'inputs larger than L2 (%.1f GB of delta/beta + %.1f GB slice store per GPU streamed every step)' % (gb, gb),
+                       'parallelism': par},
+            'e2e': main['e2e'], 'e2e_host_object': extras.get('e2e_host_object'),
+            'gpu_launches': main['gpu_launches'], 'clocks': main['clocks'], 'roofline': main['roofline'],
+            'headline': headline, 'cufft_comparison': extras.get('cufft_comparison'), 'cpu_baseline': extras.get('cpu_baseline'),
+            'loss': main['loss'],
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -517,7 +557,11 @@ def main():
     ap.add_argument('--impl', default='bdof', choices=['bdof', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
     ap.add_argument('--no-host-object', action='store_true', help='skip the extra end-to-end leg with delta/beta and the gradients in host memory')
-    ap.add_argument('--sm-reserve', type=int, default=0, help='SMs left free for NCCL while the sweep runs (N > 1)')
+    ap.add_argument('--no-cufft', action='store_true', help='skip the cuFFT comparison leg (unfused reference loop on torch.fft)')
+    ap.add_argument('--no-headline', action='store_true', help='skip the 4096^2 x 512 headline record of the default run')
+    ap.add_argument('--fields-per-exchange', type=int, default=1, help='fields (projection angles) each rank accumulates per gradient exchange; '
+                    'the reference drivers use minibatch_size = 10 (reconstruct_fullfield.py:30)')
+    ap.add_argument('--sm-reserve', type=int, default=-1, help='SMs left free for NCCL while the sweep runs (N > 1); -1 = the exchange\'s own default')
     ap.add_argument('--exchange', default='auto', choices=['auto', 'ce', 'nccl', 'hybrid'], help='N > 1: gradient exchange (copy engines over peer memory, or NCCL all-reduce)')
     ap.add_argument('--buckets', type=int, default=0, help='z-buckets of the gradient all-reduce (N > 1)')
     ap.add_argument('--shape', default=None, help='experiment: B,NY,NX,NZ overrides the workload shape')

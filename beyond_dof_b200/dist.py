@@ -136,6 +136,21 @@ def data_parallel_step(n_items, local_loss_and_grad, grad_buffer, shard='contigu
     return allreduce_scalar(float(local)), grad_buffer
 
 
+def auto_sm_reserve(batch, ny, nx, n_sm=148, max_reserve=24):
+    """Largest number of SMs (<= max_reserve) the persistent sweep kernels can leave to NCCL without adding a round of tiles
+    (8 lines per tile up to 2048-long lines, 4 for 4096, 16 below 256): e.g. 2048^2, B = 1: the y kernels run 256 column
+    tiles in two rounds on anything from 128 to 148 SMs, so 20 SMs are free for the collective at no cost there."""
+    def rounds(lines, length, ctas):
+        lpc = 4 if length >= 4096 else (8 if length >= 256 else 16)
+        tiles = max(1, batch * lines // lpc)
+        return -(-tiles // ctas)
+    best = 0
+    for r in range(0, max_reserve + 1):
+        if rounds(ny, nx, n_sm - r) == rounds(ny, nx, n_sm) and rounds(nx, ny, n_sm - r) == rounds(nx, ny, n_sm):
+            best = r
+    return best
+
+
 def pick_exchange():
     """'ce' or 'nccl' for the gradient exchange of this process group.  Measured on B200 / NVLink 5 (8.6 GB gradient,
     tools/dp_diag.py): between TWO GPUs one copy-engine stream sustains ~550 GB/s and the exchange costs no SMs (step 29.9 ms

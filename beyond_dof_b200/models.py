@@ -113,6 +113,132 @@ def fullfield_loss_and_grad(obj_delta, obj_beta, theta_batch, prj_batch, probe_r
     return loss, (g_d, g_b), exit_wave
 
 
+class _HostPipe:
+    """Pinned staging + worker threads for moving pageable NumPy volumes across PCIe at more than the ~6-10 GB/s a single
+    cudaMemcpy from pageable memory sustains: worker threads copy row chunks into (out of) pinned buffers (NumPy releases the
+    GIL for plain copies), a copy stream moves them with cudaMemcpyAsync, and the layout conversion (bdof_pack_db_rows /
+    bdof_unpack_db_rows) runs per chunk on that stream, all overlapped chunk by chunk."""
+    _inst = {}
+
+    def __init__(self, dev, chunk_bytes=128 << 20, depth=3, threads=8):
+        from concurrent.futures import ThreadPoolExecutor
+        self.dev = dev
+        self.chunk_bytes = int(chunk_bytes)
+        self.depth = depth
+        self.pool = ThreadPoolExecutor(max_workers=threads)
+        self.threads = threads
+        self.stream = torch.cuda.Stream(device=dev)
+        n = self.chunk_bytes // 4
+        self.pin = [[torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(2)] for _ in range(depth)]
+        self.devbuf = [[torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)] for _ in range(depth)]
+        self.events = [torch.cuda.Event() for _ in range(depth)]
+
+    @classmethod
+    def get(cls, dev):
+        key = (dev.index,)
+        if key not in cls._inst:
+            cls._inst[key] = cls(dev)
+        return cls._inst[key]
+
+    def _par_copy(self, dst, src):
+        """dst[:] = src (flat float32 NumPy views of equal length) with all worker threads"""
+        n = dst.shape[0]
+        step = -(-n // self.threads)
+        futs = [self.pool.submit(np.copyto, dst[i:i + step], src[i:i + step]) for i in range(0, n, step)]
+        for f in futs:
+            f.result()
+
+    def upload_packed(self, od, ob, db):
+        """od, ob: contiguous float32 NumPy [Y,X,Z]; db: [Z,1,Y,X,2] CUDA tensor, filled in the native layout."""
+        Y, X, Z = od.shape
+        rows_per = max(1, self.chunk_bytes // (X * Z * 4))
+        fd, fb = od.reshape(-1), ob.reshape(-1)
+        main = torch.cuda.current_stream(self.dev)
+        self.stream.wait_stream(main)
+        k = 0
+        for r0 in range(0, Y, rows_per):
+            nr = min(rows_per, Y - r0)
+            n = nr * X * Z
+            slot = k % self.depth
+            if k >= self.depth:
+                self.events[slot].synchronize()                # the device has consumed this slot's pinned buffers
+            pd, pb = self.pin[slot]
+            self._par_copy(pd.numpy()[:n], fd[r0 * X * Z:r0 * X * Z + n])
+            self._par_copy(pb.numpy()[:n], fb[r0 * X * Z:r0 * X * Z + n])
+            with torch.cuda.stream(self.stream):
+                dd, dbb = self.devbuf[slot]
+                dd[:n].copy_(pd[:n], non_blocking=True)
+                dbb[:n].copy_(pb[:n], non_blocking=True)
+                check(lib.bdof_pack_db_rows(_ptr(dd), _ptr(dbb), _ptr(db), Y, r0, nr, X, Z, ctypes.c_void_p(self.stream.cuda_stream)))
+                self.events[slot].record(self.stream)
+            k += 1
+        main.wait_stream(self.stream)
+
+    def download_unpacked(self, db, out_d, out_b):
+        """db: [Z,1,Y,X,2] CUDA tensor -> out_d, out_b contiguous float32 NumPy [Y,X,Z]."""
+        Y, X, Z = out_d.shape
+        rows_per = max(1, self.chunk_bytes // (X * Z * 4))
+        fd, fb = out_d.reshape(-1), out_b.reshape(-1)
+        main = torch.cuda.current_stream(self.dev)
+        self.stream.wait_stream(main)
+        chunks = [(r0, min(rows_per, Y - r0)) for r0 in range(0, Y, rows_per)]
+
+        def issue(k):
+            r0, nr = chunks[k]
+            n = nr * X * Z
+            slot = k % self.depth
+            with torch.cuda.stream(self.stream):
+                dd, dbb = self.devbuf[slot]
+                check(lib.bdof_unpack_db_rows(_ptr(db), _ptr(dd), _ptr(dbb), Y, r0, nr, X, Z, ctypes.c_void_p(self.stream.cuda_stream)))
+                pd, pb = self.pin[slot]
+                pd[:n].copy_(dd[:n], non_blocking=True)
+                pb[:n].copy_(dbb[:n], non_blocking=True)
+                self.events[slot].record(self.stream)
+        for k in range(min(self.depth, len(chunks))):
+            issue(k)
+        for k, (r0, nr) in enumerate(chunks):
+            n = nr * X * Z
+            slot = k % self.depth
+            self.events[slot].synchronize()
+            pd, pb = self.pin[slot]
+            self._par_copy(fd[r0 * X * Z:r0 * X * Z + n], pd.numpy()[:n])
+            self._par_copy(fb[r0 * X * Z:r0 * X * Z + n], pb.numpy()[:n])
+            if k + self.depth < len(chunks):
+                issue(k + self.depth)
+        main.wait_stream(self.stream)
+
+
+def fullfield_loss_and_grad_host(obj_delta, obj_beta, prj_batch, probe_real, probe_imag, energy_ev, psize_cm, free_prop_cm=None,
+                                 propagate_last=True, out=None):
+    """The cnn_propagator driver's call loss_grad(obj_delta, obj_beta, ...) (cnn_propagator/fullfield.py:329,346) for ONE
+    un-rotated field with everything in HOST memory: NumPy delta/beta [Y,X,Z] in, loss and NumPy gradients out.  The volumes
+    cross PCIe through the pinned, multi-threaded chunk pipeline of _HostPipe (H2D + layout conversion overlapped; gradient
+    layout conversion + D2H overlapped); the multislice itself runs in place on the packed object.
+    out: optional (g_delta, g_beta) float32 NumPy arrays to fill."""
+    dev = _device()
+    od = np.ascontiguousarray(obj_delta, dtype=np.float32)
+    ob = np.ascontiguousarray(obj_beta, dtype=np.float32)
+    Y, X, Z = od.shape
+    key = ('ffh', (1, Y, X, Z), float(energy_ev), float(psize_cm), free_prop_cm, propagate_last, dev.index)
+    plan = _cached_plan(key, lambda: MultislicePlan(Y, X, 1, Z, energy_ev, psize_cm, free_prop_cm=free_prop_cm,
+                                                     propagate_last=propagate_last, store_slices=True))
+    plan.use_current_stream()
+    pipe = _HostPipe.get(dev)
+    db = torch.empty((Z, 1, Y, X, 2), dtype=torch.float32, device=dev)
+    pipe.upload_packed(od, ob, db)
+    probe = _probe_c64(probe_real, probe_imag, (Y, X))
+    plan.set_t_stash(db)
+    exit_wave = plan.forward(db, probe)
+    is_cplx = (isinstance(prj_batch, torch.Tensor) and prj_batch.is_complex()) or np.iscomplexobj(prj_batch)
+    target = _to_dev(prj_batch, torch.complex64 if is_cplx else torch.float32).abs().to(torch.float32).reshape(1, Y, X)
+    loss, g_exit = plan.loss_mag(exit_wave, target)
+    plan.adjoint(db, g_exit)
+    g_d, g_b = out if out is not None else (np.empty((Y, X, Z), np.float32), np.empty((Y, X, Z), np.float32))
+    pipe.download_unpacked(db, g_d, g_b)
+    plan.set_t_stash(None)
+    return float(loss.item()), (g_d, g_b)
+
+
 def pack_object(obj_delta, obj_beta):
     """[Y,X,Z] delta/beta -> slice-major interleaved object [Z,Y,X,2] on the current device."""
     od = _to_dev(obj_delta, torch.float32).contiguous()
@@ -266,11 +392,16 @@ class FullfieldObjective:
         # the forward leaves the transmission of every slice where the adjoint will write that slice's gradient
         self.plan.set_t_stash(self.grad)
 
-    def enable_data_parallel(self, n_buckets=None, exchange='auto'):
+    def enable_data_parallel(self, n_buckets=None, exchange='auto', sm_reserve=-1):
         """Average the object gradient over the ranks of the default process group every step, bucket by
         bucket along z while the adjoint sweep is still running.  exchange='ce': copy engines over NVLink peer
         memory (dist.CopyEngineExchange; the gradient then lives in the exchange's exportable buffer);
-        'nccl': NCCL all-reduce on a communication stream; 'auto': dist.pick_exchange()."""
+        'nccl': NCCL all-reduce on a communication stream; 'hybrid': NCCL reduce-scatter + copy-engine all-gather;
+        'auto': dist.pick_exchange().
+        sm_reserve: SMs the persistent sweep kernels leave to the NCCL kernels (they own every SM otherwise -- one 226 KB
+        CTA each -- and the collective then time-slices with the sweep instead of overlapping it); -1 = the largest number
+        that does not add a round of tiles to the sweep kernels for this field shape (dist.auto_sm_reserve) whenever the
+        exchange runs NCCL kernels, 0 for the copy-engine exchange."""
         from . import dist as bdist
         self._dp = bdist
         if exchange == 'auto':
@@ -279,6 +410,7 @@ class FullfieldObjective:
             n_buckets = 16 if exchange == 'ce' else 8          # measured optima on 2 x B200 (2048^2 x 256)
         self._buckets = self.plan.set_gradient_buckets(n_buckets)
         self._ce = None
+        self._hybrid = False
         if exchange == 'ce':
             if self.in_place:
                 raise ValueError('the copy-engine exchange needs the gradient in its own buffer (in_place=False)')
@@ -295,29 +427,74 @@ class FullfieldObjective:
             self._hybrid = True
         else:
             self._comm_stream = torch.cuda.Stream(device=self.db.device)
+        Z, B, Y, X, _ = self.db.shape
+        if sm_reserve < 0:
+            sm_reserve = bdist.auto_sm_reserve(B, Y, X) if exchange in ('nccl', 'hybrid') else 0
+        check(lib.bdof_set_sm_reserve(int(sm_reserve)))
+        names = {'ce': 'copy engines over NVLink peer memory (push partial shards, owner sums, gather)',
+                 'hybrid': 'NCCL reduce-scatter (AVG) + copy-engine all-gather over NVLink peer memory',
+                 'nccl': 'NCCL all-reduce (AVG) on a communication stream'}
+        self.exchange_name = '%s; %d SMs left to the collective' % (names.get(exchange, exchange), sm_reserve)
         return self
 
-    def step_device(self, target_dev):
-        """forward + loss + adjoint (+ gradient all-reduce when data parallel) with the target already on
-        the device; returns the device loss of this rank."""
-        self.plan.forward(self.db, self.probe, out=self.exit)
-        loss, g = self.plan.loss_mag(self.exit, target_dev)
-        self.plan.adjoint(self.db, g, grad_out=None if self.in_place else self.grad)
-        if getattr(self, '_dp', None) is not None:
-            if self._ce is not None and getattr(self, '_hybrid', False):
-                self._ce.reduce_scatter_gather(self._buckets, self._comm_stream)
-                self._ce.finish()
-            elif self._ce is not None:
-                self._ce.exchange(self._buckets)
-                self._ce.finish()
-            else:
-                works = self._dp.allreduce_gradient(self.grad, average=True, buckets=self._buckets, comm_stream=self._comm_stream)
-                self._dp.finish_allreduce(self.grad, works, comm_stream=self._comm_stream)
-        return loss
+    def _exchange(self):
+        if self._ce is not None and self._hybrid:
+            self._ce.reduce_scatter_gather(self._buckets, self._comm_stream)
+            self._ce.finish()
+        elif self._ce is not None:
+            self._ce.exchange(self._buckets)
+            self._ce.finish()
+        else:
+            works = self._dp.allreduce_gradient(self.grad, average=True, buckets=self._buckets, comm_stream=self._comm_stream)
+            self._dp.finish_allreduce(self.grad, works, comm_stream=self._comm_stream)
 
-    def step(self, prj_mag_host):
+    def step_device(self, target_dev, accumulate=1):
+        """forward + loss + adjoint (+ gradient all-reduce when data parallel) with the target already on
+        the device; returns the device loss of this rank.
+        accumulate = K > 1: K fields (projection angles of one minibatch, reconstruct_fullfield.py:30 minibatch_size) are
+        evaluated one after the other and their gradients summed in self.grad_acc before ONE exchange -- the reference's
+        ratio of compute to communication.  The stand-in for the K rotated copies of the object is the same field K times
+        (same arithmetic and traffic); the summation pass stands in for the back-rotation, which accumulates too."""
+        dp = getattr(self, '_dp', None) is not None
+        if accumulate <= 1:
+            self.plan.forward(self.db, self.probe, out=self.exit)
+            loss, g = self.plan.loss_mag(self.exit, target_dev)
+            self.plan.adjoint(self.db, g, grad_out=None if self.in_place else self.grad)
+            if dp:
+                self._exchange()
+            return loss
+        if self.in_place:
+            raise ValueError('gradient accumulation needs the gradient in its own buffer (in_place=False)')
+        if getattr(self, 'grad_acc', None) is None:
+            self.grad_acc = torch.empty_like(self.grad)
+        total = None
+        for k in range(accumulate):
+            last = k == accumulate - 1
+            self.plan.forward(self.db, self.probe, out=self.exit)
+            loss, g = self.plan.loss_mag(self.exit, target_dev)
+            total = loss if total is None else total + loss
+            self.plan.adjoint(self.db, g, grad_out=self.grad)
+            if last:
+                # the exchange owns self.grad (it may be the copy-engine exchange's exportable buffer): the total is formed there
+                if k > 0:
+                    self.grad.add_(self.grad_acc)
+            elif k == 0:
+                self.grad_acc.copy_(self.grad)
+            else:
+                self.grad_acc.add_(self.grad)
+        if dp:
+            # buckets are final only after the summation above: one event for all of them
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.db.device))
+            keep = self._buckets
+            self._buckets = [(lo, hi, ev) for lo, hi, _ in keep]
+            self._exchange()
+            self._buckets = keep
+        return total / accumulate
+
+    def step(self, prj_mag_host, accumulate=1):
         self.target.copy_(prj_mag_host, non_blocking=True)
-        loss = self.step_device(self.target)
+        loss = self.step_device(self.target, accumulate=accumulate)
         self.loss_host.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(self.loss_host)

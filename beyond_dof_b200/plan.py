@@ -96,6 +96,20 @@ class MultislicePlan:
             lib.bdof_plan_destroy(h)
             self._h = ctypes.c_void_p()
 
+    def use_current_stream(self):
+        """Bind the plan to torch's CURRENT stream of its device.  Called at the top of every compute method, so that the
+        libbdof kernels run on the same stream as the torch-side work around them (packing, probe set-up, losses) even when a
+        cached plan is reused under a different stream than the one it was created on.  The new stream is ordered after
+        whatever the plan still has in flight on the old one."""
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream != self.stream.cuda_stream:
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+            cur.wait_event(ev)
+            self.stream = cur
+            check(lib.bdof_plan_set_stream(self._h, ctypes.c_void_p(cur.cuda_stream)))
+        return self
+
     # ---- layout helpers -----------------------------------------------------------------
     @property
     def db_shape(self):
@@ -103,6 +117,7 @@ class MultislicePlan:
 
     def pack(self, grid_delta_batch, grid_beta_batch):
         """[B,Y,X,Z] float32 device tensors -> slice-major interleaved db [Z,B,Y,X,2]."""
+        self.use_current_stream()
         d = grid_delta_batch.to(self.device, torch.float32).contiguous()
         b = grid_beta_batch.to(self.device, torch.float32).contiguous()
         B, Y, X, Z = d.shape
@@ -111,6 +126,7 @@ class MultislicePlan:
         return db
 
     def unpack(self, db):
+        self.use_current_stream()
         Z, B, Y, X, _ = db.shape
         d = torch.empty((B, Y, X, Z), dtype=torch.float32, device=self.device)
         b = torch.empty((B, Y, X, Z), dtype=torch.float32, device=self.device)
@@ -120,6 +136,7 @@ class MultislicePlan:
     # ---- compute ------------------------------------------------------------------------
     def forward(self, db, probe, out=None):
         """db [Z,B,Y,X,2] float32, probe [Y,X] complex64 -> exit wave [B,Y,X] complex64."""
+        self.use_current_stream()
         assert db.is_cuda and db.dtype == torch.float32 and db.is_contiguous() and tuple(db.shape) == self.db_shape, \
             'db must be a contiguous float32 CUDA tensor of shape %s' % (self.db_shape,)
         probe = probe.to(self.device, torch.complex64).contiguous()
@@ -131,6 +148,7 @@ class MultislicePlan:
 
     def loss_mag(self, exit_wave, target_mag, want_grad=True, loss_scale=1.0):
         """mean((|psi| - |y|)^2) * loss_scale and G = dL/dRe + i dL/dIm (fullfield.py:115)."""
+        self.use_current_stream()
         target_mag = target_mag.to(self.device, torch.float32).contiguous()
         loss = torch.empty((), dtype=torch.float64, device=self.device)
         g = torch.empty_like(exit_wave) if want_grad else None
@@ -142,6 +160,7 @@ class MultislicePlan:
         """Back-propagate grad_exit.  By default db is overwritten in place with (dL/ddelta, dL/dbeta);
         pass grad_out [Z,B,Y,X,2] to keep db intact (mandatory with z_broadcast)."""
         assert self.store_slices, 'plan was created with store_slices=False'
+        self.use_current_stream()
         grad_exit = grad_exit.to(self.device, torch.complex64).contiguous()
         gp = torch.empty((self.ny, self.nx), dtype=torch.complex64, device=self.device) if want_probe_grad else None
         if grad_out is not None:
@@ -160,12 +179,14 @@ class MultislicePlan:
         if out is None:
             out = np.empty((self.batch, self.ny, self.nx), dtype=np.complex64)
         assert d.shape == (self.batch, self.ny, self.nx, self.n_slice) and b.shape == d.shape
+        self.use_current_stream()
         check(lib.bdof_forward_host(self._h, _hptr(d), _hptr(b), _hptr(pr), _hptr(out)))
         return out
 
     def slice_step(self, field, db_slice, out=None, propagate=True):
         """One slice: out = P(field * t(db_slice)) (or only the modulation).  field [B,Y,X] complex64,
         db_slice [B,Y,X,2] float32.  The global phase exp(i k dz) is not applied."""
+        self.use_current_stream()
         assert field.is_cuda and field.dtype == torch.complex64 and field.is_contiguous()
         assert db_slice.is_cuda and db_slice.dtype == torch.float32 and db_slice.is_contiguous()
         if out is None:
@@ -205,6 +226,7 @@ class MultislicePlan:
 
     def free_prop(self, field, out=None):
         """The plan's free-space step on its own: [B,Y,X] complex64 -> [B,Y,X]."""
+        self.use_current_stream()
         field = field.to(self.device, torch.complex64).contiguous()
         if out is None:
             out = torch.empty_like(field)
@@ -221,6 +243,14 @@ class MultislicePlan:
         ms = (ctypes.c_double * n)()
         check(lib.bdof_profile_end(self._h, n, counts, ms))
         return {self.VARIANT_NAMES[i]: (int(counts[i]), float(ms[i])) for i in range(n) if counts[i]}
+
+    def last_times(self):
+        """Device time of the last forward and the last adjoint call (one event pair around each call's whole launch
+        sequence; synchronises): {'forward': (ms, launches), 'adjoint': (ms, launches)}."""
+        ms = (ctypes.c_double * 2)()
+        n = (ctypes.c_int * 2)()
+        check(lib.bdof_plan_last_times(self._h, ms, n))
+        return {'forward': (float(ms[0]), int(n[0])), 'adjoint': (float(ms[1]), int(n[1]))}
 
     def workspace_bytes(self):
         n = ctypes.c_size_t()

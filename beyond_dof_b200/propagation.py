@@ -20,16 +20,24 @@ from .plan import MultislicePlan, _ptr, _hptr
 from .util import PI, PI_CNN, get_kernel
 
 _PLAN_CACHE = {}
-_PLAN_CACHE_MAX = 8
+_PLAN_CACHE_MAX = 8                    # plans
+_PLAN_CACHE_MAX_BYTES = 32 << 30       # device memory the cached plans may own together (work fields + slice stores)
 
 
 def _cached_plan(key, make):
+    """Memoised plans, evicted oldest first when there are more than _PLAN_CACHE_MAX of them or when their workspaces add up
+    to more than _PLAN_CACHE_MAX_BYTES (a 2048^2 x 256 plan with a slice store owns 8.7 GB).  Plans re-bind to the
+    caller's current stream on every call (MultislicePlan.use_current_stream), so reuse across streams is safe."""
     p = _PLAN_CACHE.get(key)
     if p is None:
-        if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
-            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
         p = make()
         _PLAN_CACHE[key] = p
+        total = sum(q.workspace_bytes() for q in _PLAN_CACHE.values())
+        while len(_PLAN_CACHE) > 1 and (len(_PLAN_CACHE) > _PLAN_CACHE_MAX or total > _PLAN_CACHE_MAX_BYTES):
+            old_key = next(iter(_PLAN_CACHE))
+            if old_key == key:
+                break
+            total -= _PLAN_CACHE.pop(old_key).workspace_bytes()
     return p
 
 

@@ -84,6 +84,9 @@ int  bdof_kernel_factors(double dist_nm, double lmbda_nm, const double* voxel_nm
 int  bdof_plan_create(bdof_plan** out, int ny, int nx, int batch, int n_slice, uint32_t flags,
                       void* cuda_stream);
 void bdof_plan_destroy(bdof_plan* p);
+/* Re-bind the plan to another stream of its device (every later call is ordered on it).  The caller is responsible for
+ * ordering the new stream after work already queued on the old one (the Python host does so with an event). */
+int  bdof_plan_set_stream(bdof_plan* p, void* cuda_stream);
 
 /* Per-slice propagator.  h_hy/h_hx: centred complex128 factors (host). phase0 (re,im) is the
  * global phase exp(i k dz) kept out of the fp32 tables and restored analytically.
@@ -124,6 +127,13 @@ int  bdof_pack_db(const float* d_delta_byxz, const float* d_beta_byxz, float* d_
                   int nx, int n_slice, void* cuda_stream);
 int  bdof_unpack_db(const float* d_db, float* d_delta_byxz, float* d_beta_byxz, int batch, int ny,
                     int nx, int n_slice, void* cuda_stream);
+
+/* Row-chunked variants for pipelined host transfers: the chunk buffers hold rows [row0, row0 + n_rows) of the
+ * total_rows = B*Y rows of the reference-layout arrays ([rows][X][Z], z fastest); d_db is the whole slice-major object. */
+int  bdof_pack_db_rows(const float* d_delta_chunk, const float* d_beta_chunk, float* d_db, long long total_rows, long long row0,
+                       int n_rows, int nx, int n_slice, void* cuda_stream);
+int  bdof_unpack_db_rows(const float* d_db, float* d_delta_chunk, float* d_beta_chunk, long long total_rows, long long row0,
+                         int n_rows, int nx, int n_slice, void* cuda_stream);
 
 /* Ptychography windows.  Object db_obj [n_slice][oy][ox][2]; positions (y0,x0) = window origin
  * (may be negative / overhang: zero padding as ptychography.py:45-61); output
@@ -225,10 +235,6 @@ int  bdof_dp_bucket(bdof_dp* c, size_t offset_bytes, size_t n_bytes, void* ready
 int  bdof_dp_gather(bdof_dp* c, size_t offset_bytes, size_t n_bytes, void* ready_event);
 int  bdof_dp_finish(bdof_dp* c, void* cuda_stream);
 
-/* In-situ timing: between begin and end every line-kernel launch of this plan is bracketed by CUDA
- * events on the plan's stream; end() synchronises and returns, per pass variant (0 row fwd with
- * transmission, 1 row conv, 2 row adjoint, 3 row FFT, 4 row IFFT, 5 col conv, 6 col FFT, 7 col IFFT,
- * 8 col conv with 2-D H), the launch count and the summed device time in ms. */
 /* Leave n_sms streaming multiprocessors free of the persistent pass kernels (process-wide), so that
  * communication kernels (NCCL all-reduce of the gradient buckets) can run concurrently with the sweep. */
 int  bdof_set_sm_reserve(int n_sms);
@@ -237,8 +243,23 @@ int  bdof_set_sm_reserve(int n_sms);
  * phase stamps; ignored by the production build. */
 int  bdof_debug_set_buffer(void* d_buf);
 
+/* In-situ timing: between begin and end every pass-kernel launch of this plan is bracketed by CUDA
+ * events on the plan's stream; end() synchronises and returns, per kernel variant, the launch count
+ * and the summed device time in ms.  Variants: 0 row conv with transmission, 1 row conv, 2 row conv with
+ * the adjoint epilogue, 3 row FFT, 4 row IFFT, 5 col conv (incl. the pipelined column pass), 6 col FFT,
+ * 7 col IFFT, 8 col conv with a general 2-D H, 9 (unused: the pipelined column pass reports as 5),
+ * 10 sweep kernel forward, 11 sweep kernel adjoint, 12 resident small-field kernel forward,
+ * 13 resident small-field kernel adjoint.
+ * The event pairs break the programmatic-dependent-launch overlap between consecutive kernels, so the
+ * per-launch times are an upper bound (sum > the un-instrumented step): use them for SHARES only. */
 int  bdof_profile_begin(bdof_plan* p);
 int  bdof_profile_end(bdof_plan* p, int n_variants, int* counts, double* ms_total);
+
+/* Device time of the two halves of the LAST bdof_forward / bdof_adjoint call of this plan, measured by one
+ * event pair around each call's whole launch sequence (always on; no per-launch events, so the kernels
+ * overlap exactly as in production).  Synchronises the stream.  ms_out[0] = forward, ms_out[1] = adjoint;
+ * launches_out[0/1] = kernels launched by each. */
+int  bdof_plan_last_times(bdof_plan* p, double* ms_out, int* launches_out);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,206 @@
+"""GPU tier: parity at the DEPTH and SIZE of the BASELINE configurations.
+
+SURVEY 7.4-1 measured a naive complex64 chain failing the 1e-5 intensity bar at 256 slices, so the fp32 error budget of the
+engine (global phase out of the fp32 tables, float64-generated twiddles / h, range-reduced transmission) has to be shown at
+128 ... 512 slices, not at 12.  Every case compares the CUDA path (through the C ABI) with the complex128 oracle on the same
+seeded inputs and records the measured errors in gpurun_out/parity_depth.json (copied to profiles/parity_r02.json).
+
+Gradient parity is asserted at OPERATOR level (the same exit-plane gradient G through bdof_adjoint and the oracle adjoint,
+bar 1e-4) and end to end for targets with an O(1) misfit; DESIGN.md section 2 ("gradient conditioning") explains why the
+loss head of a near-converged target amplifies any complex64 forward error.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2, ROOT
+from oracle import multislice_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+TOL_INTENSITY = 1e-5
+TOL_GRAD = 1e-4
+_RECORD = os.path.join(ROOT, 'gpurun_out', 'parity_depth.json')
+
+
+def record(case, **vals):
+    os.makedirs(os.path.dirname(_RECORD), exist_ok=True)
+    try:
+        with open(_RECORD) as f:
+            d = json.load(f)
+    except Exception:
+        d = {}
+    d[case] = {k: (float(v) if isinstance(v, (float, np.floating)) else v) for k, v in vals.items()}
+    with open(_RECORD, 'w') as f:
+        json.dump(d, f, indent=1, sort_keys=True)
+
+
+@pytest.fixture(scope='module')
+def bd():
+    import beyond_dof_b200 as pkg
+    assert torch.cuda.is_available()
+    from beyond_dof_b200 import capi  # noqa: F401
+    return pkg
+
+
+def intensity_err(psi, ref):
+    return rel_l2(np.abs(psi) ** 2, np.abs(ref) ** 2)
+
+
+def _gpu_forward_and_operator_adjoint(gd, gb, pr, pi, G, free, propagate_last, energy=5000, psize=1e-7):
+    from beyond_dof_b200.plan import MultislicePlan
+    B, Y, X, Z = gd.shape
+    plan = MultislicePlan(Y, X, B, Z, energy, psize, free_prop_cm=free, propagate_last=propagate_last, store_slices=True)
+    db = plan.pack(torch.as_tensor(gd).cuda(), torch.as_tensor(gb).cuda())
+    probe = torch.as_tensor((np.asarray(pr) + 1j * np.asarray(pi)).astype(np.complex64)).cuda()
+    plan.set_t_stash(db)
+    psi = plan.forward(db, probe)
+    plan.adjoint(db, torch.as_tensor(G.astype(np.complex64)).cuda())
+    g_d, g_b = plan.unpack(db)
+    return psi.cpu().numpy(), g_d.cpu().numpy(), g_b.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------
+# (a) 256 x 256 field, 256 and 512 slices, both last-slice conventions (npfuncs.py:35-41, util.py:464-483)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n_slice', [256, 512])
+@pytest.mark.parametrize('propagate_last', [False, True])
+def test_depth_256_forward_and_operator_gradient(bd, n_slice, propagate_last):
+    shape = (1, 256, 256, n_slice)
+    gd, gb = mo.random_phantom(shape, seed=1234)                     # config-2 recipe: delta <= 1e-5, beta <= 1e-6
+    one, zero = np.ones(shape[1:3]), np.zeros(shape[1:3])
+    rng = np.random.default_rng(7)
+    G = rng.standard_normal(shape[:3]) + 1j * rng.standard_normal(shape[:3])
+    psio, slices = mo.multislice_forward(gd, gb, one, zero, 5000, 1e-7, propagate_last=propagate_last, return_slices=True)
+    gdo, gbo, _ = mo.multislice_adjoint(gd, gb, slices, G, 5000, 1e-7, propagate_last=propagate_last)
+    psi, g_d, g_b = _gpu_forward_and_operator_adjoint(gd, gb, one, zero, G, None, propagate_last)
+    e_i, e_f, e_d, e_b = intensity_err(psi, psio), rel_l2(psi, psio), rel_l2(g_d, gdo), rel_l2(g_b, gbo)
+    record('depth_256x256x%d_%s' % (n_slice, 'tf' if propagate_last else 'numpy'), intensity=e_i, field=e_f, grad_delta=e_d,
+           grad_beta=e_b, tol_intensity=TOL_INTENSITY, tol_grad=TOL_GRAD)
+    assert e_i < TOL_INTENSITY
+    assert e_d < TOL_GRAD and e_b < TOL_GRAD
+
+
+def test_depth_strong_object_512_slices(bd):
+    # 100 x stronger object (k delta up to 0.25 rad per slice: the range-reduced transmission path), 512 slices
+    shape = (1, 128, 256, 512)
+    gd, gb = mo.random_phantom(shape, seed=99, delta_scale=1e-3, beta_scale=2e-5)
+    pr, pi = mo.gaussian_probe(shape[1:3], 40., 30., 0.5)
+    rng = np.random.default_rng(8)
+    G = rng.standard_normal(shape[:3]) + 1j * rng.standard_normal(shape[:3])
+    psio, slices = mo.multislice_forward(gd, gb, pr, pi, 5000, 1e-7, free_prop_cm=1e-4, propagate_last=True, return_slices=True)
+    gdo, gbo, _ = mo.multislice_adjoint(gd, gb, slices, G, 5000, 1e-7, free_prop_cm=1e-4, propagate_last=True)
+    psi, g_d, g_b = _gpu_forward_and_operator_adjoint(gd, gb, pr, pi, G, 1e-4, True)
+    e_i, e_d, e_b = intensity_err(psi, psio), rel_l2(g_d, gdo), rel_l2(g_b, gbo)
+    record('depth_strong_128x256x512_tf_free1e-4', intensity=e_i, grad_delta=e_d, grad_beta=e_b)
+    assert e_i < TOL_INTENSITY and e_d < TOL_GRAD and e_b < TOL_GRAD
+
+
+# ---------------------------------------------------------------------------------------------
+# (b) config-3 shard: 128 scan positions x 64^2 probe x 128 slices, TF semantics, far field, through the model entry point
+# ---------------------------------------------------------------------------------------------
+def test_config3_shard_ptycho_loss_and_grad(bd):
+    Y = X = 256
+    Z = 128
+    probe_size = (64, 64)
+    od, ob = mo.random_phantom((Y, X, Z), seed=1234)
+    gt_d, gt_b = mo.random_phantom((Y, X, Z), seed=4321, delta_scale=2e-4, beta_scale=2e-4)       # O(1) misfit
+    pr, pi = mo.gaussian_probe(probe_size, 6., 6., 0.5)                                            # reconstruct_ptycho.py:92-94
+    jj, ii = np.meshgrid(np.arange(32), np.arange(32))
+    pos_all = np.stack([32 + 6 * ii.ravel(), 32 + 6 * jj.ravel()], 1)                             # 32 x 32 grid
+    pos = pos_all[3 * 128:4 * 128]                                                                 # the shard of rank 3 of 8
+    _, prj = mo.ptycho_loss(gt_d, gt_b, pos, np.zeros((len(pos),) + probe_size), pr, pi, probe_size, 5000, 1e-7, n_dp_batch=128)
+    lo, gdo, gbo, psio = mo.ptycho_loss_and_grad(od, ob, pos, prj, pr, pi, probe_size, 5000, 1e-7)
+    loss, (g_d, g_b) = bd.ptycho_loss_and_grad(od, ob, 0.0, pos, prj, pr, pi, probe_size, 5000, 1e-7)
+    e_l = abs(loss.item() - lo) / abs(lo)
+    e_d, e_b = rel_l2(g_d.cpu().numpy(), gdo), rel_l2(g_b.cpu().numpy(), gbo)
+    # exit waves of the same shard through the forward-only entry
+    from beyond_dof_b200.models import _ptycho_exit_waves, pack_object
+    ex = _ptycho_exit_waves(pack_object(od, ob), 0.0, pos, pr, pi, probe_size, 5000, 1e-7).cpu().numpy()
+    e_i = intensity_err(ex, psio)
+    record('config3_shard_128pos_64x64x128_tf_inf', loss=e_l, intensity=e_i, grad_delta=e_d, grad_beta=e_b)
+    assert e_i < TOL_INTENSITY
+    assert e_l < 1e-5
+    assert e_d < TOL_GRAD and e_b < TOL_GRAD
+
+
+# ---------------------------------------------------------------------------------------------
+# (c) config-4 shape: 256^2 x 256, B = 2, free_prop_cm = 1e-4 (reconstruct_fullfield.py:67), TF semantics
+# ---------------------------------------------------------------------------------------------
+def test_config4_shape_loss_and_grad(bd):
+    from test_gpu_parity import _gpu_loss_and_grad
+    shape = (2, 256, 256, 256)
+    rng = np.random.default_rng(1234)
+    gd = np.clip(rng.normal(8.7e-7, 1e-7, shape), 0, None).astype(np.float32)          # fullfield.py:273-274 initial guess
+    gb = np.clip(rng.normal(5.1e-8, 1e-8, shape), 0, None).astype(np.float32)
+    one, zero = np.ones(shape[1:3]), np.zeros(shape[1:3])
+    target = rng.random(shape[:3]) + 0.5                                               # O(1) misfit
+    lo, gdo, gbo, psio = mo.loss_and_grad(gd, gb, one, zero, 5000, 1e-7, target, free_prop_cm=1e-4, propagate_last=True)
+    l, g_d, g_b, psi = _gpu_loss_and_grad(bd, gd, gb, one, zero, 5000, 1e-7, target, 1e-4, True)
+    e_i, e_d, e_b = intensity_err(psi, psio), rel_l2(g_d, gdo), rel_l2(g_b, gbo)
+    record('config4_shape_2x256x256x256_tf_free1e-4', loss=abs(l - lo) / abs(lo), intensity=e_i, grad_delta=e_d, grad_beta=e_b)
+    assert e_i < TOL_INTENSITY
+    assert abs(l - lo) < 1e-5 * abs(lo)
+    assert e_d < TOL_GRAD and e_b < TOL_GRAD
+
+
+# ---------------------------------------------------------------------------------------------
+# (e) the reference's own Gaussian probe on the mixed-radix shapes (VERDICT r01 weak #1 / ADVICE): the far field of a smooth
+#     probe on an elongated field is zero to fp32 precision almost everywhere, so the LOSS-HEAD gradient psi/|psi| is
+#     ill-conditioned for any complex64 forward model.  The honest statement is an operator-level assertion on that very
+#     input: forward field and the adjoint of a fixed exit-plane gradient, both against the oracle.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('shape', [(3, 72, 72, 5), (2, 18, 18, 4), (1, 1000, 24, 2), (2, 63, 100, 2)])
+@pytest.mark.parametrize('free', [None, 'inf', 1e-4])
+def test_mixed_radix_reference_gaussian_probe_operator_level(bd, shape, free):
+    gd, gb = mo.random_phantom(shape, seed=61, delta_scale=5e-4, beta_scale=5e-5)
+    pr, pi = mo.gaussian_probe(shape[1:3], 6., 6., 0.5)                    # the original input of commit 2735e6f's test
+    rng = np.random.default_rng(62)
+    G = rng.standard_normal(shape[:3]) + 1j * rng.standard_normal(shape[:3])
+    psio, slices = mo.multislice_forward(gd, gb, pr, pi, 5000, 1e-7, free_prop_cm=free, propagate_last=True, return_slices=True)
+    gdo, gbo, _ = mo.multislice_adjoint(gd, gb, slices, G, 5000, 1e-7, free_prop_cm=free, propagate_last=True)
+    psi, g_d, g_b = _gpu_forward_and_operator_adjoint(gd, gb, pr, pi, G, free, True)
+    assert rel_l2(psi, psio) < 1e-5 and intensity_err(psi, psio) < TOL_INTENSITY
+    assert rel_l2(g_d, gdo) < TOL_GRAD and rel_l2(g_b, gbo) < TOL_GRAD
+    # loss-head gradient on the same input, restricted to detector pixels above the fp32 floor of the far field
+    # (|psi| >= 1e-4 max|psi|): there the bar holds; below it psi/|psi| is rounding noise in complex64
+    from beyond_dof_b200.plan import MultislicePlan
+    B, Y, X, Z = shape
+    target = rng.random(shape[:3]) * np.abs(psio).max() * 0.5
+    plan = MultislicePlan(Y, X, B, Z, 5000, 1e-7, free_prop_cm=free, propagate_last=True, store_slices=True)
+    db = plan.pack(torch.as_tensor(gd).cuda(), torch.as_tensor(gb).cuda())
+    probe = torch.as_tensor((pr + 1j * pi).astype(np.complex64)).cuda()
+    ex = plan.forward(db, probe)
+    _, g_exit = plan.loss_mag(ex, torch.as_tensor(target.astype(np.float32)).cuda())
+    _, g_or = mo.loss_mag(psio, target)
+    mask = np.abs(psio) >= 1e-4 * np.abs(psio).max()
+    assert rel_l2(g_exit.cpu().numpy()[mask], g_or[mask]) < TOL_GRAD
+
+
+# ---------------------------------------------------------------------------------------------
+# (d) config 2 at full size (slow: ~5 min of oracle time on one host core): BDOF_SLOW=1 enables
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.skipif(os.environ.get('BDOF_SLOW', '0') != '1', reason='set BDOF_SLOW=1 (about 5 minutes of CPU oracle time)')
+def test_config2_full_size_forward_and_truncated_gradient(bd):
+    shape = (1, 2048, 2048, 256)
+    gd, gb = mo.random_phantom(shape, seed=1234)
+    one, zero = np.ones(shape[1:3]), np.zeros(shape[1:3])
+    psi = bd.multislice_propagate_batch_numpy(torch.as_tensor(gd).cuda(), torch.as_tensor(gb).cuda(), one, zero, 5000, 1e-7,
+                                              obj_batch_shape=shape).cpu().numpy()
+    psio = mo.multislice_propagate_batch_numpy(gd, gb, one, zero, 5000, 1e-7, None, shape)
+    e_i, e_f = intensity_err(psi, psio), rel_l2(psi, psio)
+    # gradient on the z-truncated twin (the first 16 slices): operator level and with the config-2 style target
+    zt = 16
+    gdt, gbt = np.ascontiguousarray(gd[..., :zt]), np.ascontiguousarray(gb[..., :zt])
+    rng = np.random.default_rng(9)
+    G = rng.standard_normal(shape[:3]) + 1j * rng.standard_normal(shape[:3])
+    pso, slices = mo.multislice_forward(gdt, gbt, one, zero, 5000, 1e-7, return_slices=True)
+    gdo, gbo, _ = mo.multislice_adjoint(gdt, gbt, slices, G, 5000, 1e-7)
+    _, g_d, g_b = _gpu_forward_and_operator_adjoint(gdt, gbt, one, zero, G, None, False)
+    e_d, e_b = rel_l2(g_d, gdo), rel_l2(g_b, gbo)
+    record('config2_2048x2048x256_numpy', intensity=e_i, field=e_f, grad_delta_first16=e_d, grad_beta_first16=e_b)
+    assert e_i < TOL_INTENSITY
+    assert e_d < TOL_GRAD and e_b < TOL_GRAD

@@ -1,6 +1,8 @@
 """Summarise an .ncu-rep (read offline with `ncu -i`) into a small text file for profiles/.
-usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/out.txt"""
-import csv, re, subprocess, sys
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/out.txt [TRAFFIC_KEY]
+With TRAFFIC_KEY (e.g. 2048x2048) the mean dram__bytes_read.sum + dram__bytes_write.sum per profiled sweep launch is written
+to profiles/traffic.json under that key, with the summary file as its source (bench.py reports it as roofline.traffic)."""
+import csv, json, os, re, subprocess, sys
 from collections import defaultdict
 
 KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
@@ -26,14 +28,23 @@ def short(name):
     return 'line_kernel N=%s T=%s radices=%sx%sx%s lines/CTA=%s %s' % (n, t, r1, r2, r3, lpc, kind)
 
 
-def main(rep, out):
+def to_bytes(val, unit):
+    v = float(val.replace(',', ''))
+    return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(unit, 1)
+
+
+def main(rep, out, traffic_key=None):
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     lines = ['ncu summary of %s (ncu --set full --clock-control none; per-launch values, cold cache, serialised)' % rep, '']
     seen = set()
+    per_kernel = {}
     for i, d in enumerate(data):
         name = short(d[hdr.index('Kernel Name')])
+        if 'sweep_kernel' in name and 'dram__bytes_read.sum' in hdr:
+            r, w = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+            per_kernel.setdefault(name, []).append(to_bytes(d[r], units[r]) + to_bytes(d[w], units[w]))
         if name in seen:
             continue
         seen.add(name)
@@ -63,7 +74,19 @@ def main(rep, out):
         lines.append('')
     open(out, 'w').write('\n'.join(lines))
     print('wrote', out)
+    if traffic_key and per_kernel:
+        path = os.path.join(os.path.dirname(os.path.abspath(out)), 'traffic.json')
+        try:
+            tj = json.load(open(path))
+        except Exception:
+            tj = {}
+        means = {k: sum(v) / len(v) for k, v in per_kernel.items()}
+        tj[traffic_key] = {'bytes_per_launch': sum(means.values()) / len(means), 'per_kernel': means,
+                           'source': 'ncu --set full, %s (dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the %d sweep '
+                                     'kernel instantiations profiled)' % (os.path.relpath(out, os.path.dirname(os.path.dirname(os.path.abspath(out)))), len(means))}
+        json.dump(tj, open(path, 'w'), indent=1, sort_keys=True)
+        print('updated', path)
 
 
 if __name__ == '__main__':
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
