@@ -4,6 +4,7 @@
 #include "common.h"
 #include "regfft.cuh"
 #include "sweepfft.cuh"
+#include "residentfft.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -189,7 +190,7 @@ __global__ void k_modulate(const float2* __restrict__ in, const float2* __restri
                            long long n, float k) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    out[i] = cmul(in[i], transmission(db[i], k));
+    out[i] = cmul1p(in[i], transmission_any_m1(db[i], k));
 }
 
 // adjoint of k_modulate: grad = -k (Im, Re)(conj(G) psi t), G <- conj(t) G
@@ -197,12 +198,12 @@ __global__ void k_modulate_adj(float2* __restrict__ G, const float2* __restrict_
                                float2* __restrict__ grad, long long n, float k) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float2 tr = transmission(db[i], k);
-    const float2 u = cmul(psi[i], tr);
+    const float2 tr = transmission_any_m1(db[i], k);         // tau = t - 1
+    const float2 u = cmul1p(psi[i], tr);
     const float2 g = G[i];
     const float2 w = cmulc(u, g);
     grad[i] = make_float2(-k * w.y, -k * w.x);
-    G[i] = cmulc(g, tr);
+    G[i] = cmulc1p(g, tr);
 }
 
 // out = in * (re + i im)
@@ -345,7 +346,7 @@ __global__ void k_cnn_step(const float2* __restrict__ in, const float2* __restri
         float2 v = edge;
         if (y >= 0 && y < ny && x >= 0 && x < nx) {
             const long long o = fbase + (long long)y * nx + x;
-            v = cmul(in[o], transmission(db[o], k_dz));
+            v = cmul1p(in[o], transmission_any_m1(db[o], k_dz));
         }
         tile[i] = v;
     }
@@ -396,6 +397,8 @@ struct bdof_plan {
     bool generic = false;      // a side is not one of the power-of-two lengths: every pass runs the mixed-radix kernel (genericfft.cu)
     bool sweep = true;         // one kernel per slice and direction (sweepfft.cuh); BDOF_SWEEP=0 at plan creation selects the
                                // per-pass kernels (row pass + column pass per slice) instead
+    bool resident = true;      // small square fields: one kernel per direction with the field resident on chip (residentfft.cuh);
+                               // BDOF_RESIDENT=0 at plan creation selects the sweep kernels instead
     bool row_prefetch = false; // row passes L2-prefetch their own side inputs at tile start (BDOF_ROW_PREFETCH=1 enables; measured slower)
     bool l2_prefetch = false;  // column passes prefetch the next row pass's DRAM inputs into L2 (BDOF_L2_PREFETCH=1 enables;
                                // measured slower on B200 at 2048^2: the prefetch traffic slows the column pass itself)
@@ -554,6 +557,7 @@ extern "C" int bdof_plan_create(bdof_plan** out, int ny, int nx, int batch, int 
     p->ax.n = nx; p->ay.n = ny;
     p->generic = bdof_size_supported(ny) != 1 || bdof_size_supported(nx) != 1;
     if (const char* e = getenv("BDOF_SWEEP")) p->sweep = (e[0] != '0');
+    if (const char* e = getenv("BDOF_RESIDENT")) p->resident = (e[0] != '0');
     if (const char* e = getenv("BDOF_L2_PREFETCH")) p->l2_prefetch = (e[0] != '0');
     if (const char* e = getenv("BDOF_ROW_PREFETCH")) p->row_prefetch = (e[0] != '0');
     int r = 0;
@@ -720,6 +724,32 @@ static int col_pass(bdof_plan* p, int variant, const LineParams& q) {
 static bool use_sweep(const bdof_plan* p) {
     return p->sweep && !p->generic && !p->full_kernel && p->n_slice >= 2 && pipe_parts(p->nx) > 0 && pipe_parts(p->ny) > 0;
 }
+// Small square fields run as ONE kernel per direction with the field resident on chip (residentfft.cuh); same schedule and
+// multiplier tables as the sweep kernels.  BDOF_RESIDENT=0 selects the sweep kernels instead.
+static bool use_resident(const bdof_plan* p) {
+    return p->resident && use_sweep(p) && p->ny == p->nx && bdof_resident_supported(p->nx) && p->ax.h_seq != nullptr && p->ay.h_seq != nullptr;
+}
+static int resident_launch(bdof_plan* p, bool adj, ResidentParams q) {
+    q.hx = adj ? p->ax.h_seq_adj : p->ax.h_seq;
+    q.hy = adj ? p->ay.h_seq_adj : p->ay.h_seq;
+    q.tw = p->ax.tw;
+    q.slab = p->slabs;
+    q.slice_stride = p->F;
+    q.n_slice = p->n_slice; q.batch = p->batch;
+    q.propagate_last = (p->flags & BDOF_PROPAGATE_LAST) ? 1 : 0;
+    q.k_dz = float(p->k_dz);
+    if (!p->profile) return bdof_launch_resident(p->nx, adj ? 1 : 0, q, p->stream);
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a));
+    CUDA_TRY(cudaEventCreate(&b));
+    CUDA_TRY(cudaEventRecord(a, p->stream));
+    int r = bdof_launch_resident(p->nx, adj ? 1 : 0, q, p->stream);
+    CUDA_TRY(cudaEventRecord(b, p->stream));
+    p->prof_events.push_back(a); p->prof_events.push_back(b);
+    p->prof_variant.push_back(adj ? V_RESIDENT_ADJ : V_RESIDENT_FWD);
+    return r;
+}
+
 // kernel of slice i: x kernel (rows) for even i, y kernel (columns) for odd i
 static int sweep_launch(bdof_plan* p, int i, bool adj, SweepParams q) {
     const bool col = (i & 1) != 0;
@@ -798,10 +828,25 @@ extern "C" int bdof_forward(bdof_plan* p, const float* d_db_f, const float* d_pr
     p->stash_valid = false;
     const unsigned long long launches0 = g_launches.load();
     CUDA_TRY(cudaEventRecord(p->t_ev[0], p->stream));
-    k_broadcast_probe<<<blocks_for(per, 256), 256, 0, p->stream>>>(d_probe, cur, per, p->batch);
-    BDOF_TRY(launch_check("k_broadcast_probe"));
+    const bool resident = use_resident(p);
     std::complex<double> phase{1.0, 0.0};
-    if (use_sweep(p)) {
+    if (resident) {
+        // the whole object part of the chain in one launch: the field never leaves the SM
+        float2* obj_out = (p->free_mode == BDOF_FREE_NONE) ? d_exit : p->work[0];
+        ResidentParams q{};
+        q.in = d_probe; q.out = obj_out; q.db = d_db;
+        q.db_slice_stride = (p->flags & BDOF_Z_BROADCAST) ? 0 : p->F;
+        q.stash = (store && p->t_stash) ? p->t_stash : nullptr;
+        q.store = store ? 1 : 0;
+        BDOF_TRY(resident_launch(p, false, q));
+        for (int i = 0; i < Z; ++i) if (slice_propagates(p, i)) phase *= p->phase0;
+        cur = obj_out;
+        p->stash_valid = store && p->t_stash != nullptr;
+    } else {
+        k_broadcast_probe<<<blocks_for(per, 256), 256, 0, p->stream>>>(d_probe, cur, per, p->batch);
+        BDOF_TRY(launch_check("k_broadcast_probe"));
+    }
+    if (!resident && use_sweep(p)) {
         // slice i runs as ONE kernel along axis a(i) (x for even i, y for odd i): second half of the propagation
         // of slice i-1, modulation by slice i, first half of the propagation of slice i
         float2* obj_out = (p->free_mode == BDOF_FREE_NONE) ? d_exit : p->work[0];
@@ -829,7 +874,7 @@ extern "C" int bdof_forward(bdof_plan* p, const float* d_db_f, const float* d_pr
     }
     // where the object part of the chain leaves its result
     float2* obj_out = (p->free_mode == BDOF_FREE_NONE) ? d_exit : (store ? p->work[0] : nullptr);
-    for (int i = 0; i < Z && !use_sweep(p); ++i) {
+    for (int i = 0; i < Z && !use_sweep(p); ++i) {      // (resident implies use_sweep)
         const float2* db_i = d_db + ((p->flags & BDOF_Z_BROADCAST) ? 0 : (long long)i * p->F);
         const bool last = (i == Z - 1);
         float2* dst;
@@ -912,7 +957,18 @@ extern "C" int bdof_adjoint(bdof_plan* p, float* d_db_inout, const float* d_grad
         BDOF_TRY(row_pass(p, V_ROW_CONV, row_params(p, p->tmp, G, p->ax.hf_adj)));
     }
     const int n_buckets = int(p->bucket_events.size());
-    const bool sweep = use_sweep(p);
+    const bool resident = use_resident(p);
+    const bool sweep = use_sweep(p) && !resident;
+    if (resident) {
+        ResidentParams q{};
+        q.in = G; q.out = d_grad_probe ? G : nullptr;
+        q.db = db; q.db_slice_stride = zb ? 0 : p->F;
+        q.tstash = p->stash_valid ? p->t_stash : nullptr;
+        q.grad = gout ? gout : db;
+        BDOF_TRY(resident_launch(p, true, q));
+        for (int j = 0; j < n_buckets; ++j) CUDA_TRY(cudaEventRecord(p->bucket_events[j], p->stream));
+        if (p->stash_valid && (p->t_stash == (gout ? gout : db))) p->stash_valid = false;
+    }
     if (sweep) {
         if (slice_propagates(p, Z - 1)) {
             // adjoint of the trailing half propagation (TF semantics), into the work field the sweep runs on
@@ -940,7 +996,7 @@ extern "C" int bdof_adjoint(bdof_plan* p, float* d_db_inout, const float* d_grad
             }
         }
     }
-    for (int i = Z - 1; i >= 0 && !sweep; --i) {
+    for (int i = Z - 1; i >= 0 && !sweep && !resident; --i) {
         const float2* db_i = db + (zb ? 0 : (long long)i * p->F);
         float2* grad_i = gout ? gout + (long long)i * p->F : db + (long long)i * p->F;
         const float2* psi_i = p->slabs + (long long)i * p->F;

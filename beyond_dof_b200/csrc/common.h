@@ -32,7 +32,7 @@ struct LineParams {
 };
 
 enum Variant { V_ROW_CONV_T = 0, V_ROW_CONV, V_ROW_CONV_ADJ, V_ROW_FWD, V_ROW_INV, V_COL_CONV, V_COL_FWD, V_COL_INV, V_COL_CONV2D,
-               V_COL_CONV_PIPE, V_SWEEP_FWD, V_SWEEP_ADJ, V_COUNT };
+               V_COL_CONV_PIPE, V_SWEEP_FWD, V_SWEEP_ADJ, V_RESIDENT_FWD, V_RESIDENT_ADJ, V_COUNT };
 
 // Pipelined passes (pipefft.cuh): number of parts of the stage exchange per FFT length, 0 = not available.
 // Lengths with T == R1 (4096) use the cyclic-shift scheme and a twiddle table that includes the all-ones row 0.
@@ -65,18 +65,23 @@ __device__ __forceinline__ void sincos_fast(float x, float* s, float* c) {
     *c = cc;
 }
 
-// t = exp(i k delta) * exp(-k beta)   (npfuncs.py:38)
-__device__ __forceinline__ float2 transmission(float2 db, float k) {
+// Transmission of one slice, t = exp(i k delta) * exp(-k beta) (npfuncs.py:38), returned as tau = t - 1.
+// Why t - 1: for X-ray objects k*delta per slice is ~1e-4, so Re(t) = 1 - 1e-8: fp32 drops the cos term of EVERY slice
+// (the same sign each time) and the field's modulus grows by x^2/2 per slice -- a bias that compounds linearly with depth
+// (measured: half of the 6.8e-6 intensity error after 512 slices of the config-2 phantom).  tau keeps the small terms, and
+// psi * t is formed as psi + psi * tau with FMAs (cmul1p), at the same instruction count as a complex multiply.
+// General path: 3-term Cody-Waite reduction + cephes polynomials (sincos_fast), tau = t - 1 directly.
+__device__ __forceinline__ float2 transmission_m1(float2 db, float k) {
     float s, c;
     sincos_fast(k * db.x, &s, &c);
     float m = expf(-k * db.y);
-    return make_float2(m * c, m * s);
+    return make_float2(fmaf(m, c, -1.0f), m * s);
 }
 
 // Same function for |k delta| <= pi/4 and |k beta| <= 0.5 (every X-ray configuration: k*delta per slice
-// is O(1e-4..1e-1)): no range reduction, no quadrant selects, exp by a degree-7 Taylor polynomial
-// (truncation 0.5^8/8! = 1e-7).  Callers pick it with a warp-uniform vote and fall back to transmission().
-__device__ __forceinline__ float2 transmission_small(float2 db, float k) {
+// is O(1e-4..1e-1)): no range reduction, no quadrant selects; cos - 1 and exp - 1 by polynomials without the leading 1
+// (exp: degree-7 Taylor, truncation 0.5^8/8! = 1e-7).  Callers pick it with a warp-uniform vote.
+__device__ __forceinline__ float2 transmission_small_m1(float2 db, float k) {
     const float x = k * db.x, y = -k * db.y;
     const float x2 = x * x;
     float sp = fmaf(x2, -1.9515295891e-4f, 8.3321608736e-3f);
@@ -85,31 +90,37 @@ __device__ __forceinline__ float2 transmission_small(float2 db, float k) {
     float cp = fmaf(x2, 2.443315711809948e-5f, -1.388731625493765e-3f);
     cp = fmaf(cp, x2, 4.166664568298827e-2f);
     cp = fmaf(cp, x2, -0.5f);
-    cp = fmaf(cp, x2, 1.0f);
+    const float cm1 = cp * x2;                       // cos x - 1
     float m = fmaf(y, 1.98412698e-4f, 1.38888889e-3f);
     m = fmaf(m, y, 8.33333333e-3f);
     m = fmaf(m, y, 4.16666667e-2f);
     m = fmaf(m, y, 1.66666667e-1f);
     m = fmaf(m, y, 0.5f);
     m = fmaf(m, y, 1.0f);
-    m = fmaf(m, y, 1.0f);
-    return make_float2(m * cp, m * sp);
+    const float em1 = m * y;                         // exp y - 1
+    return make_float2(fmaf(em1, cm1, em1 + cm1), fmaf(em1, sp, sp));
 }
 // |k delta| <= 2^-4 and |k beta| <= 2^-6 (one thin slice of any X-ray object): truncation errors
 // x^7/5040 = 7e-13 (sin), x^6/720 = 8e-11 (cos), y^4/24 = 2.5e-9 (exp) are below fp32 resolution
-__device__ __forceinline__ float2 transmission_tiny(float2 db, float k) {
+__device__ __forceinline__ float2 transmission_tiny_m1(float2 db, float k) {
     const float x = k * db.x, y = -k * db.y;
     const float x2 = x * x;
     const float sp = fmaf(fmaf(x2, 8.33333333e-3f, -1.66666667e-1f) * x2, x, x);
-    const float cp = fmaf(fmaf(x2, 4.16666667e-2f, -0.5f), x2, 1.0f);
-    const float m = fmaf(fmaf(fmaf(y, 1.66666667e-1f, 0.5f), y, 1.0f), y, 1.0f);
-    return make_float2(m * cp, m * sp);
+    const float cm1 = fmaf(x2, 4.16666667e-2f, -0.5f) * x2;
+    const float em1 = fmaf(fmaf(y, 1.66666667e-1f, 0.5f), y, 1.0f) * y;
+    return make_float2(fmaf(em1, cm1, em1 + cm1), fmaf(em1, sp, sp));
 }
 __device__ __forceinline__ bool transmission_is_tiny(float2 db, float k) {
     return fabsf(k * db.x) <= 0.0625f && fabsf(k * db.y) <= 0.015625f;
 }
 __device__ __forceinline__ bool transmission_is_small(float2 db, float k) {
     return fabsf(k * db.x) <= 0.78539816f && fabsf(k * db.y) <= 0.5f;
+}
+// per-element tier selection (kernels off the hot path)
+__device__ __forceinline__ float2 transmission_any_m1(float2 db, float k) {
+    if (transmission_is_tiny(db, k)) return transmission_tiny_m1(db, k);
+    if (transmission_is_small(db, k)) return transmission_small_m1(db, k);
+    return transmission_m1(db, k);
 }
 
 }  // namespace bdof
@@ -122,7 +133,10 @@ int bdof_launch_check(const char* what);
 int bdof_sm_reserve();    // SMs the persistent line kernels leave free (bdof_set_sm_reserve / BDOF_SM_RESERVE)
 bool bdof_use_pdl();      // programmatic dependent launch of the line kernels (BDOF_PDL=0 disables)
 
-namespace bdof { struct SweepParams; }
+namespace bdof { struct SweepParams; struct ResidentParams; }
+// resident small-field kernels (residentfft.cuh, resident_inst.cu): one CTA per field through all slices
+int bdof_resident_supported(int n);
+int bdof_launch_resident(int n, int adj, const bdof::ResidentParams& p, cudaStream_t st);
 // sweep kernels (sweepfft.cuh): col = 0 x kernel (rows), 1 y kernel (columns); adj = 0 forward, 1 adjoint;
 // the field is [rows][cols] complex64 row-major with rows = batch * ny
 #define BDOF_DECL_LINE(N) int bdof_launch_line_##N(int variant, const bdof::LineParams& p, long long n_lines, cudaStream_t st); \

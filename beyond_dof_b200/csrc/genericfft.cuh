@@ -40,15 +40,17 @@ struct GenArgs {
 GEN_HD float2 g_cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 GEN_HD float2 g_conj(float2 a) { return make_float2(a.x, -a.y); }
 
-// t = exp(i k delta) exp(-k beta): the device build uses the same routine as every other kernel
-GEN_HD float2 g_transmission(float2 db, float k) {
+// tau = exp(i k delta) exp(-k beta) - 1: the device build uses the same routine as every other kernel (common.h)
+GEN_HD float2 g_transmission_m1(float2 db, float k) {
 #ifdef __CUDA_ARCH__
-    return transmission(db, k);
+    return transmission_any_m1(db, k);
 #else
-    const float m = expf(-k * db.y);
-    return make_float2(m * cosf(k * db.x), m * sinf(k * db.x));
+    const double m = exp(-double(k) * db.y), x = double(k) * db.x;
+    return make_float2(float(m * cos(x) - 1.0), float(m * sin(x)));
 #endif
 }
+// a * (1 + tau)
+GEN_HD float2 g_cmul1p(float2 a, float2 tau) { return make_float2(a.x + (a.x * tau.x - a.y * tau.y), a.y + (a.x * tau.y + a.y * tau.x)); }
 
 // radices of n: 4s first, then 2, 3, 5, 7; returns the number of stages or 0 when n has another prime factor
 inline __host__ int gen_factorize(int n, int* radix) {
@@ -90,7 +92,7 @@ GEN_HD void gen_load(const GenArgs& a, long long tile, int tid, int nthreads, fl
         }
         if (a.pre_transmit) {
             const long long dbase = (long long)b * p.db_batch_stride + (long long)li * p.line_stride;
-            v = g_cmul(v, g_transmission(p.db[dbase + e], p.k_dz));
+            v = g_cmul1p(v, g_transmission_m1(p.db[dbase + e], p.k_dz));
         }
         A[l * n + e] = v;
     }
@@ -213,11 +215,11 @@ GEN_HD void gen_store(const GenArgs& a, long long tile, int tid, int nthreads, c
             // G_u = conj(v) is the gradient w.r.t. u = psi t:  dL/ddelta = -k Im(conj(G_u) u), dL/dbeta = -k Re(conj(G_u) u),
             // G = conj(t) G_u   (same epilogue as line_kernel POST_ADJ)
             const long long dbase = (long long)b * p.db_batch_stride + (long long)li * p.line_stride;
-            const float2 tr = g_transmission(p.db[dbase + e], p.k_dz);
-            const float2 u = g_cmul(p.psi[base + e], tr);
+            const float2 tr = g_transmission_m1(p.db[dbase + e], p.k_dz);      // tau = t - 1
+            const float2 u = g_cmul1p(p.psi[base + e], tr);
             const float2 w = g_cmul(u, v);
             p.grad[dbase + e] = make_float2(-p.k_dz * w.y, -p.k_dz * w.x);
-            p.out[base + e] = g_conj(g_cmul(v, tr));
+            p.out[base + e] = g_conj(g_cmul1p(v, tr));
         } else if (a.mode == GEN_FWD) {
             int es = e + p.out_shift;                 // circular output shift (fftshift): far field
             if (es >= n) es -= n;

@@ -530,12 +530,12 @@ __global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, c
                     if (__all_sync(0xffffffffu, small)) {
                         static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) {
                             constexpr int i = decltype(I)::value;
-                            sx[T * i] = cmul(sx[T * i], transmission_small(d[i], p.k_dz));
+                            sx[T * i] = cmul1p(sx[T * i], transmission_small_m1(d[i], p.k_dz));
                         });
                     } else {
                         static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) {
                             constexpr int i = decltype(I)::value;
-                            sx[T * i] = cmul(sx[T * i], transmission(d[i], p.k_dz));
+                            sx[T * i] = cmul1p(sx[T * i], transmission_m1(d[i], p.k_dz));
                         });
                     }
                     ++chunk_seq;
@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, c
                     const float2* sb = my_stage + buf * ST::CHUNK_ELEMS + t;
                     static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) {
                         constexpr int i = decltype(I)::value;
-                        v[c * ST::CHK + i] = cmul(v[c * ST::CHK + i], transmission(sb[T * i], p.k_dz));
+                        v[c * ST::CHK + i] = cmul1p(v[c * ST::CHK + i], transmission_any_m1(sb[T * i], p.k_dz));
                     });
                     ++chunk_seq;
                     stream_advance(line, c);
@@ -651,17 +651,17 @@ __global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, c
                     });
                     float2 trs[ST::CHK];
                     if (__all_sync(0xffffffffu, small)) {
-                        static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) { constexpr int i = decltype(I)::value; trs[i] = transmission_small(d[i], p.k_dz); });
+                        static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) { constexpr int i = decltype(I)::value; trs[i] = transmission_small_m1(d[i], p.k_dz); });
                     } else {
-                        static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) { constexpr int i = decltype(I)::value; trs[i] = transmission(d[i], p.k_dz); });
+                        static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) { constexpr int i = decltype(I)::value; trs[i] = transmission_m1(d[i], p.k_dz); });
                     }
                     static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) {
                         constexpr int i = decltype(I)::value;
                         const float2 vq = sx[T * i];                        // conj(G_u)
-                        const float2 u = cmul(sb[ST::CHUNK_ELEMS + T * i], trs[i]);
+                        const float2 u = cmul1p(sb[ST::CHUNK_ELEMS + T * i], trs[i]);      // trs = tau = t - 1
                         const float2 w = cmul(u, vq);                       // u * conj(G_u)
                         gp[c * ST::CHUNK_ELEMS + T * i] = make_float2(-p.k_dz * w.y, -p.k_dz * w.x);
-                        dstc[c * ST::CHUNK_ELEMS + T * i] = cmul_conj(vq, trs[i]);   // G_u conj(t)
+                        dstc[c * ST::CHUNK_ELEMS + T * i] = cmul_conj1p(vq, trs[i]);   // G_u conj(t)
                     });
                     ++chunk_seq;
                     stream_advance(line, c);                                // (line barrier inside)
@@ -677,11 +677,11 @@ __global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, c
                     static_for<ST::CHK>([&](auto I) __attribute__((always_inline)) {
                         constexpr int i = decltype(I)::value;
                         constexpr int q = c * ST::CHK + i;
-                        const float2 tr = transmission(sb[T * i], p.k_dz);
-                        const float2 u = cmul(sb[ST::CHUNK_ELEMS + T * i], tr);
+                        const float2 tr = transmission_any_m1(sb[T * i], p.k_dz);     // tau = t - 1
+                        const float2 u = cmul1p(sb[ST::CHUNK_ELEMS + T * i], tr);
                         const float2 w = cmul(u, v[q]);              // u * conj(G_u) = u * v
                         gp[T * q] = make_float2(-p.k_dz * w.y, -p.k_dz * w.x);
-                        dst[T * q] = cmul_conj(v[q], tr);           // conj(v) conj(t) = G_u conj(t)
+                        dst[T * q] = cmul_conj1p(v[q], tr);         // conj(v) conj(t) = G_u conj(t)
                     });
                     ++chunk_seq;
                     stream_advance(line, c);

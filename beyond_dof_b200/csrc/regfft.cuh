@@ -82,6 +82,17 @@ __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {
     return upk(fma2(pk(-a.y, -a.x), pk(b.y, b.y), mul2(pk(a.x, -a.y), pk(b.x, b.x))));
 }
 __device__ __forceinline__ float2 conjf2(float2 a) { return make_float2(a.x, -a.y); }
+// a * (1 + tau) = a + a * tau, a * conj(1 + tau), conj(a * (1 + tau)): products with a transmission given as tau = t - 1
+// (common.h); two packed FMAs each, like a plain complex multiply
+__device__ __forceinline__ float2 cmul1p(float2 a, float2 tau) {
+    return upk(fma2(pk(-a.y, a.x), pk(tau.y, tau.y), fma2(pk(a.x, a.y), pk(tau.x, tau.x), pk(a.x, a.y))));
+}
+__device__ __forceinline__ float2 cmulc1p(float2 a, float2 tau) {
+    return upk(fma2(pk(a.y, -a.x), pk(tau.y, tau.y), fma2(pk(a.x, a.y), pk(tau.x, tau.x), pk(a.x, a.y))));
+}
+__device__ __forceinline__ float2 cmul_conj1p(float2 a, float2 tau) {
+    return upk(fma2(pk(-a.y, -a.x), pk(tau.y, tau.y), fma2(pk(a.x, -a.y), pk(tau.x, tau.x), pk(a.x, -a.y))));
+}
 // forward: a * (-i); inverse: a * (+i)
 template <bool INV>
 __device__ __forceinline__ float2 mul_mi(float2 a) {

@@ -1,0 +1,44 @@
+// Instantiation unit and launcher of the resident small-field kernels (residentfft.cuh).
+#include "../../include/bdof.h"
+#include "common.h"
+#include "residentfft.cuh"
+
+using namespace bdof;
+
+template <int N> struct ResCfg;
+template <> struct ResCfg<64>  { using C = LineCfg<64, 8, 8, 8, 1>; };
+
+template <class Cfg>
+static int launch_resident(int adj, const ResidentParams& p, cudaStream_t st) {
+    using SM = ResidentSmem<Cfg>;
+    auto kf = resident_forward_kernel<Cfg>;
+    auto ka = resident_adjoint_kernel<Cfg>;
+    static int slots[2] = {0, 0};
+    if (slots[adj] == 0) {
+        int dev = 0, n_sm = 0, occ = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        if (adj) {
+            CUDA_TRY(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::BYTES)));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ka, Cfg::N * Cfg::T, SM::BYTES));
+        } else {
+            CUDA_TRY(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::BYTES)));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf, Cfg::N * Cfg::T, SM::BYTES));
+        }
+        if (occ < 1) return bdof_fail(BDOF_E_UNSUPPORTED, "resident kernel does not fit on an SM (%zu bytes smem)", SM::BYTES);
+        slots[adj] = occ * (n_sm > 0 ? n_sm : 148);
+    }
+    const unsigned grid = unsigned(p.batch < slots[adj] ? p.batch : slots[adj]);
+    if (adj) ka<<<grid, Cfg::N * Cfg::T, SM::BYTES, st>>>(p);
+    else     kf<<<grid, Cfg::N * Cfg::T, SM::BYTES, st>>>(p);
+    return bdof_launch_check(adj ? "resident_adjoint_kernel" : "resident_forward_kernel");
+}
+
+int bdof_resident_supported(int n) { return n == 64 ? 1 : 0; }
+
+int bdof_launch_resident(int n, int adj, const ResidentParams& p, cudaStream_t st) {
+    switch (n) {
+        case 64: return launch_resident<ResCfg<64>::C>(adj, p, st);
+    }
+    return bdof_fail(BDOF_E_UNSUPPORTED, "no resident kernel for %d x %d fields", n, n);
+}

@@ -24,7 +24,7 @@ struct SweepParams {
     float2* out;             // field out (may alias in)
     const float2* db;        // (delta, beta) of this slice, row-major
     float2* grad;            // adjoint: gradient of this slice, row-major (may alias db)
-                             // forward: nullable transmission stash -- t_i = exp(k(i delta - beta)) of this slice is written here
+                             // forward: nullable transmission stash -- tau_i = exp(k(i delta - beta)) - 1 of this slice is written here
                              // (row-major, may alias db) so that the adjoint kernel of the slice lands t instead of recomputing it
     float2* slab;            // psi entering this slice in TILE layout (forward: written, adjoint: read)
     const float2* h;         // multiplier of this axis (forward) or its conjugate (adjoint), 1/N folded in
@@ -39,7 +39,7 @@ struct SweepParams {
     int slab_prefetch;       // adjoint: L2-prefetch the slab tile at tile start
     int stagger_ns;          // x kernels: the upper half of the lines starts every convolution this much later, so that
                              // its stage exchanges (shared-memory pipe) overlap the other half's butterflies (FP pipe)
-    int db_is_t;             // adjoint: `db` holds the stashed transmission t_i, not (delta, beta)
+    int db_is_t;             // adjoint: `db` holds the stashed transmission tau_i = t_i - 1, not (delta, beta)
     float k_dz;
     long long* dbg;
 };
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                 SWEEP_STAMP(3);
                 land_wait();            // delta/beta of this tile
                 SWEEP_STAMP(4);
-                // t = exp(k(i delta - beta)) in place.  ROLLED on purpose: a straight-line version (64 x 20 instructions)
+                // tau = exp(k(i delta - beta)) - 1 in place (common.h: why t - 1).  ROLLED on purpose: a straight-line version (64 x 20 instructions)
                 // pushed the kernel past the instruction cache and cost ~10k cycles on the first tile of every launch
                 const int q_end = (active && !(ADJ && p.db_is_t)) ? E : 0;
                 // software pipeline: the next group's (delta, beta) are loaded while this group is evaluated (its shared-memory
@@ -263,13 +263,13 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                     const bool small = md <= 0.78539816f && mb <= 0.5f;
                     if (__all_sync(0xffffffffu, tiny)) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) Lme[(q0 + i) * LQ] = transmission_tiny(d[i], kdz);
+                        for (int i = 0; i < 4; ++i) Lme[(q0 + i) * LQ] = transmission_tiny_m1(d[i], kdz);
                     } else if (__all_sync(0xffffffffu, small)) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) Lme[(q0 + i) * LQ] = transmission_small(d[i], kdz);
+                        for (int i = 0; i < 4; ++i) Lme[(q0 + i) * LQ] = transmission_small_m1(d[i], kdz);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) Lme[(q0 + i) * LQ] = transmission(d[i], kdz);
+                        for (int i = 0; i < 4; ++i) Lme[(q0 + i) * LQ] = transmission_m1(d[i], kdz);
                     }
                 }
                 SWEEP_STAMP(5);
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                         float2* sp = p.slab + tile_off + (Lme - L);
                         static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; sp[q * LQ] = v[q]; });
                     }
-                    if (active) static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = cmul(v[q], Lme[q * LQ]); });
+                    if (active) static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = cmul1p(v[q], Lme[q * LQ]); });
                     if (p.grad != nullptr) {
                         // stash t for the adjoint: L leaves by TMA (tensor store for column tiles, bulk rows otherwise); the next
                         // landing is issued from inside the following convolution once the store has finished reading L
@@ -301,9 +301,8 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                         if (has_next) land(LAND_IN, tile + tile_step);
                     }
                 } else {
-                    // G = G_u conj(t)
-                    // G = G_u conj(t)
-                    if (active) static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = cmulc(v[q], Lme[q * LQ]); });
+                    // G = G_u conj(t), t = 1 + tau
+                    if (active) static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = cmulc1p(v[q], Lme[q * LQ]); });
                     __syncthreads();
                     land(LAND_SLAB, tile);
                     SWEEP_STAMP(6);

@@ -222,7 +222,7 @@ class MultislicePlan:
         return out
 
     VARIANT_NAMES = ['row_conv_transmit', 'row_conv', 'row_conv_adjoint', 'row_fft', 'row_ifft', 'col_conv', 'col_fft',
-                     'col_ifft', 'col_conv_2d', 'col_conv_pipe', 'sweep_forward', 'sweep_adjoint']
+                     'col_ifft', 'col_conv_2d', 'col_conv_pipe', 'sweep_forward', 'sweep_adjoint', 'resident_forward', 'resident_adjoint']
 
     def free_prop(self, field, out=None):
         """The plan's free-space step on its own: [B,Y,X] complex64 -> [B,Y,X]."""

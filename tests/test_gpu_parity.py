@@ -538,3 +538,79 @@ def test_np_funcs_variant_returns_probe_array(bd, golden_dir):
                                                        torch.as_tensor(zero).cuda(), 5000, 1e-7, obj_batch_shape=gd.shape)
     wo, po = mo.multislice_propagate_batch_numpy_cnn(gd, gb, one, zero, 5000, 1e-7, obj_batch_shape=gd.shape)
     assert wf.is_cuda and rel_l2(wf.cpu().numpy(), wo) < 1e-5 and rel_l2(pa.cpu().numpy(), po) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# resident small-field kernels (residentfft.cuh): one launch per direction, the field stays on the SM
+# ---------------------------------------------------------------------------------------------
+def _run_plan_env(shape, gd, gb, pr, pi, target, env, propagate_last=False, free=None, in_place_stash=False, z_broadcast=False):
+    from beyond_dof_b200.plan import MultislicePlan
+    B, Y, X, Z = shape
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)                                     # read when the plan is created
+    try:
+        plan = MultislicePlan(Y, X, B, Z, 5000, 1e-7, free_prop_cm=free, propagate_last=propagate_last, store_slices=True,
+                              z_broadcast=z_broadcast)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+    if z_broadcast:
+        db = plan.pack(torch.as_tensor(gd[..., :1]).cuda(), torch.as_tensor(gb[..., :1]).cuda())
+    else:
+        db = plan.pack(torch.as_tensor(gd).cuda(), torch.as_tensor(gb).cuda())
+    probe = torch.as_tensor((np.asarray(pr) + 1j * np.asarray(pi)).astype(np.complex64)).cuda()
+    l0 = plan_launches()
+    if in_place_stash:
+        plan.set_t_stash(db)
+    psi = plan.forward(db, probe)
+    loss, g = plan.loss_mag(psi, torch.as_tensor(target.astype(np.float32)).cuda())
+    if in_place_stash:
+        _, gp = plan.adjoint(db, g, want_probe_grad=True)
+        gout = db
+    else:
+        gout = torch.empty((Z, B, Y, X, 2), dtype=torch.float32, device='cuda')
+        _, gp = plan.adjoint(db, g, grad_out=gout, want_probe_grad=True)
+    torch.cuda.synchronize()
+    n_launch = plan_launches() - l0
+    g_d, g_b = plan.unpack(gout)
+    return psi.cpu().numpy(), g_d.cpu().numpy(), g_b.cpu().numpy(), gp.cpu().numpy(), n_launch, loss.item()
+
+
+@pytest.mark.parametrize('case', [((3, 64, 64, 6), False, None), ((3, 64, 64, 7), True, 'inf'), ((200, 64, 64, 3), True, None),
+                                  ((2, 64, 64, 2), False, 1e-4), ((5, 64, 64, 9), True, 1e-4)])
+@pytest.mark.parametrize('in_place_stash', [False, True])
+def test_resident_kernels_match_sweep_kernels_and_oracle(bd, case, in_place_stash):
+    shape, propagate_last, free = case
+    gd, gb = mo.random_phantom(shape, seed=71, delta_scale=4e-4, beta_scale=4e-5)
+    pr, pi = mo.gaussian_probe(shape[1:3], 20., 15., 0.5)
+    rng = np.random.default_rng(72)
+    target = rng.random(shape[:3]) * (64 if free == 'inf' else 1.0) + 0.5
+    a = _run_plan_env(shape, gd, gb, pr, pi, target, {'BDOF_RESIDENT': '1'}, propagate_last, free, in_place_stash)
+    b = _run_plan_env(shape, gd, gb, pr, pi, target, {'BDOF_RESIDENT': '0'}, propagate_last, free, in_place_stash)
+    assert a[4] < b[4]                                        # one launch per direction instead of one per slice and direction
+    assert rel_l2(a[0], b[0]) < 2e-6
+    assert rel_l2(a[1], b[1]) < 2e-5 and rel_l2(a[2], b[2]) < 2e-5 and rel_l2(a[3], b[3]) < 2e-5
+    if shape[0] <= 8:
+        lo, gdo, gbo, psio = mo.loss_and_grad(gd, gb, pr, pi, 5000, 1e-7, target, free_prop_cm=free, propagate_last=propagate_last)
+        assert intensity_err(a[0], psio) < TOL_INTENSITY and abs(a[5] - lo) < 1e-5 * abs(lo)
+        assert rel_l2(a[1], gdo) < TOL_GRAD and rel_l2(a[2], gbo) < TOL_GRAD
+
+
+def test_resident_kernels_z_broadcast_and_forward_only(bd):
+    shape = (4, 64, 64, 10)
+    gd1, gb1 = mo.random_phantom((4, 64, 64, 1), seed=73, delta_scale=4e-4, beta_scale=4e-5)
+    gd, gb = np.repeat(gd1, 10, axis=3), np.repeat(gb1, 10, axis=3)
+    pr, pi = mo.gaussian_probe((64, 64), 20., 15., 0.5)
+    rng = np.random.default_rng(74)
+    target = rng.random(shape[:3]) + 0.5
+    lo, gdo, gbo, psio = mo.loss_and_grad(gd, gb, pr, pi, 5000, 1e-7, target)
+    a = _run_plan_env(shape, gd, gb, pr, pi, target, {'BDOF_RESIDENT': '1'}, z_broadcast=True)
+    assert intensity_err(a[0], psio) < TOL_INTENSITY
+    assert rel_l2(a[1], gdo) < TOL_GRAD and rel_l2(a[2], gbo) < TOL_GRAD
+    # forward-only plan (no slice store) through the drop-in entry point
+    psi = bd.multislice_propagate_batch(gd, gb, pr, pi, 5000, 1e-7, free_prop_cm='inf', obj_batch_shape=shape)
+    ref = mo.multislice_propagate_batch(gd, gb, pr, pi, 5000, 1e-7, free_prop_cm='inf', obj_batch_shape=shape)
+    assert intensity_err(psi, ref) < TOL_INTENSITY
