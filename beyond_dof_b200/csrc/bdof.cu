@@ -436,17 +436,122 @@ static int upload(float2** dst, const std::vector<float2>& v) {
 }
 
 // centred complex128 factor -> ifftshift, scale, fp32 (and conjugate)
-static void shift_factor(const double* h, int n, double scale, std::vector<float2>& out, std::vector<float2>& out_adj) {
+static std::vector<std::complex<double>> conv_diag_gain(int n);
+// `generic`: the pass runs on the mixed-radix kernel, whose transform the gain model does not describe (gain 1)
+static void shift_factor(const double* h, int n, double scale, std::vector<float2>& out, std::vector<float2>& out_adj, bool generic) {
     out.resize(n); out_adj.resize(n);
     const int s = n / 2;                            // ifftshift(a)[i] = a[(i + n//2) % n]
+    const std::vector<std::complex<double>> g = generic ? std::vector<std::complex<double>>((size_t)n, 1.0) : conv_diag_gain(n);
     for (int i = 0; i < n; ++i) {
         const int src = (i + s) % n;
-        double re = h[2 * src] * scale, im = h[2 * src + 1] * scale;
-        out[i] = make_float2(float(re), float(im));
-        out_adj[i] = make_float2(float(re), float(-im));
+        const std::complex<double> hh(h[2 * src] * scale, h[2 * src + 1] * scale);
+        const std::complex<double> f = hh / g[i], a = std::conj(hh) / g[i];     // the realised pair multiplies bin i by g[i]
+        out[i] = make_float2(float(f.real()), float(f.imag()));
+        out_adj[i] = make_float2(float(a.real()), float(a.imag()));
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// diagonal gain of the REALISED fp32 transform pair
+// ------------------------------------------------------------------------------------------
+// The butterflies' twiddle constants and the stage-twiddle table are fp32 roundings of the exact roots of unity, so the
+// transform the kernels compute is a fixed linear operator ~1e-7 away from the DFT.  Its effect on one convolution
+// IFFT(h FFT(x)) is, to first order, a per-frequency complex gain g_k (plus incoherent leakage between frequencies): bin k
+// is multiplied by h_k g_k instead of h_k, the SAME way in every slice, so the error compounds linearly with depth -- measured
+// 1.3e-5 on the far-field intensity of BASELINE config 3 (64^2 Gaussian probe, 128 slices), 4.4e-5 for a strongly scattering
+// object at 512 slices; tools/fp32_fft_error_model.py reproduces both in float64 arithmetic with fp32-rounded constants.
+// g_k is computable exactly on the host: the two-stage plan is  X[k1 + R1 k2] = sum_j A2[k2,j] W[j,k1] sum_r A1[k1,r] x[j + R2 r]
+// with A1, A2 the realised in-register DFTs (regfft.cuh, emulated here in double with the same fp32 constants) and W the
+// fp32 table, and the inverse is the conj trick on the same operator.  Dividing the multiplier tables by g_k removes the
+// coherent part (config 3: 1.3e-5 -> 2e-7 in the model).
+typedef std::complex<double> cdbl;
+
+static cdbl emu_tw32(int M, int R) {       // W_R^M = exp(-2 pi i M / R) as mul_tw<M, R, false> applies it
+    M %= R; if (M < 0) M += R;
+    if ((4 * M) % R == 0) {
+        switch ((4 * M) / R) { case 0: return {1.0, 0.0}; case 1: return {0.0, -1.0}; case 2: return {-1.0, 0.0}; default: return {0.0, 1.0}; }
+    }
+    const double a = 2.0 * M_PI * double(M) / double(R);
+    const float c = float(cos(a)), sn = float(sin(a));
+    return {double(c), -double(sn)};
+}
+static void emu_regfft(std::vector<cdbl>& v) {      // RegFFT<R, false>::run in double with fp32-rounded constants
+    const int R = int(v.size());
+    const cdbl mi(0.0, -1.0);
+    if (R == 1) return;
+    if (R == 2) { const cdbl a = v[0], b = v[1]; v[0] = a + b; v[1] = a - b; return; }
+    if (R == 4) {
+        const cdbl t0 = v[0] + v[2], t1 = v[0] - v[2], t2 = v[1] + v[3], t3 = (v[1] - v[3]) * mi;
+        v[0] = t0 + t2; v[2] = t0 - t2; v[1] = t1 + t3; v[3] = t1 - t3;
+        return;
+    }
+    const int A = (R == 8) ? 2 : 4, B = R / A;
+    for (int n2 = 0; n2 < B; ++n2) {
+        std::vector<cdbl> t(A);
+        for (int n1 = 0; n1 < A; ++n1) t[n1] = v[B * n1 + n2];
+        emu_regfft(t);
+        for (int k1 = 0; k1 < A; ++k1) v[B * k1 + n2] = t[k1] * emu_tw32((n2 * k1) % R, R);
+    }
+    std::vector<cdbl> out(R);
+    for (int k1 = 0; k1 < A; ++k1) {
+        std::vector<cdbl> u(B);
+        for (int n2 = 0; n2 < B; ++n2) u[n2] = v[B * k1 + n2];
+        emu_regfft(u);
+        for (int k2 = 0; k2 < B; ++k2) out[k1 + A * k2] = u[k2];
+    }
+    v = out;
+}
+// rho[k][r] = realised / exact entry of the radix-R butterfly
+static std::vector<cdbl> emu_small_ratio(int R) {
+    std::vector<cdbl> rho((size_t)R * R);
+    for (int r = 0; r < R; ++r) {
+        std::vector<cdbl> e(R, cdbl(0.0, 0.0));
+        e[r] = 1.0;
+        emu_regfft(e);
+        for (int k = 0; k < R; ++k) {
+            const double a = 2.0 * M_PI * double((long long)r * k % R) / double(R);
+            rho[(size_t)k * R + r] = e[k] * cdbl(cos(a), sin(a));      // divide by exp(-i a)
+        }
+    }
+    return rho;
+}
+static StageRadices radices_for(int n);
+// g_k per FFT bin (natural order) of one convolution of length n; all ones where the model does not apply
+static std::vector<cdbl> conv_diag_gain(int n) {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("BDOF_FFT_GAIN"); enabled = (e && e[0] == '0') ? 0 : 1; }
+    std::vector<cdbl> g((size_t)n, cdbl(1.0, 0.0));
+    const StageRadices rr = radices_for(n);
+    if (!enabled || rr.r1 == 0 || rr.r3 != 1 || pipe_shift(n)) return g;
+    const int R1 = rr.r1, R2 = rr.r2;
+    const std::vector<cdbl> rho1 = emu_small_ratio(R1), rho2 = emu_small_ratio(R2);
+    // tau[j][k1] = fp32 table entry / exact W_n^{j k1} (row 0 is the implicit 1)
+    std::vector<cdbl> tau((size_t)R2 * R1, cdbl(1.0, 0.0));
+    for (int j = 1; j < R2; ++j)
+        for (int k1 = 0; k1 < R1; ++k1) {
+            const double a = -2.0 * M_PI * double((long long)j * k1 % n) / double(n);
+            const cdbl tab(double(float(cos(a))), double(float(sin(a))));
+            tau[(size_t)j * R1 + k1] = tab * cdbl(cos(a), -sin(a));
+        }
+    std::vector<cdbl> s1(R1), c2(R2);                 // row sums of rho1, column sums of rho2
+    for (int k1 = 0; k1 < R1; ++k1) { cdbl a = 0.0; for (int r = 0; r < R1; ++r) a += rho1[(size_t)k1 * R1 + r]; s1[k1] = a / double(R1); }
+    for (int j = 0; j < R2; ++j) { cdbl a = 0.0; for (int k2 = 0; k2 < R2; ++k2) a += rho2[(size_t)k2 * R2 + j]; c2[j] = a; }
+    for (int k = 0; k < n; ++k) {
+        // forward: k is the OUTPUT index k1 + R1 k2
+        const int k1 = k % R1, k2 = k / R1;
+        cdbl gf = 0.0;
+        for (int j = 0; j < R2; ++j) gf += rho2[(size_t)k2 * R2 + j] * tau[(size_t)j * R1 + k1];
+        gf = gf / double(R2) * s1[k1];
+        // inverse (conj trick): k is the INPUT index j + R2 r
+        const int j = k % R2, r = k / R2;
+        cdbl gi = 0.0;
+        for (int q1 = 0; q1 < R1; ++q1) gi += tau[(size_t)j * R1 + q1] * rho1[(size_t)q1 * R1 + r];
+        gi = std::conj(gi * c2[j] / double(n));
+        g[k] = gf * gi;
+    }
+    return g;
+}
 
 // ------------------------------------------------------------------------------------------
 // error-feedback multiplier tables
@@ -482,9 +587,11 @@ static int build_axis_sequence(bdof_plan* p, AxisTables& a, int col, const doubl
     h_schedule(p, col, napp);
     std::vector<float2> seq((size_t)(Z + 1) * n), seq_adj((size_t)(Z + 1) * n);
     const long double scale = 1.0L / (long double)n;
+    const std::vector<cdbl> gain = p->generic ? std::vector<cdbl>((size_t)n, 1.0) : conv_diag_gain(n);
     for (int i = 0; i < n; ++i) {
         const int src = (i + s) % n;                    // ifftshift, as shift_factor()
         const cld h((long double)h_centred[2 * src], (long double)h_centred[2 * src + 1]);
+        const cld g((long double)gain[i].real(), (long double)gain[i].imag());      // the realised pair multiplies bin i by g
         const bool degenerate = std::abs(h) < 1e-30L;
         cld P(1.0L, 0.0L), Q(1.0L, 0.0L);               // exact and realised cumulative products
         for (int e = 0; e <= Z; ++e) {
@@ -496,11 +603,12 @@ static int build_axis_sequence(bdof_plan* p, AxisTables& a, int col, const doubl
                 const cld r = P / Q / hn;               // = 1 + (accumulated relative error so far)
                 want = h * (cld(1.0L, 0.0L) + (r - cld(1.0L, 0.0L)) / (long double)napp[e]);    // first-order root
             }
-            const float re = float(want.real() * scale), im = float(want.imag() * scale);
+            const cld tab = want / g, tab_adj = std::conj(want) / g;
+            const float re = float(tab.real() * scale), im = float(tab.imag() * scale);
             seq[(size_t)e * n + i] = make_float2(re, im);
-            seq_adj[(size_t)e * n + i] = make_float2(re, -im);
+            seq_adj[(size_t)e * n + i] = make_float2(float(tab_adj.real() * scale), float(tab_adj.imag() * scale));
             if (napp[e] > 0 && !degenerate) {
-                const cld got((long double)re * (long double)n, (long double)im * (long double)n);
+                const cld got = cld((long double)re * (long double)n, (long double)im * (long double)n) * g;   // effective multiplier
                 for (int k = 0; k < napp[e]; ++k) Q *= got;
             }
         }
@@ -612,9 +720,9 @@ extern "C" int bdof_plan_workspace_bytes(const bdof_plan* p, size_t* bytes_out) 
 extern "C" int bdof_set_kernel(bdof_plan* p, const double* h_hy, const double* h_hx, double phase0_re, double phase0_im, double k_dz) {
     if (!p || !h_hy || !h_hx) return fail(BDOF_E_BADARG, "null");
     std::vector<float2> a, b;
-    shift_factor(h_hx, p->nx, 1.0 / p->nx, a, b);
+    shift_factor(h_hx, p->nx, 1.0 / p->nx, a, b, p->generic);
     BDOF_TRY(upload(&p->ax.h, a)); BDOF_TRY(upload(&p->ax.h_adj, b));
-    shift_factor(h_hy, p->ny, 1.0 / p->ny, a, b);
+    shift_factor(h_hy, p->ny, 1.0 / p->ny, a, b, p->generic);
     BDOF_TRY(upload(&p->ay.h, a)); BDOF_TRY(upload(&p->ay.h_adj, b));
     p->phase0 = {phase0_re, phase0_im};
     p->k_dz = k_dz;
@@ -647,9 +755,9 @@ extern "C" int bdof_set_free_prop(bdof_plan* p, int mode, const double* h_hy, co
     if (mode == BDOF_FREE_TF) {
         if (!h_hy || !h_hx) return fail(BDOF_E_BADARG, "free-space factors missing");
         std::vector<float2> a, b;
-        shift_factor(h_hx, p->nx, 1.0 / p->nx, a, b);
+        shift_factor(h_hx, p->nx, 1.0 / p->nx, a, b, p->generic);
         BDOF_TRY(upload(&p->ax.hf, a)); BDOF_TRY(upload(&p->ax.hf_adj, b));
-        shift_factor(h_hy, p->ny, 1.0 / p->ny, a, b);
+        shift_factor(h_hy, p->ny, 1.0 / p->ny, a, b, p->generic);
         BDOF_TRY(upload(&p->ay.hf, a)); BDOF_TRY(upload(&p->ay.hf_adj, b));
         p->phasef = {phase0_re, phase0_im};
     }
@@ -1161,6 +1269,13 @@ extern "C" int bdof_forward_host(bdof_plan* p, const float* h_delta, const float
     // the staging volumes are as large as the object (17 GB at 2048^2 x 256): do not keep them for the life of the plan
     cudaFree(p->e2e_delta); cudaFree(p->e2e_beta); cudaFree(p->e2e_db); cudaFree(p->e2e_probe); cudaFree(p->e2e_exit);
     p->e2e_delta = p->e2e_beta = nullptr; p->e2e_db = nullptr; p->e2e_probe = p->e2e_exit = nullptr;
+    return 0;
+}
+
+extern "C" int bdof_debug_fft_gain(int n, double* gain_out) {
+    if (n < 1 || !gain_out) return fail(BDOF_E_BADARG, "bad argument");
+    const std::vector<cdbl> g = conv_diag_gain(n);
+    for (int k = 0; k < n; ++k) { gain_out[2 * k] = g[k].real(); gain_out[2 * k + 1] = g[k].imag(); }
     return 0;
 }
 

@@ -239,6 +239,12 @@ int  bdof_dp_finish(bdof_dp* c, void* cuda_stream);
  * communication kernels (NCCL all-reduce of the gradient buckets) can run concurrently with the sweep. */
 int  bdof_set_sm_reserve(int n_sms);
 
+/* Developer / test hook (host only, no device needed): the per-bin complex gain g_k of one realised fp32 convolution
+ * IFFT(h FFT(x)) of length n -- the diagonal part of the deviation of the kernels' transform pair (fp32-rounded twiddle
+ * constants) from the exact DFT -- that the multiplier tables are divided by.  gain_out: n complex128 (re, im).  All ones for
+ * lengths the model does not cover (mixed radix, 4096, 8192). */
+int  bdof_debug_fft_gain(int n, double* gain_out);
+
 /* Developer hook: device buffer that instrumented builds (-DBDOF_PHASE_TIMING) fill with clock64()
  * phase stamps; ignored by the production build. */
 int  bdof_debug_set_buffer(void* d_buf);
