@@ -467,6 +467,106 @@ def run_gpu(args):
     return 0
 
 
+def run_config3(args):
+    """BASELINE configs[2]: ptychography forward model + loss gradient, 256 x 256 object x 128 slices, 1024 probe positions
+    (32 x 32 raster, pos = 32 + 6 j) batch-sharded over the ranks (contiguous blocks, cnn_propagator/ptychography.py:
+    292-297), 64 x 64 Gaussian probe (reconstruct_ptycho.py:92-94), far-field detector, TF semantics.  One step = one update on
+    ALL 1024 positions: window cut -> multislice forward (resident kernels) -> far field -> loss -> adjoint -> deterministic window
+    accumulation -> NCCL all-reduce of the 67 MB object gradient -> Adam -> clip, with this rank's measured diffraction
+    magnitudes copied from pinned host memory every step and the loss read back.  Total work is fixed: strong scaling."""
+    import torch
+    import torch.distributed as dist
+    from beyond_dof_b200 import capi
+    from beyond_dof_b200.models import PtychographyObjective
+    from beyond_dof_b200.dist import shard_contiguous
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        import datetime
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=90))
+    n, nz, ps, n_pos = 256, 128, 64, 1024
+    g = torch.Generator(device=dev).manual_seed(1234)
+    obj = torch.rand((nz, n, n, 2), device=dev, generator=g) * torch.tensor([1e-5, 1e-6], device=dev)
+    yy = torch.arange(ps, dtype=torch.float64) - (ps - 1) / 2
+    r2 = yy[:, None] ** 2 + yy[None, :] ** 2
+    mag, phase = torch.exp(-r2 / (2 * 6.0 ** 2)), 0.5 * torch.exp(-r2 / (2 * 6.0 ** 2))
+    probe = torch.complex(mag * torch.cos(phase), mag * torch.sin(phase)).to(torch.complex64).to(dev)
+    jj, ii = np.meshgrid(np.arange(32), np.arange(32))
+    pos_all = np.stack([32 + 6 * ii.ravel(), 32 + 6 * jj.ravel()], 1)
+    mine = pos_all[shard_contiguous(n_pos, rank, world)]
+    pty = PtychographyObjective(obj, probe, (ps, ps), ENERGY_EV, PSIZE_CM, n_pos_per_step=len(mine), n_pos_total=n_pos, step_size=1e-7)
+    if world > 1:
+        pty.enable_data_parallel()
+    prj_host = (0.05 + torch.rand((len(mine), ps, ps), generator=torch.Generator().manual_seed(4321 + rank))).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        pty.step(mine, prj_host)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = capi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        loss = pty.step(mine, prj_host)
+    ev1.record()
+    barrier()
+    launches = capi.launch_count() - l0
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    units = n_pos * ps * ps * nz
+    value = units / (ms_step * 1e-3) / 1e9
+    if rank == 0:
+        clocks = sampler.stop()
+        lt = pty.plan.last_times()
+        peak, peak_src = measured_peaks()
+        ms_k = lt['forward'][0] + lt['adjoint'][0]
+        px = len(mine) * ps * ps
+        # resident kernels: psi never leaves the SM; per pixel*slice the forward reads (delta, beta) 8 B and writes the stored psi 8 B
+        # and the stash 8 B, the adjoint reads stash 8 B + psi 8 B and writes the gradient 8 B -> 48 B (DESIGN.md 4.6)
+        alg = px * nz * 48.0
+        line = {
+            'metric': 'multislice Gpixel*slice/s (forward + adjoint)', 'value': value, 'unit': 'Gpixel*slice/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'c64', 'data': 'synthetic',
+            'config': {'workload': 'ptychography 256x256x128 object, 1024 probe positions (64x64 Gaussian probe, far field) sharded over the ranks '
+                                   '(BASELINE configs[2]); window cut + multislice forward/adjoint + window accumulation + all-reduce + Adam',
+                       'ny': ps, 'nx': ps, 'n_slice': nz, 'batch_per_gpu': len(mine), 'semantics': 'tf (every slice propagates), far field',
+                       'l2': 'every step streams %.2f GB of windows, stored slices and gradients per GPU' % (px * nz * 24 / 1e9),
+                       'parallelism': 'dp%d over scan positions, NCCL all-reduce of the %.0f MB object gradient per step' % (world, obj.numel() * 4 / 1e6)},
+            'recon_iter_per_s': 1e3 / ms_step,
+            'e2e': {'value': value, 'unit': 'Gpixel*slice/s', 'h2d_bytes_per_step': prj_host.numel() * 4 + len(mine) * 8, 'd2h_bytes_per_step': 8,
+                    'api': 'beyond_dof_b200.models.PtychographyObjective.step(positions, diffraction magnitudes in pinned host memory) -> loss '
+                           '(the timed region IS the public call: H2D copies, update, loss read-back)'},
+            'gpu_launches': int(launches), 'clocks': clocks,
+            'roofline': {'bound': 'hbm', 'kernel': 'resident_forward_kernel + resident_adjoint_kernel (one launch each per step)',
+                         'achieved': alg / (ms_k * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': alg / (ms_k * 1e-3) / 1e9 / peak,
+                         'traffic': None, 'alg_bytes_per_launch': alg / 2, 'avg_launch_ms': ms_k / 2, 'forward_ms': lt['forward'][0],
+                         'adjoint_ms': lt['adjoint'][0], 'peak_source': peak_src,
+                         'note': 'forward_ms / adjoint_ms are the whole bdof_forward / bdof_adjoint calls (resident kernel + far-field passes); '
+                                 'the field is on chip, so this kernel is bound by fp32 issue and shared memory, not by HBM (SURVEY 8d)'},
+            'cpu_baseline': None, 'loss': float(loss),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def run_config4(args):
     """BASELINE configs[3]: full-field tomographic reconstruction, 256^3 object, angles sharded over the ranks,
     minibatch of 10 angles per rank and update (reconstruct_fullfield.py:30,60), Adam, NCCL all-reduce of the object
@@ -553,7 +653,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS) + ['config4'])
+    ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS) + ['config3', 'config4'])
     ap.add_argument('--impl', default='bdof', choices=['bdof', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
     ap.add_argument('--no-host-object', action='store_true', help='skip the extra end-to-end leg with delta/beta and the gradients in host memory')
@@ -568,11 +668,11 @@ def main():
     ap.add_argument('--diag', action='store_true', help='N > 1: print the plain all-reduce time and the step time without exchange')
     ap.add_argument('--in-place', action='store_true', help='adjoint overwrites delta/beta with the gradient (needed for the 4096^2x512 size)')
     args = ap.parse_args()
-    if args.workload == 'config4':
+    if args.workload in ('config3', 'config4'):
         if args.impl == 'reference':
             print(json.dumps({'impl': 'reference', 'unavailable': 'the reference arm is defined on the default workload (config2)'}))
             return 0
-        return run_config4(args)
+        return run_config3(args) if args.workload == 'config3' else run_config4(args)
     if args.impl == 'reference':
         return run_reference(args)
     return run_gpu(args)

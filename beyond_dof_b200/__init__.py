@@ -18,6 +18,9 @@ _LAZY = {
     'fullfield_loss_and_grad': 'models',
     'ptycho_loss_and_grad': 'models',
     'TomographyObjective': 'models',
+    'PtychographyObjective': 'models',
+    'FullfieldObjective': 'models',
+    'fullfield_loss_and_grad_host': 'models',
     'apply_rotation': 'rotation',
     'rotation_table': 'rotation',
     'adam_step': 'rotation',

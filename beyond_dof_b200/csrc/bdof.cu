@@ -329,6 +329,58 @@ __global__ void k_patch_scatter_add(const float2* __restrict__ gpatch, int oy, i
     }
 }
 
+// The same accumulation as a GATHER, in scan-position order: deterministic (bit-identical run to run and for any split of the
+// positions into launches that keeps their order), which the fp32 atomics above are not.  A block owns 128 consecutive x of one
+// object row y and PSCAT_ZB consecutive slices; it first compacts, IN ORDER, the positions whose window touches its pixels
+// (ballot prefix sums), then every thread adds the window pixels that fall on its own object pixel.
+constexpr int PSCAT_THREADS = 128, PSCAT_ZB = 8, PSCAT_MAX_POS = 4096;
+__global__ void __launch_bounds__(PSCAT_THREADS) k_patch_gather_add(const float2* __restrict__ gpatch, int n_slice, int oy, int ox,
+                                                                     const int* __restrict__ pos, int n_pos, int py, int px,
+                                                                     float2* __restrict__ gobj) {
+    __shared__ int s_idx[PSCAT_MAX_POS];
+    __shared__ int s_warp_count[PSCAT_THREADS / 32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0b = blockIdx.x * PSCAT_THREADS, y = blockIdx.y, z0 = blockIdx.z * PSCAT_ZB;
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    for (int base = 0; base < n_pos; base += PSCAT_THREADS) {
+        const int ip = base + tid;
+        bool hit = false;
+        if (ip < n_pos) {
+            const int wy = pos[2 * ip], wx = pos[2 * ip + 1];
+            hit = (y >= wy && y < wy + py) && (wx < x0b + PSCAT_THREADS && wx + px > x0b);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_warp_count[warp] = __popc(m);
+        __syncthreads();
+        int off = s_total;
+        for (int w = 0; w < warp; ++w) off += s_warp_count[w];
+        if (hit) s_idx[off + __popc(m & ((1u << lane) - 1u))] = ip;
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < PSCAT_THREADS / 32; ++w) t += s_warp_count[w]; s_total += t; }
+        __syncthreads();
+    }
+    const int n_hit = s_total;
+    const int x = x0b + tid;
+    if (x >= ox) return;
+    for (int z = z0; z < z0 + PSCAT_ZB && z < n_slice; ++z) {
+        float ax = 0.f, ay = 0.f;
+        for (int k = 0; k < n_hit; ++k) {
+            const int ip = s_idx[k];
+            const int wy = pos[2 * ip], wx = pos[2 * ip + 1];
+            const int xx = x - wx;
+            if (xx >= 0 && xx < px) {
+                const float2 v = gpatch[(((long long)z * n_pos + ip) * py + (y - wy)) * px + xx];
+                ax += v.x; ay += v.y;
+            }
+        }
+        float2* o = gobj + ((long long)z * oy + y) * ox + x;
+        const float2 cur = *o;
+        *o = make_float2(cur.x + ax, cur.y + ay);
+    }
+}
+
 // real-space propagator step (propagation.py:85-99): out = conv2d_valid(pad(in * t, edge), kernel)
 constexpr int CNN_MAX_K = 33;
 __constant__ float2 c_cnn_kernel[CNN_MAX_K * CNN_MAX_K];
@@ -1215,6 +1267,17 @@ extern "C" int bdof_patch_scatter_add(const float* d_grad_patches, int n_slice, 
     return launch_check("k_patch_scatter_add");
 }
 
+extern "C" int bdof_patch_gather_add(const float* d_grad_patches, int n_slice, int oy, int ox, const int* d_pos_yx, int n_pos, int py, int px,
+                                     float* d_grad_obj, void* st) {
+    if (!d_grad_patches || !d_pos_yx || !d_grad_obj || n_pos < 1 || n_slice < 1) return fail(BDOF_E_BADARG, "bad argument");
+    if (n_pos > PSCAT_MAX_POS) return fail(BDOF_E_UNSUPPORTED, "more than %d scan positions per call", PSCAT_MAX_POS);
+    if (oy > 65535 || (n_slice + PSCAT_ZB - 1) / PSCAT_ZB > 65535) return fail(BDOF_E_UNSUPPORTED, "object too large");
+    dim3 grid((ox + PSCAT_THREADS - 1) / PSCAT_THREADS, oy, (n_slice + PSCAT_ZB - 1) / PSCAT_ZB);
+    k_patch_gather_add<<<grid, PSCAT_THREADS, 0, (cudaStream_t)st>>>(reinterpret_cast<const float2*>(d_grad_patches), n_slice, oy, ox, d_pos_yx,
+                                                                    n_pos, py, px, reinterpret_cast<float2*>(d_grad_obj));
+    return launch_check("k_patch_gather_add");
+}
+
 extern "C" int bdof_cnn_forward(const float* d_db, const float* d_probe, float* d_exit, float* d_work, int batch, int ny, int nx,
                                 int n_slice, const double* h_kernel, int ks, double k_dz, void* st_) {
     if (!d_db || !d_probe || !d_exit || !d_work || !h_kernel) return fail(BDOF_E_BADARG, "null");
@@ -1270,6 +1333,19 @@ extern "C" int bdof_forward_host(bdof_plan* p, const float* h_delta, const float
     cudaFree(p->e2e_delta); cudaFree(p->e2e_beta); cudaFree(p->e2e_db); cudaFree(p->e2e_probe); cudaFree(p->e2e_exit);
     p->e2e_delta = p->e2e_beta = nullptr; p->e2e_db = nullptr; p->e2e_probe = p->e2e_exit = nullptr;
     return 0;
+}
+
+// out[b] = in[b] * m   (complex64; m [n_per] shared by the batch) -- the kernel multiply of the IR free-space step
+__global__ void k_field_multiply(const float2* __restrict__ in, const float2* __restrict__ m, float2* __restrict__ out, long long n_per,
+                                 long long n_total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_total; i += (long long)gridDim.x * blockDim.x)
+        out[i] = cmul(in[i], m[i % n_per]);
+}
+extern "C" int bdof_field_multiply(const float* d_in, const float* d_mult, float* d_out, int batch, long long n_per, void* st) {
+    if (!d_in || !d_mult || !d_out || batch < 1 || n_per < 1) return fail(BDOF_E_BADARG, "bad argument");
+    k_field_multiply<<<LOSS_BLOCKS, 256, 0, (cudaStream_t)st>>>(reinterpret_cast<const float2*>(d_in), reinterpret_cast<const float2*>(d_mult),
+                                                              reinterpret_cast<float2*>(d_out), n_per, n_per * batch);
+    return launch_check("k_field_multiply");
 }
 
 extern "C" int bdof_debug_fft_gain(int n, double* gain_out) {

@@ -259,7 +259,7 @@ def unpack_object(db_obj):
 
 def ptycho_loss_and_grad(obj_delta, obj_beta, theta, probe_pos_batch, prj_batch, probe_real, probe_imag, probe_size,
                          energy_ev, psize_cm, n_dp_batch=None, scale_by_npos=True, n_pos_total=None, want_grad=True,
-                         db_obj=None, grad_obj_out=None, rotation='nearest'):
+                         db_obj=None, grad_obj_out=None, rotation='nearest', deterministic=True):
     """Ptychography forward model + loss + gradient for one rotation angle theta (radians; the object is rotated with the
     reference's nearest-neighbour table first, cnn_propagator/ptychography.py:32-34, and the gradient rotated back).
 
@@ -269,6 +269,8 @@ def ptycho_loss_and_grad(obj_delta, obj_beta, theta, probe_pos_batch, prj_batch,
     loss = mean((|Psi| - |prj|)^2) (* n_pos_total if scale_by_npos, ptychography.py:94).
     Returns (loss, (g_delta, g_beta)); with db_obj / grad_obj_out (slice-major [Z,Y,X,2]) the
     object and its gradient stay in the native layout and (loss, grad_obj_out) is returned.
+    deterministic: accumulate the window gradients as an ordered gather (bdof_patch_gather_add: bit-reproducible) instead of
+    fp32 atomics (bdof_patch_scatter_add).
     """
     th = _scalar_theta(theta)
     dev = _device()
@@ -309,11 +311,12 @@ def ptycho_loss_and_grad(obj_delta, obj_beta, theta, probe_pos_batch, prj_batch,
     plan.adjoint(patches, g_exit)
     if grad_obj_out is None:
         grad_obj_out = torch.zeros_like(db_obj)
+    scatter = lib.bdof_patch_gather_add if deterministic else lib.bdof_patch_scatter_add
     if db_obj is obj_unrot:
-        check(lib.bdof_patch_scatter_add(_ptr(patches), Z, OY, OX, _ptr(origin), n, py, px, _ptr(grad_obj_out), st))
+        check(scatter(_ptr(patches), Z, OY, OX, _ptr(origin), n, py, px, _ptr(grad_obj_out), st))
     else:
         g_rot = torch.zeros_like(db_obj)
-        check(lib.bdof_patch_scatter_add(_ptr(patches), Z, OY, OX, _ptr(origin), n, py, px, _ptr(g_rot), st))
+        check(scatter(_ptr(patches), Z, OY, OX, _ptr(origin), n, py, px, _ptr(g_rot), st))
         if tab is not None:
             _rot.rotate_db_adjoint(g_rot, tab, grad_obj_out)
         else:
@@ -609,6 +612,81 @@ class TomographyObjective:
         _rot.adam_step(self.obj, self.grad, self.i_batch, self.m, self.v, step_size=self.step_size)
         if self.clip:
             _rot.finite_support(self.obj, self.mask, self.shrink_threshold)
+        self.i_batch += 1
+        self.loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.loss_host)
+
+
+class PtychographyObjective:
+    """One optimiser step of the ptychography reconstruction loop (cnn_propagator/ptychography.py:286-310, one rotation angle
+    per step) with the object resident on the GPU in the native layout: cut this rank's minibatch of probe windows, multislice
+    forward to the far field (the resident small-field kernels when the probe is 64 x 64), loss, adjoint, DETERMINISTIC
+    accumulation of the window gradients into the object gradient, all-reduce over the data-parallel ranks (positions are
+    sharded contiguously, dist.shard_contiguous = ptychography.py:292-297), Adam, clip >= 0 (ptychography.py:307-310).
+
+    db_obj: [Z,Y,X,2] float32 CUDA tensor (delta, beta), updated in place by step().
+    """
+
+    def __init__(self, db_obj, probe, probe_size, energy_ev, psize_cm, n_pos_per_step, n_pos_total=None, step_size=1e-7,
+                 scale_by_npos=True, clip=True):
+        Z, OY, OX, _ = db_obj.shape
+        self.obj = db_obj
+        self.py, self.px = int(probe_size[0]), int(probe_size[1])
+        self.n = int(n_pos_per_step)
+        self.half = (np.array([self.py, self.px]) / 2).astype('int')                 # ptychography.py:184
+        dev = db_obj.device
+        self.plan = MultislicePlan(self.py, self.px, self.n, Z, energy_ev, psize_cm, free_prop_cm='inf', propagate_last=True,
+                                   store_slices=True, device=dev)
+        self.probe = probe.to(dev, torch.complex64).contiguous()
+        self.patches = torch.empty((Z, self.n, self.py, self.px, 2), dtype=torch.float32, device=dev)
+        self.plan.set_t_stash(self.patches)          # windows are re-cut every step and overwritten in place by the adjoint
+        self.grad = torch.zeros_like(db_obj)
+        self.m = torch.zeros_like(db_obj)
+        self.v = torch.zeros_like(db_obj)
+        self.target = torch.empty((self.n, self.py, self.px), dtype=torch.float32, device=dev)
+        self.exit = torch.empty((self.n, self.py, self.px), dtype=torch.complex64, device=dev)
+        self.origin = torch.empty((self.n, 2), dtype=torch.int32, device=dev)
+        self.origin_host = torch.empty((self.n, 2), dtype=torch.int32).pin_memory()
+        self.loss_host = torch.empty((), dtype=torch.float64).pin_memory()
+        self.scale = float(n_pos_total if n_pos_total is not None else self.n) if scale_by_npos else 1.0
+        self.step_size = float(step_size)
+        self.clip = bool(clip)
+        self.i_batch = 0
+        self._dp = None
+
+    def enable_data_parallel(self):
+        """The object gradient (67 MB at 256 x 256 x 128) is averaged over the ranks with one NCCL all-reduce after the window
+        accumulation, when no multislice kernel is running (comm.Allreduce + grads / size, ptychography.py:302-306)."""
+        from . import dist as bdist
+        self._dp = bdist
+        return self
+
+    def loss_and_grad(self, pos_batch, target_dev):
+        """pos_batch: [n, 2] integer (y, x) scan positions of this rank; returns the device loss of this rank's positions."""
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        Z, OY, OX, _ = self.obj.shape
+        pos = np.asarray(pos_batch).astype(np.int64)
+        assert pos.shape == (self.n, 2)
+        self.origin_host.copy_(torch.as_tensor((pos - self.half[None, :]).astype(np.int32)))
+        self.origin.copy_(self.origin_host, non_blocking=True)
+        check(lib.bdof_patch_gather(_ptr(self.obj), Z, OY, OX, _ptr(self.origin), self.n, self.py, self.px, _ptr(self.patches), st))
+        self.plan.forward(self.patches, self.probe, out=self.exit)
+        loss, g = self.plan.loss_mag(self.exit, target_dev, loss_scale=self.scale)
+        self.plan.adjoint(self.patches, g)
+        self.grad.zero_()
+        check(lib.bdof_patch_gather_add(_ptr(self.patches), Z, OY, OX, _ptr(self.origin), self.n, self.py, self.px, _ptr(self.grad), st))
+        if self._dp is not None:
+            self._dp.finish_allreduce(self.grad, self._dp.allreduce_gradient(self.grad, average=True))
+        return loss
+
+    def step(self, pos_batch, prj_mag_host):
+        """prj_mag_host: [n, py, px] float32 measured far-field magnitudes of these positions (pinned host or device)."""
+        self.target.copy_(prj_mag_host, non_blocking=True)
+        loss = self.loss_and_grad(pos_batch, self.target)
+        _rot.adam_step(self.obj, self.grad, self.i_batch, self.m, self.v, step_size=self.step_size)
+        if self.clip:
+            _rot.finite_support(self.obj, None, None)
         self.i_batch += 1
         self.loss_host.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -114,20 +114,93 @@ def multislice_propagate_batch(grid_delta_batch, grid_beta_batch, probe_real, pr
                         obj_batch_shape, propagate_last=True, h=h)
 
 
+def get_kernel_ir(dist_nm, lmbda_nm, voxel_nm, grid_shape):
+    """Impulse-response Fresnel kernel, H = fftshift(fft2(h)) dx dy (tensorflow_recon/util.py:188-216), float64 on the host;
+    the reference's np.arange grid is kept literally (its length is what np.arange makes of the float end point)."""
+    size_nm = np.array(voxel_nm) * np.array(grid_shape)
+    k = 2 * PI / lmbda_nm
+    ymin, xmin = np.array(size_nm)[:2] / -2.
+    dy, dx = voxel_nm[0:2]
+    x = np.arange(xmin, xmin + size_nm[1], dx)
+    y = np.arange(ymin, ymin + size_nm[0], dy)
+    x, y = np.meshgrid(x, y)
+    h = np.exp(1j * k * dist_nm) / (1j * lmbda_nm * dist_nm) * np.exp(1j * k / (2 * dist_nm) * (x ** 2 + y ** 2))
+    return np.fft.fftshift(np.fft.fft2(h), axes=(-2, -1)) * voxel_nm[0] * voxel_nm[1]
+
+
+def propagation_algorithm(dist_nm, lmbda_nm, voxel_nm, grid_shape):
+    """'TF' or 'IR': the sampling criterion of multislice_propagate (util.py:396-404, 416-419):
+    TF when the mean voxel exceeds lambda d / L, L = (prod of the grid's physical sides)^(1/3)."""
+    voxel_nm = np.asarray(voxel_nm, dtype=np.float64)
+    mean_voxel_nm = np.prod(voxel_nm) ** (1. / 3)
+    size_nm = np.array(grid_shape) * voxel_nm
+    crit_samp = lmbda_nm * dist_nm / (np.prod(size_nm) ** (1. / 3))
+    return 'TF' if mean_voxel_nm > crit_samp else 'IR'
+
+
 def multislice_propagate(grid_delta, grid_beta, probe_real, probe_imag, energy_ev, psize_cm, h=None, free_prop_cm=None,
                          pad=None):
-    """Un-batched [Y,X,Z] variant (util.py:360-429); all shipped configurations take its TF branch."""
+    """Un-batched [Y,X,Z] variant (util.py:360-429).  Differences from the batched function that are reproduced here:
+      * EVERY slice propagates, also when n_slice == 1 (no modulate-only special case, util.py:406-408);
+      * per slice and for a finite free_prop_cm the algorithm is chosen by the sampling criterion (propagation_algorithm):
+        - per slice, 'IR' = ifftshift(ifft2(fft2(fftshift(psi)) * h)) with the SAME transfer-function kernel h (util.py:401-404):
+          for even sides that is the convolution whose multiplier is h in natural FFT order (no ifftshift of h);
+        - free space, 'IR' = ifftshift(fft2(fftshift(fft2(psi)) * get_kernel_ir(d))) -- the reference applies a FORWARD
+          transform twice there (util.py:424-427); reproduced literally.
+    Sides must be even for the IR orderings (fftshift == ifftshift); odd sides raise."""
+    as_torch = _is_torch(grid_delta)
     if pad is not None:
-        if _is_torch(grid_delta):
+        if as_torch:
             flat = [int(v) for pr in reversed(list(pad)) for v in pr]
             grid_delta = torch.nn.functional.pad(grid_delta, flat)
             grid_beta = torch.nn.functional.pad(grid_beta, flat)
         else:
             grid_delta = np.pad(grid_delta, pad, 'constant')
             grid_beta = np.pad(grid_beta, pad, 'constant')
-    out = _run_forward(grid_delta[None], grid_beta[None], probe_real, probe_imag, energy_ev, psize_cm, free_prop_cm,
-                       None, propagate_last=True, h=h)
-    return out[0]
+    Y, X, Z = (int(v) for v in grid_delta.shape)
+    voxel_nm = np.array([psize_cm] * 3) * 1.e7
+    lmbda_nm = 1240. / energy_ev
+    shape3 = [Y, X, Z]
+    slice_alg = propagation_algorithm(voxel_nm[-1], lmbda_nm, voxel_nm, shape3)
+    free_alg = None
+    if free_prop_cm is not None and not isinstance(free_prop_cm, str):
+        free_alg = propagation_algorithm(free_prop_cm * 1e7, lmbda_nm, voxel_nm, shape3)
+    if (slice_alg == 'IR' or free_alg == 'IR') and (Y % 2 or X % 2):
+        raise NotImplementedError('the IR orderings of multislice_propagate are implemented for even field sides only')
+    hh = None if h is None else (h.detach().cpu().numpy() if _is_torch(h) else np.asarray(h))
+    if slice_alg == 'IR':
+        # multiplier h applied in natural FFT order: hand the plan fftshift(h), whose ifftshift is h again
+        hk = get_kernel(voxel_nm[-1], lmbda_nm, voxel_nm, shape3) if hh is None else hh
+        hh = np.fft.fftshift(hk, axes=(-2, -1))
+    plan_free = free_prop_cm if free_alg != 'IR' else None
+    key = ('fwd1', (Y, X, Z), float(energy_ev), float(psize_cm), plan_free, slice_alg, _h_key(hh), torch.cuda.current_device())
+    dev = _device()
+    d = _to_dev(grid_delta, torch.float32)[None]
+    b = _to_dev(grid_beta, torch.float32)[None]
+    if Z == 1:
+        # one slice that DOES propagate: append a vacuum slice and drop its propagation with the NumPy semantics
+        plan1 = _cached_plan(key + ('z1',), lambda: MultislicePlan(Y, X, 1, 2, energy_ev, psize_cm, free_prop_cm=plan_free,
+                                                                    propagate_last=False, h=hh))
+        zero = torch.zeros_like(d)
+        db = plan1.pack(torch.cat([d, zero], dim=3), torch.cat([b, zero], dim=3))
+        out = plan1.forward(db, _probe_c64(probe_real, probe_imag, (Y, X)))
+    else:
+        plan = _cached_plan(key, lambda: MultislicePlan(Y, X, 1, Z, energy_ev, psize_cm, free_prop_cm=plan_free, propagate_last=True,
+                                                         h=hh))
+        db = plan.pack(d, b)
+        out = plan.forward(db, _probe_c64(probe_real, probe_imag, (Y, X)))
+    if free_alg == 'IR':
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        far = _cached_plan(('far', (Y, X), torch.cuda.current_device()),
+                           lambda: MultislicePlan(Y, X, 1, 1, energy_ev, psize_cm, free_prop_cm='inf'))
+        H = torch.as_tensor(get_kernel_ir(free_prop_cm * 1e7, lmbda_nm, voxel_nm, shape3)).to(dev, torch.complex64).contiguous()
+        spec = far.free_prop(out)                                  # fftshift(fft2(psi))
+        check(lib.bdof_field_multiply(_ptr(spec), _ptr(H), _ptr(spec), 1, Y * X, st))
+        out = far.free_prop(spec)                                  # ifftshift(fft2(.)) == fftshift(fft2(.)) for even sides
+    out = out[0]
+    if as_torch:
+        return out if grid_delta.is_cuda else out.cpu()
+    return out.cpu().numpy()
 
 
 def cnn_kernel(energy_ev, psize_cm, grid_shape_yxz, kernel_size):

@@ -143,6 +143,12 @@ int  bdof_patch_gather(const float* d_db_obj, int n_slice, int oy, int ox, const
 int  bdof_patch_scatter_add(const float* d_grad_patches, int n_slice, int oy, int ox, const int* d_pos_yx,
                             int n_pos, int py, int px, float* d_grad_obj, void* cuda_stream);
 
+/* bdof_patch_scatter_add as a deterministic gather: every object pixel sums, in scan-position order, the window pixels that
+ * fall on it and adds the sum to d_grad_obj (+=); no atomics, bit-reproducible.  At most 4096
+ * positions per call. */
+int  bdof_patch_gather_add(const float* d_grad_patches, int n_slice, int oy, int ox, const int* d_pos_yx, int n_pos,
+                           int py, int px, float* d_grad_obj, void* cuda_stream);
+
 /* Real-space propagator of cnn_propagator/propagation.py:18-133: h_kernel is the cropped
  * kernel_size^2 complex128 kernel (host).  db as above; exit [batch][ny][nx]. */
 int  bdof_cnn_forward(const float* d_db, const float* d_probe, float* d_exit, float* d_work, int batch,
@@ -203,6 +209,10 @@ int  bdof_slice_step(bdof_plan* p, const float* d_in, const float* d_db_slice, f
  * bucket j's gradient is final, so a communication stream can reduce it while the sweep continues.
  * n_buckets = 0 disables. */
 int  bdof_plan_set_bucket_events(bdof_plan* p, int n_buckets, void** cuda_events);
+
+/* d_out[b] = d_in[b] * d_mult, complex64, d_mult [n_per] shared by the batch (may alias in place): the multiply by
+ * get_kernel_ir between the two transforms of the IR free-space step of multislice_propagate (tensorflow_recon/util.py:424-427). */
+int  bdof_field_multiply(const float* d_in, const float* d_mult, float* d_out, int batch, long long n_per, void* cuda_stream);
 
 /* The free-space step of the plan on its own (npfuncs.py:43-61): out = free_prop(in), [batch][ny][nx]. */
 int  bdof_free_prop(bdof_plan* p, const float* d_in, float* d_out);

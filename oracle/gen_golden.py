@@ -183,11 +183,31 @@ for tag, free in (("none", None), ("inf", "inf"), ("free", 2e-6)):
 np.savez_compressed(out, **res)
 '''
 
+CHILD_IR = r'''
+import sys, json
+import numpy as np
+from unittest.mock import MagicMock
+for m in ("tensorflow", "dxchange", "h5py", "matplotlib", "matplotlib.pyplot"):
+    sys.modules[m] = MagicMock()
+sys.path.insert(0, sys.argv[1] + "/tensorflow_recon")
+import util                                   # get_kernel_ir, tensorflow_recon/util.py:188-216 (NumPy branch; the TIFF write is mocked)
+out = sys.argv[2]
+res = {}
+for name, args in {
+    "ir64": (1e-4 * 1e7, 0.248, [1., 1., 1.], [64, 64, 64]),
+    "ir48x80": (3e-4 * 1e7, 1240. / 800, [0.67, 0.67, 0.67], [48, 80, 8]),
+    "ir128_aniso": (2e-4 * 1e7, 0.248, [1.0, 2.0, 2.5], [128, 64, 4]),
+}.items():
+    res["kernel_" + name] = util.get_kernel_ir(*args)
+    res["kernel_" + name + "_args"] = np.array(json.dumps(args))
+np.savez_compressed(out, **res)
+'''
+
 
 def main():
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]
-    for name, code in (('ref_fft.npz', CHILD_FFT), ('ref_cnn.npz', CHILD_CNN), ('ref_rot.npz', CHILD_ROT), ('ref_npfuncs_cnn.npz', CHILD_NPF)):
+    for name, code in (('ref_fft.npz', CHILD_FFT), ('ref_cnn.npz', CHILD_CNN), ('ref_rot.npz', CHILD_ROT), ('ref_npfuncs_cnn.npz', CHILD_NPF), ('ref_ir.npz', CHILD_IR)):
         if only and name not in only:
             continue
         path = os.path.join(OUT, name)

@@ -176,6 +176,69 @@ def multislice_propagate_batch(grid_delta_batch, grid_beta_batch, probe_real, pr
                               psize_cm, free_prop_cm, obj_batch_shape, h=h, propagate_last=True, pi=PI_TF)
 
 
+def get_kernel_ir(dist_nm, lmbda_nm, voxel_nm, grid_shape, pi=PI_TF):
+    """tensorflow_recon/util.py:188-216, NumPy branch: H = fftshift(fft2(h)) dx dy of the impulse response h."""
+    size_nm = np.array(voxel_nm) * np.array(grid_shape)
+    k = 2 * pi / lmbda_nm
+    ymin, xmin = np.array(size_nm)[:2] / -2.
+    dy, dx = voxel_nm[0:2]
+    x = np.arange(xmin, xmin + size_nm[1], dx)
+    y = np.arange(ymin, ymin + size_nm[0], dy)
+    x, y = np.meshgrid(x, y)
+    h = np.exp(1j * k * dist_nm) / (1j * lmbda_nm * dist_nm) * np.exp(1j * k / (2 * dist_nm) * (x ** 2 + y ** 2))
+    return fftshift(fft2(h)) * voxel_nm[0] * voxel_nm[1]
+
+
+def multislice_propagate_unbatched(grid_delta, grid_beta, probe_real, probe_imag, energy_ev, psize_cm, h=None,
+                                   free_prop_cm=None, pad=None, pi=PI_TF):
+    """Restatement of tensorflow_recon/util.py:360-429 (un-batched [Y,X,Z] TF function) in complex128, line by line:
+    every slice propagates; the TF / IR orderings are chosen by the sampling criterion per slice (:396-404) and for the
+    free-space step (:416-427), where the 'IR' branch applies fft2 twice as written in the reference."""
+    grid_delta = np.asarray(grid_delta, dtype=np.float64)
+    grid_beta = np.asarray(grid_beta, dtype=np.float64)
+    if pad is not None:
+        grid_delta = np.pad(grid_delta, pad, 'constant')
+        grid_beta = np.pad(grid_beta, pad, 'constant')
+    voxel_nm = np.array([psize_cm] * 3) * 1.e7
+    wavefront = np.zeros([grid_delta.shape[0], grid_delta.shape[1]], dtype=np.complex64)
+    wavefront = (wavefront + (np.asarray(probe_real) + 1j * np.asarray(probe_imag)).astype(np.complex64)).astype(np.complex128)
+    lmbda_nm = 1240. / energy_ev
+    mean_voxel_nm = np.prod(voxel_nm) ** (1. / 3)
+    size_nm = np.array(grid_delta.shape) * voxel_nm
+    n_slice = grid_delta.shape[-1]
+    delta_nm = voxel_nm[-1]
+    if h is None:
+        h = get_kernel(delta_nm, lmbda_nm, voxel_nm, grid_delta.shape, pi=pi)
+    k = 2. * pi * delta_nm / lmbda_nm
+    sh = lambda a: fftshift(a, axes=[-2, -1])
+    ish = lambda a: ifftshift(a, axes=[-2, -1])
+    for i in range(n_slice):
+        c = np.exp(1j * k * grid_delta[:, :, i]) * np.exp(-k * grid_beta[:, :, i])
+        wavefront = wavefront * c
+        l = np.prod(size_nm) ** (1. / 3)
+        crit_samp = lmbda_nm * delta_nm / l
+        if mean_voxel_nm > crit_samp:
+            wavefront = ifft2(ish(sh(fft2(wavefront)) * h))
+        else:
+            wavefront = fft2(sh(wavefront))
+            wavefront = ish(ifft2(wavefront * h))
+    if free_prop_cm is not None:
+        if free_prop_cm == 'inf':
+            wavefront = sh(fft2(wavefront))
+        else:
+            dist_nm = free_prop_cm * 1e7
+            l = np.prod(size_nm) ** (1. / 3)
+            crit_samp = lmbda_nm * dist_nm / l
+            if mean_voxel_nm > crit_samp:
+                hf = get_kernel(dist_nm, lmbda_nm, voxel_nm, list(grid_delta.shape), pi=pi)
+                wavefront = ifft2(ish(sh(fft2(wavefront)) * hf))
+            else:
+                hf = get_kernel_ir(dist_nm, lmbda_nm, voxel_nm, list(grid_delta.shape), pi=pi)
+                wavefront = sh(fft2(wavefront)) * hf
+                wavefront = ish(fft2(wavefront))
+    return wavefront
+
+
 # ---------------------------------------------------------------------------------------------
 # loss head and hand adjoint (SURVEY.md 7.1).  No adjoint exists in the reference: it
 # differentiates with TF / autograd.  Pinned against torch.autograd in tests/test_oracle.py.

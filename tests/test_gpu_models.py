@@ -340,3 +340,64 @@ def test_ptycho_with_bilinear_rotation(bd):
     loss, (g_d, g_b) = bd.ptycho_loss_and_grad(od, ob, theta, pos, prj, pr, pi, probe_size, 5000, 1e-7, rotation='bilinear')
     assert abs(loss.item() - lo) < 1e-5 * abs(lo)
     assert rel_l2(g_d.cpu().numpy(), go[..., 0]) < 1e-4 and rel_l2(g_b.cpu().numpy(), go[..., 1]) < 1e-4
+
+
+def test_patch_gather_add_is_the_deterministic_scatter(bd):
+    # the ordered gather accumulates exactly what the atomic scatter-add does, bit-reproducibly
+    import ctypes
+    from beyond_dof_b200.capi import lib, check
+    from beyond_dof_b200.plan import _ptr
+    Z, OY, OX, n, py, px = 5, 70, 150, 37, 24, 40
+    g = torch.Generator(device='cuda').manual_seed(3)
+    patches = torch.randn((Z, n, py, px, 2), device='cuda', generator=g)
+    pos = torch.stack([torch.randint(-10, OY - 5, (n,), generator=torch.Generator().manual_seed(4)),
+                       torch.randint(-20, OX - 5, (n,), generator=torch.Generator().manual_seed(5))], 1).to(torch.int32).cuda().contiguous()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ref = torch.zeros((Z, OY, OX, 2), dtype=torch.float64, device='cuda')
+    for i in range(n):                                             # plain accumulation in float64
+        y0, x0 = int(pos[i, 0]), int(pos[i, 1])
+        ys, xs = slice(max(y0, 0), min(y0 + py, OY)), slice(max(x0, 0), min(x0 + px, OX))
+        ref[:, ys, xs] += patches[:, i, ys.start - y0:ys.stop - y0, xs.start - x0:xs.stop - x0].double()
+    outs = []
+    for _ in range(3):
+        out = torch.zeros((Z, OY, OX, 2), dtype=torch.float32, device='cuda')
+        check(lib.bdof_patch_gather_add(_ptr(patches), Z, OY, OX, _ptr(pos), n, py, px, _ptr(out), st))
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert rel_l2(outs[0].cpu().numpy(), ref.cpu().numpy()) < 2e-7
+    # accumulates (+=) and agrees with the atomic version
+    at = torch.zeros_like(outs[0])
+    check(lib.bdof_patch_scatter_add(_ptr(patches), Z, OY, OX, _ptr(pos), n, py, px, _ptr(at), st))
+    assert rel_l2(at.cpu().numpy(), outs[0].cpu().numpy()) < 1e-6
+    check(lib.bdof_patch_gather_add(_ptr(patches), Z, OY, OX, _ptr(pos), n, py, px, _ptr(outs[0]), st))
+    assert rel_l2(outs[0].cpu().numpy(), 2 * ref.cpu().numpy()) < 2e-7
+
+
+def test_ptychography_objective_step_matches_oracle_update(bd):
+    # one update of the reconstruction loop (cnn_propagator/ptychography.py:292-310) against the oracle gradient + Adam
+    from beyond_dof_b200.models import PtychographyObjective, pack_object, unpack_object
+    Y, X, Z = 96, 96, 6
+    probe_size = (64, 64)
+    od, ob = mo.random_phantom((Y, X, Z), seed=90, delta_scale=3e-4, beta_scale=3e-5)
+    gt_d, gt_b = mo.random_phantom((Y, X, Z), seed=91, delta_scale=5e-3, beta_scale=5e-3)
+    pr, pi = mo.gaussian_probe(probe_size, 6., 6., 0.5)
+    pos = np.array([(32, 32), (38, 50), (60, 40), (48, 48), (30, 64), (64, 64), (0, 0), (90, 95)])
+    _, prj = mo.ptycho_loss(gt_d, gt_b, pos, np.zeros((len(pos),) + probe_size), pr, pi, probe_size, 5000, 1e-7)
+    lo, gdo, gbo, _ = mo.ptycho_loss_and_grad(od, ob, pos, prj, pr, pi, probe_size, 5000, 1e-7)
+    obj = pack_object(od, ob)
+    pty = PtychographyObjective(obj, torch.as_tensor((pr + 1j * pi).astype(np.complex64)), probe_size, 5000, 1e-7,
+                                n_pos_per_step=len(pos), step_size=1e-7)
+    loss = pty.step(pos, torch.as_tensor(np.abs(prj).astype(np.float32)).pin_memory())
+    assert abs(loss - lo) < 1e-5 * abs(lo)
+    g_d, g_b = unpack_object(pty.grad)
+    assert rel_l2(g_d.cpu().numpy(), gdo) < 1e-4 and rel_l2(g_b.cpu().numpy(), gbo) < 1e-4
+    xd, _, _ = mo.apply_gradient_adam(od.astype(np.float64), gdo, 0, None, None, step_size=1e-7)
+    xb, _, _ = mo.apply_gradient_adam(ob.astype(np.float64), gbo, 0, None, None, step_size=1e-7)
+    nd, nb = unpack_object(pty.obj)
+    assert rel_l2(nd.cpu().numpy(), np.clip(xd, 0, None)) < 1e-5 and rel_l2(nb.cpu().numpy(), np.clip(xb, 0, None)) < 1e-5
+    # bit-reproducible: the same step from the same state gives the same gradient
+    obj2 = pack_object(od, ob)
+    pty2 = PtychographyObjective(obj2, torch.as_tensor((pr + 1j * pi).astype(np.complex64)), probe_size, 5000, 1e-7,
+                                 n_pos_per_step=len(pos), step_size=1e-7)
+    pty2.step(pos, torch.as_tensor(np.abs(prj).astype(np.float32)).pin_memory())
+    assert torch.equal(pty.grad, pty2.grad) and torch.equal(pty.obj, pty2.obj)

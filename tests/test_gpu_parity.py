@@ -614,3 +614,34 @@ def test_resident_kernels_z_broadcast_and_forward_only(bd):
     psi = bd.multislice_propagate_batch(gd, gb, pr, pi, 5000, 1e-7, free_prop_cm='inf', obj_batch_shape=shape)
     ref = mo.multislice_propagate_batch(gd, gb, pr, pi, 5000, 1e-7, free_prop_cm='inf', obj_batch_shape=shape)
     assert intensity_err(psi, ref) < TOL_INTENSITY
+
+
+# ---------------------------------------------------------------------------------------------
+# a-4: the un-batched multislice_propagate with its TF / IR orderings (tensorflow_recon/util.py:360-429)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('case', [
+    ((64, 64, 6), 1e-7, None), ((64, 128, 5), 1e-7, 'inf'),
+    ((64, 64, 64), 1e-7, 1e-4),          # the example of ADVICE r01: 64^3, 5 keV, free_prop_cm = 1e-4 -> crit_samp 3.9 nm > 1 nm -> IR
+    ((128, 64, 3), 1e-7, 2e-4),          # IR free-space step on a non-square field
+    ((64, 64, 1), 1e-7, None),           # a single slice DOES propagate here
+    ((64, 64, 4), 3e-10, None),          # voxel below lambda / n: the per-slice IR ordering
+    ((48, 80, 3), 1e-7, 'inf'),          # mixed-radix sides, TF branch
+])
+def test_unbatched_multislice_propagate_matches_oracle(bd, case):
+    from beyond_dof_b200.propagation import propagation_algorithm
+    shape, psize, free = case
+    Y, X, Z = shape
+    gd, gb = mo.random_phantom((1, Y, X, Z), seed=81, delta_scale=3e-4, beta_scale=3e-5)
+    pr, pi = mo.gaussian_probe((Y, X), 12., 10., 0.5)
+    ref = mo.multislice_propagate_unbatched(gd[0], gb[0], pr, pi, 5000, psize, free_prop_cm=free)
+    out = bd.multislice_propagate(gd[0], gb[0], pr, pi, 5000, psize, free_prop_cm=free)
+    assert out.shape == (Y, X) and out.dtype == np.complex64
+    assert rel_l2(out, ref) < 1e-5
+    voxel = np.array([psize] * 3) * 1e7
+    if free == 1e-4 or free == 2e-4:
+        assert propagation_algorithm(free * 1e7, 0.248, voxel, [Y, X, Z]) == 'IR'
+    if psize == 3e-10:
+        assert propagation_algorithm(voxel[-1], 0.248, voxel, [Y, X, Z]) == 'IR'
+    # torch in, torch out; zero padding (util.py:362-364)
+    t = bd.multislice_propagate(torch.as_tensor(gd[0]).cuda(), torch.as_tensor(gb[0]).cuda(), pr, pi, 5000, psize, free_prop_cm=free)
+    assert t.is_cuda and rel_l2(t.cpu().numpy(), ref) < 1e-5

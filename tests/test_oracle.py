@@ -254,3 +254,30 @@ def test_np_funcs_variant_matches_reference(golden_dir):
         if free is None:
             assert pa.shape == (5, 2, 32, 40) and rel_l2(pa, g['npf_probe_array']) < 1e-13
             assert np.array_equal(pa[-1], wf)
+
+
+def test_get_kernel_ir_matches_reference_golden(golden_dir):
+    # tensorflow_recon/util.py:188-216 executed unmodified (oracle/gen_golden.py, CHILD_IR) vs the oracle restatement and the
+    # host function the product uses for the IR free-space step of multislice_propagate
+    import json
+    from beyond_dof_b200.propagation import get_kernel_ir
+    g = np.load(os.path.join(golden_dir, 'ref_ir.npz'))
+    names = [k for k in g.files if not k.endswith('_args')]
+    assert len(names) == 3
+    for k in names:
+        args = json.loads(str(g[k + '_args']))
+        assert np.array_equal(mo.get_kernel_ir(*args), g[k])
+        assert np.array_equal(get_kernel_ir(*args), g[k])
+
+
+def test_unbatched_oracle_reduces_to_batched_tf_semantics():
+    # where the sampling criterion picks 'TF' everywhere the un-batched function is the batched TF one with B = 1
+    gd, gb = mo.random_phantom((1, 32, 48, 5), seed=3, delta_scale=3e-4, beta_scale=3e-5)
+    pr, pi = mo.gaussian_probe((32, 48), 8., 8., 0.5)
+    a = mo.multislice_propagate_unbatched(gd[0], gb[0], pr, pi, 5000, 1e-7, free_prop_cm='inf')
+    b = mo.multislice_propagate_batch(gd, gb, pr, pi, 5000, 1e-7, free_prop_cm='inf')[0]
+    assert rel_l2(a, b) < 1e-14
+    # ... except for a single slice, which the un-batched function propagates (util.py:406-408 vs :484-488)
+    a1 = mo.multislice_propagate_unbatched(gd[0, ..., :1], gb[0, ..., :1], pr, pi, 5000, 1e-7)
+    b1 = mo.multislice_propagate_batch(gd[..., :1], gb[..., :1], pr, pi, 5000, 1e-7)[0]
+    assert rel_l2(a1, b1) > 1e-3
