@@ -22,7 +22,7 @@ SYMBOLS = [
     'bdof_plan_set_bucket_events', 'bdof_set_sm_reserve', 'bdof_rotate_gather', 'bdof_rotate_scatter_add', 'bdof_rotate_adjoint_csr', 'bdof_adam_step',
     'bdof_finite_support', 'bdof_plan_set_t_stash', 'bdof_rotate_bilinear', 'bdof_rotate_bilinear_adjoint',
     'bdof_dp_create', 'bdof_dp_destroy', 'bdof_dp_handle_bytes', 'bdof_dp_export', 'bdof_dp_connect', 'bdof_dp_grad_ptr',
-    'bdof_dp_bucket', 'bdof_dp_gather', 'bdof_dp_finish', 'bdof_plan_last_times', 'bdof_pack_db_rows', 'bdof_unpack_db_rows', 'bdof_plan_set_stream', 'bdof_debug_fft_gain', 'bdof_field_multiply', 'bdof_patch_gather_add',
+    'bdof_dp_bucket', 'bdof_dp_gather', 'bdof_dp_finish', 'bdof_plan_last_times', 'bdof_pack_db_rows', 'bdof_unpack_db_rows', 'bdof_plan_set_stream', 'bdof_debug_fft_gain', 'bdof_field_multiply', 'bdof_patch_gather_add', 'bdof_plan_set_windows', 'bdof_plan_is_resident',
 ]
 
 
@@ -91,11 +91,13 @@ def _load():
     lib.bdof_plan_set_stream.argtypes = [vp, vp]
     lib.bdof_debug_fft_gain.argtypes = [i32, vp]
     lib.bdof_field_multiply.argtypes = [vp, vp, vp, i32, i64, vp]
+    lib.bdof_plan_set_windows.argtypes = [vp, i32, i32, vp]
+    lib.bdof_plan_is_resident.argtypes = [vp]
     lib.bdof_pack_db_rows.argtypes = [vp, vp, vp, i64, i64, i32, i32, i32, vp]
     lib.bdof_unpack_db_rows.argtypes = [vp, vp, vp, i64, i64, i32, i32, i32, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if fn.restype is ctypes.c_int and name not in ('bdof_version', 'bdof_size_supported', 'bdof_dp_handle_bytes'):
+        if fn.restype is ctypes.c_int and name not in ('bdof_version', 'bdof_size_supported', 'bdof_dp_handle_bytes', 'bdof_plan_is_resident'):
             fn.restype = i32
     return lib
 

@@ -463,6 +463,9 @@ struct bdof_plan {
     float2* work[2] = {nullptr, nullptr};   // ping-pong fields (no-store forward) / G buffer
     float2* slabs = nullptr;   // n_slice fields (STORE_SLICES)
     float2* t_stash = nullptr; // caller-owned [n_slice][batch][ny][nx] complex64: the sweep forward leaves t_i there for the adjoint
+    // window mode (bdof_plan_set_windows): d_db of bdof_forward / bdof_adjoint is the OBJECT, the batch its windows
+    const int* win_origin = nullptr;
+    int win_oy = 0, win_ox = 0;
     bool stash_valid = false;  // the last forward filled t_stash and nothing has overwritten it since
     double* partial = nullptr;
     std::complex<double> total_phase{1.0, 0.0};
@@ -989,6 +992,7 @@ extern "C" int bdof_forward(bdof_plan* p, const float* d_db_f, const float* d_pr
     const unsigned long long launches0 = g_launches.load();
     CUDA_TRY(cudaEventRecord(p->t_ev[0], p->stream));
     const bool resident = use_resident(p);
+    if (p->win_origin && !resident) return fail(BDOF_E_UNSUPPORTED, "window mode needs the resident small-field kernels (square 64 x 64 fields)");
     std::complex<double> phase{1.0, 0.0};
     if (resident) {
         // the whole object part of the chain in one launch: the field never leaves the SM
@@ -997,6 +1001,10 @@ extern "C" int bdof_forward(bdof_plan* p, const float* d_db_f, const float* d_pr
         q.in = d_probe; q.out = obj_out; q.db = d_db;
         q.db_slice_stride = (p->flags & BDOF_Z_BROADCAST) ? 0 : p->F;
         q.stash = (store && p->t_stash) ? p->t_stash : nullptr;
+        if (p->win_origin) {
+            q.win = p->win_origin; q.oy = p->win_oy; q.ox = p->win_ox;
+            q.db_slice_stride = (p->flags & BDOF_Z_BROADCAST) ? 0 : (long long)p->win_oy * p->win_ox;
+        }
         q.store = store ? 1 : 0;
         BDOF_TRY(resident_launch(p, false, q));
         for (int i = 0; i < Z; ++i) if (slice_propagates(p, i)) phase *= p->phase0;
@@ -1093,6 +1101,8 @@ extern "C" int bdof_adjoint(bdof_plan* p, float* d_db_inout, const float* d_grad
     if (!p->forward_done) return fail(BDOF_E_STATE, "bdof_adjoint before bdof_forward");
     const bool zb = p->flags & BDOF_Z_BROADCAST;
     if (zb && !d_grad_out) return fail(BDOF_E_BADARG, "BDOF_Z_BROADCAST needs d_grad_out");
+    if (p->win_origin && !d_grad_out) return fail(BDOF_E_BADARG, "window mode needs d_grad_out (the per-window gradients)");
+    if (p->win_origin && !use_resident(p)) return fail(BDOF_E_UNSUPPORTED, "window mode needs the resident small-field kernels");
     float2* db = reinterpret_cast<float2*>(d_db_inout);
     float2* gout = reinterpret_cast<float2*>(d_grad_out);
     float2* G = p->work[0];
@@ -1125,6 +1135,10 @@ extern "C" int bdof_adjoint(bdof_plan* p, float* d_db_inout, const float* d_grad
         q.db = db; q.db_slice_stride = zb ? 0 : p->F;
         q.tstash = p->stash_valid ? p->t_stash : nullptr;
         q.grad = gout ? gout : db;
+        if (p->win_origin) {
+            q.win = p->win_origin; q.oy = p->win_oy; q.ox = p->win_ox;
+            q.db_slice_stride = zb ? 0 : (long long)p->win_oy * p->win_ox;
+        }
         BDOF_TRY(resident_launch(p, true, q));
         for (int j = 0; j < n_buckets; ++j) CUDA_TRY(cudaEventRecord(p->bucket_events[j], p->stream));
         if (p->stash_valid && (p->t_stash == (gout ? gout : db))) p->stash_valid = false;
@@ -1634,6 +1648,14 @@ extern "C" int bdof_slice_step(bdof_plan* p, const float* d_in, const float* d_d
     k_modulate<<<blocks_for(p->F, 256), 256, 0, p->stream>>>(in, db, out, p->F, float(p->k_dz));
     return launch_check("k_modulate");
 }
+
+extern "C" int bdof_plan_set_windows(bdof_plan* p, int oy, int ox, const int* d_origin_yx) {
+    if (!p || (d_origin_yx && (oy < 1 || ox < 1))) return fail(BDOF_E_BADARG, "bad argument");
+    p->win_origin = d_origin_yx; p->win_oy = oy; p->win_ox = ox;
+    if (d_origin_yx) { p->t_stash = nullptr; p->stash_valid = false; }
+    return 0;
+}
+extern "C" int bdof_plan_is_resident(const bdof_plan* p) { return (p && p->have_kernel && use_resident(p)) ? 1 : 0; }
 
 extern "C" int bdof_plan_set_t_stash(bdof_plan* p, float* d_stash) {
     if (!p) return fail(BDOF_E_BADARG, "null");

@@ -25,7 +25,9 @@ namespace bdof {
 struct ResidentParams {
     const float2* in;          // forward: probe [n][n] (shared by the batch); adjoint: G [batch][n][n]
     float2* out;               // forward: field after the object [batch][n][n]; adjoint: G at the entrance plane (nullable)
-    const float2* db;          // (delta, beta) [n_slice][batch][n][n]
+    const float2* db;          // (delta, beta) [n_slice][batch][n][n]; with `win`: the OBJECT [n_slice][oy][ox] the fields are windows of
+    const int* win;            // nullable: (y0, x0) window origin per field (ptychography.py:62-76); pixels outside the object are vacuum
+    int oy, ox;                //   object sides (window mode)
     float2* stash;             // forward: nullable, tau_i = t_i - 1 out, layout of db
     const float2* tstash;      // adjoint: nullable, tau_i in (then db is not read)
     float2* grad;              // adjoint: (dL/ddelta, dL/dbeta) out, layout of db (may alias db / tstash)
@@ -82,9 +84,21 @@ struct ResidentMap {
     static constexpr int N = Cfg::N, T = Cfg::T;
     int l, t;
     __device__ __forceinline__ ResidentMap(int tid) : l(COL ? tid % N : tid / T), t(COL ? tid / N : tid % T) {}
-    // row-major index of element q
+    // row-major index of element q, and its row / column
     __device__ __forceinline__ int g(int q) const { return COL ? (t + T * q) * N + l : l * N + t + T * q; }
+    __device__ __forceinline__ int y(int q) const { return COL ? t + T * q : l; }
+    __device__ __forceinline__ int x(int q) const { return COL ? l : t + T * q; }
 };
+
+// (delta, beta) of element q of field b in slice s: from the per-field array, or straight from the object through the
+// field's window (the object slice is L2 resident: 512 KB at 256^2, and no window copy of the object ever exists in HBM)
+template <class Map>
+__device__ __forceinline__ float2 resident_load_db(const ResidentParams& p, int s, long long fbase, int wy0, int wx0, const Map& m, int q) {
+    if (p.win == nullptr) return __ldg(p.db + (long long)s * p.db_slice_stride + fbase + m.g(q));
+    const int yy = wy0 + m.y(q), xx = wx0 + m.x(q);
+    if (yy < 0 || yy >= p.oy || xx < 0 || xx >= p.ox) return make_float2(0.f, 0.f);
+    return __ldg(p.db + (long long)s * p.db_slice_stride + (long long)yy * p.ox + xx);
+}
 
 template <class Cfg, bool COL>
 __device__ __forceinline__ void resident_fft(float2 (&v)[Cfg::E], const ResidentMap<Cfg, COL>& m, float2* X, const float2* s_tw) {
@@ -160,8 +174,8 @@ __device__ __forceinline__ void resident_stage_h(const ResidentParams& p, int s,
 // forward: step s < n_slice = slice s; step n_slice = the trailing half propagation of the TF semantics
 // ------------------------------------------------------------------------------------------------------------------
 template <class Cfg, bool COL>
-__device__ __forceinline__ void resident_forward_step(const ResidentParams& p, int s, int n_steps, long long fbase, int tid,
-                                                      float2 (&v)[Cfg::E], float2 (&d)[Cfg::E], float2* X, const float2* s_tw,
+__device__ __forceinline__ void resident_forward_step(const ResidentParams& p, int s, int n_steps, long long fbase, int wy0, int wx0,
+                                                      int tid, float2 (&v)[Cfg::E], float2 (&d)[Cfg::E], float2* X, const float2* s_tw,
                                                       float2* s_h) {
     constexpr int E = Cfg::E, N = Cfg::N, NT = Cfg::N * Cfg::T;
     const ResidentMap<Cfg, COL> m(tid);
@@ -170,9 +184,8 @@ __device__ __forceinline__ void resident_forward_step(const ResidentParams& p, i
     float2 dn[E] = {};
     if (s + 1 < Z) {
         const ResidentMap<Cfg, !COL> mn(tid);
-        const float2* src = p.db + (long long)(s + 1) * p.db_slice_stride + fbase;
 #pragma unroll
-        for (int q = 0; q < E; ++q) dn[q] = __ldg(src + mn.g(q));
+        for (int q = 0; q < E; ++q) dn[q] = resident_load_db(p, s + 1, fbase, wy0, wx0, mn, q);
     }
     if (s + 1 < n_steps) resident_stage_h<Cfg>(p, s + 1, tid, s_h);
     if (s > 0) resident_conv<Cfg, COL>(v, m, X, s_tw, s_h + (s & 1) * N);
@@ -216,17 +229,18 @@ __global__ void __launch_bounds__(Cfg::N* Cfg::T) resident_forward_kernel(const 
         const long long fbase = (long long)b * N * N;
         __syncthreads();                               // tables staged / the previous field is done with the shared buffers
         resident_stage_h<Cfg>(p, 0, tid, s_h);
+        const int wy0 = p.win ? p.win[2 * b] : 0, wx0 = p.win ? p.win[2 * b + 1] : 0;
         float2 v[E], d[E];
         {
             const ResidentMap<Cfg, false> m0(tid);
 #pragma unroll
-            for (int q = 0; q < E; ++q) { v[q] = __ldg(p.in + m0.g(q)); d[q] = __ldg(p.db + fbase + m0.g(q)); }
+            for (int q = 0; q < E; ++q) { v[q] = __ldg(p.in + m0.g(q)); d[q] = resident_load_db(p, 0, fbase, wy0, wx0, m0, q); }
         }
         __syncthreads();
 #pragma unroll 1
         for (int s = 0; s < n_steps; ++s) {
-            if (s & 1) resident_forward_step<Cfg, true>(p, s, n_steps, fbase, tid, v, d, X, s_tw, s_h);
-            else       resident_forward_step<Cfg, false>(p, s, n_steps, fbase, tid, v, d, X, s_tw, s_h);
+            if (s & 1) resident_forward_step<Cfg, true>(p, s, n_steps, fbase, wy0, wx0, tid, v, d, X, s_tw, s_h);
+            else       resident_forward_step<Cfg, false>(p, s, n_steps, fbase, wy0, wx0, tid, v, d, X, s_tw, s_h);
         }
         float2* op = p.out + fbase;
         if ((n_steps - 1) & 1) {
@@ -246,9 +260,9 @@ __global__ void __launch_bounds__(Cfg::N* Cfg::T) resident_forward_kernel(const 
 //   B_s --C_a^H--> G_u --[G = conj(t_s) G_u ; grad_s = -k (Im, Re)(psi_s conj(G))]--> --C_a^H--> B_{s-1}
 // ------------------------------------------------------------------------------------------------------------------
 template <class Cfg, bool COL>
-__device__ __forceinline__ void resident_adjoint_step(const ResidentParams& p, int s, long long fbase, int tid, float2 (&v)[Cfg::E],
-                                                      float2 (&d)[Cfg::E], float2 (&psi)[Cfg::E], float2* X, const float2* s_tw,
-                                                      float2* s_h) {
+__device__ __forceinline__ void resident_adjoint_step(const ResidentParams& p, int s, long long fbase, int wy0, int wx0, int tid,
+                                                      float2 (&v)[Cfg::E], float2 (&d)[Cfg::E], float2 (&psi)[Cfg::E], float2* X,
+                                                      const float2* s_tw, float2* s_h) {
     constexpr int E = Cfg::E, N = Cfg::N, NT = Cfg::N * Cfg::T;
     const ResidentMap<Cfg, COL> m(tid);
     const int Z = p.n_slice;
@@ -257,11 +271,13 @@ __device__ __forceinline__ void resident_adjoint_step(const ResidentParams& p, i
     float2 dn[E] = {}, pn[E] = {};
     if (s >= 1 && s - 1 < Z) {
         const ResidentMap<Cfg, !COL> mn(tid);
-        const float2* src = from_stash ? p.tstash + (long long)(s - 1) * p.slice_stride + fbase
-                                       : p.db + (long long)(s - 1) * p.db_slice_stride + fbase;
+        const float2* tsrc = p.tstash + (long long)(s - 1) * p.slice_stride + fbase;
         const float2* sp = p.slab + (long long)(s - 1) * p.slice_stride + fbase + tid;
 #pragma unroll
-        for (int q = 0; q < E; ++q) { dn[q] = __ldg(src + mn.g(q)); pn[q] = __ldg(sp + q * NT); }
+        for (int q = 0; q < E; ++q) {
+            dn[q] = from_stash ? __ldg(tsrc + mn.g(q)) : resident_load_db(p, s - 1, fbase, wy0, wx0, mn, q);
+            pn[q] = __ldg(sp + q * NT);
+        }
     }
     if (s >= 1) resident_stage_h<Cfg>(p, s - 1, tid, s_h);
     const float2* h = s_h + (s & 1) * N;
@@ -310,16 +326,19 @@ __global__ void __launch_bounds__(Cfg::N* Cfg::T) resident_adjoint_kernel(const 
         const long long fbase = (long long)b * N * N;
         __syncthreads();
         resident_stage_h<Cfg>(p, s0, tid, s_h);
+        const int wy0 = p.win ? p.win[2 * b] : 0, wx0 = p.win ? p.win[2 * b + 1] : 0;
         float2 v[E], d[E], psi[E];
         auto first_loads = [&](auto map) __attribute__((always_inline)) {
 #pragma unroll
             for (int q = 0; q < E; ++q) v[q] = __ldg(p.in + fbase + map.g(q));
             if (s0 < Z) {
-                const float2* src = from_stash ? p.tstash + (long long)s0 * p.slice_stride + fbase
-                                               : p.db + (long long)s0 * p.db_slice_stride + fbase;
+                const float2* tsrc = p.tstash + (long long)s0 * p.slice_stride + fbase;
                 const float2* sp = p.slab + (long long)s0 * p.slice_stride + fbase + tid;
 #pragma unroll
-                for (int q = 0; q < E; ++q) { d[q] = __ldg(src + map.g(q)); psi[q] = __ldg(sp + q * NT); }
+                for (int q = 0; q < E; ++q) {
+                    d[q] = from_stash ? __ldg(tsrc + map.g(q)) : resident_load_db(p, s0, fbase, wy0, wx0, map, q);
+                    psi[q] = __ldg(sp + q * NT);
+                }
             } else {
 #pragma unroll
                 for (int q = 0; q < E; ++q) { d[q] = make_float2(0.f, 0.f); psi[q] = make_float2(0.f, 0.f); }
@@ -330,8 +349,8 @@ __global__ void __launch_bounds__(Cfg::N* Cfg::T) resident_adjoint_kernel(const 
         __syncthreads();
 #pragma unroll 1
         for (int s = s0; s >= 0; --s) {
-            if (s & 1) resident_adjoint_step<Cfg, true>(p, s, fbase, tid, v, d, psi, X, s_tw, s_h);
-            else       resident_adjoint_step<Cfg, false>(p, s, fbase, tid, v, d, psi, X, s_tw, s_h);
+            if (s & 1) resident_adjoint_step<Cfg, true>(p, s, fbase, wy0, wx0, tid, v, d, psi, X, s_tw, s_h);
+            else       resident_adjoint_step<Cfg, false>(p, s, fbase, wy0, wx0, tid, v, d, psi, X, s_tw, s_h);
         }
         if (p.out != nullptr) {
             const ResidentMap<Cfg, false> m(tid);       // step 0 is an x step

@@ -640,7 +640,11 @@ class PtychographyObjective:
                                    store_slices=True, device=dev)
         self.probe = probe.to(dev, torch.complex64).contiguous()
         self.patches = torch.empty((Z, self.n, self.py, self.px, 2), dtype=torch.float32, device=dev)
-        self.plan.set_t_stash(self.patches)          # windows are re-cut every step and overwritten in place by the adjoint
+        # resident plans (64 x 64 probes) read the object straight through the windows: no window copy of the object is cut and
+        # `patches` only receives the per-window gradients; otherwise the windows are cut every step and overwritten in place
+        self.windowed = self.plan.is_resident()
+        if not self.windowed:
+            self.plan.set_t_stash(self.patches)
         self.grad = torch.zeros_like(db_obj)
         self.m = torch.zeros_like(db_obj)
         self.v = torch.zeros_like(db_obj)
@@ -670,10 +674,16 @@ class PtychographyObjective:
         assert pos.shape == (self.n, 2)
         self.origin_host.copy_(torch.as_tensor((pos - self.half[None, :]).astype(np.int32)))
         self.origin.copy_(self.origin_host, non_blocking=True)
-        check(lib.bdof_patch_gather(_ptr(self.obj), Z, OY, OX, _ptr(self.origin), self.n, self.py, self.px, _ptr(self.patches), st))
-        self.plan.forward(self.patches, self.probe, out=self.exit)
-        loss, g = self.plan.loss_mag(self.exit, target_dev, loss_scale=self.scale)
-        self.plan.adjoint(self.patches, g)
+        if self.windowed:
+            self.plan.set_windows((Z, OY, OX), self.origin)
+            self.plan.forward(self.obj, self.probe, out=self.exit)
+            loss, g = self.plan.loss_mag(self.exit, target_dev, loss_scale=self.scale)
+            self.plan.adjoint(self.obj, g, grad_out=self.patches)
+        else:
+            check(lib.bdof_patch_gather(_ptr(self.obj), Z, OY, OX, _ptr(self.origin), self.n, self.py, self.px, _ptr(self.patches), st))
+            self.plan.forward(self.patches, self.probe, out=self.exit)
+            loss, g = self.plan.loss_mag(self.exit, target_dev, loss_scale=self.scale)
+            self.plan.adjoint(self.patches, g)
         self.grad.zero_()
         check(lib.bdof_patch_gather_add(_ptr(self.patches), Z, OY, OX, _ptr(self.origin), self.n, self.py, self.px, _ptr(self.grad), st))
         if self._dp is not None:

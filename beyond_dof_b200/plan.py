@@ -134,11 +134,30 @@ class MultislicePlan:
         return d, b
 
     # ---- compute ------------------------------------------------------------------------
+    def is_resident(self):
+        """True when the plan runs the resident small-field kernels (one launch per direction, field on chip)."""
+        return bool(lib.bdof_plan_is_resident(self._h))
+
+    def set_windows(self, obj_shape_zyx, origin):
+        """Window mode (resident plans only): the batch elements are windows of one object [Z,OY,OX,2]; origin [B,2] int32 CUDA
+        tensor of (y0, x0).  forward()/adjoint() then take the OBJECT instead of db.  origin=None switches it off."""
+        if origin is None:
+            self._win = None
+            check(lib.bdof_plan_set_windows(self._h, 0, 0, None))
+            return
+        Z, OY, OX = (int(v) for v in obj_shape_zyx)
+        assert origin.is_cuda and origin.dtype == torch.int32 and origin.is_contiguous() and tuple(origin.shape) == (self.batch, 2)
+        self._win = (Z, OY, OX, origin)
+        self._stash = None
+        check(lib.bdof_plan_set_windows(self._h, OY, OX, _ptr(origin)))
+
     def forward(self, db, probe, out=None):
-        """db [Z,B,Y,X,2] float32, probe [Y,X] complex64 -> exit wave [B,Y,X] complex64."""
+        """db [Z,B,Y,X,2] float32 (window mode: the object [Z,OY,OX,2]), probe [Y,X] complex64 -> exit wave [B,Y,X] complex64."""
         self.use_current_stream()
-        assert db.is_cuda and db.dtype == torch.float32 and db.is_contiguous() and tuple(db.shape) == self.db_shape, \
-            'db must be a contiguous float32 CUDA tensor of shape %s' % (self.db_shape,)
+        win = getattr(self, '_win', None)
+        want = self.db_shape if win is None else ((1 if self.z_broadcast else win[0]), win[1], win[2], 2)
+        assert db.is_cuda and db.dtype == torch.float32 and db.is_contiguous() and tuple(db.shape) == want, \
+            'db must be a contiguous float32 CUDA tensor of shape %s' % (want,)
         probe = probe.to(self.device, torch.complex64).contiguous()
         assert tuple(probe.shape) == (self.ny, self.nx)
         if out is None:

@@ -122,6 +122,16 @@ int  bdof_adjoint(bdof_plan* p, float* d_db_inout, const float* d_grad_exit, flo
  * memory: every tile of t is read just before the gradient of the same tile replaces it. */
 int  bdof_plan_set_t_stash(bdof_plan* p, float* d_stash);
 
+/* Window mode (resident small-field kernels only: square 64 x 64 fields, separable kernel): the batch elements are windows of
+ * ONE object d_obj_db [n_slice][oy][ox][2] -- the probe windows of the ptychography model (tensorflow_recon/ptychography.py:62-76).
+ * d_origin_yx [batch][2] int32 (device) = window origins, pixels outside the object are vacuum.  While set, bdof_forward /
+ * bdof_adjoint take the OBJECT as d_db / d_db_inout (read only) and read (delta, beta) straight through the windows (the
+ * object slice is L2 resident), so no [n_slice][batch][ny][nx] copy of the object is ever cut; the transmission stash is off
+ * and bdof_adjoint writes the per-window gradients to d_grad_out (required; accumulate them with bdof_patch_gather_add).
+ * d_origin_yx = NULL switches the mode off.  bdof_plan_is_resident tells whether the plan runs the resident kernels. */
+int  bdof_plan_set_windows(bdof_plan* p, int oy, int ox, const int* d_origin_yx);
+int  bdof_plan_is_resident(const bdof_plan* p);
+
 /* layout conversion: reference [B,Y,X,Z] float32 planes <-> slice-major interleaved db */
 int  bdof_pack_db(const float* d_delta_byxz, const float* d_beta_byxz, float* d_db, int batch, int ny,
                   int nx, int n_slice, void* cuda_stream);

@@ -373,11 +373,12 @@ def test_patch_gather_add_is_the_deterministic_scatter(bd):
     assert rel_l2(outs[0].cpu().numpy(), 2 * ref.cpu().numpy()) < 2e-7
 
 
-def test_ptychography_objective_step_matches_oracle_update(bd):
-    # one update of the reconstruction loop (cnn_propagator/ptychography.py:292-310) against the oracle gradient + Adam
+@pytest.mark.parametrize('probe_size', [(64, 64), (72, 72)])
+def test_ptychography_objective_step_matches_oracle_update(bd, probe_size):
+    # one update of the reconstruction loop (cnn_propagator/ptychography.py:292-310) against the oracle gradient + Adam;
+    # 64 x 64: the resident kernels reading the object through the windows, 72 x 72 (the reference's default): cut windows
     from beyond_dof_b200.models import PtychographyObjective, pack_object, unpack_object
     Y, X, Z = 96, 96, 6
-    probe_size = (64, 64)
     od, ob = mo.random_phantom((Y, X, Z), seed=90, delta_scale=3e-4, beta_scale=3e-5)
     gt_d, gt_b = mo.random_phantom((Y, X, Z), seed=91, delta_scale=5e-3, beta_scale=5e-3)
     pr, pi = mo.gaussian_probe(probe_size, 6., 6., 0.5)
@@ -387,14 +388,17 @@ def test_ptychography_objective_step_matches_oracle_update(bd):
     obj = pack_object(od, ob)
     pty = PtychographyObjective(obj, torch.as_tensor((pr + 1j * pi).astype(np.complex64)), probe_size, 5000, 1e-7,
                                 n_pos_per_step=len(pos), step_size=1e-7)
+    assert pty.windowed == (probe_size == (64, 64))
     loss = pty.step(pos, torch.as_tensor(np.abs(prj).astype(np.float32)).pin_memory())
-    assert abs(loss - lo) < 1e-5 * abs(lo)
+    assert abs(loss - lo) < 2e-5 * abs(lo)
     g_d, g_b = unpack_object(pty.grad)
     assert rel_l2(g_d.cpu().numpy(), gdo) < 1e-4 and rel_l2(g_b.cpu().numpy(), gbo) < 1e-4
-    xd, _, _ = mo.apply_gradient_adam(od.astype(np.float64), gdo, 0, None, None, step_size=1e-7)
-    xb, _, _ = mo.apply_gradient_adam(ob.astype(np.float64), gbo, 0, None, None, step_size=1e-7)
+    # the update is Adam on THAT gradient (first step: x - step g / (|g| + eps), which is ill-conditioned in g where |g| ~ eps, so
+    # the expected update is formed from the gradient the GPU produced) followed by the clip
+    xd, _, _ = mo.apply_gradient_adam(od.astype(np.float64), g_d.cpu().numpy().astype(np.float64), 0, None, None, step_size=1e-7)
+    xb, _, _ = mo.apply_gradient_adam(ob.astype(np.float64), g_b.cpu().numpy().astype(np.float64), 0, None, None, step_size=1e-7)
     nd, nb = unpack_object(pty.obj)
-    assert rel_l2(nd.cpu().numpy(), np.clip(xd, 0, None)) < 1e-5 and rel_l2(nb.cpu().numpy(), np.clip(xb, 0, None)) < 1e-5
+    assert rel_l2(nd.cpu().numpy(), np.clip(xd, 0, None)) < 2e-6 and rel_l2(nb.cpu().numpy(), np.clip(xb, 0, None)) < 2e-6
     # bit-reproducible: the same step from the same state gives the same gradient
     obj2 = pack_object(od, ob)
     pty2 = PtychographyObjective(obj2, torch.as_tensor((pr + 1j * pi).astype(np.complex64)), probe_size, 5000, 1e-7,
