@@ -14,6 +14,7 @@ _LAZY = {
     'multislice_propagate_batch': 'propagation',
     'multislice_propagate': 'propagation',
     'multislice_propagate_cnn': 'propagation',
+    'cnn_loss_and_grad': 'propagation',
     'MultislicePlan': 'plan',
     'fullfield_loss_and_grad': 'models',
     'ptycho_loss_and_grad': 'models',

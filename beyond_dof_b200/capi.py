@@ -22,7 +22,7 @@ SYMBOLS = [
     'bdof_plan_set_bucket_events', 'bdof_set_sm_reserve', 'bdof_rotate_gather', 'bdof_rotate_scatter_add', 'bdof_rotate_adjoint_csr', 'bdof_adam_step',
     'bdof_finite_support', 'bdof_plan_set_t_stash', 'bdof_rotate_bilinear', 'bdof_rotate_bilinear_adjoint',
     'bdof_dp_create', 'bdof_dp_destroy', 'bdof_dp_handle_bytes', 'bdof_dp_export', 'bdof_dp_connect', 'bdof_dp_grad_ptr',
-    'bdof_dp_bucket', 'bdof_dp_gather', 'bdof_dp_finish', 'bdof_plan_last_times', 'bdof_pack_db_rows', 'bdof_unpack_db_rows', 'bdof_plan_set_stream', 'bdof_debug_fft_gain', 'bdof_field_multiply', 'bdof_patch_gather_add', 'bdof_plan_set_windows', 'bdof_plan_is_resident',
+    'bdof_dp_bucket', 'bdof_dp_gather', 'bdof_dp_finish', 'bdof_plan_last_times', 'bdof_pack_db_rows', 'bdof_unpack_db_rows', 'bdof_plan_set_stream', 'bdof_debug_fft_gain', 'bdof_field_multiply', 'bdof_patch_gather_add', 'bdof_plan_set_windows', 'bdof_plan_is_resident', 'bdof_cnn_forward_store', 'bdof_cnn_adjoint', 'bdof_free_prop_adjoint',
 ]
 
 
@@ -59,6 +59,9 @@ def _load():
     lib.bdof_patch_gather_add.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp, vp]
     lib.bdof_cnn_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, i32, f64, vp]
     lib.bdof_forward_host.argtypes = [vp, vp, vp, vp, vp]
+    lib.bdof_cnn_forward_store.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, i32, f64, vp]
+    lib.bdof_cnn_adjoint.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, i32, f64, vp]
+    lib.bdof_free_prop_adjoint.argtypes = [vp, vp, vp]
     lib.bdof_plan_workspace_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
     lib.bdof_free_prop.argtypes = [vp, vp, vp]
     lib.bdof_profile_begin.argtypes = [vp]

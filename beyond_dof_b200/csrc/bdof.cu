@@ -417,6 +417,43 @@ __global__ void k_cnn_step(const float2* __restrict__ in, const float2* __restri
     out[fbase + (long long)y * nx + x] = make_float2(ax, ay);
 }
 
+// adjoint of k_cnn_step: G_u[y,x] = sum_ab conj(K[a,b]) G'[y - p + a, x - p + b] (zero outside the field: the edge value is a
+// constant), grad = -k (Im, Re)(conj(G_u) psi t), G = conj(t) G_u
+template <int TILE>
+__global__ void k_cnn_step_adj(const float2* __restrict__ gin, const float2* __restrict__ psi, const float2* __restrict__ db,
+                               float2* __restrict__ grad, float2* __restrict__ gout, int ny, int nx, int ks, float k_dz) {
+    extern __shared__ float2 tile[];          // (TILE + ks - 1)^2
+    const int pad = (ks - 1) / 2, W = TILE + ks - 1;
+    const int b = blockIdx.z;
+    const int y0 = blockIdx.y * TILE, x0 = blockIdx.x * TILE;
+    const long long fbase = (long long)b * ny * nx;
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < W * W; i += blockDim.x * blockDim.y) {
+        const int ty = i / W, tx = i - ty * W;
+        const int y = y0 + ty - pad, x = x0 + tx - pad;
+        float2 v = make_float2(0.f, 0.f);
+        if (y >= 0 && y < ny && x >= 0 && x < nx) v = gin[fbase + (long long)y * nx + x];
+        tile[i] = v;
+    }
+    __syncthreads();
+    const int y = y0 + threadIdx.y, x = x0 + threadIdx.x;
+    if (y >= ny || x >= nx) return;
+    float ax = 0.f, ay = 0.f;
+    for (int a = 0; a < ks; ++a)
+        for (int c = 0; c < ks; ++c) {
+            const float2 kk = c_cnn_kernel[a * ks + c];
+            const float2 v = tile[(threadIdx.y + a) * W + (threadIdx.x + c)];
+            ax += kk.x * v.x + kk.y * v.y;      // conj(K) * v
+            ay += kk.x * v.y - kk.y * v.x;
+        }
+    const long long o = fbase + (long long)y * nx + x;
+    const float2 gu = make_float2(ax, ay);
+    const float2 tau = transmission_any_m1(db[o], k_dz);
+    const float2 u = cmul1p(psi[o], tau);
+    const float2 w = cmulc(u, gu);              // u conj(G_u)
+    grad[o] = make_float2(-k_dz * w.y, -k_dz * w.x);
+    gout[o] = cmulc1p(gu, tau);
+}
+
 static inline unsigned blocks_for(long long n, int threads) { return unsigned((n + threads - 1) / threads); }
 
 // ------------------------------------------------------------------------------------------
@@ -1324,6 +1361,72 @@ extern "C" int bdof_cnn_forward(const float* d_db, const float* d_probe, float* 
     return 0;
 }
 
+static int cnn_upload_kernel(const double* h_kernel, int ks, cudaStream_t st, std::complex<double>* ksum_out) {
+    if (ks < 1 || ks % 2 == 0 || ks > CNN_MAX_K) return fail(BDOF_E_BADARG, "kernel_size must be odd and <= %d", CNN_MAX_K);
+    std::vector<float2> kf((size_t)ks * ks);
+    std::complex<double> ksum = 0.0;
+    for (int i = 0; i < ks * ks; ++i) {
+        kf[i] = make_float2(float(h_kernel[2 * i]), float(h_kernel[2 * i + 1]));
+        ksum += std::complex<double>(h_kernel[2 * i], h_kernel[2 * i + 1]);
+    }
+    // synchronous with respect to the host buffer (kf dies at return)
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_cnn_kernel, kf.data(), kf.size() * sizeof(float2), 0, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (ksum_out) *ksum_out = ksum;
+    return 0;
+}
+
+// forward that keeps the field entering every slice: d_slices [n_slice + 1][batch][ny][nx], slices[0] = the probe, slices[i + 1] =
+// the field after slice i; the (unscaled) chain output is slices[n_slice]
+extern "C" int bdof_cnn_forward_store(const float* d_db, const float* d_probe, float* d_slices, int batch, int ny, int nx, int n_slice,
+                                      const double* h_kernel, int ks, double k_dz, void* st_) {
+    if (!d_db || !d_probe || !d_slices || !h_kernel || batch < 1 || ny < 1 || nx < 1 || n_slice < 1) return fail(BDOF_E_BADARG, "bad argument");
+    cudaStream_t st = (cudaStream_t)st_;
+    std::complex<double> ksum;
+    BDOF_TRY(cnn_upload_kernel(h_kernel, ks, st, &ksum));
+    const long long per = (long long)ny * nx, F = per * batch;
+    float2* sl = reinterpret_cast<float2*>(d_slices);
+    k_broadcast_probe<<<blocks_for(per, 256), 256, 0, st>>>(reinterpret_cast<const float2*>(d_probe), sl, per, batch);
+    BDOF_TRY(launch_check("k_broadcast_probe"));
+    constexpr int TILE = 16;
+    const size_t smem = size_t(TILE + ks - 1) * (TILE + ks - 1) * sizeof(float2);
+    dim3 grid((nx + TILE - 1) / TILE, (ny + TILE - 1) / TILE, batch), block(TILE, TILE);
+    std::complex<double> edge = 1.0;
+    for (int i = 0; i < n_slice; ++i) {
+        k_cnn_step<TILE><<<grid, block, smem, st>>>(sl + (long long)i * F, reinterpret_cast<const float2*>(d_db) + (long long)i * F,
+                                                   sl + (long long)(i + 1) * F, ny, nx, ks, float(k_dz),
+                                                   make_float2(float(edge.real()), float(edge.imag())));
+        BDOF_TRY(launch_check("k_cnn_step"));
+        edge *= ksum;
+    }
+    return 0;
+}
+
+// back-propagate d_G (gradient w.r.t. the unscaled chain output slices[n_slice]; [2][batch][ny][nx], the second field is work
+// space) through the stored chain: d_grad_out [n_slice][batch][ny][nx][2]; on return d_G[0] holds the gradient w.r.t. the probe
+// broadcast (per batch element)
+extern "C" int bdof_cnn_adjoint(const float* d_db, const float* d_slices, float* d_G, float* d_grad_out, int batch, int ny, int nx, int n_slice,
+                                const double* h_kernel, int ks, double k_dz, void* st_) {
+    if (!d_db || !d_slices || !d_G || !d_grad_out || !h_kernel || batch < 1 || ny < 1 || nx < 1 || n_slice < 1) return fail(BDOF_E_BADARG, "bad argument");
+    cudaStream_t st = (cudaStream_t)st_;
+    BDOF_TRY(cnn_upload_kernel(h_kernel, ks, st, nullptr));
+    const long long F = (long long)ny * nx * batch;
+    const float2* sl = reinterpret_cast<const float2*>(d_slices);
+    float2* G[2] = {reinterpret_cast<float2*>(d_G), reinterpret_cast<float2*>(d_G) + F};
+    constexpr int TILE = 16;
+    const size_t smem = size_t(TILE + ks - 1) * (TILE + ks - 1) * sizeof(float2);
+    dim3 grid((nx + TILE - 1) / TILE, (ny + TILE - 1) / TILE, batch), block(TILE, TILE);
+    int cur = 0;
+    for (int i = n_slice - 1; i >= 0; --i) {
+        k_cnn_step_adj<TILE><<<grid, block, smem, st>>>(G[cur], sl + (long long)i * F, reinterpret_cast<const float2*>(d_db) + (long long)i * F,
+                                                       reinterpret_cast<float2*>(d_grad_out) + (long long)i * F, G[cur ^ 1], ny, nx, ks, float(k_dz));
+        BDOF_TRY(launch_check("k_cnn_step_adj"));
+        cur ^= 1;
+    }
+    if (cur != 0) CUDA_TRY(cudaMemcpyAsync(G[0], G[1], (size_t)F * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
 extern "C" int bdof_forward_host(bdof_plan* p, const float* h_delta, const float* h_beta, const float* h_probe, float* h_exit) {
     if (!p || !h_delta || !h_beta || !h_probe || !h_exit) return fail(BDOF_E_BADARG, "null");
     const size_t vol = (size_t)p->F * p->n_slice;
@@ -1597,6 +1700,30 @@ extern "C" int bdof_profile_end(bdof_plan* p, int n_variants, int* counts, doubl
     return 0;
 }
 
+// adjoint of the plan's free-space step on its own (the head of bdof_adjoint): out = free_prop^H(in)
+extern "C" int bdof_free_prop_adjoint(bdof_plan* p, const float* d_in_f, float* d_out_f) {
+    if (!p || !d_in_f || !d_out_f) return fail(BDOF_E_BADARG, "null");
+    const float2* in = reinterpret_cast<const float2*>(d_in_f);
+    float2* out = reinterpret_cast<float2*>(d_out_f);
+    if (p->free_mode == BDOF_FREE_INF) {
+        LineParams cc = col_params(p, in, p->tmp, nullptr);
+        cc.in_shift = p->ny / 2;
+        BDOF_TRY(col_pass(p, V_COL_INV, cc));
+        LineParams r = row_params(p, p->tmp, out, nullptr);
+        r.in_shift = p->nx / 2;
+        return row_pass(p, V_ROW_INV, r);
+    }
+    if (p->free_mode == BDOF_FREE_TF) {
+        const std::complex<double> c = std::conj(p->phasef);
+        k_scale_complex<<<blocks_for(p->F, 256), 256, 0, p->stream>>>(in, out, p->F, float(c.real()), float(c.imag()));
+        BDOF_TRY(launch_check("k_scale_complex"));
+        BDOF_TRY(col_pass(p, V_COL_CONV, col_params(p, out, p->tmp, p->ay.hf_adj)));
+        return row_pass(p, V_ROW_CONV, row_params(p, p->tmp, out, p->ax.hf_adj));
+    }
+    if (in != out) CUDA_TRY(cudaMemcpyAsync(out, in, (size_t)p->F * sizeof(float2), cudaMemcpyDeviceToDevice, p->stream));
+    return 0;
+}
+
 extern "C" int bdof_plan_last_times(bdof_plan* p, double* ms_out, int* launches_out) {
     if (!p || !ms_out || !launches_out) return fail(BDOF_E_BADARG, "null");
     if (!p->forward_done) return fail(BDOF_E_STATE, "no forward has run on this plan");
@@ -1652,7 +1779,7 @@ extern "C" int bdof_slice_step(bdof_plan* p, const float* d_in, const float* d_d
 extern "C" int bdof_plan_set_windows(bdof_plan* p, int oy, int ox, const int* d_origin_yx) {
     if (!p || (d_origin_yx && (oy < 1 || ox < 1))) return fail(BDOF_E_BADARG, "bad argument");
     p->win_origin = d_origin_yx; p->win_oy = oy; p->win_ox = ox;
-    if (d_origin_yx) { p->t_stash = nullptr; p->stash_valid = false; }
+    p->stash_valid = false;
     return 0;
 }
 extern "C" int bdof_plan_is_resident(const bdof_plan* p) { return (p && p->have_kernel && use_resident(p)) ? 1 : 0; }

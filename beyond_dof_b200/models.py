@@ -641,10 +641,10 @@ class PtychographyObjective:
         self.probe = probe.to(dev, torch.complex64).contiguous()
         self.patches = torch.empty((Z, self.n, self.py, self.px, 2), dtype=torch.float32, device=dev)
         # resident plans (64 x 64 probes) read the object straight through the windows: no window copy of the object is cut and
-        # `patches` only receives the per-window gradients; otherwise the windows are cut every step and overwritten in place
+        # `patches` holds the transmission stash between forward and adjoint and then the per-window gradients; otherwise the
+        # windows are cut every step and overwritten in place
         self.windowed = self.plan.is_resident()
-        if not self.windowed:
-            self.plan.set_t_stash(self.patches)
+        self.plan.set_t_stash(self.patches)
         self.grad = torch.zeros_like(db_obj)
         self.m = torch.zeros_like(db_obj)
         self.v = torch.zeros_like(db_obj)

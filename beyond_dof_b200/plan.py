@@ -148,7 +148,6 @@ class MultislicePlan:
         Z, OY, OX = (int(v) for v in obj_shape_zyx)
         assert origin.is_cuda and origin.dtype == torch.int32 and origin.is_contiguous() and tuple(origin.shape) == (self.batch, 2)
         self._win = (Z, OY, OX, origin)
-        self._stash = None
         check(lib.bdof_plan_set_windows(self._h, OY, OX, _ptr(origin)))
 
     def forward(self, db, probe, out=None):
@@ -250,6 +249,15 @@ class MultislicePlan:
         if out is None:
             out = torch.empty_like(field)
         check(lib.bdof_free_prop(self._h, _ptr(field), _ptr(out)))
+        return out
+
+    def free_prop_adjoint(self, grad, out=None):
+        """Adjoint of the plan's free-space step on its own: [B,Y,X] complex64 -> [B,Y,X]."""
+        self.use_current_stream()
+        grad = grad.to(self.device, torch.complex64).contiguous()
+        if out is None:
+            out = torch.empty_like(grad)
+        check(lib.bdof_free_prop_adjoint(self._h, _ptr(grad), _ptr(out)))
         return out
 
     def profile_begin(self):

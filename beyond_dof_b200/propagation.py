@@ -214,12 +214,14 @@ def cnn_kernel(energy_ev, psize_cm, grid_shape_yxz, kernel_size):
     return kern[mid[0] - half:mid[0] + half + 1, mid[1] - half:mid[1] + half + 1]
 
 
-def multislice_propagate_cnn(grid_delta, grid_beta, probe_real, probe_imag, energy_ev, psize_cm, kernel_size=17,
-                             free_prop_cm=None, debug=False):
-    """Real-space ("cnn") multislice (propagation.py:18-133): per slice modulate, pad with the tracked
-    plane-wave edge value, convolve with the kernel_size^2 crop of IFFT(H); rescale by the corner pixel."""
+def _cnn_free_plan(Y, X, B, energy_ev, psize_cm, free_prop_cm):
+    """free-space step of the cnn propagator (propagation.py:112-128: 'inf' or the TF kernel with PI = 3.1415927) as a plan"""
+    key = ('cnnfree', (B, Y, X), float(energy_ev), tuple(np.atleast_1d(psize_cm).astype(float)), free_prop_cm, torch.cuda.current_device())
+    return _cached_plan(key, lambda: MultislicePlan(Y, X, B, 1, energy_ev, psize_cm, free_prop_cm=free_prop_cm, pi=PI_CNN))
+
+
+def _cnn_setup(grid_delta, grid_beta, probe_real, probe_imag, energy_ev, psize_cm, kernel_size):
     assert kernel_size % 2 == 1, 'kernel_size must be an odd number.'
-    as_torch = _is_torch(grid_delta)
     B, Y, X, Z = (int(s) for s in grid_delta.shape)
     dev = _device()
     voxel_nm = np.array(psize_cm) * 1.e7
@@ -232,22 +234,72 @@ def multislice_propagate_cnn(grid_delta, grid_beta, probe_real, probe_imag, ener
     db = torch.empty((Z, B, Y, X, 2), dtype=torch.float32, device=dev)
     check(lib.bdof_pack_db(_ptr(d), _ptr(b), _ptr(db), B, Y, X, Z, st))
     probe = _probe_c64(probe_real, probe_imag, (Y, X))
-    out = torch.empty((B, Y, X), dtype=torch.complex64, device=dev)
-    work = torch.empty((2, B, Y, X), dtype=torch.complex64, device=dev)
-    check(lib.bdof_cnn_forward(_ptr(db), _ptr(probe), _ptr(out), _ptr(work), B, Y, X, Z, _hptr(kern), kernel_size,
-                               float(k_dz), st))
-    # propagation.py:79,109-110: rescale by the corner pixel
+    return (B, Y, X, Z), dev, k_dz, kern, db, probe, st
+
+
+def multislice_propagate_cnn(grid_delta, grid_beta, probe_real, probe_imag, energy_ev, psize_cm, kernel_size=17,
+                             free_prop_cm=None, debug=False):
+    """Real-space ("cnn") multislice (propagation.py:18-133): per slice modulate, pad with the tracked
+    plane-wave edge value, convolve with the kernel_size^2 crop of IFFT(H); rescale by the corner pixel.
+    debug=True also returns (probe_array, seconds): the magnitude of the field after every slice (propagation.py:107,130)."""
+    import time
+    t0 = time.time()
+    as_torch = _is_torch(grid_delta)
+    (B, Y, X, Z), dev, k_dz, kern, db, probe, st = _cnn_setup(grid_delta, grid_beta, probe_real, probe_imag, energy_ev, psize_cm,
+                                                              kernel_size)
+    probe_array = None
+    if debug:
+        slices = torch.empty((Z + 1, B, Y, X), dtype=torch.complex64, device=dev)
+        check(lib.bdof_cnn_forward_store(_ptr(db), _ptr(probe), _ptr(slices), B, Y, X, Z, _hptr(kern), kernel_size, float(k_dz), st))
+        out = slices[Z]
+        probe_array = slices[1:].abs()
+    else:
+        out = torch.empty((B, Y, X), dtype=torch.complex64, device=dev)
+        work = torch.empty((2, B, Y, X), dtype=torch.complex64, device=dev)
+        check(lib.bdof_cnn_forward(_ptr(db), _ptr(probe), _ptr(out), _ptr(work), B, Y, X, Z, _hptr(kern), kernel_size,
+                                   float(k_dz), st))
+    # propagation.py:79,109-110: rescale by the corner pixel of batch element 0
     out = out * (probe[0, 0] / out[0, 0, 0])
     if free_prop_cm is not None:
-        if isinstance(free_prop_cm, str):
-            out = torch.fft.fftshift(torch.fft.fft2(out), dim=(1, 2))
-        else:
-            hf = torch.as_tensor(np.fft.ifftshift(get_kernel(free_prop_cm * 1e7, lmbda_nm, voxel_nm, (Y, X, Z), pi=PI_CNN))).to(dev, torch.complex64)
-            out = torch.fft.ifft2(torch.fft.fft2(out) * hf)
-    if as_torch:
-        res = out if grid_delta.is_cuda else out.cpu()
-    else:
-        res = out.cpu().numpy()
+        out = _cnn_free_plan(Y, X, B, energy_ev, psize_cm, free_prop_cm).free_prop(out)
+    conv = (lambda t: t if grid_delta.is_cuda else t.cpu()) if as_torch else (lambda t: t.cpu().numpy())
+    res = conv(out)
     if debug:
-        return res, None, 0.0
+        pa = conv(probe_array)
+        return res, (pa if as_torch else list(pa)), time.time() - t0
     return res
+
+
+def cnn_loss_and_grad(grid_delta, grid_beta, probe_real, probe_imag, energy_ev, psize_cm, target_mag, kernel_size=17,
+                      free_prop_cm=None):
+    """loss = mean((|psi| - target)^2) through multislice_propagate_cnn and its gradient (g_delta, g_beta) [B,Y,X,Z] -- the pair
+    autograd.grad(calculate_loss, [0, 1]) returns in the cnn_propagator drivers (fullfield.py:93-121,329; ptychography.py:30-81,
+    248) for already rotated / cut batches.  The chain runs on bdof_cnn_forward_store / bdof_cnn_adjoint; the corner-pixel
+    rescaling (propagation.py:79,109-110) and its gradient, which couples every batch element to pixel [0,0,0], are applied here."""
+    as_torch = _is_torch(grid_delta)
+    (B, Y, X, Z), dev, k_dz, kern, db, probe, st = _cnn_setup(grid_delta, grid_beta, probe_real, probe_imag, energy_ev, psize_cm,
+                                                              kernel_size)
+    slices = torch.empty((Z + 1, B, Y, X), dtype=torch.complex64, device=dev)
+    check(lib.bdof_cnn_forward_store(_ptr(db), _ptr(probe), _ptr(slices), B, Y, X, Z, _hptr(kern), kernel_size, float(k_dz), st))
+    psi_z = slices[Z]
+    initial, f = probe[0, 0].to(torch.complex128), psi_z[0, 0, 0].to(torch.complex128)
+    s_ = initial / f
+    psi = (psi_z * s_.to(torch.complex64)).contiguous()
+    fplan = _cnn_free_plan(Y, X, B, energy_ev, psize_cm, free_prop_cm)
+    exit_wave = fplan.free_prop(psi) if free_prop_cm is not None else psi
+    loss, g = fplan.loss_mag(exit_wave, _to_dev(target_mag, torch.float32))
+    if free_prop_cm is not None:
+        g = fplan.free_prop_adjoint(g)
+    g_f = torch.sum(torch.conj(-initial * psi_z.to(torch.complex128) / f ** 2) * g.to(torch.complex128))
+    G = torch.empty((2, B, Y, X), dtype=torch.complex64, device=dev)
+    G[0] = torch.conj(s_).to(torch.complex64) * g
+    G[0, 0, 0, 0] += g_f.to(torch.complex64)
+    check(lib.bdof_cnn_adjoint(_ptr(db), _ptr(slices), _ptr(G), _ptr(db), B, Y, X, Z, _hptr(kern), kernel_size, float(k_dz), st))
+    g_d = torch.empty((B, Y, X, Z), dtype=torch.float32, device=dev)
+    g_b = torch.empty((B, Y, X, Z), dtype=torch.float32, device=dev)
+    check(lib.bdof_unpack_db(_ptr(db), _ptr(g_d), _ptr(g_b), B, Y, X, Z, st))
+    if as_torch and not grid_delta.is_cuda:
+        g_d, g_b = g_d.cpu(), g_b.cpu()
+    elif not as_torch:
+        g_d, g_b = g_d.cpu().numpy(), g_b.cpu().numpy()
+    return loss, (g_d, g_b), exit_wave

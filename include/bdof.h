@@ -126,8 +126,9 @@ int  bdof_plan_set_t_stash(bdof_plan* p, float* d_stash);
  * ONE object d_obj_db [n_slice][oy][ox][2] -- the probe windows of the ptychography model (tensorflow_recon/ptychography.py:62-76).
  * d_origin_yx [batch][2] int32 (device) = window origins, pixels outside the object are vacuum.  While set, bdof_forward /
  * bdof_adjoint take the OBJECT as d_db / d_db_inout (read only) and read (delta, beta) straight through the windows (the
- * object slice is L2 resident), so no [n_slice][batch][ny][nx] copy of the object is ever cut; the transmission stash is off
- * and bdof_adjoint writes the per-window gradients to d_grad_out (required; accumulate them with bdof_patch_gather_add).
+ * object slice is L2 resident), so no [n_slice][batch][ny][nx] copy of the object is ever cut; bdof_adjoint writes the
+ * per-window gradients to d_grad_out (required; accumulate them with bdof_patch_gather_add), which may also serve as the
+ * transmission stash (bdof_plan_set_t_stash).
  * d_origin_yx = NULL switches the mode off.  bdof_plan_is_resident tells whether the plan runs the resident kernels. */
 int  bdof_plan_set_windows(bdof_plan* p, int oy, int ox, const int* d_origin_yx);
 int  bdof_plan_is_resident(const bdof_plan* p);
@@ -164,6 +165,17 @@ int  bdof_patch_gather_add(const float* d_grad_patches, int n_slice, int oy, int
 int  bdof_cnn_forward(const float* d_db, const float* d_probe, float* d_exit, float* d_work, int batch,
                       int ny, int nx, int n_slice, const double* h_kernel, int kernel_size, double k_dz,
                       void* cuda_stream);
+
+/* Gradient through the real-space propagator (what autograd.grad(calculate_loss) differentiates in cnn_propagator/fullfield.py:
+ * 93-121,329 and ptychography.py:30-81,248).  bdof_cnn_forward_store keeps the field entering every slice: d_slices
+ * [n_slice + 1][batch][ny][nx] complex64, slices[0] = the probe, slices[n_slice] = the chain output BEFORE the corner-pixel
+ * rescaling of propagation.py:109-110 (the host side applies it and its gradient).  bdof_cnn_adjoint back-propagates d_G
+ * (gradient w.r.t. slices[n_slice]; [2][batch][ny][nx], second field = work space): d_grad_out [n_slice][batch][ny][nx][2] =
+ * (dL/ddelta, dL/dbeta); on return d_G[0] is the gradient w.r.t. the entrance field of every batch element. */
+int  bdof_cnn_forward_store(const float* d_db, const float* d_probe, float* d_slices, int batch, int ny, int nx, int n_slice,
+                            const double* h_kernel, int kernel_size, double k_dz, void* cuda_stream);
+int  bdof_cnn_adjoint(const float* d_db, const float* d_slices, float* d_G, float* d_grad_out, int batch, int ny, int nx,
+                      int n_slice, const double* h_kernel, int kernel_size, double k_dz, void* cuda_stream);
 
 /* nearest-neighbour rotation of the object about the y axis, in the (x, z) plane, and its transpose
  * (apply_rotation and the autograd of its fancy index, cnn_propagator/util.py:374-402).  d_obj_db [nz][ny][nx][2];
@@ -226,6 +238,9 @@ int  bdof_field_multiply(const float* d_in, const float* d_mult, float* d_out, i
 
 /* The free-space step of the plan on its own (npfuncs.py:43-61): out = free_prop(in), [batch][ny][nx]. */
 int  bdof_free_prop(bdof_plan* p, const float* d_in, float* d_out);
+
+/* Adjoint of the free-space step on its own: out = free_prop^H(in) (the first stage of bdof_adjoint). */
+int  bdof_free_prop_adjoint(bdof_plan* p, const float* d_in, float* d_out);
 
 /* Bytes of device memory the plan owns (work fields + slice store). */
 int  bdof_plan_workspace_bytes(const bdof_plan* p, size_t* bytes_out);

@@ -375,6 +375,75 @@ def multislice_propagate_cnn(grid_delta, grid_beta, probe_real, probe_imag, ener
     return probe
 
 
+def cnn_loss_and_grad(grid_delta, grid_beta, probe_real, probe_imag, energy_ev, psize_cm, target_mag, kernel_size=17,
+                      free_prop_cm=None):
+    """loss = mean((|psi| - target)^2) through multislice_propagate_cnn and its gradient w.r.t. delta, beta [B,Y,X,Z] -- what
+    autograd.grad(calculate_loss) differentiates in cnn_propagator/fullfield.py:93-121,329 and ptychography.py:30-81,248.
+    Hand adjoint: per slice psi' = conv_valid(pad(psi t, edge), K) is linear in u = psi t with a constant edge, so
+    G_u[y,x] = sum_ab conj(K[a,b]) G'[y - p + a, x - p + b]; the final rescaling by psi_0[0,0,0] / psi_Z[0,0,0] (batch element
+    0's corner pixel, propagation.py:79,109-110) couples every batch element to that one pixel.  Pinned against
+    torch.autograd in tests/test_oracle.py (no reference gradient exists to run: HIPS autograd is absent)."""
+    gd = np.asarray(grid_delta, dtype=np.float64)
+    gb = np.asarray(grid_beta, dtype=np.float64)
+    B, Y, X, Z = gd.shape
+    lmbda_nm = 1240. / energy_ev
+    voxel_nm = np.array(psize_cm) * 1.e7
+    k = 2. * np.pi * voxel_nm[-1] / lmbda_nm
+    kern = cnn_kernel(energy_ev, psize_cm, np.array([Y, X, Z]), kernel_size)
+    pad = (kernel_size - 1) // 2
+    probe = np.tile(np.asarray(probe_real) + 1j * np.asarray(probe_imag), [B, 1, 1]).astype(np.complex128)
+    initial = probe[0, 0, 0]
+    edge_val = 1.0 + 0j
+    ksum = kern.sum()
+    slices = []
+    for i in range(Z):
+        slices.append(probe)
+        u = probe * np.exp(1j * k * gd[..., i] - k * gb[..., i])
+        padded = np.pad(u, [[0, 0], [pad, pad], [pad, pad]], mode='constant', constant_values=edge_val)
+        out = np.zeros_like(u)
+        for a in range(kernel_size):
+            for b in range(kernel_size):
+                out += kern[a, b] * padded[:, 2 * pad - a:2 * pad - a + Y, 2 * pad - b:2 * pad - b + X]
+        probe = out
+        edge_val = ksum * edge_val
+    f = probe[0, 0, 0]
+    psi = probe * (initial / f)
+    hf = None
+    if free_prop_cm is not None:
+        if isinstance(free_prop_cm, str):
+            exit_wave = fftshift(fft2(psi), axes=[1, 2])
+        else:
+            hf = get_kernel(free_prop_cm * 1e7, lmbda_nm, voxel_nm, np.array([Y, X, Z]), pi=PI_CNN)
+            exit_wave = _propagate(psi, hf)
+    else:
+        exit_wave = psi
+    loss, g = loss_mag(exit_wave, target_mag)
+    if free_prop_cm is not None:
+        if isinstance(free_prop_cm, str):
+            g = ifft2(ifftshift(g, axes=[1, 2])) * (Y * X)
+        else:
+            g = ifft2(ifftshift(fftshift(fft2(g), axes=[1, 2]) * np.conj(hf), axes=[1, 2]))
+    # rescaling psi = s psi_Z, s = initial / f, f = psi_Z[0,0,0]
+    s_ = initial / f
+    g_f = np.sum(np.conj(-initial * probe / f ** 2) * g)
+    g = np.conj(s_) * g
+    g[0, 0, 0] += g_f
+    g_d = np.zeros_like(gd)
+    g_b = np.zeros_like(gd)
+    for i in range(Z - 1, -1, -1):
+        gp = np.pad(g, [[0, 0], [pad, pad], [pad, pad]], mode='constant', constant_values=0)
+        gu = np.zeros_like(g)
+        for a in range(kernel_size):
+            for b in range(kernel_size):
+                gu += np.conj(kern[a, b]) * gp[:, a:a + Y, b:b + X]          # G'[y - p + a, x - p + b]
+        t = np.exp(1j * k * gd[..., i] - k * gb[..., i])
+        w = np.conj(gu) * (slices[i] * t)
+        g_d[..., i] = -k * w.imag
+        g_b[..., i] = -k * w.real
+        g = np.conj(t) * gu
+    return loss, g_d, g_b, exit_wave
+
+
 # ---------------------------------------------------------------------------------------------
 # model heads (rotation = identity, theta = 0: rotation is a "next" row, SURVEY 8f-1)
 # ---------------------------------------------------------------------------------------------

@@ -405,3 +405,33 @@ def test_ptychography_objective_step_matches_oracle_update(bd, probe_size):
                                  n_pos_per_step=len(pos), step_size=1e-7)
     pty2.step(pos, torch.as_tensor(np.abs(prj).astype(np.float32)).pin_memory())
     assert torch.equal(pty.grad, pty2.grad) and torch.equal(pty.obj, pty2.obj)
+
+
+@pytest.mark.parametrize('ks', [5, 17])
+@pytest.mark.parametrize('free', [None, 'inf', 2e-6])
+def test_cnn_propagator_gradient_matches_oracle(bd, ks, free):
+    # a-5 gradient (autograd.grad(calculate_loss) in cnn_propagator/fullfield.py:329): CUDA adjoint of the real-space chain,
+    # incl. the corner-pixel rescaling, against the oracle's hand adjoint (itself pinned to torch.autograd)
+    shape = (2, 40, 48, 6)
+    gd, gb = mo.random_phantom(shape, seed=31, delta_scale=1e-3, beta_scale=1e-4)
+    pr, pi = mo.gaussian_probe(shape[1:3], 16., 14., 0.5)
+    pr = pr + 0.5
+    rng = np.random.default_rng(32)
+    target = rng.random(shape[:3]) * (20 if free == 'inf' else 1) + 0.3
+    lo, gdo, gbo, psio = mo.cnn_loss_and_grad(gd, gb, pr, pi, 5000, [1e-7] * 3, target, kernel_size=ks, free_prop_cm=free)
+    loss, (g_d, g_b), psi = bd.cnn_loss_and_grad(gd, gb, pr, pi, 5000, [1e-7] * 3, target, kernel_size=ks, free_prop_cm=free)
+    assert rel_l2(psi.cpu().numpy(), psio) < 1e-5
+    assert abs(loss.item() - lo) < 2e-5 * abs(lo)
+    assert rel_l2(g_d, gdo) < 1e-4 and rel_l2(g_b, gbo) < 1e-4
+
+
+def test_cnn_propagator_debug_returns_slice_magnitudes(bd):
+    # propagation.py:107,130: debug=True returns (probe, [|probe| after every slice], seconds)
+    shape = (2, 32, 40, 4)
+    gd, gb = mo.random_phantom(shape, seed=33, delta_scale=1e-3, beta_scale=1e-4)
+    one, zero = np.ones(shape[1:3]), np.zeros(shape[1:3])
+    res, pa, secs = bd.multislice_propagate_cnn(gd, gb, one, zero, 5000, [1e-7] * 3, kernel_size=5, debug=True)
+    plain = bd.multislice_propagate_cnn(gd, gb, one, zero, 5000, [1e-7] * 3, kernel_size=5)
+    assert rel_l2(res, plain) < 1e-6 and len(pa) == 4 and pa[0].shape == shape[:3] and secs > 0
+    # the magnitude after the last slice, rescaled like the result, is |result|
+    assert rel_l2(pa[-1] * abs(1.0 / (res[0, 0, 0] / plain[0, 0, 0])) * np.abs(plain[0, 0, 0]) / pa[-1][0, 0, 0], np.abs(plain)) < 1e-5

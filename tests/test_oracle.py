@@ -281,3 +281,49 @@ def test_unbatched_oracle_reduces_to_batched_tf_semantics():
     a1 = mo.multislice_propagate_unbatched(gd[0, ..., :1], gb[0, ..., :1], pr, pi, 5000, 1e-7)
     b1 = mo.multislice_propagate_batch(gd[..., :1], gb[..., :1], pr, pi, 5000, 1e-7)[0]
     assert rel_l2(a1, b1) > 1e-3
+
+
+@pytest.mark.parametrize('free', [None, 'inf', 2e-6])
+def test_cnn_hand_adjoint_matches_torch_autograd(free):
+    # a-5 gradient: the reference differentiates multislice_propagate_cnn with HIPS autograd (cnn_propagator/fullfield.py:329);
+    # the oracle's hand adjoint (incl. the corner-pixel rescaling that couples the batch) against torch.autograd in complex128
+    B, Y, X, Z, ks = 2, 12, 14, 3, 5
+    psize = [1e-7] * 3
+    gd, gb = mo.random_phantom((B, Y, X, Z), seed=5, delta_scale=2e-3, beta_scale=2e-4)
+    gd, gb = gd.astype(np.float64), gb.astype(np.float64)
+    pr, pi = mo.gaussian_probe((Y, X), 6., 6., 0.5)
+    pr = pr + 0.5
+    rng = np.random.default_rng(6)
+    target = rng.random((B, Y, X)) * (10 if free == 'inf' else 1) + 0.2
+    loss, g_d, g_b, psi = mo.cnn_loss_and_grad(gd, gb, pr, pi, 5000, psize, target, kernel_size=ks, free_prop_cm=free)
+    assert rel_l2(psi, mo.multislice_propagate_cnn(gd, gb, pr, pi, 5000, psize, kernel_size=ks, free_prop_cm=free)) < 1e-13
+    # torch restatement of propagation.py:77-128
+    k = 2. * np.pi * 1.0 / (1240. / 5000)
+    kern = torch.as_tensor(mo.cnn_kernel(5000, psize, np.array([Y, X, Z]), ks))
+    pad = (ks - 1) // 2
+    td = torch.tensor(gd, requires_grad=True)
+    tb = torch.tensor(gb, requires_grad=True)
+    probe = torch.as_tensor(np.tile(pr + 1j * pi, [B, 1, 1]))
+    initial = probe[0, 0, 0]
+    edge = torch.tensor(1.0 + 0j, dtype=torch.complex128)
+    for i in range(Z):
+        u = probe * torch.exp(torch.complex(-k * tb[..., i], k * td[..., i]))
+        padded = edge * torch.ones((B, Y + 2 * pad, X + 2 * pad), dtype=torch.complex128)
+        padded = padded.clone()
+        padded[:, pad:pad + Y, pad:pad + X] = u
+        out = torch.zeros_like(u)
+        for a in range(ks):
+            for b in range(ks):
+                out = out + kern[a, b] * padded[:, 2 * pad - a:2 * pad - a + Y, 2 * pad - b:2 * pad - b + X]
+        probe = out
+        edge = kern.sum() * edge
+    probe = probe * (initial / probe[0, 0, 0])
+    if free == 'inf':
+        probe = torch.fft.fftshift(torch.fft.fft2(probe), dim=(1, 2))
+    elif free is not None:
+        hf = torch.as_tensor(mo.get_kernel(free * 1e7, 1240. / 5000, np.array(psize) * 1e7, [Y, X, Z], pi=mo.PI_CNN))
+        probe = torch.fft.ifft2(torch.fft.ifftshift(torch.fft.fftshift(torch.fft.fft2(probe), dim=(1, 2)) * hf, dim=(1, 2)))
+    tl = ((probe.abs() - torch.as_tensor(target)) ** 2).mean()
+    tl.backward()
+    assert abs(tl.item() - loss) < 1e-12 * abs(loss)
+    assert rel_l2(g_d, td.grad.numpy()) < 1e-10 and rel_l2(g_b, tb.grad.numpy()) < 1e-10
