@@ -29,6 +29,9 @@ _LAZY = {
     'ptycho_position_losses': 'models',
     'dynamic_dropping': 'models',
     'get_kernel': 'util',
+    'get_kernel_ir': 'propagation',
+    'create_fullfield_data_numpy': 'simulation',
+    'create_ptychography_data_batch_numpy': 'simulation',
     'gen_mesh': 'util',
 }
 
@@ -37,6 +40,6 @@ def __getattr__(name):
     if name in _LAZY:
         mod = importlib.import_module('.' + _LAZY[name], __name__)
         return getattr(mod, name)
-    if name in ('capi', 'plan', 'propagation', 'models', 'util', 'build', 'dist', 'rotation', 'tiling', 'np_funcs'):
+    if name in ('capi', 'plan', 'propagation', 'models', 'util', 'build', 'dist', 'rotation', 'tiling', 'np_funcs', 'simulation'):
         return importlib.import_module('.' + name, __name__)
     raise AttributeError(name)

@@ -203,11 +203,61 @@ for name, args in {
 np.savez_compressed(out, **res)
 '''
 
+CHILD_SIM = r'''
+import sys, os, types, tempfile
+import numpy as np
+from unittest.mock import MagicMock
+for m in ("tensorflow", "tensorflow.contrib", "tensorflow.contrib.image", "dxchange", "matplotlib", "matplotlib.pyplot"):
+    sys.modules[m] = MagicMock()
+# in-memory stand-in for h5py that keeps what the simulators write to exchange/data
+STORE = {}
+class _Dat:
+    def __init__(self, shape, dtype): self.a = np.zeros(shape, dtype=dtype)
+    def __setitem__(self, k, v): self.a[k] = v
+class _Grp:
+    def create_dataset(self, name, shape=None, dtype=None, **kw):
+        d = _Dat(shape, dtype); STORE[name] = d; return d
+class _File:
+    def __init__(self, *a, **k): pass
+    def create_group(self, name): return _Grp()
+    def close(self): pass
+h5 = types.ModuleType("h5py"); h5.File = _File
+sys.modules["h5py"] = h5
+sys.path.insert(0, sys.argv[1] + "/tensorflow_recon")
+import simulation                      # tensorflow_recon/simulation.py, unmodified
+out = sys.argv[2]
+sys.path.insert(0, sys.argv[3] + "/oracle")
+import multislice_oracle as mo
+res = {}
+tmp = tempfile.mkdtemp()
+rng = np.random.default_rng(41)
+Y, X, Z = 24, 24, 8
+yy, xx, zz = np.meshgrid(np.arange(Y), np.arange(X), np.arange(Z), indexing="ij")
+blob = ((yy - 11) ** 2 + (xx - 13) ** 2 + 4 * (zz - 4) ** 2 < 60) * 1.0 + ((yy - 6) ** 2 + (xx - 7) ** 2 < 9) * 0.5
+gd = blob * 3e-4 * (1 + 0.2 * rng.random((Y, X, Z)))
+gb = blob * 3e-5
+np.save(os.path.join(tmp, "grid_delta.npy"), gd); np.save(os.path.join(tmp, "grid_beta.npy"), gb)
+res["phantom_delta"] = gd; res["phantom_beta"] = gb
+simulation.create_fullfield_data_numpy(5000, 1e-7, None, 4, tmp, tmp, "ff_plane.h5", batch_size=2, probe_type="plane",
+                                       theta_st=0, theta_end=np.pi)
+res["ff_plane"] = STORE["data"].a.copy()
+simulation.create_fullfield_data_numpy(5000, 1e-7, 1e-4, 3, tmp, tmp, "ff_gauss.h5", batch_size=1, probe_type="gaussian",
+                                       theta_st=0, theta_end=2 * np.pi, probe_mag_sigma=8., probe_phase_sigma=8., probe_phase_max=0.5)
+res["ff_gauss_free"] = STORE["data"].a.copy()
+pos = [(3, 3), (12, 12), (20, 22), (9, 15), (0, 23)]
+simulation.create_ptychography_data_batch_numpy(5000, 1e-7, 2, tmp, tmp, "pty.h5", pos, probe_type="gaussian", probe_size=(18, 18),
+                                                theta_st=0, theta_end=np.pi / 3, probe_circ_mask=None, minibatch_size=3,
+                                                probe_mag_sigma=3., probe_phase_sigma=3., probe_phase_max=0.5)
+res["pty_pos"] = np.array(pos)
+res["pty"] = STORE["data"].a.copy()
+np.savez_compressed(out, **res)
+'''
+
 
 def main():
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]
-    for name, code in (('ref_fft.npz', CHILD_FFT), ('ref_cnn.npz', CHILD_CNN), ('ref_rot.npz', CHILD_ROT), ('ref_npfuncs_cnn.npz', CHILD_NPF), ('ref_ir.npz', CHILD_IR)):
+    for name, code in (('ref_fft.npz', CHILD_FFT), ('ref_cnn.npz', CHILD_CNN), ('ref_rot.npz', CHILD_ROT), ('ref_npfuncs_cnn.npz', CHILD_NPF), ('ref_ir.npz', CHILD_IR), ('ref_sim.npz', CHILD_SIM)):
         if only and name not in only:
             continue
         path = os.path.join(OUT, name)

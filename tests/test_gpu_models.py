@@ -435,3 +435,32 @@ def test_cnn_propagator_debug_returns_slice_magnitudes(bd):
     assert rel_l2(res, plain) < 1e-6 and len(pa) == 4 and pa[0].shape == shape[:3] and secs > 0
     # the magnitude after the last slice, rescaled like the result, is |result|
     assert rel_l2(pa[-1] * abs(1.0 / (res[0, 0, 0] / plain[0, 0, 0])) * np.abs(plain[0, 0, 0]) / pa[-1][0, 0, 0], np.abs(plain)) < 1e-5
+
+
+def test_simulators_match_reference_outputs(bd, golden_dir, tmp_path):
+    # create_fullfield_data_numpy / create_ptychography_data_batch_numpy (tensorflow_recon/simulation.py:80-161,
+    # 283-386) executed unmodified in the build container (oracle/gen_golden.py CHILD_SIM, in-memory stand-in for h5py) vs the
+    # drop-ins, which rotate with the same scipy call and project on the GPU
+    from beyond_dof_b200 import simulation
+    g = np.load(os.path.join(golden_dir, 'ref_sim.npz'))
+    ph = str(tmp_path)
+    np.save(os.path.join(ph, 'grid_delta.npy'), g['phantom_delta'])
+    np.save(os.path.join(ph, 'grid_beta.npy'), g['phantom_beta'])
+    out = simulation.create_fullfield_data_numpy(5000, 1e-7, None, 4, ph, ph, 'ff_plane.h5', batch_size=2, probe_type='plane',
+                                                 theta_st=0, theta_end=np.pi)
+    assert out.shape == g['ff_plane'].shape and out.dtype == np.complex64
+    assert rel_l2(out, g['ff_plane']) < 1e-5 and rel_l2(np.abs(out) ** 2, np.abs(g['ff_plane']) ** 2) < 1e-5
+    out = simulation.create_fullfield_data_numpy(5000, 1e-7, 1e-4, 3, ph, ph, 'ff_gauss.h5', batch_size=1, probe_type='gaussian',
+                                                 theta_st=0, theta_end=2 * np.pi, probe_mag_sigma=8., probe_phase_sigma=8.,
+                                                 probe_phase_max=0.5)
+    assert rel_l2(out, g['ff_gauss_free']) < 1e-5
+    out = simulation.create_ptychography_data_batch_numpy(5000, 1e-7, 2, ph, ph, 'pty.h5', [tuple(p) for p in g['pty_pos']],
+                                                          probe_type='gaussian', probe_size=(18, 18), theta_st=0, theta_end=np.pi / 3,
+                                                          probe_circ_mask=None, minibatch_size=3, probe_mag_sigma=3.,
+                                                          probe_phase_sigma=3., probe_phase_max=0.5)
+    assert out.shape == g['pty'].shape
+    assert rel_l2(out, g['pty']) < 1e-5 and rel_l2(np.abs(out) ** 2, np.abs(g['pty']) ** 2) < 1e-5
+    # the file lands where the reference writes it (HDF5 exchange/data, or <fname>.npy without h5py)
+    assert os.path.exists(os.path.join(ph, 'pty.h5')) or os.path.exists(os.path.join(ph, 'pty.h5.npy'))
+    with pytest.raises(NotImplementedError):
+        simulation.create_fullfield_data_numpy(5000, 1e-7, None, 1, ph, ph, 'x.h5', probe_type='point')
