@@ -60,6 +60,7 @@ def build_lib(force=False, verbose=True):
     jobs = [(os.path.join(CSRC, 'bdof.cu'), os.path.join(OBJ, 'bdof.o'), [], os.path.join(OBJ, 'bdof.log'))]
     jobs.append((os.path.join(CSRC, 'dpexchange.cu'), os.path.join(OBJ, 'dpexchange.o'), [], os.path.join(OBJ, 'dpexchange.log')))
     jobs.append((os.path.join(CSRC, 'genericfft.cu'), os.path.join(OBJ, 'genericfft.o'), [], os.path.join(OBJ, 'genericfft.log')))
+    jobs.append((os.path.join(CSRC, 'tilehalo.cu'), os.path.join(OBJ, 'tilehalo.o'), [], os.path.join(OBJ, 'tilehalo.log')))
     jobs.append((os.path.join(CSRC, 'resident_inst.cu'), os.path.join(OBJ, 'resident_inst.o'), [], os.path.join(OBJ, 'resident_inst.log')))
     for n in SIZES:
         jobs.append((os.path.join(CSRC, 'line_inst.cu'), os.path.join(OBJ, 'line_%d.o' % n), ['-DBDOF_N=%d' % n],

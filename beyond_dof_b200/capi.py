@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, os.environ.get('BDOF_LIB', 'libbdof.so'))
 PROPAGATE_LAST = 1 << 0
 STORE_SLICES = 1 << 1
 Z_BROADCAST = 1 << 2
+STEPWISE = 1 << 3
 FREE_NONE, FREE_INF, FREE_TF = 0, 1, 2
 
 # every symbol include/bdof.h declares (checked by tests/test_capi.py)
@@ -23,6 +24,8 @@ SYMBOLS = [
     'bdof_finite_support', 'bdof_plan_set_t_stash', 'bdof_rotate_bilinear', 'bdof_rotate_bilinear_adjoint',
     'bdof_dp_create', 'bdof_dp_destroy', 'bdof_dp_handle_bytes', 'bdof_dp_export', 'bdof_dp_connect', 'bdof_dp_grad_ptr',
     'bdof_dp_bucket', 'bdof_dp_gather', 'bdof_dp_finish', 'bdof_plan_last_times', 'bdof_pack_db_rows', 'bdof_unpack_db_rows', 'bdof_plan_set_stream', 'bdof_debug_fft_gain', 'bdof_field_multiply', 'bdof_patch_gather_add', 'bdof_plan_set_windows', 'bdof_plan_is_resident', 'bdof_cnn_forward_store', 'bdof_cnn_adjoint', 'bdof_free_prop_adjoint',
+    'bdof_tiles_create', 'bdof_tiles_destroy', 'bdof_tiles_handle_bytes', 'bdof_tiles_export', 'bdof_tiles_connect',
+    'bdof_tiles_block_ptr', 'bdof_tiles_cut', 'bdof_tiles_paste', 'bdof_tiles_halo_exchange', 'bdof_slice_step_seq',
 ]
 
 
@@ -67,6 +70,7 @@ def _load():
     lib.bdof_profile_begin.argtypes = [vp]
     lib.bdof_debug_set_buffer.argtypes = [vp]
     lib.bdof_slice_step.argtypes = [vp, vp, vp, vp, i32]
+    lib.bdof_slice_step_seq.argtypes = [vp, vp, vp, vp, i32, i32]
     lib.bdof_plan_set_bucket_events.argtypes = [vp, i32, vp]
     lib.bdof_set_sm_reserve.argtypes = [i32]
     lib.bdof_profile_end.argtypes = [vp, i32, vp, vp]
@@ -90,6 +94,16 @@ def _load():
     lib.bdof_dp_bucket.argtypes = [vp, sz, sz, vp]
     lib.bdof_dp_gather.argtypes = [vp, sz, sz, vp]
     lib.bdof_dp_finish.argtypes = [vp, vp]
+    lib.bdof_tiles_create.argtypes = [ctypes.POINTER(vp), i32, i32, i32, i32, i32, i32]
+    lib.bdof_tiles_destroy.argtypes = [vp]
+    lib.bdof_tiles_destroy.restype = None
+    lib.bdof_tiles_handle_bytes.argtypes = []
+    lib.bdof_tiles_export.argtypes = [vp, vp]
+    lib.bdof_tiles_connect.argtypes = [vp, vp]
+    lib.bdof_tiles_block_ptr.argtypes = [vp, i32, ctypes.POINTER(vp)]
+    lib.bdof_tiles_cut.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp]
+    lib.bdof_tiles_paste.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, vp]
+    lib.bdof_tiles_halo_exchange.argtypes = [vp, i32, vp]
     lib.bdof_plan_last_times.argtypes = [vp, vp, vp]
     lib.bdof_plan_set_stream.argtypes = [vp, vp]
     lib.bdof_debug_fft_gain.argtypes = [i32, vp]
@@ -100,7 +114,7 @@ def _load():
     lib.bdof_unpack_db_rows.argtypes = [vp, vp, vp, i64, i64, i32, i32, i32, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if fn.restype is ctypes.c_int and name not in ('bdof_version', 'bdof_size_supported', 'bdof_dp_handle_bytes', 'bdof_plan_is_resident'):
+        if fn.restype is ctypes.c_int and name not in ('bdof_version', 'bdof_size_supported', 'bdof_dp_handle_bytes', 'bdof_plan_is_resident', 'bdof_tiles_handle_bytes'):
             fn.restype = i32
     return lib
 

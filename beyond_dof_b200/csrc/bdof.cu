@@ -922,7 +922,7 @@ static int col_pass(bdof_plan* p, int variant, const LineParams& q) {
 // sweep kernels: one launch per slice and direction (sweepfft.cuh)
 // ------------------------------------------------------------------------------------------
 static bool use_sweep(const bdof_plan* p) {
-    return p->sweep && !p->generic && !p->full_kernel && p->n_slice >= 2 && pipe_parts(p->nx) > 0 && pipe_parts(p->ny) > 0;
+    return p->sweep && !(p->flags & BDOF_STEPWISE) && !p->generic && !p->full_kernel && p->n_slice >= 2 && pipe_parts(p->nx) > 0 && pipe_parts(p->ny) > 0;
 }
 // Small square fields run as ONE kernel per direction with the field resident on chip (residentfft.cuh); same schedule and
 // multiplier tables as the sweep kernels.  BDOF_RESIDENT=0 selects the sweep kernels instead.
@@ -1766,12 +1766,16 @@ extern "C" int bdof_free_prop(bdof_plan* p, const float* d_in_f, float* d_out_f)
 // single-slice stepping (tiling with halo exchange) and gradient buckets (overlapped all-reduce)
 // ------------------------------------------------------------------------------------------
 extern "C" int bdof_slice_step(bdof_plan* p, const float* d_in, const float* d_db_slice, float* d_out, int propagate) {
+    return bdof_slice_step_seq(p, d_in, d_db_slice, d_out, propagate, -1);
+}
+extern "C" int bdof_slice_step_seq(bdof_plan* p, const float* d_in, const float* d_db_slice, float* d_out, int propagate, int slice_index) {
     if (!p || !d_in || !d_db_slice || !d_out) return fail(BDOF_E_BADARG, "null");
+    if (slice_index >= 0 && !(p->flags & BDOF_STEPWISE)) return fail(BDOF_E_STATE, "bdof_slice_step_seq needs a plan created with BDOF_STEPWISE");
     if (!p->have_kernel) return fail(BDOF_E_STATE, "bdof_set_kernel has not been called");
     const float2* in = reinterpret_cast<const float2*>(d_in);
     const float2* db = reinterpret_cast<const float2*>(d_db_slice);
     float2* out = reinterpret_cast<float2*>(d_out);
-    if (propagate) return propagate_slice(p, in, db, out, nullptr, -1);     // a step on its own: the plain table
+    if (propagate) return propagate_slice(p, in, db, out, nullptr, slice_index);     // -1: a step on its own, the plain table
     k_modulate<<<blocks_for(p->F, 256), 256, 0, p->stream>>>(in, db, out, p->F, float(p->k_dz));
     return launch_check("k_modulate");
 }

@@ -25,7 +25,7 @@ def multislice_propagate_batch_numpy(grid_delta_batch, grid_beta_batch, probe_re
     B, Y, X, Z = shape
     key = ('npf', shape, float(energy_ev), float(psize_cm), free_prop_cm, torch.cuda.current_device() if torch.cuda.is_available() else -1)
     plan = _cached_plan(key, lambda: MultislicePlan(Y, X, B, Z, energy_ev, psize_cm, free_prop_cm=free_prop_cm,
-                                                     propagate_last=False, pi=PI))
+                                                     propagate_last=False, pi=PI, stepwise=True))
     db = plan.pack(_to_dev(grid_delta_batch, torch.float32), _to_dev(grid_beta_batch, torch.float32))
     field = _probe_c64(probe_real, probe_imag, (Y, X)).unsqueeze(0).expand(B, Y, X).contiguous()
     p0 = complex(kernel_factors(plan.voxel_nm[-1], plan.lmbda_nm, plan.voxel_nm, [Y, X, Z], pi=PI)[0])
@@ -33,7 +33,7 @@ def multislice_propagate_batch_numpy(grid_delta_batch, grid_beta_batch, probe_re
     probe_array = torch.empty((Z, B, Y, X), dtype=torch.complex64, device=field.device)
     for i in range(Z):
         prop = i < Z - 1
-        field = plan.slice_step(field, db[i], propagate=prop)
+        field = plan.slice_step(field, db[i], propagate=prop, index=i)
         if prop:
             phase *= p0
         torch.mul(field, phase, out=probe_array[i])

@@ -37,7 +37,7 @@ class MultislicePlan:
     """
 
     def __init__(self, ny, nx, batch, n_slice, energy_ev, psize_cm, free_prop_cm=None, propagate_last=False,
-                 store_slices=False, z_broadcast=False, h=None, pi=PI, device=None):
+                 store_slices=False, z_broadcast=False, h=None, pi=PI, device=None, stepwise=False):
         if not torch.cuda.is_available():
             raise RuntimeError('beyond_dof_b200 needs a CUDA device: the multislice path has no CPU fallback')
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
@@ -60,6 +60,9 @@ class MultislicePlan:
             flags |= capi.STORE_SLICES
         if self.z_broadcast:
             flags |= capi.Z_BROADCAST
+        self.stepwise = bool(stepwise)
+        if self.stepwise:
+            flags |= capi.STEPWISE          # driven slice by slice (slice_step(..., index=i)): per-pass schedule and tables
         self._h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             self.stream = torch.cuda.current_stream(self.device)
@@ -201,15 +204,18 @@ class MultislicePlan:
         check(lib.bdof_forward_host(self._h, _hptr(d), _hptr(b), _hptr(pr), _hptr(out)))
         return out
 
-    def slice_step(self, field, db_slice, out=None, propagate=True):
+    def slice_step(self, field, db_slice, out=None, propagate=True, index=None):
         """One slice: out = P(field * t(db_slice)) (or only the modulation).  field [B,Y,X] complex64,
-        db_slice [B,Y,X,2] float32.  The global phase exp(i k dz) is not applied."""
+        db_slice [B,Y,X,2] float32.  The global phase exp(i k dz) is not applied.
+        index: position of this slice in a chain stepped in order on a stepwise=True plan (selects that slice's entry of the
+        error-feedback multiplier sequence); None = the plain table."""
         self.use_current_stream()
         assert field.is_cuda and field.dtype == torch.complex64 and field.is_contiguous()
         assert db_slice.is_cuda and db_slice.dtype == torch.float32 and db_slice.is_contiguous()
         if out is None:
             out = torch.empty_like(field)
-        check(lib.bdof_slice_step(self._h, _ptr(field), _ptr(db_slice), _ptr(out), 1 if propagate else 0))
+        check(lib.bdof_slice_step_seq(self._h, _ptr(field), _ptr(db_slice), _ptr(out), 1 if propagate else 0,
+                                      -1 if index is None else int(index)))
         return out
 
     def set_t_stash(self, buf):

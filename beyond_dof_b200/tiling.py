@@ -160,3 +160,167 @@ def tiled_multislice(db_tiles, field_tiles, layout, step_fn, n_slice, propagate_
         if prop:
             halo_exchange(field_tiles, layout, rank)
     return field_tiles
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Production path (BASELINE config 5): blocks with aprons in peer-mapped memory, strips stored straight into the neighbours'
+# aprons by a kernel (libbdof: csrc/tilehalo.cu).  The functions above remain as the small reference implementation over
+# torch.distributed point-to-point (CPU / gloo tests).
+# ---------------------------------------------------------------------------------------------------------------------------
+FAST_LENGTHS = (256, 512, 1024, 2048, 4096, 8192)
+
+
+def axis_tiles(block, halo, lengths=FAST_LENGTHS):
+    """Cover one axis of a block of `block` pixels with n windows of ONE power-of-two length L (the register-resident FFT
+    kernels), each owning a contiguous share of the block and seeing at least `halo` pixels beyond it on both sides.  The shares
+    need not be equal and the window need not divide anything: L and n minimise the transformed length n * L.
+    Returns (L, [(window_start, own_start, own_len)], apron) with positions relative to the block; windows may start at -apron."""
+    best = None
+    for L in lengths:
+        if L <= 2 * halo:
+            continue
+        n = -(-block // (L - 2 * halo))
+        if best is None or n * L < best[0] * best[1]:
+            best = (n, L)
+    if best is None:
+        raise ValueError('halo %d too large for the available FFT lengths' % halo)
+    n, L = best
+    edges = [round(k * block / n) for k in range(n + 1)]
+    out, apron = [], 0
+    for k in range(n):
+        own = edges[k + 1] - edges[k]
+        start = edges[k] - (L - own) // 2
+        out.append((start, edges[k], own))
+        apron = max(apron, -start, start + L - block)
+    return L, out, apron
+
+
+class TiledMultislice:
+    """Tiling-based forward multislice of ONE large field over the ranks of the default process group (one process per GPU).
+
+    grid = (gy, gx) blocks; this rank owns block (rank // gx, rank % gx) of the [NY, NX] field.  Every block is covered by local
+    FFT windows (axis_tiles) that see `halo` pixels beyond what they own; per slice the windows are cut from the block (with its
+    apron), stepped with the exact FFT propagator (bdof_slice_step), their owned parts pasted back, and the block's border strips
+    stored into the neighbours' aprons over NVLink peer memory (bdof_tiles_halo_exchange).  The approximation is the truncation
+    of the Fresnel kernel at `halo` pixels (error vs halo).
+
+    db_block_fn(y0, x0, h, w) -> [h, w, 2] float32 CUDA tensor with (delta, beta) of the global pixels y0..y0+h-1, x0..x0+w-1
+    taken PERIODICALLY (the caller wraps indices): an axially repeating object (z_broadcast), evaluated once at set-up.
+    """
+
+    def __init__(self, ny, nx, grid, halo, energy_ev, psize_cm, n_slice, db_block_fn, propagate_last=False, group=None,
+                 lengths=FAST_LENGTHS):
+        import ctypes
+        from .capi import lib, check
+        from .plan import MultislicePlan
+        from .dist import _DeviceBuffer
+        self._lib, self._check = lib, check
+        rank, w = world()
+        gy, gx = int(grid[0]), int(grid[1])
+        if gy * gx != w:
+            raise ValueError('tile grid %dx%d needs %d ranks, the process group has %d' % (gy, gx, gy * gx, w))
+        if ny % gy or nx % gx:
+            raise ValueError('the field must split evenly into the block grid')
+        self.rank, self.gy, self.gx = rank, gy, gx
+        self.ny, self.nx, self.by, self.bx = int(ny), int(nx), ny // gy, nx // gx
+        self.n_slice, self.propagate_last = int(n_slice), bool(propagate_last)
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        self.ly, ty, ay = axis_tiles(self.by, halo, lengths)
+        self.lx, tx, ax = axis_tiles(self.bx, halo, lengths)
+        self.apron = max(ay, ax)
+        self.n_tiles = len(ty) * len(tx)
+        origin = [(sy, sx) for (sy, _, _) in ty for (sx, _, _) in tx]
+        own = [(oy, ox, hy, hx) for (_, oy, hy) in ty for (_, ox, hx) in tx]
+        self.origin = torch.tensor(origin, dtype=torch.int32, device=self.device).contiguous()
+        self.own = torch.tensor(own, dtype=torch.int32, device=self.device).contiguous()
+        self.redundancy = self.n_tiles * self.ly * self.lx / float(self.by * self.bx)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.bdof_tiles_create(ctypes.byref(self._h), rank, gy, gx, self.by, self.bx, self.apron))
+            hb = lib.bdof_tiles_handle_bytes()
+            mine = ctypes.create_string_buffer(hb)
+            check(lib.bdof_tiles_export(self._h, mine))
+            if w > 1:
+                handles = [None] * w
+                dist.all_gather_object(handles, bytes(mine.raw), group=group)
+                check(lib.bdof_tiles_connect(self._h, ctypes.c_char_p(b''.join(handles))))
+            else:
+                check(lib.bdof_tiles_connect(self._h, ctypes.c_char_p(bytes(mine.raw))))
+            self.pitch = self.bx + 2 * self.apron
+            self.rows = self.by + 2 * self.apron
+            self.buf = []
+            for which in (0, 1):
+                ptr = ctypes.c_void_p()
+                check(lib.bdof_tiles_block_ptr(self._h, which, ctypes.byref(ptr)))
+                t = torch.as_tensor(_DeviceBuffer(ptr.value, self.rows * self.pitch * 2, self), device=self.device)
+                self.buf.append(torch.view_as_complex(t.view(self.rows, self.pitch, 2)))
+        # one plan for all windows of this rank: single slice steps with the exact FFT propagator
+        self.plan = MultislicePlan(self.ly, self.lx, self.n_tiles, max(self.n_slice, 2), energy_ev, psize_cm, device=self.device,
+                                   propagate_last=self.propagate_last, stepwise=True)
+        self.phase0 = complex(self.plan_phase0(energy_ev, psize_cm))
+        # (delta, beta) windows, cut once (axially repeating object): block with apron from the caller, then the same cut kernel
+        y0 = (rank // gx) * self.by - self.apron
+        x0 = (rank % gx) * self.bx - self.apron
+        dbb = db_block_fn(y0, x0, self.rows, self.pitch).to(self.device, torch.float32).contiguous()
+        assert tuple(dbb.shape) == (self.rows, self.pitch, 2)
+        self.db_tiles = torch.empty((self.n_tiles, self.ly, self.lx, 2), dtype=torch.float32, device=self.device)
+        self.tiles = [torch.empty((self.n_tiles, self.ly, self.lx), dtype=torch.complex64, device=self.device) for _ in range(2)]
+        st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        self.buf[0].copy_(torch.view_as_complex(dbb))
+        check(lib.bdof_tiles_cut(self._h, 0, self._p(self.origin), self.n_tiles, self.ly, self.lx, self._p(self.db_tiles), st))
+        torch.cuda.current_stream(self.device).synchronize()
+        if w > 1:
+            dist.barrier(group=group)             # nobody stores into a peer that has not opened the handles yet
+        self._group = group
+
+    @staticmethod
+    def _p(t):
+        import ctypes
+        return ctypes.c_void_p(t.data_ptr())
+
+    @staticmethod
+    def plan_phase0(energy_ev, psize_cm):
+        from .util import PI
+        dz_nm = psize_cm * 1e7
+        return np.exp(1j * 2 * PI / (1240. / energy_ev) * dz_nm)
+
+    def interior(self, which):
+        a = self.apron
+        return self.buf[which][a:a + self.by, a:a + self.bx]
+
+    def run(self, probe_block_fn=None):
+        """Propagate through all slices.  probe_block_fn(y0, x0, h, w) -> complex64 [h, w] entrance wave of those global pixels
+        (periodic); default: plane wave.  Returns this rank's block of the exit wave [by, bx] complex64 (a view of the buffer)."""
+        import ctypes
+        lib, check = self._lib, self._check
+        st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        cur = 0
+        if probe_block_fn is None:
+            self.buf[0].fill_(1.0)
+        else:
+            y0 = (self.rank // self.gx) * self.by - self.apron
+            x0 = (self.rank % self.gx) * self.bx - self.apron
+            self.buf[0].copy_(probe_block_fn(y0, x0, self.rows, self.pitch))
+        n_prop = 0
+        for i in range(self.n_slice):
+            prop = True if self.propagate_last else (i < self.n_slice - 1)
+            check(lib.bdof_tiles_cut(self._h, cur, self._p(self.origin), self.n_tiles, self.ly, self.lx, self._p(self.tiles[0]), st))
+            self.plan.slice_step(self.tiles[0], self.db_tiles, out=self.tiles[1], propagate=prop, index=i)
+            check(lib.bdof_tiles_paste(self._h, cur ^ 1, self._p(self.tiles[1]), self._p(self.origin), self._p(self.own), self.n_tiles,
+                                       self.ly, self.lx, st))
+            if prop and i < self.n_slice - 1:
+                check(lib.bdof_tiles_halo_exchange(self._h, cur ^ 1, st))
+            n_prop += 1 if prop else 0
+            cur ^= 1
+        self.total_phase = self.phase0 ** n_prop          # the engine keeps exp(i k dz) per propagation out of its fp32 chain
+        return self.interior(cur)
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            torch.cuda.synchronize(self.device)
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dist.barrier(group=self._group)
+            self.buf = []
+            self._lib.bdof_tiles_destroy(self._h)
+            import ctypes
+            self._h = ctypes.c_void_p()

@@ -59,7 +59,9 @@ enum {
     BDOF_PROPAGATE_LAST = 1u << 0,  /* TF semantics: every slice propagates (util.py:464-483);
                                        default = NumPy semantics, last slice only modulates */
     BDOF_STORE_SLICES   = 1u << 1,  /* keep psi entering every slice for bdof_adjoint */
-    BDOF_Z_BROADCAST    = 1u << 2   /* db holds ONE slice that repeats along z (axially invariant) */
+    BDOF_Z_BROADCAST    = 1u << 2,  /* db holds ONE slice that repeats along z (axially invariant) */
+    BDOF_STEPWISE       = 1u << 3   /* the plan is driven slice by slice (bdof_slice_step_seq: tiling, per-slice outputs): one row
+                                       pass + one column pass per slice, multiplier tables sequenced for that schedule */
 };
 
 /* free-space step after the object (npfuncs.py:43-61) */
@@ -224,6 +226,10 @@ int  bdof_forward_host(bdof_plan* p, const float* h_delta_byxz, const float* h_b
  * [batch][ny][nx][2]; in/out [batch][ny][nx] complex64; out must not alias in.  The global phase
  * exp(i k dz) per propagation is NOT applied (it cancels in every |psi|-based quantity). */
 int  bdof_slice_step(bdof_plan* p, const float* d_in, const float* d_db_slice, float* d_out, int propagate);
+/* The same for slice `slice_index` of a chain that is stepped in order on a BDOF_STEPWISE plan: uses that slice's entry of the
+ * error-feedback multiplier sequence (the product of the fp32 tables applied so far stays within one rounding of the exact
+ * power of H), so that 1000 steps do not accumulate the rounding of one fixed table. */
+int  bdof_slice_step_seq(bdof_plan* p, const float* d_in, const float* d_db_slice, float* d_out, int propagate, int slice_index);
 
 /* Gradient buckets for the data-parallel all-reduce (Horovod allreduce, tensorflow_recon/fullfield.py:412):
  * the z range is split into n_buckets contiguous buckets counted from the last slice; bdof_adjoint
@@ -283,6 +289,29 @@ int  bdof_debug_fft_gain(int n, double* gain_out);
 /* Developer hook: device buffer that instrumented builds (-DBDOF_PHASE_TIMING) fill with clock64()
  * phase stamps; ignored by the production build. */
 int  bdof_debug_set_buffer(void* d_buf);
+
+/* Tiling-based multislice across GPUs (BASELINE config 5; csrc/tilehalo.cu).  The global field is a gy x gx grid of blocks, one
+ * per rank (one process per GPU); rank r owns block (r / gx, r % gx) of by x bx pixels, kept with an apron of `apron` pixels on
+ * every side in two exportable buffers [by + 2 apron][bx + 2 apron] complex64 (ping-pong between slices).  Set-up as for
+ * bdof_dp_*: every rank exports a handle, the host side all-gathers them and passes the concatenation to bdof_tiles_connect.
+ * Per slice: bdof_tiles_cut (local FFT windows [n_tiles][ly][lx] out of buffer `which`; d_origin_yx [n_tiles][2] relative to the
+ * block interior, may reach into the apron), bdof_slice_step on the windows, bdof_tiles_paste (the OWNED rectangle of every
+ * window, d_own_yxhw [n_tiles][4] = y0, x0, height, width relative to the block interior, into the interior of the other
+ * buffer), bdof_tiles_halo_exchange on that buffer: one kernel stores the border strips straight into the aprons of the 8
+ * neighbours' buffers over NVLink peer memory (periodic wrap at the global border), flags are raised with stream memory
+ * operations and `cuda_stream` waits for the 8 neighbours' flags.  Collective; nothing synchronises with the host.
+ * The same cut / paste also serve (delta, beta) blocks (8 bytes per pixel as well). */
+typedef struct bdof_tiles bdof_tiles;
+int  bdof_tiles_create(bdof_tiles** out, int rank, int gy, int gx, int by, int bx, int apron);
+void bdof_tiles_destroy(bdof_tiles* c);
+int  bdof_tiles_handle_bytes(void);
+int  bdof_tiles_export(bdof_tiles* c, void* h_handle_out);
+int  bdof_tiles_connect(bdof_tiles* c, const void* h_all_handles);
+int  bdof_tiles_block_ptr(bdof_tiles* c, int which, void** d_out);
+int  bdof_tiles_cut(bdof_tiles* c, int which, const int* d_origin_yx, int n_tiles, int ly, int lx, float* d_tiles, void* cuda_stream);
+int  bdof_tiles_paste(bdof_tiles* c, int which, const float* d_tiles, const int* d_origin_yx, const int* d_own_yxhw, int n_tiles,
+                      int ly, int lx, void* cuda_stream);
+int  bdof_tiles_halo_exchange(bdof_tiles* c, int which, void* cuda_stream);
 
 /* In-situ timing: between begin and end every pass-kernel launch of this plan is bracketed by CUDA
  * events on the plan's stream; end() synchronises and returns, per kernel variant, the launch count
