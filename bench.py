@@ -567,6 +567,119 @@ def run_config3(args):
     return 0
 
 
+def run_config5(args):
+    """BASELINE configs[4]: tiling-based forward multislice of ONE 16384 x 16384 field through 1000 slices of an axially repeating
+    zone plate, split over the ranks in a 1x1 / 1x2 / 2x2 / 2x4 block grid; per slice every rank steps its
+    local FFT windows and stores its border strips into the neighbours' aprons over NVLink peer memory (tiling.TiledMultislice,
+    csrc/tilehalo.cu).  One step = the whole propagation; total work is fixed: strong scaling.  e2e = the same call plus the
+    read-back of the exit intensity's checksum (the field itself stays distributed on the GPUs, as a simulation would keep it)."""
+    import torch
+    import torch.distributed as dist
+    from beyond_dof_b200 import capi
+    from beyond_dof_b200.tiling import TiledMultislice
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        import datetime
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
+    grid = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}[world]
+    n = args.tile_field
+    nz = args.tile_slices
+    halo = args.halo
+    lmbda = 1240. / ENERGY_EV
+    f_nm = (n / 2 - 192) * 4.0 / lmbda * 1.0            # outer zone width 4 px at r_N = n/2 - 192 px (SURVEY 8d recipe, 1 nm voxels)
+    n_zones = int(((n / 2 - 192) ** 2) / (lmbda * f_nm))
+
+    def db_block(y0, x0, h, w):
+        ys = (torch.arange(y0, y0 + h, device=dev) % n).double() - (n - 1) / 2
+        xs = (torch.arange(x0, x0 + w, device=dev) % n).double() - (n - 1) / 2
+        out = torch.empty((h, w, 2), dtype=torch.float32, device=dev)
+        for r0 in range(0, h, 1024):                  # bounded temporaries
+            r2 = ys[r0:r0 + 1024, None] ** 2 + xs[None, :] ** 2
+            zone = torch.floor(r2 / (lmbda * f_nm)).long()
+            mask = ((zone % 2) == 1) & (zone <= n_zones)
+            out[r0:r0 + 1024, :, 0] = mask * 1.0e-4
+            out[r0:r0 + 1024, :, 1] = mask * 1.0e-5
+        return out
+    tm = TiledMultislice(n, n, grid, halo, ENERGY_EV, PSIZE_CM, nz, db_block)
+
+    def step():
+        out = tm.run()
+        return (out.abs() ** 2).sum(dtype=torch.float64)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = capi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        chk = step()
+    ev1.record()
+    barrier()
+    launches = capi.launch_count() - l0
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(chk, op=dist.ReduceOp.SUM)
+    ms_step = t.item() / args.steps
+    # e2e: the public call + the scalar read-back
+    host = torch.empty((), dtype=torch.float64).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host.copy_(step(), non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    units = float(n) * n * nz
+    value = units / (ms_step * 1e-3) / 1e9
+    if rank == 0:
+        clocks = sampler.stop()
+        peak, peak_src = measured_peaks()
+        line = {
+            'metric': 'multislice Gpixel*slice/s (forward, tiled)', 'value': value, 'unit': 'Gpixel*slice/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'c64', 'data': 'synthetic',
+            'config': {'workload': 'tiling-based forward multislice, %dx%d field x %d slices of an axially repeating zone plate, %dx%d block grid '
+                                   'with per-slice NVLink halo exchange (BASELINE configs[4])' % (n, n, nz, grid[0], grid[1]),
+                       'ny': n, 'nx': n, 'n_slice': nz, 'halo': halo, 'window': [tm.ly, tm.lx], 'windows_per_gpu': tm.n_tiles, 'apron': tm.apron,
+                       'redundant_compute': tm.redundancy, 'semantics': 'numpy (last slice modulates only)',
+                       'l2': 'every slice streams the %.1f GB of this GPU\'s windows' % (tm.n_tiles * tm.ly * tm.lx * 8 / 1e9),
+                       'parallelism': 'one field over %d GPU(s): %dx%d blocks, border strips stored into the neighbours\' aprons over NVLink peer '
+                                      'memory by one kernel per slice, stream-memop flags' % (world, grid[0], grid[1])},
+            'e2e': {'value': units / (ms_e2e * 1e-3) / 1e9, 'unit': 'Gpixel*slice/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 8,
+                    'api': 'beyond_dof_b200.tiling.TiledMultislice.run() + read-back of the exit intensity sum (wall clock); the object is analytic '
+                           'and lives on the GPUs, nothing is uploaded per step'},
+            'gpu_launches': int(launches), 'clocks': clocks,
+            'roofline': {'bound': 'hbm', 'kernel': 'line_kernel row pass with transmission + column pass (per window batch)',
+                         'achieved': value / world * tm.redundancy * 40.0, 'peak': peak, 'unit': 'GB/s',
+                         'frac': value / world * tm.redundancy * 40.0 / peak, 'traffic': None, 'peak_source': peak_src,
+                         'note': 'whole-step figure per GPU: forward contract 40 B per TRANSFORMED pixel*slice (windows incl. halo), cut/paste '
+                                 'copies and the exchange counted as overhead'},
+            'cpu_baseline': None, 'exit_intensity_sum': float(chk.item()),
+        }
+        print(json.dumps(line), flush=True)
+    tm.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def run_config4(args):
     """BASELINE configs[3]: full-field tomographic reconstruction, 256^3 object, angles sharded over the ranks,
     minibatch of 10 angles per rank and update (reconstruct_fullfield.py:30,60), Adam, NCCL all-reduce of the object
@@ -653,10 +766,13 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS) + ['config3', 'config4'])
+    ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS) + ['config3', 'config4', 'config5'])
     ap.add_argument('--impl', default='bdof', choices=['bdof', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
     ap.add_argument('--no-host-object', action='store_true', help='skip the extra end-to-end leg with delta/beta and the gradients in host memory')
+    ap.add_argument('--halo', type=int, default=8, help='config5: halo of the local FFT windows (the reference kernel_size 17 = 8 px)')
+    ap.add_argument('--tile-field', type=int, default=16384, help='config5: side of the global field')
+    ap.add_argument('--tile-slices', type=int, default=1000, help='config5: slices')
     ap.add_argument('--no-cufft', action='store_true', help='skip the cuFFT comparison leg (unfused reference loop on torch.fft)')
     ap.add_argument('--no-headline', action='store_true', help='skip the 4096^2 x 512 headline record of the default run')
     ap.add_argument('--fields-per-exchange', type=int, default=1, help='fields (projection angles) each rank accumulates per gradient exchange; '
@@ -668,11 +784,11 @@ def main():
     ap.add_argument('--diag', action='store_true', help='N > 1: print the plain all-reduce time and the step time without exchange')
     ap.add_argument('--in-place', action='store_true', help='adjoint overwrites delta/beta with the gradient (needed for the 4096^2x512 size)')
     args = ap.parse_args()
-    if args.workload in ('config3', 'config4'):
+    if args.workload in ('config3', 'config4', 'config5'):
         if args.impl == 'reference':
             print(json.dumps({'impl': 'reference', 'unavailable': 'the reference arm is defined on the default workload (config2)'}))
             return 0
-        return run_config3(args) if args.workload == 'config3' else run_config4(args)
+        return {'config3': run_config3, 'config4': run_config4, 'config5': run_config5}[args.workload](args)
     if args.impl == 'reference':
         return run_reference(args)
     return run_gpu(args)
