@@ -111,6 +111,10 @@ def _halo_pattern_check(rank, world, grid, ny, nx, halo, lengths):
         src, dst = rep % 2, (rep + 1) % 2
         tm.buf[src].copy_(full)
         tm.buf[dst].zero_()
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()                                 # (test only: nobody pushes into an apron that is still being cleared)
         check(lib.bdof_tiles_cut(tm._h, src, tm._p(tm.origin), tm.n_tiles, tm.ly, tm.lx, tm._p(tm.tiles[0]), st))
         check(lib.bdof_tiles_paste(tm._h, dst, tm._p(tm.tiles[0]), tm._p(tm.origin), tm._p(tm.own), tm.n_tiles, tm.ly, tm.lx, st))
         check(lib.bdof_tiles_halo_exchange(tm._h, dst, st))
