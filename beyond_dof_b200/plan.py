@@ -34,10 +34,12 @@ class MultislicePlan:
       propagate_last=True   TF path, every slice propagates          (util.py:464-488)
       free_prop_cm          None | 'inf' | float (cm)                (npfuncs.py:43-61)
       h                     optional caller-supplied centred H [ny,nx] (util.py:459-461)
+      factors               optional (phase0, hy, hx): the separable factors of a centred H directly (tiling: windows use the
+                            GLOBAL field's frequency grid)
     """
 
     def __init__(self, ny, nx, batch, n_slice, energy_ev, psize_cm, free_prop_cm=None, propagate_last=False,
-                 store_slices=False, z_broadcast=False, h=None, pi=PI, device=None, stepwise=False):
+                 store_slices=False, z_broadcast=False, h=None, pi=PI, device=None, stepwise=False, factors=None):
         if not torch.cuda.is_available():
             raise RuntimeError('beyond_dof_b200 needs a CUDA device: the multislice path has no CPU fallback')
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
@@ -70,7 +72,9 @@ class MultislicePlan:
                                        ctypes.c_void_p(self.stream.cuda_stream)))
             grid_shape = [self.ny, self.nx, self.n_slice]
             fac = None
-            if h is None:
+            if factors is not None:
+                fac = factors                            # (phase0, hy[ny], hx[nx]) centred separable factors supplied by the caller
+            elif h is None:
                 fac = kernel_factors(delta_nm, self.lmbda_nm, voxel_nm, grid_shape, pi=pi)
             else:
                 fac = factor_kernel(h)

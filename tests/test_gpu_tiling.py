@@ -174,7 +174,7 @@ def test_tiled_multislice_ranks_vs_global_fft():
     assert err < 2e-3, err                                  # halo 48: the truncation error of the Fresnel kernel's tails
 
 
-@pytest.mark.parametrize('halo', [8, 16, 32, 64])
+@pytest.mark.parametrize('halo', [8, 24, 40, 60])
 def test_tiled_multislice_error_vs_halo_single_rank(halo):
     # the halo-vs-error study of SURVEY 8d/e on a 2048 x 2048 x 32 twin of config 5 (one rank, many windows, periodic wrap
     # through the rank's own apron), against the exact global-FFT engine; measured errors are recorded for DESIGN.md
@@ -190,7 +190,7 @@ def test_tiled_multislice_error_vs_halo_single_rank(halo):
     gd = db[..., 0][None, :, :, None].expand(1, ny, nx, Z).contiguous()
     gb = db[..., 1][None, :, :, None].expand(1, ny, nx, Z).contiguous()
     ref = bd.multislice_propagate_batch_numpy(gd, gb, np.ones((ny, nx)), np.zeros((ny, nx)), 5000, 1e-7, obj_batch_shape=(1, ny, nx, Z))[0]
-    tm = tiling.TiledMultislice(ny, nx, (1, 1), halo, 5000, 1e-7, Z, fn, lengths=(512,))
+    tm = tiling.TiledMultislice(ny, nx, (1, 1), halo, 5000, 1e-7, Z, fn, lengths=(256,))
     out = tm.run() * complex(tm.total_phase)
     err = rel_l2((out.abs() ** 2).cpu().numpy(), (ref.abs() ** 2).cpu().numpy())
     path = os.path.join(ROOT, 'gpurun_out', 'tiling_halo_error.json')
@@ -198,8 +198,10 @@ def test_tiled_multislice_error_vs_halo_single_rank(halo):
         rec = json.load(open(path))
     except Exception:
         rec = {}
-    rec[str(halo)] = {'intensity_rel_l2': err, 'n_tiles': tm.n_tiles, 'window': tm.ly, 'redundancy': tm.redundancy, 'apron': tm.apron}
+    eff = int((tm.ly - int(tm.own[:, 2].max())) // 2)             # windows are centred on what they own: the halo they really see
+    rec[str(halo)] = {'intensity_rel_l2': err, 'effective_halo': eff, 'n_tiles': tm.n_tiles, 'window': tm.ly, 'redundancy': tm.redundancy,
+                      'apron': tm.apron}
     os.makedirs(os.path.dirname(path), exist_ok=True)
     json.dump(rec, open(path, 'w'), indent=1, sort_keys=True)
     tm.close()
-    assert err < {8: 5e-2, 16: 3e-2, 32: 1e-2, 64: 5e-3}[halo]
+    assert err < {8: 5e-3, 24: 3e-3, 40: 2e-3, 60: 1e-3}[halo]
