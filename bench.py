@@ -349,10 +349,11 @@ def run_gpu(args):
         db = _make_db(torch, dev, nz, B, ny, nx, 1234 + rank)
         probe = torch.ones((ny, nx), dtype=torch.complex64, device=dev)
         obj = FullfieldObjective(db, probe, ENERGY_EV, PSIZE_CM, in_place=in_place)
-        th = (0.9 + 0.1 * torch.rand((B, ny, nx), generator=torch.Generator().manual_seed(4321 + rank))).pin_memory()
+        shape = (B, ny, nx) if (K == 1 or in_place) else (K, B, ny, nx)             # one measured projection per field
+        th = (0.9 + 0.1 * torch.rand(shape, generator=torch.Generator().manual_seed(4321 + rank))).pin_memory()
         return obj, th, th.to(dev)
 
-    def measure(obj, target_host, target_dev, ny, nx, nz, B, steps, warmup, traffic_key):
+    def measure(obj, target_host, target_dev, ny, nx, nz, B, steps, warmup, traffic_key, K=K):
         """value (device-resident inputs), e2e (public API, pinned host projections in, loss out), roofline"""
         units = B * ny * nx * nz * world * K
 
@@ -376,7 +377,7 @@ def run_gpu(args):
             step_e2e()
         ms_e2e, _ = _time_steps(torch, dist, world, dev, step_e2e, steps)
         e2e = {'value': units / (ms_e2e * 1e-3) / 1e9, 'unit': 'Gpixel*slice/s',
-               'h2d_bytes_per_step': target_host.numel() * target_host.element_size() * K, 'd2h_bytes_per_step': 8,
+               'h2d_bytes_per_step': target_host.numel() * target_host.element_size(), 'd2h_bytes_per_step': 8,
                'api': 'beyond_dof_b200.models.FullfieldObjective.step(projection magnitudes in pinned host memory) -> loss'}
         return {'value': value, 'ms_per_step': ms_step, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
                 'roofline': roof, 'loss': float(loss.item())}
@@ -430,7 +431,7 @@ def run_gpu(args):
                 headline = {'skipped': 'needs %.0f GB of device memory, %.0f GB free' % (need / 1e9, free_b / 1e9)}
             else:
                 hobj, hth, htd = build(hy, hx, hz, 1, True)
-                h = measure(hobj, hth, htd, hy, hx, hz, 1, max(2, min(args.steps, 5)), 3, '%dx%d' % (hy, hx))
+                h = measure(hobj, hth, htd, hy, hx, hz, 1, max(2, min(args.steps, 5)), 3, '%dx%d' % (hy, hx), K=1)
                 headline = {'workload': hdesc + ', gradient written in place over delta/beta', 'ny': hy, 'nx': hx, 'n_slice': hz,
                             'value': h['value'], 'unit': 'Gpixel*slice/s', 'ms_per_step': h['ms_per_step'], 'e2e': h['e2e'],
                             'roofline': h['roofline'], 'gpu_launches': h['gpu_launches'], 'clocks': h['clocks'], 'loss': h['loss'],

@@ -503,6 +503,7 @@ struct bdof_plan {
     // window mode (bdof_plan_set_windows): d_db of bdof_forward / bdof_adjoint is the OBJECT, the batch its windows
     const int* win_origin = nullptr;
     int win_oy = 0, win_ox = 0;
+    bool grad_accumulate = false;   // bdof_adjoint ADDS to d_grad_out (bdof_plan_set_grad_accumulate; sweep kernels only)
     bool stash_valid = false;  // the last forward filled t_stash and nothing has overwritten it since
     double* partial = nullptr;
     std::complex<double> total_phase{1.0, 0.0};
@@ -1139,6 +1140,12 @@ extern "C" int bdof_adjoint(bdof_plan* p, float* d_db_inout, const float* d_grad
     const bool zb = p->flags & BDOF_Z_BROADCAST;
     if (zb && !d_grad_out) return fail(BDOF_E_BADARG, "BDOF_Z_BROADCAST needs d_grad_out");
     if (p->win_origin && !d_grad_out) return fail(BDOF_E_BADARG, "window mode needs d_grad_out (the per-window gradients)");
+    if (p->grad_accumulate) {
+        if (!d_grad_out) return fail(BDOF_E_BADARG, "gradient accumulation needs d_grad_out (the accumulator)");
+        if (!use_sweep(p) || use_resident(p)) return fail(BDOF_E_UNSUPPORTED, "fused gradient accumulation is a sweep-kernel feature");
+        if (p->stash_valid && p->t_stash == reinterpret_cast<float2*>(d_grad_out))
+            return fail(BDOF_E_STATE, "the transmission stash must not live in the accumulator");
+    }
     if (p->win_origin && !use_resident(p)) return fail(BDOF_E_UNSUPPORTED, "window mode needs the resident small-field kernels");
     float2* db = reinterpret_cast<float2*>(d_db_inout);
     float2* gout = reinterpret_cast<float2*>(d_grad_out);
@@ -1196,6 +1203,7 @@ extern "C" int bdof_adjoint(bdof_plan* p, float* d_db_inout, const float* d_grad
         q.grad = gout ? gout + (long long)i * p->F : db + (long long)i * p->F;
         q.slab = p->slabs + (long long)i * p->F;
         q.conv1 = slice_propagates(p, i); q.conv2 = (i > 0);
+        q.grad_accumulate = p->grad_accumulate ? 1 : 0;
         q.store_out = (i > 0 || d_grad_probe != nullptr);
         BDOF_TRY(sweep_launch(p, i, true, q));
         if (n_buckets > 0) {
@@ -1787,6 +1795,12 @@ extern "C" int bdof_plan_set_windows(bdof_plan* p, int oy, int ox, const int* d_
     return 0;
 }
 extern "C" int bdof_plan_is_resident(const bdof_plan* p) { return (p && p->have_kernel && use_resident(p)) ? 1 : 0; }
+
+extern "C" int bdof_plan_set_grad_accumulate(bdof_plan* p, int on) {
+    if (!p) return fail(BDOF_E_BADARG, "null");
+    p->grad_accumulate = on != 0;
+    return 0;
+}
 
 extern "C" int bdof_plan_set_t_stash(bdof_plan* p, float* d_stash) {
     if (!p) return fail(BDOF_E_BADARG, "null");

@@ -64,6 +64,16 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int 
                  "r"(smem_u32(src_smem))
                  : "memory");
 }
+// the same as a reduction: global[...] += shared (fp32 add performed by the TMA unit / L2)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, int c0, int c1, const void* src_smem) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(c0), "r"(c1),
+                 "r"(smem_u32(src_smem))
+                 : "memory");
+}
+// fire-and-forget vector reduction at L2: *p += (a, b)
+__device__ __forceinline__ void red_add_f32x2(float2* p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
 // contiguous shared -> global bulk copy (bytes a multiple of 16), tracked by the thread's bulk async-group
 __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)

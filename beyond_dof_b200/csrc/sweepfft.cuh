@@ -39,6 +39,8 @@ struct SweepParams {
     int slab_prefetch;       // adjoint: L2-prefetch the slab tile at tile start
     int stagger_ns;          // x kernels: the upper half of the lines starts every convolution this much later, so that
                              // its stage exchanges (shared-memory pipe) overlap the other half's butterflies (FP pipe)
+    int grad_accumulate;     // adjoint: ADD the gradient to `grad` (fused accumulation over the fields of a minibatch): vector
+                             // reductions at L2 from the x kernels (red.global.add.v2.f32), TMA reduce-stores from the y kernels
     int db_is_t;             // adjoint: `db` holds the stashed transmission tau_i = t_i - 1, not (delta, beta)
     float k_dz;
     long long* dbg;
@@ -156,15 +158,20 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
     shift_init<PC>(st, t);
 
     // y kernels: strided stores leave through L by tensor copies
-    auto tma_store_tile = [&](const CUtensorMap* tm, long long done_tile) __attribute__((always_inline)) {
+    auto tma_store_tile = [&](const CUtensorMap* tm, long long done_tile, bool reduce_add = false) __attribute__((always_inline)) {
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
             const long long tl = done_tile * LPC;
             const int bb = int(tl / p.lines_per_batch);
             const int c0 = int(tl - (long long)bb * p.lines_per_batch);
+            if (reduce_add) {
 #pragma unroll 1
-            for (int j = 0; j < SM::NBOX; ++j) tma_store_2d(tm, 2 * c0, bb * N + j * SM::BOXR, L + j * SM::BOXR * LPC);
+                for (int j = 0; j < SM::NBOX; ++j) tma_reduce_add_2d(tm, 2 * c0, bb * N + j * SM::BOXR, L + j * SM::BOXR * LPC);
+            } else {
+#pragma unroll 1
+                for (int j = 0; j < SM::NBOX; ++j) tma_store_2d(tm, 2 * c0, bb * N + j * SM::BOXR, L + j * SM::BOXR * LPC);
+            }
             bulk_commit_group();
         }
     };
@@ -315,14 +322,16 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                             const float2 w = cmulc(Lme[q * LQ], v[q]);
                             Lme[q * LQ] = make_float2(-kdz * w.y, -kdz * w.x);
                         });
-                        tma_store_tile(&tm_grad, tile);
+                        tma_store_tile(&tm_grad, tile, p.grad_accumulate != 0);
                         if (has_next) deferred = LAND_IN;
                     } else {
                         float2* gp = p.grad + tile_off + (Lme - L);
+                        const bool acc = p.grad_accumulate != 0;
                         if (active) static_for<E>([&](auto Q) __attribute__((always_inline)) {
                             constexpr int q = decltype(Q)::value;
                             const float2 w = cmulc(Lme[q * LQ], v[q]);
-                            gp[q * LQ] = make_float2(-kdz * w.y, -kdz * w.x);
+                            if (acc) red_add_f32x2(gp + q * LQ, -kdz * w.y, -kdz * w.x);
+                            else gp[q * LQ] = make_float2(-kdz * w.y, -kdz * w.x);
                         });
                         __syncthreads();
                         if (has_next) land(LAND_IN, tile + tile_step);

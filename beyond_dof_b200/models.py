@@ -452,12 +452,14 @@ class FullfieldObjective:
             self._dp.finish_allreduce(self.grad, works, comm_stream=self._comm_stream)
 
     def step_device(self, target_dev, accumulate=1):
-        """forward + loss + adjoint (+ gradient all-reduce when data parallel) with the target already on
-        the device; returns the device loss of this rank.
-        accumulate = K > 1: K fields (projection angles of one minibatch, reconstruct_fullfield.py:30 minibatch_size) are
-        evaluated one after the other and their gradients summed in self.grad_acc before ONE exchange -- the reference's
-        ratio of compute to communication.  The stand-in for the K rotated copies of the object is the same field K times
-        (same arithmetic and traffic); the summation pass stands in for the back-rotation, which accumulates too."""
+        """forward + loss + adjoint (+ gradient all-reduce when data parallel) with the target(s) already on the device;
+        returns the device loss of this rank.
+        accumulate = K > 1: K fields (the projection angles of one minibatch: minibatch_size = 10 in reconstruct_fullfield.py:30)
+        are evaluated one after the other and their gradients SUMMED in self.grad before ONE exchange -- the reference's ratio of
+        compute to communication.  The sum is fused into the adjoint kernels' gradient stores (bdof_plan_set_grad_accumulate:
+        L2 reductions / TMA reduce-stores), so it costs no extra pass; the transmission stash then lives in its own buffer.
+        target_dev: [B,Y,X] (shared by the K fields) or [K,B,Y,X].  The stand-in for the K rotated copies of the object is the
+        same field K times (same arithmetic and traffic)."""
         dp = getattr(self, '_dp', None) is not None
         if accumulate <= 1:
             self.plan.forward(self.db, self.probe, out=self.exit)
@@ -468,36 +470,35 @@ class FullfieldObjective:
             return loss
         if self.in_place:
             raise ValueError('gradient accumulation needs the gradient in its own buffer (in_place=False)')
-        if getattr(self, 'grad_acc', None) is None:
-            self.grad_acc = torch.empty_like(self.grad)
+        if getattr(self, 'stash', None) is None:
+            self.stash = torch.empty_like(self.db)
+        self.plan.set_t_stash(self.stash)
         total = None
-        for k in range(accumulate):
-            last = k == accumulate - 1
-            self.plan.forward(self.db, self.probe, out=self.exit)
-            loss, g = self.plan.loss_mag(self.exit, target_dev)
-            total = loss if total is None else total + loss
-            self.plan.adjoint(self.db, g, grad_out=self.grad)
-            if last:
-                # the exchange owns self.grad (it may be the copy-engine exchange's exportable buffer): the total is formed there
-                if k > 0:
-                    self.grad.add_(self.grad_acc)
-            elif k == 0:
-                self.grad_acc.copy_(self.grad)
-            else:
-                self.grad_acc.add_(self.grad)
+        try:
+            for k in range(accumulate):
+                self.plan.forward(self.db, self.probe, out=self.exit)
+                loss, g = self.plan.loss_mag(self.exit, target_dev[k] if target_dev.dim() == 4 else target_dev)
+                total = loss if total is None else total + loss
+                self.plan.set_grad_accumulate(k > 0)
+                self.plan.adjoint(self.db, g, grad_out=self.grad)
+        finally:
+            self.plan.set_grad_accumulate(False)
+            self.plan.set_t_stash(self.grad)
         if dp:
-            # buckets are final only after the summation above: one event for all of them
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(self.db.device))
-            keep = self._buckets
-            self._buckets = [(lo, hi, ev) for lo, hi, _ in keep]
+            # the buckets' events are those of the LAST adjoint, whose stores complete the sums
             self._exchange()
-            self._buckets = keep
         return total / accumulate
 
     def step(self, prj_mag_host, accumulate=1):
-        self.target.copy_(prj_mag_host, non_blocking=True)
-        loss = self.step_device(self.target, accumulate=accumulate)
+        """prj_mag_host: [B,Y,X] float32 in pinned host memory, or [K,B,Y,X] with accumulate = K (one projection per field)."""
+        if accumulate > 1 and prj_mag_host.dim() == 4:
+            if getattr(self, 'targets', None) is None or self.targets.shape != prj_mag_host.shape:
+                self.targets = torch.empty(tuple(prj_mag_host.shape), dtype=torch.float32, device=self.db.device)
+            self.targets.copy_(prj_mag_host, non_blocking=True)
+            loss = self.step_device(self.targets, accumulate=accumulate)
+        else:
+            self.target.copy_(prj_mag_host, non_blocking=True)
+            loss = self.step_device(self.target, accumulate=accumulate)
         self.loss_host.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(self.loss_host)

@@ -232,6 +232,11 @@ class MultislicePlan:
         self._stash = buf
         check(lib.bdof_plan_set_t_stash(self._h, _ptr(buf) if buf is not None else None))
 
+    def set_grad_accumulate(self, on):
+        """While on, adjoint(..., grad_out=acc) ADDS the gradient to acc (fused in the sweep kernels' gradient stores): the sum over
+        the fields of a minibatch costs no extra pass.  The transmission stash must live in another buffer than acc."""
+        check(lib.bdof_plan_set_grad_accumulate(self._h, 1 if on else 0))
+
     def set_gradient_buckets(self, n_buckets):
         """Split z into n_buckets (counted from the last slice); returns [(z_lo, z_hi, event)] in the order
         the adjoint sweep completes them.  The events are recorded inside bdof_adjoint."""

@@ -135,6 +135,13 @@ int  bdof_plan_set_t_stash(bdof_plan* p, float* d_stash);
 int  bdof_plan_set_windows(bdof_plan* p, int oy, int ox, const int* d_origin_yx);
 int  bdof_plan_is_resident(const bdof_plan* p);
 
+/* Fused gradient accumulation over the fields of a minibatch (the reference sums the gradients of minibatch_size projection
+ * angles before one exchange, reconstruct_fullfield.py:30): while on, bdof_adjoint ADDS its gradient to d_grad_out instead of
+ * overwriting it -- vector reductions at L2 (red.global.add.v2.f32) from the row kernels, TMA reduce-stores
+ * (cp.reduce.async.bulk.tensor) from the column kernels; one contribution per address and call, so the sum over calls is
+ * deterministic.  Sweep-kernel plans only; the transmission stash must then live in another buffer. */
+int  bdof_plan_set_grad_accumulate(bdof_plan* p, int on);
+
 /* layout conversion: reference [B,Y,X,Z] float32 planes <-> slice-major interleaved db */
 int  bdof_pack_db(const float* d_delta_byxz, const float* d_beta_byxz, float* d_db, int batch, int ny,
                   int nx, int n_slice, void* cuda_stream);

@@ -647,3 +647,50 @@ def test_unbatched_multislice_propagate_matches_oracle(bd, case):
     # torch in, torch out; zero padding (util.py:362-364)
     t = bd.multislice_propagate(torch.as_tensor(gd[0]).cuda(), torch.as_tensor(gb[0]).cuda(), pr, pi, 5000, psize, free_prop_cm=free)
     assert t.is_cuda and rel_l2(t.cpu().numpy(), ref) < 1e-5
+
+
+@pytest.mark.parametrize('shape', [(2, 64, 128, 5), (1, 256, 512, 4), (1, 1024, 2048, 3), (1, 4096, 1024, 2), (3, 128, 128, 3)])
+def test_fused_gradient_accumulation_over_a_minibatch(bd, shape):
+    # bdof_plan_set_grad_accumulate: the adjoint ADDS its gradient (L2 reductions from the row kernels, TMA reduce-stores from the
+    # column kernels) -- the sum over the K fields of a minibatch (reconstruct_fullfield.py:30) without an extra pass
+    from beyond_dof_b200.plan import MultislicePlan
+    B, Y, X, Z = shape
+    gd, gb = mo.random_phantom(shape, seed=91, delta_scale=4e-4, beta_scale=4e-5)
+    pr, pi = mo.gaussian_probe(shape[1:3], max(shape[1:3]) / 2., max(shape[1:3]) / 3., 0.5)
+    probe = torch.as_tensor((pr + 1j * pi).astype(np.complex64)).cuda()
+    rng = np.random.default_rng(92)
+    targets = [torch.as_tensor((rng.random(shape[:3]) + 0.5).astype(np.float32)).cuda() for _ in range(3)]
+    plan = MultislicePlan(Y, X, B, Z, 5000, 1e-7, store_slices=True)
+    db = plan.pack(torch.as_tensor(gd).cuda(), torch.as_tensor(gb).cuda())
+    singles = []
+    for t in targets:
+        psi = plan.forward(db, probe)
+        _, g = plan.loss_mag(psi, t)
+        go = torch.empty_like(db)
+        plan.adjoint(db, g, grad_out=go)
+        singles.append(go)
+    want = (singles[0].double() + singles[1].double() + singles[2].double())
+    stash = torch.empty_like(db)
+    acc = torch.full_like(db, float('nan'))                   # the first field overwrites
+    plan.set_t_stash(stash)
+    for k, t in enumerate(targets):
+        psi = plan.forward(db, probe)
+        _, g = plan.loss_mag(psi, t)
+        plan.set_grad_accumulate(k > 0)
+        plan.adjoint(db, g, grad_out=acc)
+    plan.set_grad_accumulate(False)
+    assert rel_l2(acc.cpu().numpy(), want.cpu().numpy()) < 1e-6
+    # deterministic: one contribution per address and call
+    acc2 = torch.empty_like(db)
+    for k, t in enumerate(targets):
+        psi = plan.forward(db, probe)
+        _, g = plan.loss_mag(psi, t)
+        plan.set_grad_accumulate(k > 0)
+        plan.adjoint(db, g, grad_out=acc2)
+    plan.set_grad_accumulate(False)
+    assert torch.equal(acc, acc2)
+    # the objective's accumulate=K path
+    from beyond_dof_b200.models import FullfieldObjective
+    obj = FullfieldObjective(db.clone(), probe, 5000, 1e-7)
+    loss = obj.step_device(torch.stack(targets), accumulate=3)
+    assert rel_l2(obj.grad.cpu().numpy(), want.cpu().numpy()) < 1e-6
