@@ -3,13 +3,14 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config2|headline|config1] [--impl reference]
 
-One "step" = forward multislice + |psi| loss + adjoint gradient over one synthetic field per GPU.
-Default workload (N=1) is BASELINE.json configs[1]: random delta/beta phantom 2048 x 2048 x 256,
-forward + adjoint on one B200.  1 unit = one pixel advanced through one slice (forward + adjoint
-counts the slice once).  With N>1 ranks (torchrun) every rank owns one such field (one projection
-angle of the data-parallel reconstruction, weak scaling) and the mean of the object gradient over ranks
-is formed every step, overlapped with the adjoint sweep (--exchange auto: copy engines over NVLink peer
-memory between two GPUs, NCCL all-reduce for three or more).
+One "step" = one minibatch of the data-parallel reconstruction on every GPU: K = 10 fields (projection angles; minibatch_size of
+reconstruct_fullfield.py:30,60), each forward multislice + |psi| loss + adjoint gradient, the K gradients summed (fused into the
+adjoint kernels' stores), then -- with N > 1 ranks -- ONE exchange: the mean of the object gradient over ranks.
+Default workload is BASELINE.json configs[1]: random delta/beta phantom 2048 x 2048 x 256, forward + adjoint.  1 unit = one
+pixel advanced through one slice (forward + adjoint counts the slice once).  Weak scaling: every rank evaluates its own K
+fields; the exchange (8.6 GB) is overlapped with the last adjoint sweep (--exchange auto: copy engines over NVLink peer
+memory between two GPUs, NCCL all-reduce for three or more).  --fields-per-exchange 1 is the harshest ratio
+(one field per exchange); the other BASELINE configs: --workload config3 | config4 | config5.
 
 Keys of the JSON line: see the contract in the task description; in short
   value        device-timed whole-job throughput, inputs resident in HBM
@@ -230,7 +231,9 @@ def _sweep_roofline(obj, px, nz, ms_step, value_per_gpu, peak, peak_src, traffic
                              'adjoint': {'alg_bytes_per_px': 56, 'achieved_gbs': px * 56 * nz / (a_ms * 1e-3) / 1e9}},
             'peak_source': peak_src,
             'whole_step': {'alg_bytes_per_px_slice': STEP_BYTES, 'achieved_per_gpu': value_per_gpu * STEP_BYTES,
-                           'frac': value_per_gpu * STEP_BYTES / peak}}
+                           'frac': value_per_gpu * STEP_BYTES / peak},
+            'note': 'the contract figure stays 96 B per pixel*slice; when K > 1 fields are summed per step the adjoint of every field but the '
+                    'first also reads the running sum (+8 B), which is not counted'}
 
 
 def cufft_comparison(torch, dev, ny, nx, n_sample, steps=3):
@@ -776,8 +779,8 @@ def main():
     ap.add_argument('--tile-slices', type=int, default=1000, help='config5: slices')
     ap.add_argument('--no-cufft', action='store_true', help='skip the cuFFT comparison leg (unfused reference loop on torch.fft)')
     ap.add_argument('--no-headline', action='store_true', help='skip the 4096^2 x 512 headline record of the default run')
-    ap.add_argument('--fields-per-exchange', type=int, default=1, help='fields (projection angles) each rank accumulates per gradient exchange; '
-                    'the reference drivers use minibatch_size = 10 (reconstruct_fullfield.py:30)')
+    ap.add_argument('--fields-per-exchange', type=int, default=10, help='fields (projection angles) each rank evaluates and sums per step / gradient '
+                    'exchange: the minibatch_size = 10 of the reference drivers (reconstruct_fullfield.py:30,60); the same at every N')
     ap.add_argument('--sm-reserve', type=int, default=-1, help='SMs left free for NCCL while the sweep runs (N > 1); -1 = the exchange\'s own default')
     ap.add_argument('--exchange', default='auto', choices=['auto', 'ce', 'nccl', 'hybrid'], help='N > 1: gradient exchange (copy engines over peer memory, or NCCL all-reduce)')
     ap.add_argument('--buckets', type=int, default=0, help='z-buckets of the gradient all-reduce (N > 1)')
