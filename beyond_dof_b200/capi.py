@@ -25,7 +25,7 @@ SYMBOLS = [
     'bdof_dp_create', 'bdof_dp_destroy', 'bdof_dp_handle_bytes', 'bdof_dp_export', 'bdof_dp_connect', 'bdof_dp_grad_ptr',
     'bdof_dp_bucket', 'bdof_dp_gather', 'bdof_dp_finish', 'bdof_plan_last_times', 'bdof_pack_db_rows', 'bdof_unpack_db_rows', 'bdof_plan_set_stream', 'bdof_debug_fft_gain', 'bdof_field_multiply', 'bdof_patch_gather_add', 'bdof_plan_set_windows', 'bdof_plan_is_resident', 'bdof_cnn_forward_store', 'bdof_cnn_adjoint', 'bdof_free_prop_adjoint',
     'bdof_tiles_create', 'bdof_tiles_destroy', 'bdof_tiles_handle_bytes', 'bdof_tiles_export', 'bdof_tiles_connect',
-    'bdof_tiles_block_ptr', 'bdof_tiles_cut', 'bdof_tiles_paste', 'bdof_tiles_halo_exchange', 'bdof_slice_step_seq', 'bdof_plan_set_grad_accumulate',
+    'bdof_tiles_block_ptr', 'bdof_tiles_cut', 'bdof_tiles_paste', 'bdof_tiles_halo_exchange', 'bdof_slice_step_seq', 'bdof_plan_set_grad_accumulate', 'bdof_regularizers',
 ]
 
 
@@ -80,6 +80,7 @@ def _load():
     lib.bdof_rotate_adjoint_csr.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, vp]
     lib.bdof_adam_step.argtypes = [vp, vp, vp, vp, i64, i32, f64, f64, f64, f64, vp]
     lib.bdof_finite_support.argtypes = [vp, vp, i64, f64, vp]
+    lib.bdof_regularizers.argtypes = [vp, vp, i32, i32, i32, f64, f64, f64, vp, vp, vp]
     lib.bdof_plan_set_t_stash.argtypes = [vp, vp]
     lib.bdof_plan_set_grad_accumulate.argtypes = [vp, i32]
     lib.bdof_rotate_bilinear.argtypes = [vp, vp, i64, f64, i32, i32, i32, vp]

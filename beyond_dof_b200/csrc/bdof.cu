@@ -1662,6 +1662,65 @@ extern "C" int bdof_adam_step(float* d_x, const float* d_g, float* d_m, float* d
     return launch_check("k_adam");
 }
 
+// L1 and 3-D total-variation regularisers of the TF driver (tensorflow_recon/fullfield.py:389-396, util.py:913-923 /
+// cnn_propagator/util.py:61-70: periodic first differences, L1) on the native object [nz][ny][nx][2]: ONE pass adds
+//   alpha_d sign(delta) + gamma dTV/ddelta   to the delta gradient,   alpha_b sign(beta)   to the beta gradient
+// and accumulates  alpha_d |delta|_1 + alpha_b |beta|_1 + gamma TV(delta)  (double partial sums, fixed order: deterministic).
+// dTV/dx_i = sum over axes of s_{i+1} - s_i with s_i = sign(x_{i-1} - x_i).
+__device__ __forceinline__ float sgnf(float v) { return float(v > 0.f) - float(v < 0.f); }
+__global__ void __launch_bounds__(LOSS_THREADS) k_regularizers(const float2* __restrict__ obj, float2* __restrict__ grad, int nz, int ny, int nx,
+                                                                float alpha_d, float alpha_b, float gamma, double* __restrict__ partial) {
+    const long long n = (long long)nz * ny * nx;
+    double acc = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int x = int(i % nx);
+        const long long r = i / nx;
+        const int y = int(r % ny), z = int(r / ny);
+        const float2 v = obj[i];
+        float gd = alpha_d * sgnf(v.x);
+        const float gb = alpha_b * sgnf(v.y);
+        acc += double(alpha_d) * fabsf(v.x) + double(alpha_b) * fabsf(v.y);
+        if (gamma != 0.f) {
+            const long long sx = 1, sy = nx, sz = (long long)ny * nx;
+            const float xm = obj[i + (x > 0 ? -sx : sx * (nx - 1))].x, xp = obj[i + (x < nx - 1 ? sx : -sx * (nx - 1))].x;
+            const float ym = obj[i + (y > 0 ? -sy : sy * (ny - 1))].x, yp = obj[i + (y < ny - 1 ? sy : -sy * (ny - 1))].x;
+            const float zm = obj[i + (z > 0 ? -sz : sz * (nz - 1))].x, zp = obj[i + (z < nz - 1 ? sz : -sz * (nz - 1))].x;
+            // s_i = sign(x_{i-1} - x_i), s_{i+1} = sign(x_i - x_{i+1})
+            gd += gamma * ((sgnf(v.x - xp) - sgnf(xm - v.x)) + (sgnf(v.x - yp) - sgnf(ym - v.x)) + (sgnf(v.x - zp) - sgnf(zm - v.x)));
+            acc += double(gamma) * (fabsf(xm - v.x) + fabsf(ym - v.x) + fabsf(zm - v.x));
+        }
+        if (grad != nullptr) {
+            float2 g = grad[i];
+            g.x += gd; g.y += gb;
+            grad[i] = g;
+        }
+    }
+    __shared__ double red[LOSS_THREADS / 32];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < LOSS_THREADS / 32; ++w) t += red[w];
+        partial[blockIdx.x] = t;
+    }
+}
+__global__ void k_add_partials(const double* __restrict__ partial, int n_partial, double* __restrict__ inout) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n_partial; i += 32) acc += partial[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) *inout += acc;
+}
+extern "C" int bdof_regularizers(const float* d_obj_db, float* d_grad_db, int nz, int ny, int nx, double alpha_d, double alpha_b, double gamma,
+                                 double* d_loss_inout, double* d_partial_work, void* st) {
+    if (!d_obj_db || !d_loss_inout || !d_partial_work || nz < 1 || ny < 1 || nx < 1) return fail(BDOF_E_BADARG, "bad argument");
+    k_regularizers<<<LOSS_BLOCKS, LOSS_THREADS, 0, (cudaStream_t)st>>>(reinterpret_cast<const float2*>(d_obj_db), reinterpret_cast<float2*>(d_grad_db), nz, ny,
+                                                                      nx, float(alpha_d), float(alpha_b), float(gamma), d_partial_work);
+    BDOF_TRY(launch_check("k_regularizers"));
+    k_add_partials<<<1, 32, 0, (cudaStream_t)st>>>(d_partial_work, LOSS_BLOCKS, d_loss_inout);
+    return launch_check("k_add_partials");
+}
+
 // finite support + non-negativity + shrink-wrap (cnn_propagator/fullfield.py:359-368): x <- clip(x * mask, 0, inf) on both
 // channels of the interleaved object; shrink_threshold >= 0 also updates mask <- mask * (delta > threshold)
 __global__ void k_finite_support(float2* __restrict__ x, float* __restrict__ mask, long long npx, float shrink_threshold) {

@@ -176,3 +176,19 @@ def rotate_db_bilinear_adjoint(grad_rot, theta, grad_obj):
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     check(lib.bdof_rotate_bilinear_adjoint(_ptr(grad_rot), grad_rot.stride(0) // 2, _ptr(grad_obj), float(theta), Y, X, Z, st))
     return grad_obj
+
+
+def regularizers(db_obj, grad_db, loss, alpha_d=None, alpha_b=None, gamma=0.0):
+    """L1 + 3-D TV regularisers of tensorflow_recon/fullfield.py:389-396 on the native object [Z,Y,X,2] (CUDA), fused in one
+    pass (bdof_regularizers): their gradient is ADDED to grad_db [Z,Y,X,2] (None: value only) and their value to the 0-d float64
+    device tensor `loss`, in place.  Returns loss."""
+    assert db_obj.is_cuda and db_obj.dtype == torch.float32 and db_obj.is_contiguous() and db_obj.dim() == 4 and db_obj.shape[-1] == 2
+    assert loss.is_cuda and loss.dtype == torch.float64 and loss.numel() == 1
+    if grad_db is not None:
+        assert grad_db.is_cuda and grad_db.dtype == torch.float32 and grad_db.is_contiguous() and grad_db.shape == db_obj.shape
+    Z, Y, X, _ = db_obj.shape
+    work = torch.empty(1184, dtype=torch.float64, device=db_obj.device)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib.bdof_regularizers(_ptr(db_obj), None if grad_db is None else _ptr(grad_db), Z, Y, X, float(alpha_d or 0.0),
+                                float(alpha_b or 0.0), float(gamma or 0.0), _ptr(loss), _ptr(work), st))
+    return loss

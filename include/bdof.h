@@ -217,6 +217,13 @@ int  bdof_rotate_bilinear_adjoint(const float* d_grad_rot_db, long long slice_st
 int  bdof_adam_step(float* d_x, const float* d_g, float* d_m, float* d_v, long long n, int i_batch, double step_size,
                     double b1, double b2, double eps, void* cuda_stream);
 
+/* the L1 and 3-D total-variation regularisers of the TF driver (tensorflow_recon/fullfield.py:389-396; TV =
+ * periodic first differences, L1: util.py:913-923 / cnn_propagator/util.py:61-70) on the native object [nz][ny][nx][2], fused:
+ * one pass adds alpha_d sign(delta) + gamma dTV/ddelta and alpha_b sign(beta) to d_grad_db (nullable: value only) and adds
+ * alpha_d |delta|_1 + alpha_b |beta|_1 + gamma TV(delta) to *d_loss_inout (double, device).  d_partial_work: 1184 doubles. */
+int  bdof_regularizers(const float* d_obj_db, float* d_grad_db, int nz, int ny, int nx, double alpha_d, double alpha_b, double gamma,
+                       double* d_loss_inout, double* d_partial_work, void* cuda_stream);
+
 /* finite support, non-negativity and shrink-wrap after every update (cnn_propagator/fullfield.py:359-368):
  * x <- clip(x * mask, 0, inf) on both channels of the interleaved object d_x_db [n_px][2]; d_mask [n_px] fp32 is nullable
  * (clip only); shrink_threshold >= 0 also updates mask <- mask * (delta > shrink_threshold) (the reference uses 1e-15). */

@@ -694,3 +694,23 @@ def test_fused_gradient_accumulation_over_a_minibatch(bd, shape):
     obj = FullfieldObjective(db.clone(), probe, 5000, 1e-7)
     loss = obj.step_device(torch.stack(targets), accumulate=3)
     assert rel_l2(obj.grad.cpu().numpy(), want.cpu().numpy()) < 1e-6
+
+
+def test_integration_md_ctypes_stub_runs_as_written(bd, gold):
+    # the raw ctypes binding a reference maintainer would add, extracted from the document and executed
+    # (only the library path is substituted), against the reference's own output on its 64^3 fixture
+    import re
+    from conftest import ROOT
+    from beyond_dof_b200 import capi
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    sec = text[text.index('## 2.'):text.index('## 3.')]
+    code = re.search(r'```python\n(.*?)```', sec, re.S).group(1)
+    assert 'ctypes.CDLL("libbdof.so")' in code
+    ns = {}
+    exec(code.replace('ctypes.CDLL("libbdof.so")', 'ctypes.CDLL(%r)' % capi.LIB_PATH), ns)
+    gd = gold['fixture64_delta_values'][gold['fixture64_delta_labels']][None]
+    psi = ns['multislice_propagate_batch_numpy'](gd, 0.1 * gd, np.ones([64, 64]), np.zeros([64, 64]), 5000, 1e-7, None, gd.shape)
+    assert intensity_err(psi, gold['psi_fixture64']) < TOL_INTENSITY
+    psi = ns['multislice_propagate_batch_numpy'](gd, 0.1 * gd, np.ones([64, 64]), np.zeros([64, 64]), 5000, 1e-7, 'inf', gd.shape)
+    ref = mo.multislice_propagate_batch_numpy(gd, 0.1 * gd, np.ones([64, 64]), np.zeros([64, 64]), 5000, 1e-7, 'inf', gd.shape)
+    assert intensity_err(psi, ref) < TOL_INTENSITY
