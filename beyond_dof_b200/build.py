@@ -42,7 +42,7 @@ def _sources_mtime():
 
 def _compile(args):
     src, obj, defs, log = args
-    cmd = [_nvcc()] + NVCC_FLAGS + defs + (['-DBDOF_ALT=%d' % ALT] if ALT in (1, 2) else []) + (['-DBDOF_PHASE_TIMING'] if ALT == 9 else []) + (['-DBDOF_NO_STAGGER'] if ALT in (3, 5) else []) + (['-DBDOF_NO_ROWPF'] if ALT in (4, 5) else []) + (['-DBDOF_NO_ROW_TILE_PREFETCH'] if ALT in (6, 8) else []) + (['-DBDOF_NO_COL_TILE_PREFETCH'] if ALT in (7, 8) else []) + ['-c', src, '-o', obj]
+    cmd = [_nvcc()] + NVCC_FLAGS + defs + (['-DBDOF_ALT=%d' % ALT] if ALT in (1, 2) else []) + (['-DBDOF_PHASE_TIMING'] if ALT == 9 else []) + (['-DBDOF_NO_STAGGER'] if ALT in (3, 5) else []) + (['-DBDOF_NO_ROWPF'] if ALT in (4, 5) else []) + (['-DBDOF_NO_ROW_TILE_PREFETCH'] if ALT in (6, 8) else []) + (['-DBDOF_NO_COL_TILE_PREFETCH'] if ALT in (7, 8) else []) + (['-DBDOF_TGROUP=4'] if ALT == 10 else []) + ['-c', src, '-o', obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     with open(log, 'w') as f:
         f.write(' '.join(cmd) + '\n' + r.stdout + r.stderr)

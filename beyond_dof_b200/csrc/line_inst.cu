@@ -93,13 +93,13 @@ static int launch_pipe_col(const LineParams& p, long long n_lines, cudaStream_t 
 }
 
 // sweep kernels (sweepfft.cuh): one kernel per slice and direction
-template <class Cfg, int LPC, int P, bool COL, bool ADJ>
+template <class Cfg, int LPC, int P, bool COL, bool ADJ, bool ACC = false>
 static int launch_sweep(const SweepParams& p0, long long rows, int cols, cudaStream_t st) {
     if constexpr (P == 0) {
         return bdof_fail(BDOF_E_UNSUPPORTED, "no sweep kernel for this FFT length");
     } else {
         using SM = PipeSmem<PipeCfg<Cfg, P>, LPC, COL>;
-        auto kern = sweep_kernel<Cfg, LPC, P, COL, ADJ>;
+        auto kern = sweep_kernel<Cfg, LPC, P, COL, ADJ, ACC>;
         static int ctas_per_sm = 0;           // per instantiation: short lines leave room for several CTAs per SM
         if (ctas_per_sm == 0) {
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SM::BYTES)));
@@ -168,6 +168,8 @@ int BDOF_CAT(bdof_launch_line_, BDOF_N)(int variant, const LineParams& p, long l
 int BDOF_CAT(bdof_launch_sweep_, BDOF_N)(int col, int adj, const SweepParams& p, long long rows, int cols, cudaStream_t st) {
     using C = typename CfgFor<BDOF_N>::C;
     constexpr int RL = CfgFor<BDOF_N>::RL, CL = CfgFor<BDOF_N>::CL, PP = pipe_parts(BDOF_N);
+    if (adj && p.grad_accumulate)
+        return col ? launch_sweep<C, CL, PP, true, true, true>(p, rows, cols, st) : launch_sweep<C, RL, PP, false, true, true>(p, rows, cols, st);
     if (col) return adj ? launch_sweep<C, CL, PP, true, true>(p, rows, cols, st) : launch_sweep<C, CL, PP, true, false>(p, rows, cols, st);
     return adj ? launch_sweep<C, RL, PP, false, true>(p, rows, cols, st) : launch_sweep<C, RL, PP, false, false>(p, rows, cols, st);
 }

@@ -48,7 +48,9 @@ struct SweepParams {
 
 enum { LAND_IN = 0, LAND_DB = 1, LAND_SLAB = 2 };
 
-template <class Cfg, int LPC, int P, bool COL, bool ADJ>
+// ACC (adjoint only): the gradient is ADDED to p.grad (fused accumulation over a minibatch); a template parameter so that the
+// plain kernels carry neither the branch nor the reduction instructions
+template <class Cfg, int LPC, int P, bool COL, bool ADJ, bool ACC = false>
 __global__ void __launch_bounds__(Cfg::T* LPC)
     sweep_kernel(const SweepParams p, const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                  const __grid_constant__ CUtensorMap tm_db, const __grid_constant__ CUtensorMap tm_grad) {
@@ -158,14 +160,15 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
     shift_init<PC>(st, t);
 
     // y kernels: strided stores leave through L by tensor copies
-    auto tma_store_tile = [&](const CUtensorMap* tm, long long done_tile, bool reduce_add = false) __attribute__((always_inline)) {
+    auto tma_store_tile = [&](const CUtensorMap* tm, long long done_tile, auto reduce_tag) __attribute__((always_inline)) {
+        constexpr bool reduce_add = decltype(reduce_tag)::value;
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
             const long long tl = done_tile * LPC;
             const int bb = int(tl / p.lines_per_batch);
             const int c0 = int(tl - (long long)bb * p.lines_per_batch);
-            if (reduce_add) {
+            if constexpr (reduce_add) {
 #pragma unroll 1
                 for (int j = 0; j < SM::NBOX; ++j) tma_reduce_add_2d(tm, 2 * c0, bb * N + j * SM::BOXR, L + j * SM::BOXR * LPC);
             } else {
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                 Lme[q * LQ] = v[q];
                 v[q] = x;
             });
-            tma_store_tile(&tm_out, tile - gridDim.x);
+            tma_store_tile(&tm_out, tile - gridDim.x, std::false_type{});
             pending = false;
         } else {
             if (active) static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = Lme[q * LQ]; });
@@ -243,40 +246,48 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                 // software pipeline: the next group's (delta, beta) are loaded while this group is evaluated (its shared-memory
                 // latency hides behind the arithmetic); not in the y kernels of long lines, which have no registers to spare
                 constexpr bool PREF = !COL || N <= 1024;
-                [[maybe_unused]] float2 dn[4];
+                // G elements per trip: the trip is a chain of dependent latencies (shared-memory load -> ~12 FP ops -> store), so
+                // the forward x kernels evaluate 8 pixels per trip for twice the instruction-level parallelism (BDOF_TGROUP)
+#ifndef BDOF_TGROUP
+#define BDOF_TGROUP 8
+#endif
+                constexpr int G = (PREF && !ADJ && E % BDOF_TGROUP == 0) ? BDOF_TGROUP : 4;
+                [[maybe_unused]] float2 dn[G];
                 if constexpr (PREF) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) dn[i] = Lme[i * LQ];
+                    for (int i = 0; i < G; ++i) dn[i] = Lme[i * LQ];
                 }
 #pragma unroll 1
-                for (int q0 = 0; q0 < q_end; q0 += 4) {
-                    float2 d[4];
+                for (int q0 = 0; q0 < q_end; q0 += G) {
+                    float2 d[G];
                     if constexpr (PREF) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) d[i] = dn[i];
-                        if (q0 + 4 < E) {
+                        for (int i = 0; i < G; ++i) d[i] = dn[i];
+                        if (q0 + G < E) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) dn[i] = Lme[(q0 + 4 + i) * LQ];
+                            for (int i = 0; i < G; ++i) dn[i] = Lme[(q0 + G + i) * LQ];
                         }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) d[i] = Lme[(q0 + i) * LQ];
+                        for (int i = 0; i < G; ++i) d[i] = Lme[(q0 + i) * LQ];
                     }
                     // the largest |k delta|, |k beta| of the group pick the series: the same decision as testing every element
                     // (rounding is monotonic), without the chain of dependent predicate updates
-                    const float md = akdz * fmaxf(fmaxf(fabsf(d[0].x), fabsf(d[1].x)), fmaxf(fabsf(d[2].x), fabsf(d[3].x)));
-                    const float mb = akdz * fmaxf(fmaxf(fabsf(d[0].y), fabsf(d[1].y)), fmaxf(fabsf(d[2].y), fabsf(d[3].y)));
+                    float md = 0.f, mb = 0.f;
+#pragma unroll
+                    for (int i = 0; i < G; ++i) { md = fmaxf(md, fabsf(d[i].x)); mb = fmaxf(mb, fabsf(d[i].y)); }
+                    md *= akdz; mb *= akdz;
                     const bool tiny = md <= 0.0625f && mb <= 0.015625f;
                     const bool small = md <= 0.78539816f && mb <= 0.5f;
                     if (__all_sync(0xffffffffu, tiny)) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) Lme[(q0 + i) * LQ] = transmission_tiny_m1(d[i], kdz);
+                        for (int i = 0; i < G; ++i) Lme[(q0 + i) * LQ] = transmission_tiny_m1(d[i], kdz);
                     } else if (__all_sync(0xffffffffu, small)) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) Lme[(q0 + i) * LQ] = transmission_small_m1(d[i], kdz);
+                        for (int i = 0; i < G; ++i) Lme[(q0 + i) * LQ] = transmission_small_m1(d[i], kdz);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) Lme[(q0 + i) * LQ] = transmission_m1(d[i], kdz);
+                        for (int i = 0; i < G; ++i) Lme[(q0 + i) * LQ] = transmission_m1(d[i], kdz);
                     }
                 }
                 SWEEP_STAMP(5);
@@ -290,7 +301,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                         // stash t for the adjoint: L leaves by TMA (tensor store for column tiles, bulk rows otherwise); the next
                         // landing is issued from inside the following convolution once the store has finished reading L
                         if constexpr (COL) {
-                            tma_store_tile(&tm_grad, tile);
+                            tma_store_tile(&tm_grad, tile, std::false_type{});
                         } else {
                             fence_proxy_async();
                             __syncthreads();
@@ -322,15 +333,14 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
                             const float2 w = cmulc(Lme[q * LQ], v[q]);
                             Lme[q * LQ] = make_float2(-kdz * w.y, -kdz * w.x);
                         });
-                        tma_store_tile(&tm_grad, tile, p.grad_accumulate != 0);
+                        tma_store_tile(&tm_grad, tile, std::integral_constant<bool, ACC>{});
                         if (has_next) deferred = LAND_IN;
                     } else {
                         float2* gp = p.grad + tile_off + (Lme - L);
-                        const bool acc = p.grad_accumulate != 0;
                         if (active) static_for<E>([&](auto Q) __attribute__((always_inline)) {
                             constexpr int q = decltype(Q)::value;
                             const float2 w = cmulc(Lme[q * LQ], v[q]);
-                            if (acc) red_add_f32x2(gp + q * LQ, -kdz * w.y, -kdz * w.x);
+                            if constexpr (ACC) red_add_f32x2(gp + q * LQ, -kdz * w.y, -kdz * w.x);
                             else gp[q * LQ] = make_float2(-kdz * w.y, -kdz * w.x);
                         });
                         __syncthreads();
@@ -391,7 +401,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC)
         if (tid == 0) bulk_wait_group_read0();
         __syncthreads();
         static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; Lme[q * LQ] = v[q]; });
-        tma_store_tile(&tm_out, tile - gridDim.x);
+        tma_store_tile(&tm_out, tile - gridDim.x, std::false_type{});
     }
     if ((COL || !ADJ) && tid == 0) bulk_wait_group_read0();
     SWEEP_GSTAMP(30);
