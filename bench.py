@@ -303,7 +303,7 @@ def host_object_leg(torch, ny, nx, nz, target_host):
         rng = np.random.default_rng(77)
         od = rng.random((ny, nx, nz), dtype=np.float32); od *= np.float32(1e-5)
         ob = rng.random((ny, nx, nz), dtype=np.float32); ob *= np.float32(1e-6)
-        prj_np = target_host.numpy()
+        prj_np = (target_host[0] if target_host.dim() == 4 else target_host).numpy()       # one field's projection
         one, zero = np.ones((ny, nx), np.float32), np.zeros((ny, nx), np.float32)
         g_d, g_b = np.empty_like(od), np.empty_like(ob)
 
