@@ -15,6 +15,7 @@ probe = torch.ones((N, N), dtype=torch.complex64, device='cuda')
 buf = torch.zeros((4 << 17,), dtype=torch.int64, device='cuda')
 tgt = torch.full((1, N, N), 0.9, device='cuda')
 gout = torch.empty_like(db)
+plan.set_t_stash(gout)            # as in production: the forward leaves tau where the adjoint writes the gradient
 for it in range(2):
     psi = plan.forward(db, probe)
     _, g = plan.loss_mag(psi, tgt)
