@@ -781,7 +781,7 @@ def main():
     ap.add_argument('--no-headline', action='store_true', help='skip the 4096^2 x 512 headline record of the default run')
     ap.add_argument('--fields-per-exchange', type=int, default=10, help='fields (projection angles) each rank evaluates and sums per step / gradient '
                     'exchange: the minibatch_size = 10 of the reference drivers (reconstruct_fullfield.py:30,60); the same at every N')
-    ap.add_argument('--sm-reserve', type=int, default=-1, help='SMs left free for NCCL while the sweep runs (N > 1); -1 = the exchange\'s own default')
+    ap.add_argument('--sm-reserve', type=int, default=0, help='SMs left free for NCCL while the sweep runs (N > 1); -1 = as many as cost no extra round of tiles')
     ap.add_argument('--exchange', default='auto', choices=['auto', 'ce', 'nccl', 'hybrid'], help='N > 1: gradient exchange (copy engines over peer memory, or NCCL all-reduce)')
     ap.add_argument('--buckets', type=int, default=0, help='z-buckets of the gradient all-reduce (N > 1)')
     ap.add_argument('--shape', default=None, help='experiment: B,NY,NX,NZ overrides the workload shape')

@@ -388,16 +388,17 @@ class FullfieldObjective:
         # the forward leaves the transmission of every slice where the adjoint will write that slice's gradient
         self.plan.set_t_stash(self.grad)
 
-    def enable_data_parallel(self, n_buckets=None, exchange='auto', sm_reserve=-1):
+    def enable_data_parallel(self, n_buckets=None, exchange='auto', sm_reserve=0):
         """Average the object gradient over the ranks of the default process group every step, bucket by
         bucket along z while the adjoint sweep is still running.  exchange='ce': copy engines over NVLink peer
         memory (dist.CopyEngineExchange; the gradient then lives in the exchange's exportable buffer);
         'nccl': NCCL all-reduce on a communication stream; 'hybrid': NCCL reduce-scatter + copy-engine all-gather;
         'auto': dist.pick_exchange().
-        sm_reserve: SMs the persistent sweep kernels leave to the NCCL kernels (they own every SM otherwise -- one 226 KB
-        CTA each -- and the collective then time-slices with the sweep instead of overlapping it); -1 = the largest number
-        that does not add a round of tiles to the sweep kernels for this field shape (dist.auto_sm_reserve) whenever the
-        exchange runs NCCL kernels, 0 for the copy-engine exchange."""
+        sm_reserve: SMs the persistent sweep kernels leave to the NCCL kernels (they own every SM otherwise, one 226 KB CTA
+        each); -1 = the largest number that does not add a round of tiles to the sweep kernels for this field shape
+        (dist.auto_sm_reserve) whenever the exchange runs NCCL kernels.  Default 0: measured on 8 x B200 (2048^2 x 256, one field
+        per exchange) the step takes 41.0 ms with 0 and 41.6 ms with 20 reserved SMs -- the collective is not SM-starved, the
+        sweep kernels slow down while 8.6 GB stream through the L2 their field lives in."""
         from . import dist as bdist
         self._dp = bdist
         if exchange == 'auto':
