@@ -330,48 +330,56 @@ __global__ void k_patch_scatter_add(const float2* __restrict__ gpatch, int oy, i
 }
 
 // The same accumulation as a GATHER, in scan-position order: deterministic (bit-identical run to run and for any split of the
-// positions into launches that keeps their order), which the fp32 atomics above are not.  A block owns 128 consecutive x of one
-// object row y and PSCAT_ZB consecutive slices; it first compacts, IN ORDER, the positions whose window touches its pixels
-// (ballot prefix sums), then every thread adds the window pixels that fall on its own object pixel.
-constexpr int PSCAT_THREADS = 128, PSCAT_ZB = 8, PSCAT_MAX_POS = 4096;
+// positions into launches that keeps their order), which the fp32 atomics above are not.  A block owns PSCAT_BX consecutive x of
+// one object row y and PSCAT_ZB consecutive slices (thread = one x, one of PSCAT_ZL slice lanes); it first compacts, IN ORDER,
+// the positions whose window touches its pixels (ballot prefix sums; origins kept in shared memory), then every thread adds the
+// window pixels that fall on its own object pixel.  Narrow x ranges keep the share of listed-but-not-covering positions low (a
+// 64-wide window over a 32-wide range: 2/3 of the listed positions cover a given pixel).
+constexpr int PSCAT_BX = 32, PSCAT_ZL = 4, PSCAT_THREADS = PSCAT_BX * PSCAT_ZL, PSCAT_ZB = 16, PSCAT_MAX_POS = 4096;
 __global__ void __launch_bounds__(PSCAT_THREADS) k_patch_gather_add(const float2* __restrict__ gpatch, int n_slice, int oy, int ox,
                                                                      const int* __restrict__ pos, int n_pos, int py, int px,
                                                                      float2* __restrict__ gobj) {
     __shared__ int s_idx[PSCAT_MAX_POS];
+    __shared__ short s_wy[PSCAT_MAX_POS], s_wx[PSCAT_MAX_POS];       // origins relative to (y, x0b): |value| < 32768 checked by the launcher
     __shared__ int s_warp_count[PSCAT_THREADS / 32];
     __shared__ int s_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0b = blockIdx.x * PSCAT_THREADS, y = blockIdx.y, z0 = blockIdx.z * PSCAT_ZB;
+    const int x0b = blockIdx.x * PSCAT_BX, y = blockIdx.y, z0 = blockIdx.z * PSCAT_ZB;
     if (tid == 0) s_total = 0;
     __syncthreads();
     for (int base = 0; base < n_pos; base += PSCAT_THREADS) {
         const int ip = base + tid;
         bool hit = false;
+        int wy = 0, wx = 0;
         if (ip < n_pos) {
-            const int wy = pos[2 * ip], wx = pos[2 * ip + 1];
-            hit = (y >= wy && y < wy + py) && (wx < x0b + PSCAT_THREADS && wx + px > x0b);
+            wy = pos[2 * ip]; wx = pos[2 * ip + 1];
+            hit = (y >= wy && y < wy + py) && (wx < x0b + PSCAT_BX && wx + px > x0b);
         }
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (lane == 0) s_warp_count[warp] = __popc(m);
         __syncthreads();
         int off = s_total;
         for (int w = 0; w < warp; ++w) off += s_warp_count[w];
-        if (hit) s_idx[off + __popc(m & ((1u << lane) - 1u))] = ip;
+        if (hit) {
+            const int k = off + __popc(m & ((1u << lane) - 1u));
+            s_idx[k] = ip; s_wy[k] = short(y - wy); s_wx[k] = short(wx - x0b);
+        }
         __syncthreads();
         if (tid == 0) { int t = 0; for (int w = 0; w < PSCAT_THREADS / 32; ++w) t += s_warp_count[w]; s_total += t; }
         __syncthreads();
     }
     const int n_hit = s_total;
-    const int x = x0b + tid;
+    const int xl = tid % PSCAT_BX, zl = tid / PSCAT_BX;
+    const int x = x0b + xl;
     if (x >= ox) return;
-    for (int z = z0; z < z0 + PSCAT_ZB && z < n_slice; ++z) {
+    const long long tile_px = (long long)py * px;
+    for (int z = z0 + zl; z < z0 + PSCAT_ZB && z < n_slice; z += PSCAT_ZL) {
+        const float2* gz = gpatch + (long long)z * n_pos * tile_px;
         float ax = 0.f, ay = 0.f;
         for (int k = 0; k < n_hit; ++k) {
-            const int ip = s_idx[k];
-            const int wy = pos[2 * ip], wx = pos[2 * ip + 1];
-            const int xx = x - wx;
+            const int xx = xl - int(s_wx[k]);
             if (xx >= 0 && xx < px) {
-                const float2 v = gpatch[(((long long)z * n_pos + ip) * py + (y - wy)) * px + xx];
+                const float2 v = gz[(long long)s_idx[k] * tile_px + int(s_wy[k]) * px + xx];
                 ax += v.x; ay += v.y;
             }
         }
@@ -1331,7 +1339,8 @@ extern "C" int bdof_patch_gather_add(const float* d_grad_patches, int n_slice, i
     if (!d_grad_patches || !d_pos_yx || !d_grad_obj || n_pos < 1 || n_slice < 1) return fail(BDOF_E_BADARG, "bad argument");
     if (n_pos > PSCAT_MAX_POS) return fail(BDOF_E_UNSUPPORTED, "more than %d scan positions per call", PSCAT_MAX_POS);
     if (oy > 65535 || (n_slice + PSCAT_ZB - 1) / PSCAT_ZB > 65535) return fail(BDOF_E_UNSUPPORTED, "object too large");
-    dim3 grid((ox + PSCAT_THREADS - 1) / PSCAT_THREADS, oy, (n_slice + PSCAT_ZB - 1) / PSCAT_ZB);
+    if (oy > 30000 || ox > 30000 || py > 30000 || px > 30000) return fail(BDOF_E_UNSUPPORTED, "object or window side > 30000");
+    dim3 grid((ox + PSCAT_BX - 1) / PSCAT_BX, oy, (n_slice + PSCAT_ZB - 1) / PSCAT_ZB);
     k_patch_gather_add<<<grid, PSCAT_THREADS, 0, (cudaStream_t)st>>>(reinterpret_cast<const float2*>(d_grad_patches), n_slice, oy, ox, d_pos_yx,
                                                                     n_pos, py, px, reinterpret_cast<float2*>(d_grad_obj));
     return launch_check("k_patch_gather_add");
