@@ -212,8 +212,10 @@ __device__ __forceinline__ void resident_forward_step(const ResidentParams& p, i
     for (int q = 0; q < E; ++q) d[q] = dn[q];
 }
 
-template <class Cfg>
-__global__ void __launch_bounds__(Cfg::N* Cfg::T) resident_forward_kernel(const ResidentParams p) {
+// MINB = 2: registers capped at 64 so that two CTAs share an SM (batches of more fields than SMs: the second CTA fills the issue
+// slots the first leaves idle, 45 % active with one)
+template <class Cfg, int MINB = 1>
+__global__ void __launch_bounds__(Cfg::N* Cfg::T, MINB) resident_forward_kernel(const ResidentParams p) {
     using SM = ResidentSmem<Cfg>;
     constexpr int E = Cfg::E, N = Cfg::N;
     extern __shared__ __align__(16) float2 smem_res[];
@@ -259,7 +261,9 @@ __global__ void __launch_bounds__(Cfg::N* Cfg::T) resident_forward_kernel(const 
 // adjoint: the same steps backwards with the conjugate tables
 //   B_s --C_a^H--> G_u --[G = conj(t_s) G_u ; grad_s = -k (Im, Re)(psi_s conj(G))]--> --C_a^H--> B_{s-1}
 // ------------------------------------------------------------------------------------------------------------------
-template <class Cfg, bool COL>
+// AHEAD: the side arrays of the next step are prefetched into registers one step ahead (one CTA per SM); otherwise they are
+// loaded at the top of their own step and land during its first convolution (register-capped variant, two CTAs per SM)
+template <class Cfg, bool COL, bool AHEAD>
 __device__ __forceinline__ void resident_adjoint_step(const ResidentParams& p, int s, long long fbase, int wy0, int wx0, int tid,
                                                       float2 (&v)[Cfg::E], float2 (&d)[Cfg::E], float2 (&psi)[Cfg::E], float2* X,
                                                       const float2* s_tw, float2* s_h) {
@@ -267,16 +271,29 @@ __device__ __forceinline__ void resident_adjoint_step(const ResidentParams& p, i
     const ResidentMap<Cfg, COL> m(tid);
     const int Z = p.n_slice;
     const bool from_stash = p.tstash != nullptr;
+    if constexpr (!AHEAD) {
+        if (s < Z) {
+            const float2* tsrc = p.tstash + (long long)s * p.slice_stride + fbase;
+            const float2* sp = p.slab + (long long)s * p.slice_stride + fbase + tid;
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                d[q] = from_stash ? __ldg(tsrc + m.g(q)) : resident_load_db(p, s, fbase, wy0, wx0, m, q);
+                psi[q] = __ldg(sp + q * NT);
+            }
+        }
+    }
     // prefetch for the NEXT step (slice s - 1), in that step's layout
-    float2 dn[E] = {}, pn[E] = {};
-    if (s >= 1 && s - 1 < Z) {
+    [[maybe_unused]] float2 dn[AHEAD ? E : 1] = {}, pn[AHEAD ? E : 1] = {};
+    if (AHEAD && s >= 1 && s - 1 < Z) {
         const ResidentMap<Cfg, !COL> mn(tid);
         const float2* tsrc = p.tstash + (long long)(s - 1) * p.slice_stride + fbase;
         const float2* sp = p.slab + (long long)(s - 1) * p.slice_stride + fbase + tid;
+        if constexpr (AHEAD) {
 #pragma unroll
-        for (int q = 0; q < E; ++q) {
-            dn[q] = from_stash ? __ldg(tsrc + mn.g(q)) : resident_load_db(p, s - 1, fbase, wy0, wx0, mn, q);
-            pn[q] = __ldg(sp + q * NT);
+            for (int q = 0; q < E; ++q) {
+                dn[q] = from_stash ? __ldg(tsrc + mn.g(q)) : resident_load_db(p, s - 1, fbase, wy0, wx0, mn, q);
+                pn[q] = __ldg(sp + q * NT);
+            }
         }
     }
     if (s >= 1) resident_stage_h<Cfg>(p, s - 1, tid, s_h);
@@ -304,12 +321,15 @@ __device__ __forceinline__ void resident_adjoint_step(const ResidentParams& p, i
         if (s > 0) resident_conv<Cfg, COL>(v, m, X, s_tw, h);
     }
     if (s > 0) resident_transpose<Cfg, COL>(v, tid, X);
+    if constexpr (AHEAD) {
 #pragma unroll
-    for (int q = 0; q < E; ++q) { d[q] = dn[q]; psi[q] = pn[q]; }
+        for (int q = 0; q < E; ++q) { d[q] = dn[q]; psi[q] = pn[q]; }
+    }
 }
 
-template <class Cfg>
-__global__ void __launch_bounds__(Cfg::N* Cfg::T) resident_adjoint_kernel(const ResidentParams p) {
+template <class Cfg, int MINB = 1>
+__global__ void __launch_bounds__(Cfg::N* Cfg::T, MINB) resident_adjoint_kernel(const ResidentParams p) {
+    constexpr bool AHEAD = (MINB == 1);
     using SM = ResidentSmem<Cfg>;
     constexpr int E = Cfg::E, N = Cfg::N, NT = Cfg::N * Cfg::T;
     extern __shared__ __align__(16) float2 smem_res[];
@@ -331,7 +351,7 @@ __global__ void __launch_bounds__(Cfg::N* Cfg::T) resident_adjoint_kernel(const 
         auto first_loads = [&](auto map) __attribute__((always_inline)) {
 #pragma unroll
             for (int q = 0; q < E; ++q) v[q] = __ldg(p.in + fbase + map.g(q));
-            if (s0 < Z) {
+            if (AHEAD && s0 < Z) {
                 const float2* tsrc = p.tstash + (long long)s0 * p.slice_stride + fbase;
                 const float2* sp = p.slab + (long long)s0 * p.slice_stride + fbase + tid;
 #pragma unroll
@@ -349,8 +369,8 @@ __global__ void __launch_bounds__(Cfg::N* Cfg::T) resident_adjoint_kernel(const 
         __syncthreads();
 #pragma unroll 1
         for (int s = s0; s >= 0; --s) {
-            if (s & 1) resident_adjoint_step<Cfg, true>(p, s, fbase, wy0, wx0, tid, v, d, psi, X, s_tw, s_h);
-            else       resident_adjoint_step<Cfg, false>(p, s, fbase, wy0, wx0, tid, v, d, psi, X, s_tw, s_h);
+            if (s & 1) resident_adjoint_step<Cfg, true, AHEAD>(p, s, fbase, wy0, wx0, tid, v, d, psi, X, s_tw, s_h);
+            else       resident_adjoint_step<Cfg, false, AHEAD>(p, s, fbase, wy0, wx0, tid, v, d, psi, X, s_tw, s_h);
         }
         if (p.out != nullptr) {
             const ResidentMap<Cfg, false> m(tid);       // step 0 is an x step
