@@ -45,7 +45,10 @@ static int launch_resident(int adj, const ResidentParams& p, cudaStream_t st) {
     }
     unsigned grid = unsigned(p.batch < slots[adj] ? p.batch : slots[adj]);
     static int two = -1;
-    if (two < 0) { const char* e = getenv("BDOF_RESIDENT_2CTA"); two = (e && e[0] == '0') ? 0 : 1; }
+    // measured (1024 fields of 64^2 x 128, B200): two register-capped CTAs per SM are 4-6 % SLOWER than one (forward 4.07 vs
+    // 3.92 ms, adjoint 3.77 vs 3.55 ms): the kernels are bound by issue slots and shared-memory wavefronts, not by latency.
+    // Kept as a switch (BDOF_RESIDENT_2CTA=1).
+    if (two < 0) { const char* e = getenv("BDOF_RESIDENT_2CTA"); two = (e && e[0] == '1') ? 1 : 0; }
     if (adj && two && slots_a2 > 0 && p.batch > slots[1]) {
         grid = unsigned(p.batch < slots_a2 ? p.batch : slots_a2);
         ka2<<<grid, Cfg::N * Cfg::T, SM::BYTES, st>>>(p);

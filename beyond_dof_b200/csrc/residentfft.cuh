@@ -212,8 +212,8 @@ __device__ __forceinline__ void resident_forward_step(const ResidentParams& p, i
     for (int q = 0; q < E; ++q) d[q] = dn[q];
 }
 
-// MINB = 2: registers capped at 64 so that two CTAs share an SM (batches of more fields than SMs: the second CTA fills the issue
-// slots the first leaves idle, 45 % active with one)
+// MINB = 2: registers capped at 64 so that two CTAs share an SM (experiment, BDOF_RESIDENT_2CTA=1: measured 4-6 % slower than one
+// CTA per SM -- the kernels are bound by issue slots and shared-memory wavefronts, not by latency)
 template <class Cfg, int MINB = 1>
 __global__ void __launch_bounds__(Cfg::N* Cfg::T, MINB) resident_forward_kernel(const ResidentParams p) {
     using SM = ResidentSmem<Cfg>;
