@@ -611,7 +611,8 @@ def run_config5(args):
             out[r0:r0 + 1024, :, 0] = mask * 1.0e-4
             out[r0:r0 + 1024, :, 1] = mask * 1.0e-5
         return out
-    tm = TiledMultislice(n, n, grid, halo, ENERGY_EV, PSIZE_CM, nz, db_block)
+    lengths = tuple(int(v) for v in args.tile_lengths.split(',')) if args.tile_lengths else None
+    tm = TiledMultislice(n, n, grid, halo, ENERGY_EV, PSIZE_CM, nz, db_block, **({'lengths': lengths} if lengths else {}))
 
     def step():
         out = tm.run()
@@ -776,6 +777,7 @@ def main():
     ap.add_argument('--no-host-object', action='store_true', help='skip the extra end-to-end leg with delta/beta and the gradients in host memory')
     ap.add_argument('--halo', type=int, default=8, help='config5: halo of the local FFT windows (the reference kernel_size 17 = 8 px)')
     ap.add_argument('--tile-field', type=int, default=16384, help='config5: side of the global field')
+    ap.add_argument('--tile-lengths', default=None, help='config5: comma-separated FFT window lengths to choose from (default: all powers of two 256..8192)')
     ap.add_argument('--tile-slices', type=int, default=1000, help='config5: slices')
     ap.add_argument('--no-cufft', action='store_true', help='skip the cuFFT comparison leg (unfused reference loop on torch.fft)')
     ap.add_argument('--no-headline', action='store_true', help='skip the 4096^2 x 512 headline record of the default run')
