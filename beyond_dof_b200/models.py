@@ -271,6 +271,7 @@ def ptycho_loss_and_grad(obj_delta, obj_beta, theta, probe_pos_batch, prj_batch,
     native = db_obj is not None
     if not native:
         db_obj = pack_object(obj_delta, obj_beta)
+    db_obj = db_obj.contiguous()
     Z, OY, OX, _ = db_obj.shape
     tab = None
     obj_unrot = db_obj
@@ -290,18 +291,29 @@ def ptycho_loss_and_grad(obj_delta, obj_beta, theta, probe_pos_batch, prj_batch,
     plan = _cached_plan(key, lambda: MultislicePlan(py, px, n, Z, energy_ev, psize_cm, free_prop_cm='inf',
                                                      propagate_last=True, store_slices=True))
     patches = torch.empty((Z, n, py, px, 2), dtype=torch.float32, device=dev)
-    check(lib.bdof_patch_gather(_ptr(db_obj), Z, OY, OX, _ptr(origin), n, py, px, _ptr(patches), st))
     probe = _probe_c64(probe_real, probe_imag, (py, px))
-    plan.set_t_stash(patches if want_grad else None)
-    exit_wave = plan.forward(patches, probe)
     is_cplx = (isinstance(prj_batch, torch.Tensor) and prj_batch.is_complex()) or np.iscomplexobj(prj_batch)
     target = _to_dev(prj_batch, torch.complex64 if is_cplx else torch.float32).abs().to(torch.float32)
     scale = float(n_pos_total if n_pos_total is not None else n) if scale_by_npos else 1.0
+    windowed = plan.is_resident()
+    if windowed:
+        # 64 x 64 probes: the resident kernels read the object straight through the windows; `patches` only holds the
+        # transmission stash and then the per-window gradients
+        plan.set_windows((Z, OY, OX), origin)
+        plan.set_t_stash(patches if want_grad else None)
+        exit_wave = plan.forward(db_obj, probe)
+    else:
+        check(lib.bdof_patch_gather(_ptr(db_obj), Z, OY, OX, _ptr(origin), n, py, px, _ptr(patches), st))
+        plan.set_t_stash(patches if want_grad else None)
+        exit_wave = plan.forward(patches, probe)
     loss, g_exit = plan.loss_mag(exit_wave, target, want_grad=want_grad, loss_scale=scale)
     loss = loss.clone()
     if not want_grad:
         return loss, None
-    plan.adjoint(patches, g_exit)
+    if windowed:
+        plan.adjoint(db_obj, g_exit, grad_out=patches)
+    else:
+        plan.adjoint(patches, g_exit)
     if grad_obj_out is None:
         grad_obj_out = torch.zeros_like(db_obj)
     scatter = lib.bdof_patch_gather_add if deterministic else lib.bdof_patch_scatter_add
