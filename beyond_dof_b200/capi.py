@@ -25,7 +25,7 @@ SYMBOLS = [
     'bdof_dp_create', 'bdof_dp_destroy', 'bdof_dp_handle_bytes', 'bdof_dp_export', 'bdof_dp_connect', 'bdof_dp_grad_ptr',
     'bdof_dp_bucket', 'bdof_dp_gather', 'bdof_dp_finish', 'bdof_plan_last_times', 'bdof_pack_db_rows', 'bdof_unpack_db_rows', 'bdof_plan_set_stream', 'bdof_debug_fft_gain', 'bdof_field_multiply', 'bdof_patch_gather_add', 'bdof_plan_set_windows', 'bdof_plan_is_resident', 'bdof_cnn_forward_store', 'bdof_cnn_adjoint', 'bdof_free_prop_adjoint',
     'bdof_tiles_create', 'bdof_tiles_destroy', 'bdof_tiles_handle_bytes', 'bdof_tiles_export', 'bdof_tiles_connect',
-    'bdof_tiles_block_ptr', 'bdof_tiles_cut', 'bdof_tiles_paste', 'bdof_tiles_halo_exchange', 'bdof_slice_step_seq', 'bdof_plan_set_grad_accumulate', 'bdof_regularizers',
+    'bdof_tiles_block_ptr', 'bdof_tiles_cut', 'bdof_tiles_paste', 'bdof_tiles_halo_exchange', 'bdof_slice_step_seq', 'bdof_plan_set_grad_accumulate', 'bdof_regularizers', 'bdof_slice_step_windows',
 ]
 
 
@@ -71,6 +71,7 @@ def _load():
     lib.bdof_debug_set_buffer.argtypes = [vp]
     lib.bdof_slice_step.argtypes = [vp, vp, vp, vp, i32]
     lib.bdof_slice_step_seq.argtypes = [vp, vp, vp, vp, i32, i32]
+    lib.bdof_slice_step_windows.argtypes = [vp, vp, i64, vp, vp, vp, i32]
     lib.bdof_plan_set_bucket_events.argtypes = [vp, i32, vp]
     lib.bdof_set_sm_reserve.argtypes = [i32]
     lib.bdof_profile_end.argtypes = [vp, i32, vp, vp]

@@ -1864,6 +1864,24 @@ extern "C" int bdof_plan_set_windows(bdof_plan* p, int oy, int ox, const int* d_
 }
 extern "C" int bdof_plan_is_resident(const bdof_plan* p) { return (p && p->have_kernel && use_resident(p)) ? 1 : 0; }
 
+// One propagating slice whose input lines are read straight out of a larger pitched buffer (tiling: the windows of a block; the
+// cut is fused into the row pass): window b's first row starts d_in_offsets[b] elements into d_buf, rows are `pitch` elements
+// apart.  Row lengths >= 1024 are fetched by bulk copies and need 16-byte aligned rows: even offsets and an even pitch.
+extern "C" int bdof_slice_step_windows(bdof_plan* p, const float* d_buf, long long pitch, const long long* d_in_offsets, const float* d_db_tiles,
+                                       float* d_out_tiles, int slice_index) {
+    if (!p || !d_buf || !d_in_offsets || !d_db_tiles || !d_out_tiles || pitch < p->nx) return fail(BDOF_E_BADARG, "bad argument");
+    if (!p->have_kernel) return fail(BDOF_E_STATE, "bdof_set_kernel has not been called");
+    if (p->full_kernel || p->generic) return fail(BDOF_E_UNSUPPORTED, "windowed stepping needs a separable kernel and power-of-two window sides");
+    if (slice_index >= 0 && !(p->flags & BDOF_STEPWISE)) return fail(BDOF_E_STATE, "a slice index needs a plan created with BDOF_STEPWISE");
+    if (p->nx >= 1024 && (pitch % 2 != 0)) return fail(BDOF_E_BADARG, "rows of 1024 pixels and more need an even pitch (16-byte aligned bulk copies)");
+    LineParams r = row_params(p, reinterpret_cast<const float2*>(d_buf), p->tmp, h_entry(p->ax, slice_index, false));
+    r.db = reinterpret_cast<const float2*>(d_db_tiles);
+    r.in_offsets = d_in_offsets;
+    r.in_line_stride = int(pitch);
+    BDOF_TRY(row_pass(p, V_ROW_CONV_T, r));
+    return col_pass(p, V_COL_CONV, col_params(p, p->tmp, reinterpret_cast<float2*>(d_out_tiles), h_entry(p->ay, slice_index, false)));
+}
+
 extern "C" int bdof_plan_set_grad_accumulate(bdof_plan* p, int on) {
     if (!p) return fail(BDOF_E_BADARG, "null");
     p->grad_accumulate = on != 0;

@@ -27,6 +27,11 @@ struct LineParams {
     const void* pf0;         // nullable
     const void* pf1;         // nullable
     long long pf_bytes;      // bytes per prefetched array (multiple of 16)
+    // Row passes reading their lines straight out of a larger pitched buffer (tiling: the windows of a block, fused cut):
+    // item b's first line starts in_offsets[b] elements into `in` and consecutive lines are in_line_stride elements apart.
+    // Null / 0 = the regular layout (b * batch_stride, line_stride).  The output and the side inputs keep the regular layout.
+    const long long* in_offsets;
+    int in_line_stride;
     int tune;                // runtime switches (BDOF_TUNE): 1 L2-prefetch the next tile's main input at tile start,
                              // 2 L2-prefetch the next line's delta/beta (forward row pass)
 };

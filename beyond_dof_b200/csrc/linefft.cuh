@@ -380,10 +380,13 @@ __global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, c
             for (int c = 0; c < ST::NBUF; ++c) stream_issue(line0, c);
     }
     // start of row `ln` of the input field (row mode)
+    // (row mode; `in_offsets` / `in_line_stride`: lines read straight out of a larger pitched buffer, common.h)
+    const long long in_lstride = (!COL && p.in_line_stride != 0) ? (long long)p.in_line_stride : (long long)p.line_stride;
     auto row_ptr = [&](long long ln) __attribute__((always_inline)) {
         const int bb = int(ln / p.lines_per_batch);
         const int lli = int(ln - (long long)bb * p.lines_per_batch);
-        return p.in + (long long)bb * p.batch_stride + (long long)lli * p.line_stride;
+        const long long b0 = (!COL && p.in_offsets != nullptr) ? p.in_offsets[bb] : (long long)bb * p.batch_stride;
+        return p.in + b0 + (long long)lli * in_lstride;
     };
     if constexpr (PREFETCH && !COL) {
         // the first row of every line slot is fetched the same way as all later ones
@@ -425,7 +428,7 @@ __global__ void __launch_bounds__(Cfg::T* LPC) line_kernel(const LineParams p, c
             }
         }
         if (!loaded) {
-            const float2* __restrict__ src = p.in + base;
+            const float2* __restrict__ src = COL ? p.in + base : row_ptr(line) + t;
             if constexpr (MODE == MODE_INV) {
                 // conj + circular input shift (ifftshift), far-field adjoint only
                 const float2* __restrict__ src0 = p.in + (base - (long long)t * estride);

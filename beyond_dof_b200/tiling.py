@@ -177,9 +177,9 @@ def axis_tiles(block, halo, lengths=FAST_LENGTHS):
     Returns (L, [(window_start, own_start, own_len)], apron) with positions relative to the block; windows may start at -apron."""
     best = None
     for L in lengths:
-        if L <= 2 * halo:
+        if L <= 2 * (halo + 1):
             continue
-        n = -(-block // (L - 2 * halo))
+        n = -(-block // (L - 2 * (halo + 1)))             # + 1: starts are rounded to even pixels below
         if best is None or n * L < best[0] * best[1]:
             best = (n, L)
     if best is None:
@@ -190,8 +190,10 @@ def axis_tiles(block, halo, lengths=FAST_LENGTHS):
     for k in range(n):
         own = edges[k + 1] - edges[k]
         start = edges[k] - (L - own) // 2
+        start -= start % 2                       # even starts: window rows stay 16-byte aligned in the block buffer (bulk copies)
         out.append((start, edges[k], own))
         apron = max(apron, -start, start + L - block)
+    apron += apron % 2
     return L, out, apron
 
 
@@ -246,6 +248,11 @@ class TiledMultislice:
         origin = [(sy, sx) for (sy, _, _) in ty for (sx, _, _) in tx]
         own = [(oy, ox, hy, hx) for (_, oy, hy) in ty for (_, ox, hx) in tx]
         self.origin = torch.tensor(origin, dtype=torch.int32, device=self.device).contiguous()
+        pitch = self.bx + 2 * self.apron
+        # element offset of every window's first row in a block buffer (the row pass reads the windows in place: fused cut)
+        self.win_offsets = torch.tensor([(self.apron + sy) * pitch + self.apron + sx for (sy, sx) in origin], dtype=torch.int64,
+                                        device=self.device).contiguous()
+        self.fused_cut = (self.bx % 2 == 0)
         self.own = torch.tensor(own, dtype=torch.int32, device=self.device).contiguous()
         self.redundancy = self.n_tiles * self.ly * self.lx / float(self.by * self.bx)
         self._h = ctypes.c_void_p()
@@ -322,8 +329,14 @@ class TiledMultislice:
         n_prop = 0
         for i in range(self.n_slice):
             prop = True if self.propagate_last else (i < self.n_slice - 1)
-            check(lib.bdof_tiles_cut(self._h, cur, self._p(self.origin), self.n_tiles, self.ly, self.lx, self._p(self.tiles[0]), st))
-            self.plan.slice_step(self.tiles[0], self.db_tiles, out=self.tiles[1], propagate=prop, index=i)
+            if prop and self.fused_cut:
+                # the row pass reads the windows straight out of the block buffer
+                self.plan.use_current_stream()
+                check(lib.bdof_slice_step_windows(self.plan._h, self._p(self.buf[cur]), self.pitch, self._p(self.win_offsets),
+                                                  self._p(self.db_tiles), self._p(self.tiles[1]), i))
+            else:
+                check(lib.bdof_tiles_cut(self._h, cur, self._p(self.origin), self.n_tiles, self.ly, self.lx, self._p(self.tiles[0]), st))
+                self.plan.slice_step(self.tiles[0], self.db_tiles, out=self.tiles[1], propagate=prop, index=i)
             check(lib.bdof_tiles_paste(self._h, cur ^ 1, self._p(self.tiles[1]), self._p(self.origin), self._p(self.own), self.n_tiles,
                                        self.ly, self.lx, st))
             if prop and i < self.n_slice - 1:

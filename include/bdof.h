@@ -245,6 +245,13 @@ int  bdof_slice_step(bdof_plan* p, const float* d_in, const float* d_db_slice, f
  * power of H), so that 1000 steps do not accumulate the rounding of one fixed table. */
 int  bdof_slice_step_seq(bdof_plan* p, const float* d_in, const float* d_db_slice, float* d_out, int propagate, int slice_index);
 
+/* The same (propagating slices only) with the CUT fused into the row pass: the batch elements are windows of a larger pitched
+ * complex64 buffer d_buf (a tiling block with its apron); window b's first row starts d_in_offsets[b] elements (device array,
+ * int64) into d_buf, consecutive rows are `pitch` elements apart.  d_db_tiles / d_out_tiles keep the window layout
+ * [batch][ny][nx].  Window rows of 1024 pixels and more need even offsets and an even pitch. */
+int  bdof_slice_step_windows(bdof_plan* p, const float* d_buf, long long pitch, const long long* d_in_offsets, const float* d_db_tiles,
+                             float* d_out_tiles, int slice_index);
+
 /* Gradient buckets for the data-parallel all-reduce (Horovod allreduce, tensorflow_recon/fullfield.py:412):
  * the z range is split into n_buckets contiguous buckets counted from the last slice; bdof_adjoint
  * records cuda_events[j] (cudaEvent_t handles owned by the caller) on the plan's stream as soon as
