@@ -41,6 +41,7 @@ def _load():
                           'there is no CPU fallback' % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     vp, i32, u32, f64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_double
+    i64 = ctypes.c_longlong
     lib.bdof_version.restype = i32
     lib.bdof_last_error.restype = ctypes.c_char_p
     lib.bdof_launch_count.restype = ctypes.c_ulonglong
