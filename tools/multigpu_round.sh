@@ -15,7 +15,12 @@ except Exception as ex:
     print(open('gpurun_out/${R}_bench_${N}gpu_${name}.err').read()[-600:])
 PY
 }
-run default --steps 5 --warmup 3
+#   c35      config3 + config5 only
+if [ "$MODE" != "c35" ]; then run default --steps 5 --warmup 3; fi
+if [ "$MODE" = "c35" ]; then
+  run config3 --workload config3 --steps 10 --warmup 3
+  run config5 --workload config5 --steps 1 --warmup 1
+fi
 if [ "$MODE" = "all" ]; then
   run config3 --workload config3 --steps 10 --warmup 3
   run config4 --workload config4 --steps 10 --warmup 3
