@@ -165,3 +165,28 @@ def test_exchange_policy_and_dynamic_dropping():
     table = np.array([1e-3, 2e-5, 8e-5, 7.9e-5, 0.5])
     assert dynamic_dropping(table).tolist() == [0, 2, 4]
     assert dynamic_dropping(torch.as_tensor(table), dropping_threshold=1e-2).tolist() == [4]
+
+
+def test_axis_tiles_cover_the_block_with_the_requested_halo():
+    # host logic of the production tiling path (tiling.axis_tiles): windows of ONE power-of-two length, contiguous owned shares
+    # that need not be equal nor divide the block, at least `halo` pixels visible beyond every share, even window starts
+    from beyond_dof_b200.tiling import axis_tiles, FAST_LENGTHS
+    for block in (1024, 2048, 4096, 8192, 16384, 3000):
+        for halo in (4, 8, 16, 32, 64, 100):
+            L, tiles, apron = axis_tiles(block, halo)
+            assert L in FAST_LENGTHS
+            assert tiles[0][1] == 0 and tiles[-1][1] + tiles[-1][2] == block
+            for (s0, o0, w0), (s1, o1, w1) in zip(tiles, tiles[1:]):
+                assert o0 + w0 == o1                                   # shares are contiguous
+            for s, o, w in tiles:
+                assert s % 2 == 0 and o - s >= halo and (s + L) - (o + w) >= halo
+                assert s >= -apron and s + L <= block + apron
+            assert apron % 2 == 0
+            # no other length does the same job with less transformed length
+            for L2 in FAST_LENGTHS:
+                if L2 > 2 * (halo + 1):
+                    n2 = -(-block // (L2 - 2 * (halo + 1)))
+                    assert n2 * L2 >= len(tiles) * L
+    # restricted choice of lengths (bench --tile-lengths)
+    L, tiles, _ = axis_tiles(8192, 8, (2048,))
+    assert L == 2048 and len(tiles) == 5
