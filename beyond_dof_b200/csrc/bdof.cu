@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <vector>
 
 using namespace bdof;
@@ -538,11 +540,12 @@ static int upload(float2** dst, const std::vector<float2>& v) {
 
 // centred complex128 factor -> ifftshift, scale, fp32 (and conjugate)
 static std::vector<std::complex<double>> conv_diag_gain(int n);
-// `generic`: the pass runs on the mixed-radix kernel, whose transform the gain model does not describe (gain 1)
+static std::vector<std::complex<double>> generic_diag_gain(int n);
+// `generic`: the pass runs on the mixed-radix kernel (its own gain model)
 static void shift_factor(const double* h, int n, double scale, std::vector<float2>& out, std::vector<float2>& out_adj, bool generic) {
     out.resize(n); out_adj.resize(n);
     const int s = n / 2;                            // ifftshift(a)[i] = a[(i + n//2) % n]
-    const std::vector<std::complex<double>> g = generic ? std::vector<std::complex<double>>((size_t)n, 1.0) : conv_diag_gain(n);
+    const std::vector<std::complex<double>> g = generic ? generic_diag_gain(n) : conv_diag_gain(n);
     for (int i = 0; i < n; ++i) {
         const int src = (i + s) % n;
         const std::complex<double> hh(h[2 * src] * scale, h[2 * src + 1] * scale);
@@ -654,6 +657,81 @@ static std::vector<cdbl> conv_diag_gain(int n) {
     return g;
 }
 
+// The same gain for the mixed-radix passes (genericfft.cuh): their Stockham stages are emulated in double with the fp32
+// table W_n^q, one basis vector at a time, which yields the whole realised matrix F~; the forward gain of bin k is the mean
+// of F~[k, m] / F[k, m] over the inputs m, the inverse (conj trick) gain the conjugate mean over the outputs of column k.
+// O(n^2 * sum of radices) once per length (cached): 72 -> microseconds, 2000 -> ~0.3 s.
+static std::vector<cdbl> generic_diag_gain(int n) {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("BDOF_FFT_GAIN"); enabled = (e && e[0] == '0') ? 0 : 1; }
+    std::vector<cdbl> g((size_t)n, cdbl(1.0, 0.0));
+    int radix[16], n_stages = 0;
+    {   // as gen_factorize(): 4s first, then 2, 3, 5, 7
+        int m = n;
+        while (m % 4 == 0 && n_stages < 16) { radix[n_stages++] = 4; m /= 4; }
+        const int primes[4] = {2, 3, 5, 7};
+        for (int pi = 0; pi < 4; ++pi) while (m % primes[pi] == 0 && n_stages < 16) { radix[n_stages++] = primes[pi]; m /= primes[pi]; }
+        if (m != 1) return g;
+    }
+    if (!enabled || n < 2) return g;
+    static std::mutex mu;
+    static std::map<int, std::vector<cdbl>> cache;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(n);
+        if (it != cache.end()) return it->second;
+    }
+    std::vector<cdbl> tw(n), ex(n);                  // fp32 table as make_full_twiddles(), exact roots
+    for (int k = 0; k < n; ++k) {
+        const double a = -2.0 * M_PI * double(k) / double(n);
+        tw[k] = cdbl(double(float(cos(a))), double(float(sin(a))));
+        ex[k] = cdbl(cos(a), sin(a));
+    }
+    std::vector<cdbl> gf((size_t)n, 0.0), gi((size_t)n, 0.0), x(n), y(n);
+    const cdbl I(0.0, 1.0);
+    for (int m0 = 0; m0 < n; ++m0) {
+        std::fill(x.begin(), x.end(), cdbl(0.0, 0.0));
+        x[m0] = 1.0;
+        int ns = 1;
+        for (int s = 0; s < n_stages; ++s) {         // gen_stage() for every work item j
+            const int R = radix[s], m = n / R, tstep = n / (ns * R), rstep = n / R;
+            for (int j = 0; j < m; ++j) {
+                const int k = j % ns;
+                cdbl v[8];
+                for (int r = 0; r < R; ++r) {
+                    v[r] = x[j + r * m];
+                    if (r > 0 && k > 0) v[r] *= tw[r * k * tstep];
+                }
+                const int o = (j / ns) * ns * R + k;
+                if (R == 2) { y[o] = v[0] + v[1]; y[o + ns] = v[0] - v[1]; }
+                else if (R == 4) {
+                    const cdbl s0 = v[0] + v[2], d0 = v[0] - v[2], s1 = v[1] + v[3], d1 = v[1] - v[3];
+                    y[o] = s0 + s1; y[o + ns] = d0 - I * d1; y[o + 2 * ns] = s0 - s1; y[o + 3 * ns] = d0 + I * d1;
+                } else {
+                    for (int q = 0; q < R; ++q) {
+                        cdbl acc = v[0];
+                        for (int r = 1; r < R; ++r) acc += v[r] * tw[((r * q) % R) * rstep];
+                        y[o + q * ns] = acc;
+                    }
+                }
+            }
+            x.swap(y);
+            ns *= R;
+        }
+        cdbl col = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const cdbl ratio = x[k] * std::conj(ex[(long long)k * m0 % n]);
+            gf[k] += ratio;
+            col += ratio;
+        }
+        gi[m0] = std::conj(col / double(n));
+    }
+    for (int k = 0; k < n; ++k) g[k] = gf[k] / double(n) * gi[k];
+    std::lock_guard<std::mutex> lk(mu);
+    cache[n] = g;
+    return g;
+}
+
 // ------------------------------------------------------------------------------------------
 // error-feedback multiplier tables
 // ------------------------------------------------------------------------------------------
@@ -688,7 +766,7 @@ static int build_axis_sequence(bdof_plan* p, AxisTables& a, int col, const doubl
     h_schedule(p, col, napp);
     std::vector<float2> seq((size_t)(Z + 1) * n), seq_adj((size_t)(Z + 1) * n);
     const long double scale = 1.0L / (long double)n;
-    const std::vector<cdbl> gain = p->generic ? std::vector<cdbl>((size_t)n, 1.0) : conv_diag_gain(n);
+    const std::vector<cdbl> gain = p->generic ? generic_diag_gain(n) : conv_diag_gain(n);
     for (int i = 0; i < n; ++i) {
         const int src = (i + s) % n;                    // ifftshift, as shift_factor()
         const cld h((long double)h_centred[2 * src], (long double)h_centred[2 * src + 1]);
@@ -1484,7 +1562,7 @@ extern "C" int bdof_field_multiply(const float* d_in, const float* d_mult, float
 
 extern "C" int bdof_debug_fft_gain(int n, double* gain_out) {
     if (n < 1 || !gain_out) return fail(BDOF_E_BADARG, "bad argument");
-    const std::vector<cdbl> g = conv_diag_gain(n);
+    const std::vector<cdbl> g = bdof_size_supported(n) == 1 ? conv_diag_gain(n) : generic_diag_gain(n);
     for (int k = 0; k < n; ++k) { gain_out[2 * k] = g[k].real(); gain_out[2 * k + 1] = g[k].imag(); }
     return 0;
 }

@@ -82,7 +82,59 @@ def test_gain_closed_form_matches_full_matrix(cfg):
 
 def test_gain_is_one_where_the_model_does_not_apply():
     from beyond_dof_b200 import capi
-    for n in (72, 4096, 8192, 100):
+    for n in (4096, 8192, 74):
         out = np.zeros(2 * n)
         assert capi.lib.bdof_debug_fft_gain(n, out.ctypes.data_as(ctypes.c_void_p)) == 0
         assert np.all(out[0::2] == 1.0) and np.all(out[1::2] == 0.0)
+
+
+def _stockham_matrix(n):
+    """The mixed-radix passes' transform (genericfft.cuh: radices 4.., 2, 3, 5, 7, autosort, full fp32 table W_n^q) applied
+    to the identity in complex128 -- written from the algorithm's definition, vectorised over the work items."""
+    radix, m = [], n
+    while m % 4 == 0:
+        radix.append(4); m //= 4
+    for p in (2, 3, 5, 7):
+        while m % p == 0:
+            radix.append(p); m //= p
+    assert m == 1
+    a = -2 * np.pi * np.arange(n) / n
+    tw = np.cos(a).astype(np.float32).astype(np.float64) + 1j * np.sin(a).astype(np.float32).astype(np.float64)
+    x = np.eye(n, dtype=np.complex128)                  # x[element, basis vector]
+    ns = 1
+    for R in radix:
+        mm = n // R
+        j = np.arange(mm)
+        k = j % ns
+        o = (j // ns) * ns * R + k
+        v = [x[j + r * mm] * np.where(k > 0, tw[(r * k * (n // (ns * R))) % n], 1.0)[:, None] if r else x[j] for r in range(R)]
+        y = np.zeros_like(x)
+        if R == 2:
+            y[o], y[o + ns] = v[0] + v[1], v[0] - v[1]
+        elif R == 4:
+            s0, d0, s1, d1 = v[0] + v[2], v[0] - v[2], v[1] + v[3], v[1] - v[3]
+            y[o], y[o + ns], y[o + 2 * ns], y[o + 3 * ns] = s0 + s1, d0 - 1j * d1, s0 - s1, d0 + 1j * d1
+        else:
+            for q in range(R):
+                acc = v[0].copy()
+                for r in range(1, R):
+                    acc += v[r] * tw[((r * q) % R) * (n // R)]
+                y[o + q * ns] = acc
+        x = y
+        ns *= R
+    return x
+
+
+@pytest.mark.parametrize('n', [72, 18, 100, 63, 1000])
+def test_mixed_radix_gain_matches_full_matrix(n):
+    from beyond_dof_b200 import capi
+    F = _stockham_matrix(n)
+    Fex = np.exp(-2j * np.pi * np.outer(np.arange(n), np.arange(n)) / n)
+    assert np.abs(F - Fex).max() < 1e-5
+    Finv = np.conj(F) / n
+    gain = np.array([(Fex[k] @ Finv[:, k]) * (F[k] @ np.conj(Fex[k]) / n) for k in range(n)])
+    out = np.zeros(2 * n)
+    assert capi.lib.bdof_debug_fft_gain(n, out.ctypes.data_as(ctypes.c_void_p)) == 0
+    g = out[0::2] + 1j * out[1::2]
+    assert 1e-9 < np.abs(g - 1).max() < 3e-7
+    assert np.abs(g - gain).max() < 1e-12

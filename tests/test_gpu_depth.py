@@ -211,6 +211,24 @@ def test_mixed_radix_reference_gaussian_probe_operator_level(bd, shape, free):
     assert rel_l2(g_exit.cpu().numpy()[mask], g_or[mask]) < TOL_GRAD
 
 
+# the reference's default probe size (72 x 72, tensorflow_recon/reconstruct_ptycho.py) at config 3's depth: the mixed-radix
+# passes carry their own gain correction (generic_diag_gain); without it the far-field intensity error is ~1e-5
+@pytest.mark.parametrize('free', ['inf', None])
+def test_mixed_radix_72_probe_at_128_slices(bd, free):
+    shape = (4, 72, 72, 128)
+    gd, gb = mo.random_phantom(shape, seed=71, delta_scale=2e-5, beta_scale=2e-6)
+    pr, pi = mo.gaussian_probe(shape[1:3], 6., 6., 0.5)
+    rng = np.random.default_rng(72)
+    G = rng.standard_normal(shape[:3]) + 1j * rng.standard_normal(shape[:3])
+    psio, slices = mo.multislice_forward(gd, gb, pr, pi, 5000, 1e-7, free_prop_cm=free, propagate_last=True, return_slices=True)
+    gdo, gbo, _ = mo.multislice_adjoint(gd, gb, slices, G, 5000, 1e-7, free_prop_cm=free, propagate_last=True)
+    psi, g_d, g_b = _gpu_forward_and_operator_adjoint(gd, gb, pr, pi, G, free, True)
+    e_i, e_f = intensity_err(psi, psio), rel_l2(psi, psio)
+    e_d, e_b = rel_l2(g_d, gdo), rel_l2(g_b, gbo)
+    record('mixed_radix_72x72x128_free_%s' % free, intensity=e_i, field=e_f, grad_delta=e_d, grad_beta=e_b)
+    assert e_i < TOL_INTENSITY and e_d < TOL_GRAD and e_b < TOL_GRAD
+
+
 # ---------------------------------------------------------------------------------------------
 # (d) config 2 at full size (slow: ~5 min of oracle time on one host core): BDOF_SLOW=1 enables
 # ---------------------------------------------------------------------------------------------
