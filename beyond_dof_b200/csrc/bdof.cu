@@ -1578,13 +1578,26 @@ extern "C" int bdof_plan_set_stream(bdof_plan* p, void* cuda_stream) {
 // ------------------------------------------------------------------------------------------
 // obj_rot[z][y][x] = obj[z_old(z,x)][y][x_old(z,x)]   (apply_rotation, cnn_propagator/util.py:374-402; the table is the
 // reference's nearest-neighbour lookup of one angle re-ordered slice-major: lookup[z][x] = (x_old, z_old))
-__global__ void k_rotate_gather(const float2* __restrict__ obj, const int2* __restrict__ lookup, float2* __restrict__ out,
+// One thread carries ROT_YCH rows of one (z, x) column: the table entry is read once per ROT_YCH pixels and the loads of a thread
+// are independent.  The rotated copy is written with streaming stores (it is ROT B times the object; the object stays in L2).
+constexpr int ROT_YCH = 8;
+__global__ void __launch_bounds__(128) k_rotate_gather(const float2* __restrict__ obj, const int2* __restrict__ lookup, float2* __restrict__ out,
                                 long long out_slice_stride, int ny, int nx, int nz) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y, z = blockIdx.z;
+    const int y0 = blockIdx.y * ROT_YCH, z = blockIdx.z;
     if (x >= nx) return;
     const int2 src = lookup[(long long)z * nx + x];
-    out[(long long)z * out_slice_stride + (long long)y * nx + x] = obj[((long long)src.y * ny + y) * nx + src.x];
+    const float2* s = obj + ((long long)src.y * ny + y0) * nx + src.x;
+    float2* o = out + (long long)z * out_slice_stride + (long long)y0 * nx + x;
+    if (y0 + ROT_YCH <= ny) {
+        float2 v[ROT_YCH];
+#pragma unroll
+        for (int j = 0; j < ROT_YCH; ++j) v[j] = __ldg(s + (long long)j * nx);
+#pragma unroll
+        for (int j = 0; j < ROT_YCH; ++j) __stcs(o + (long long)j * nx, v[j]);
+    } else {
+        for (int j = 0; y0 + j < ny; ++j) __stcs(o + (long long)j * nx, __ldg(s + (long long)j * nx));
+    }
 }
 // transpose of the gather (what autograd does to the fancy index): grad_obj[z_old][y][x_old] += grad_rot[z][y][x]
 __global__ void k_rotate_scatter_add(const float2* __restrict__ grot, long long slice_stride, const int2* __restrict__ lookup,
@@ -1600,39 +1613,78 @@ __global__ void k_rotate_scatter_add(const float2* __restrict__ grot, long long 
 }
 // the same transpose without atomics: every source pixel (z0, x0) sums the rotated pixels that read from it (CSR lists
 // built on the host from the lookup table; deterministic, and ~10x faster than fp32 atomics to scattered addresses)
-__global__ void k_rotate_adjoint_csr(const float2* __restrict__ grot, long long slice_stride, const int* __restrict__ offsets,
-                                     const int* __restrict__ dest, float2* __restrict__ gobj, int ny, int nx, int nz) {
+// `n_ang` angles at once: element a of the minibatch has its lists at offsets[a] / dest[a] and its rotated gradient at
+// grot + a * batch_stride; the sum over angles stays in registers, so gobj is read and written once.
+struct RotLists { const int* offsets[BDOF_ROT_MAX_ANGLES]; const int* dest[BDOF_ROT_MAX_ANGLES]; };
+__global__ void __launch_bounds__(128) k_rotate_adjoint_csr(const float2* __restrict__ grot, long long slice_stride, long long batch_stride,
+                                     const RotLists lists, int n_ang, int accumulate, float2* __restrict__ gobj, int ny, int nx, int nz) {
     const int x0 = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y, z0 = blockIdx.z;
+    const int y0 = blockIdx.y * ROT_YCH, z0 = blockIdx.z;
     if (x0 >= nx) return;
     const int cell = z0 * nx + x0;
-    const int beg = offsets[cell], end = offsets[cell + 1];
-    if (beg == end) return;
-    float ax = 0.f, ay = 0.f;
-    for (int k = beg; k < end; ++k) {
-        const int d = dest[k];                       // z * nx + x of a rotated pixel whose source is (z0, x0)
-        const int z = d / nx, x = d - z * nx;
-        const float2 g = grot[(long long)z * slice_stride + (long long)y * nx + x];
-        ax += g.x; ay += g.y;
+    const int nyc = min(ROT_YCH, ny - y0);
+    float2 acc[ROT_YCH];
+#pragma unroll
+    for (int j = 0; j < ROT_YCH; ++j) acc[j] = make_float2(0.f, 0.f);
+    bool any = false;
+    for (int a = 0; a < n_ang; ++a) {
+        const int beg = lists.offsets[a][cell], end = lists.offsets[a][cell + 1];
+        for (int k = beg; k < end; ++k) {
+            const int d = lists.dest[a][k];              // z * nx + x of a rotated pixel whose source is (z0, x0)
+            const int z = d / nx, x = d - z * nx;
+            const float2* g = grot + (long long)a * batch_stride + (long long)z * slice_stride + (long long)y0 * nx + x;
+            any = true;
+            if (nyc == ROT_YCH) {
+                float2 v[ROT_YCH];
+#pragma unroll
+                for (int j = 0; j < ROT_YCH; ++j) v[j] = __ldcs(g + (long long)j * nx);
+#pragma unroll
+                for (int j = 0; j < ROT_YCH; ++j) { acc[j].x += v[j].x; acc[j].y += v[j].y; }
+            } else {
+#pragma unroll
+                for (int j = 0; j < ROT_YCH; ++j)
+                    if (j < nyc) { const float2 v = __ldcs(g + (long long)j * nx); acc[j].x += v.x; acc[j].y += v.y; }
+            }
+        }
     }
-    float2* o = gobj + ((long long)z0 * ny + y) * nx + x0;
-    const float2 cur = *o;
-    *o = make_float2(cur.x + ax, cur.y + ay);
+    if (!any && accumulate) return;
+    float2* o = gobj + ((long long)z0 * ny + y0) * nx + x0;
+#pragma unroll
+    for (int j = 0; j < ROT_YCH; ++j)
+        if (j < nyc) {
+            if (accumulate) { const float2 cur = o[(long long)j * nx]; acc[j].x += cur.x; acc[j].y += cur.y; }
+            o[(long long)j * nx] = acc[j];
+        }
+}
+extern "C" int bdof_rotate_adjoint_csr_batch(const float* d_grad_rot_db, long long slice_stride_px, long long batch_stride_px, int n_angles,
+                                             const int32_t* const* d_offsets, const int32_t* const* d_dest, float* d_grad_obj_db,
+                                             int accumulate, int ny, int nx, int nz, void* st) {
+    if (!d_grad_rot_db || !d_offsets || !d_dest || !d_grad_obj_db || ny < 1 || nx < 1 || nz < 1 || n_angles < 1) return fail(BDOF_E_BADARG, "bad argument");
+    if (ny > 65535 * ROT_YCH || nz > 65535) return fail(BDOF_E_UNSUPPORTED, "ny / nz too large");
+    dim3 grid((nx + 127) / 128, (ny + ROT_YCH - 1) / ROT_YCH, nz);
+    for (int a0 = 0; a0 < n_angles; a0 += BDOF_ROT_MAX_ANGLES) {
+        RotLists l;
+        const int n = n_angles - a0 < BDOF_ROT_MAX_ANGLES ? n_angles - a0 : BDOF_ROT_MAX_ANGLES;
+        for (int a = 0; a < n; ++a) {
+            if (!d_offsets[a0 + a] || !d_dest[a0 + a]) return fail(BDOF_E_BADARG, "null list");
+            l.offsets[a] = d_offsets[a0 + a]; l.dest[a] = d_dest[a0 + a];
+        }
+        k_rotate_adjoint_csr<<<grid, 128, 0, (cudaStream_t)st>>>(reinterpret_cast<const float2*>(d_grad_rot_db) + (long long)a0 * batch_stride_px,
+                                                               slice_stride_px, batch_stride_px, l, n, (accumulate || a0 > 0) ? 1 : 0,
+                                                               reinterpret_cast<float2*>(d_grad_obj_db), ny, nx, nz);
+        if (int r = launch_check("k_rotate_adjoint_csr")) return r;
+    }
+    return 0;
 }
 extern "C" int bdof_rotate_adjoint_csr(const float* d_grad_rot_db, long long slice_stride_px, const int32_t* d_offsets,
                                        const int32_t* d_dest, float* d_grad_obj_db, int ny, int nx, int nz, void* st) {
-    if (!d_grad_rot_db || !d_offsets || !d_dest || !d_grad_obj_db || ny < 1 || nx < 1 || nz < 1) return fail(BDOF_E_BADARG, "bad argument");
-    if (ny > 65535 || nz > 65535) return fail(BDOF_E_UNSUPPORTED, "ny / nz > 65535");
-    dim3 grid((nx + 127) / 128, ny, nz);
-    k_rotate_adjoint_csr<<<grid, 128, 0, (cudaStream_t)st>>>(reinterpret_cast<const float2*>(d_grad_rot_db), slice_stride_px, d_offsets, d_dest,
-                                                           reinterpret_cast<float2*>(d_grad_obj_db), ny, nx, nz);
-    return launch_check("k_rotate_adjoint_csr");
+    return bdof_rotate_adjoint_csr_batch(d_grad_rot_db, slice_stride_px, 0, 1, &d_offsets, &d_dest, d_grad_obj_db, 1, ny, nx, nz, st);
 }
 extern "C" int bdof_rotate_gather(const float* d_obj_db, const int32_t* d_lookup_zx, float* d_out_db, long long out_slice_stride_px,
                                   int ny, int nx, int nz, void* st) {
     if (!d_obj_db || !d_lookup_zx || !d_out_db || ny < 1 || nx < 1 || nz < 1) return fail(BDOF_E_BADARG, "bad argument");
-    if (ny > 65535 || nz > 65535) return fail(BDOF_E_UNSUPPORTED, "ny / nz > 65535");
-    dim3 grid((nx + 127) / 128, ny, nz);
+    if (ny > 65535 * ROT_YCH || nz > 65535) return fail(BDOF_E_UNSUPPORTED, "ny / nz too large");
+    dim3 grid((nx + 127) / 128, (ny + ROT_YCH - 1) / ROT_YCH, nz);
     k_rotate_gather<<<grid, 128, 0, (cudaStream_t)st>>>(reinterpret_cast<const float2*>(d_obj_db), reinterpret_cast<const int2*>(d_lookup_zx),
                                                       reinterpret_cast<float2*>(d_out_db), out_slice_stride_px, ny, nx, nz);
     return launch_check("k_rotate_gather");

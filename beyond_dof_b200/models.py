@@ -588,12 +588,15 @@ class TomographyObjective:
         self.plan.forward(self.db, self.probe, out=self.exit)
         loss, g = self.plan.loss_mag(self.exit, target_dev)
         self.plan.adjoint(self.db, g)
-        self.grad.zero_()
-        for b in range(self.B):
-            if nearest:
-                _rot.rotate_db_adjoint(self.db[:, b], tabs[b], self.grad, atomic=not self.deterministic)
-            else:
-                _rot.rotate_db_bilinear_adjoint(self.db[:, b], float(theta_batch[b]), self.grad)
+        if nearest and self.deterministic:
+            _rot.rotate_db_adjoint_batch(self.db, tabs, self.grad, accumulate=False)     # whole minibatch, one pass over the gradient
+        else:
+            self.grad.zero_()
+            for b in range(self.B):
+                if nearest:
+                    _rot.rotate_db_adjoint(self.db[:, b], tabs[b], self.grad, atomic=True)
+                else:
+                    _rot.rotate_db_bilinear_adjoint(self.db[:, b], float(theta_batch[b]), self.grad)
         if self._dp is not None:
             if self._ce is not None:
                 self._ce.exchange(None)

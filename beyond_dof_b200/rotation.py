@@ -110,6 +110,20 @@ def rotate_db_adjoint(grad_rot, table_zx, grad_obj, atomic=False):
     return grad_obj
 
 
+def rotate_db_adjoint_batch(grad_rot_db, tables, grad_obj, accumulate=True):
+    """grad_obj [Z, Y, X, 2] += (accumulate=False: =) sum over the minibatch of transpose-of-rotation(grad_rot_db[:, b]) with tables[b]; grad_rot_db is a
+    plan's db [Z, B, Y, X, 2].  One pass over the object gradient (deterministic: the angles are summed in order in registers)."""
+    Z, Y, X, _ = grad_obj.shape
+    B = len(tables)
+    assert grad_rot_db.shape == (Z, B, Y, X, 2) and grad_rot_db.is_contiguous() and grad_obj.is_contiguous()
+    lists = [device_inverse(t) for t in tables]
+    offs = (ctypes.c_void_p * B)(*[o.data_ptr() for o, _ in lists])
+    dests = (ctypes.c_void_p * B)(*[d.data_ptr() for _, d in lists])
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib.bdof_rotate_adjoint_csr_batch(_ptr(grad_rot_db), B * Y * X, Y * X, B, offs, dests, _ptr(grad_obj), 1 if accumulate else 0, Y, X, Z, st))
+    return grad_obj
+
+
 def apply_rotation(obj, coord_old, src_folder=None):
     """Drop-in for cnn_propagator/util.py:374 -- obj [Y, X, Z, C] (NumPy or torch), coord_old the [X*Z, 2] table of one
     angle (read_origin_coords / rotation_table); src_folder is accepted and ignored (the reference re-reads its

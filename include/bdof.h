@@ -200,6 +200,14 @@ int  bdof_rotate_scatter_add(const float* d_grad_rot_db, long long slice_stride_
  * pixels (z*nx + x) that read from each source pixel (z0*nx + x0); d_grad_obj_db is accumulated into (+=), no atomics. */
 int  bdof_rotate_adjoint_csr(const float* d_grad_rot_db, long long slice_stride_px, const int32_t* d_offsets,
                              const int32_t* d_dest, float* d_grad_obj_db, int ny, int nx, int nz, void* cuda_stream);
+/* The whole minibatch in one pass: element a's rotated gradient starts a * batch_stride_px pixels after element 0's (the batch
+ * axis of a plan's db), its lists are d_offsets[a] / d_dest[a] (HOST arrays of n_angles DEVICE pointers).  The sum over the
+ * angles is formed in registers in angle order, so d_grad_obj_db is read and written once per BDOF_ROT_MAX_ANGLES angles;
+ * accumulate = 0 overwrites d_grad_obj_db (no zero-fill needed beforehand), 1 adds to it. */
+#define BDOF_ROT_MAX_ANGLES 16
+int  bdof_rotate_adjoint_csr_batch(const float* d_grad_rot_db, long long slice_stride_px, long long batch_stride_px, int n_angles,
+                                   const int32_t* const* d_offsets, const int32_t* const* d_dest, float* d_grad_obj_db,
+                                   int accumulate, int ny, int nx, int nz, void* cuda_stream);
 
 /* SURVEY 8f-1, TF drivers: tf.contrib.image.rotate(stack([delta, beta], -1), theta, interpolation='BILINEAR')
  * (tensorflow_recon/fullfield.py:96, ptychography.py:39) on the native object d_obj_db [nz][ny][nx][2]: rotation by theta

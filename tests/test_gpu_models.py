@@ -167,6 +167,34 @@ def test_rotation_adjoint_matches_oracle_ragged(bd):
         rotation.rotation_table([2, 17, 40], 0.5)
 
 
+def test_rotation_adjoint_batch_sums_the_minibatch_in_one_pass(bd):
+    """bdof_rotate_adjoint_csr_batch == the per-angle transposes summed; overwrite mode needs no zero-fill; more angles than
+    BDOF_ROT_MAX_ANGLES are chunked; bit-reproducible."""
+    from beyond_dof_b200 import rotation
+    rng = np.random.default_rng(73)
+    dev = torch.device('cuda')
+    for (Y, X, Z), n_ang in (((5, 33, 33), 3), ((19, 40, 40), 18), ((8, 64, 64), 10)):
+        thetas = rng.random(n_ang) * 2 * np.pi
+        tabs = [rotation.device_table([Y, X, Z], float(t), dev) for t in thetas]
+        g = torch.as_tensor(rng.standard_normal((Z, n_ang, Y, X, 2)).astype(np.float32)).cuda()
+        ref = torch.zeros((Z, Y, X, 2), device='cuda')
+        for b in range(n_ang):
+            rotation.rotate_db_adjoint(g[:, b], tabs[b], ref)
+        out = torch.full((Z, Y, X, 2), float('nan'), device='cuda')
+        rotation.rotate_db_adjoint_batch(g, tabs, out, accumulate=False)
+        assert not torch.isnan(out).any()
+        assert rel_l2(out.cpu().numpy(), ref.cpu().numpy()) < 1e-6         # same terms, one running sum instead of per-angle sums
+        out2 = torch.empty_like(out)
+        rotation.rotate_db_adjoint_batch(g, tabs, out2, accumulate=False)
+        assert torch.equal(out, out2)                                      # deterministic
+        again = out.clone()
+        rotation.rotate_db_adjoint_batch(g, tabs, again, accumulate=True)
+        assert rel_l2(again.cpu().numpy(), 2 * ref.cpu().numpy()) < 1e-6
+        o64 = sum(mo.apply_rotation_adjoint(g[:, b].permute(1, 2, 0, 3).cpu().numpy().astype(np.float64), mo.rotation_lookup([Y, X, Z], float(thetas[b])))
+                  for b in range(n_ang))
+        assert rel_l2(out.permute(1, 2, 0, 3).cpu().numpy(), o64) < 1e-6
+
+
 def test_adam_step_matches_reference(bd, gold_rot):
     from beyond_dof_b200 import rotation
     x = torch.as_tensor(gold_rot['adam_x0'].astype(np.float32)).cuda()
