@@ -76,6 +76,23 @@ int bdof_make_tensor_map(CUtensorMap* out, const void* base, long long rows, lon
     if (r != CUDA_SUCCESS) return bdof_fail(BDOF_E_BADARG, "cuTensorMapEncodeTiled failed (CUresult %d)", int(r));
     return 0;
 }
+// general form: fp32 tensor of `rank` dimensions, dims[0] innermost (contiguous), strides_bytes[i] = stride of dims[i + 1]
+static int make_tensor_map_nd(CUtensorMap* out, const void* base, int rank, const long long* dims, const long long* strides_bytes, const int* box) {
+    CUtensorMap probe;
+    if (int r = bdof_make_tensor_map(&probe, base, 1, 64, 16, 1)) return r;        // resolves the driver entry point
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+    cuuint64_t gdim[5], gstride[4];
+    cuuint32_t bx[5], estr[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = cuuint64_t(dims[i]); bx[i] = cuuint32_t(box[i]); estr[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstride[i] = cuuint64_t(strides_bytes[i]);
+    CUresult r = reinterpret_cast<EncodeTiledFn>(f)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, cuuint32_t(rank), const_cast<void*>(base), gdim, gstride, bx, estr,
+                                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return bdof_fail(BDOF_E_BADARG, "cuTensorMapEncodeTiled (rank %d) failed (CUresult %d)", rank, int(r));
+    return 0;
+}
 #define fail bdof_fail
 #define launch_check bdof_launch_check
 
@@ -1578,25 +1595,126 @@ extern "C" int bdof_plan_set_stream(bdof_plan* p, void* cuda_stream) {
 // ------------------------------------------------------------------------------------------
 // obj_rot[z][y][x] = obj[z_old(z,x)][y][x_old(z,x)]   (apply_rotation, cnn_propagator/util.py:374-402; the table is the
 // reference's nearest-neighbour lookup of one angle re-ordered slice-major: lookup[z][x] = (x_old, z_old))
-// One thread carries ROT_YCH rows of one (z, x) column: the table entry is read once per ROT_YCH pixels and the loads of a thread
-// are independent.  The rotated copy is written with streaming stores (it is ROT B times the object; the object stays in L2).
-constexpr int ROT_YCH = 8;
-__global__ void __launch_bounds__(128) k_rotate_gather(const float2* __restrict__ obj, const int2* __restrict__ lookup, float2* __restrict__ out,
-                                long long out_slice_stride, int ny, int nx, int nz) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y0 = blockIdx.y * ROT_YCH, z = blockIdx.z;
-    if (x >= nx) return;
-    const int2 src = lookup[(long long)z * nx + x];
-    const float2* s = obj + ((long long)src.y * ny + y0) * nx + src.x;
-    float2* o = out + (long long)z * out_slice_stride + (long long)y0 * nx + x;
-    if (y0 + ROT_YCH <= ny) {
-        float2 v[ROT_YCH];
+// The rotation is about y, so a run of x in the rotated frame reads a run along an oblique line of the (z, x) plane: near 90
+// degrees consecutive x read consecutive SLICES (8 useful bytes per 32-byte sector).  Both directions therefore go through
+// shared memory: a CTA owns a ROT_T x ROT_T tile of (z, x) cells, finds where the cells on the other side of the table lie (a
+// box of at most ROT_T (|cos| + |sin|) + 2 <= ROT_BOX on a side), and for every y of its chunk ONE TMA box load
+// (cp.async.bulk.tensor, ROT_BOX x 1 x ROT_BOX of the [z][y][x] tensor, double buffered on two mbarriers) brings the box in; the
+// tile is then served from shared memory with row-contiguous writes.  Anything outside the box -- clipped table entries at the
+// borders, arbitrary user tables -- is read from global memory directly, so the result never depends on the tiling; sides that
+// TMA cannot describe (odd nx, sides below the box) load the box with ordinary row-contiguous reads (TMA = false).  A tiled TMA
+// load faults ("illegal instruction") unless its innermost start coordinate is a multiple of 16 bytes (tools/tma_probe.cu), so
+// boxes start on even x.
+constexpr int ROT_T = 32, ROT_BOX = 48, ROT_THREADS = 256, ROT_CPT = ROT_T * ROT_T / ROT_THREADS, ROT_YB = 8, ROT_YA = 4;   // rows of y per CTA: gather, transpose
+constexpr int ROT_BPT = ROT_BOX * ROT_BOX / ROT_THREADS;       // box elements per thread
+constexpr unsigned ROT_BOX_BYTES = ROT_BOX * ROT_BOX * sizeof(float2);
+static_assert(ROT_BOX * ROT_BOX % ROT_THREADS == 0, "box elements divide over the threads");
+
+// element idx = tid + ROT_THREADS i of the box is (r, c) = (idx / ROT_BOX, idx % ROT_BOX): a warp covers 32 consecutive
+// elements of at most two rows
+__device__ __forceinline__ void rot_box_load(const float2* __restrict__ origin, long long row_stride, int bh, int bw, int tid, float2 (&r)[ROT_BPT]) {
 #pragma unroll
-        for (int j = 0; j < ROT_YCH; ++j) v[j] = __ldg(s + (long long)j * nx);
+    for (int i = 0; i < ROT_BPT; ++i) {
+        const int idx = tid + ROT_THREADS * i, rr = idx / ROT_BOX, cc = idx - rr * ROT_BOX;
+        r[i] = (rr < bh && cc < bw) ? __ldg(origin + (long long)rr * row_stride + cc) : make_float2(0.f, 0.f);
+    }
+}
+__device__ __forceinline__ void rot_box_store(float2* __restrict__ buf, int tid, const float2 (&r)[ROT_BPT]) {
 #pragma unroll
-        for (int j = 0; j < ROT_YCH; ++j) __stcs(o + (long long)j * nx, v[j]);
+    for (int i = 0; i < ROT_BPT; ++i) buf[tid + ROT_THREADS * i] = r[i];
+}
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* tm, int c0, int c1, int c2, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* tm, int c0, int c1, int c2, int c3, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+static bool rot_use_tma() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("BDOF_ROT_TMA"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+template <bool TMA>
+__global__ void __launch_bounds__(ROT_THREADS) k_rotate_gather(const float2* __restrict__ obj, const int2* __restrict__ lookup, float2* __restrict__ out,
+                                long long out_slice_stride, int ny, int nx, int nz, const __grid_constant__ CUtensorMap tm_obj) {
+    __shared__ __align__(128) float2 buf[2][ROT_BOX * ROT_BOX];
+    __shared__ __align__(8) unsigned long long bar[2];
+    __shared__ int s_mm[4];                              // z_min, x_min, z_max, x_max of the sources
+    const int tid = threadIdx.x;
+    // y chunks are the fastest grid dimension: the CTAs resident at one time then span whole 2-D slabs
+    const int y0 = blockIdx.x * ROT_YB, y1 = min(ny, y0 + ROT_YB), x0 = blockIdx.y * ROT_T, z0 = blockIdx.z * ROT_T;
+    if (tid == 0) {
+        s_mm[0] = s_mm[1] = 0x7fffffff; s_mm[2] = s_mm[3] = -1;
+        if constexpr (TMA) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+    }
+    __syncthreads();
+    int2 src[ROT_CPT];
+    bool ok[ROT_CPT];
+    int zmn = 0x7fffffff, xmn = 0x7fffffff, zmx = -1, xmx = -1;
+#pragma unroll
+    for (int i = 0; i < ROT_CPT; ++i) {
+        const int c = tid + ROT_THREADS * i, z = z0 + (c >> 5), x = x0 + (c & 31);
+        ok[i] = z < nz && x < nx;
+        src[i] = ok[i] ? lookup[(long long)z * nx + x] : make_int2(0, 0);
+        if (ok[i]) { zmn = min(zmn, src[i].y); zmx = max(zmx, src[i].y); xmn = min(xmn, src[i].x); xmx = max(xmx, src[i].x); }
+    }
+    zmn = __reduce_min_sync(0xffffffffu, zmn); xmn = __reduce_min_sync(0xffffffffu, xmn);
+    zmx = __reduce_max_sync(0xffffffffu, zmx); xmx = __reduce_max_sync(0xffffffffu, xmx);
+    if ((tid & 31) == 0) { atomicMin(&s_mm[0], zmn); atomicMin(&s_mm[1], xmn); atomicMax(&s_mm[2], zmx); atomicMax(&s_mm[3], xmx); }
+    __syncthreads();
+    zmn = s_mm[0]; xmn = s_mm[1] & ~1;                   // TMA boxes start on 16 bytes of the innermost dimension: even x
+    const int bh = s_mm[2] - zmn + 1, bw = s_mm[3] - xmn + 1;
+    if (s_mm[2] < 0) return;                             // no cell of this tile is inside the array
+    float2* o[ROT_CPT];
+#pragma unroll
+    for (int i = 0; i < ROT_CPT; ++i) {
+        const int c = tid + ROT_THREADS * i;
+        o[i] = out + (long long)(z0 + (c >> 5)) * out_slice_stride + x0 + (c & 31);
+    }
+    if (bh > ROT_BOX || bw > ROT_BOX) {                  // not a rotation-like table: plain gather
+        for (int y = y0; y < y1; ++y)
+#pragma unroll
+            for (int i = 0; i < ROT_CPT; ++i)
+                if (ok[i]) __stcs(o[i] + (long long)y * nx, __ldg(obj + ((long long)src[i].y * ny + y) * nx + src[i].x));
+        return;
+    }
+    int soff[ROT_CPT];
+#pragma unroll
+    for (int i = 0; i < ROT_CPT; ++i) soff[i] = (src[i].y - zmn) * ROT_BOX + (src[i].x - xmn);
+    if constexpr (TMA) {
+        if (tid == 0) { mbar_expect_tx(&bar[0], ROT_BOX_BYTES); tma_load_3d(buf[0], &tm_obj, 2 * xmn, y0, zmn, &bar[0]); }
+        for (int y = y0; y < y1; ++y) {
+            const int it = y - y0, cur = it & 1;
+            if (tid == 0 && y + 1 < y1) { mbar_expect_tx(&bar[cur ^ 1], ROT_BOX_BYTES); tma_load_3d(buf[cur ^ 1], &tm_obj, 2 * xmn, y + 1, zmn, &bar[cur ^ 1]); }
+            mbar_wait(&bar[cur], (it >> 1) & 1);
+#pragma unroll
+            for (int i = 0; i < ROT_CPT; ++i)
+                if (ok[i]) __stcs(o[i] + (long long)y * nx, buf[cur][soff[i]]);
+            __syncthreads();                             // buf[cur] is free for the load of y + 2
+        }
     } else {
-        for (int j = 0; y0 + j < ny; ++j) __stcs(o + (long long)j * nx, __ldg(s + (long long)j * nx));
+        const float2* origin = obj + (long long)zmn * ny * nx + xmn;      // box element (r, c) of row y: origin + (r ny + y) nx + c
+        const long long row_stride = (long long)ny * nx;
+        float2 r[ROT_BPT];
+        rot_box_load(origin + (long long)y0 * nx, row_stride, bh, bw, tid, r);
+        rot_box_store(buf[0], tid, r);
+        __syncthreads();
+        for (int y = y0; y < y1; ++y) {
+            const int cur = (y - y0) & 1;
+            if (y + 1 < y1) rot_box_load(origin + (long long)(y + 1) * nx, row_stride, bh, bw, tid, r);
+#pragma unroll
+            for (int i = 0; i < ROT_CPT; ++i)
+                if (ok[i]) __stcs(o[i] + (long long)y * nx, buf[cur][soff[i]]);
+            if (y + 1 < y1) rot_box_store(buf[cur ^ 1], tid, r);
+            __syncthreads();
+        }
     }
 }
 // transpose of the gather (what autograd does to the fancy index): grad_obj[z_old][y][x_old] += grad_rot[z][y][x]
@@ -1614,54 +1732,199 @@ __global__ void k_rotate_scatter_add(const float2* __restrict__ grot, long long 
 // the same transpose without atomics: every source pixel (z0, x0) sums the rotated pixels that read from it (CSR lists
 // built on the host from the lookup table; deterministic, and ~10x faster than fp32 atomics to scattered addresses)
 // `n_ang` angles at once: element a of the minibatch has its lists at offsets[a] / dest[a] and its rotated gradient at
-// grot + a * batch_stride; the sum over angles stays in registers, so gobj is read and written once.
+// grot + a * batch_stride; the sum over angles stays in registers (angles in order, list entries in order: bit-reproducible), so
+// gobj is read and written once.  Tiled like the gather: the CTA owns ROT_T x ROT_T SOURCE cells; per angle the box is centred
+// on the mean position of the cells' first readers; list entries outside it (the long lists of clipped border cells) and
+// entries beyond the second of a cell are read from global memory.
 struct RotLists { const int* offsets[BDOF_ROT_MAX_ANGLES]; const int* dest[BDOF_ROT_MAX_ANGLES]; };
-__global__ void __launch_bounds__(128) k_rotate_adjoint_csr(const float2* __restrict__ grot, long long slice_stride, long long batch_stride,
-                                     const RotLists lists, int n_ang, int accumulate, float2* __restrict__ gobj, int ny, int nx, int nz) {
-    const int x0 = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y0 = blockIdx.y * ROT_YCH, z0 = blockIdx.z;
-    if (x0 >= nx) return;
-    const int cell = z0 * nx + x0;
-    const int nyc = min(ROT_YCH, ny - y0);
-    float2 acc[ROT_YCH];
+// Cells with more than two readers are the clipped border cells of the table (rotation_lookup clips the source coordinates, so
+// at 45 degrees 17 % of the rotated pixels pile onto the border cells, hundreds on the corner cells): their tails go to a
+// per-CTA work list that the warps sum cooperatively -- lanes stride the list, fixed shuffle tree, so still bit-reproducible.
+// (One thread walking such a list serially made the back-rotation 2.0-2.6 ms at 30-60 degrees against 0.9 ms below 30.)
+constexpr int ROT_LONG = 160;
+template <bool TMA>
+__global__ void __launch_bounds__(ROT_THREADS, 2) k_rotate_adjoint_csr(const float2* __restrict__ grot, long long slice_stride, long long batch_stride,
+                                     const RotLists lists, int n_ang, int accumulate, float2* __restrict__ gobj, int ny, int nx, int nz,
+                                     const __grid_constant__ CUtensorMap tm_grot) {
+    __shared__ __align__(128) float2 buf[2][ROT_BOX * ROT_BOX];
+    __shared__ __align__(8) unsigned long long bar[2];
+    __shared__ float2 s_extra[ROT_LONG][ROT_YA];
+    __shared__ int s_long_beg[ROT_LONG], s_long_cnt[ROT_LONG];
+    __shared__ int s_sum[4];                             // sum of z, sum of x, count over the first readers; number of long cells
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int y0 = blockIdx.x * ROT_YA, x0 = blockIdx.y * ROT_T, z0 = blockIdx.z * ROT_T;      // y fastest, as the gather
+    const int nyc = min(ROT_YA, ny - y0);
+    float2 acc[ROT_CPT][ROT_YA];
+    bool ok[ROT_CPT];
+    int cell[ROT_CPT];
 #pragma unroll
-    for (int j = 0; j < ROT_YCH; ++j) acc[j] = make_float2(0.f, 0.f);
-    bool any = false;
+    for (int i = 0; i < ROT_CPT; ++i) {
+        const int c = tid + ROT_THREADS * i, z = z0 + (c >> 5), x = x0 + (c & 31);
+        ok[i] = z < nz && x < nx;
+        cell[i] = ok[i] ? z * nx + x : 0;
+#pragma unroll
+        for (int j = 0; j < ROT_YA; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    }
+    if constexpr (TMA) {
+        if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+    }
+    [[maybe_unused]] int it = 0;                         // box loads issued so far: buffer it & 1, mbarrier parity (it >> 1) & 1
     for (int a = 0; a < n_ang; ++a) {
-        const int beg = lists.offsets[a][cell], end = lists.offsets[a][cell + 1];
-        for (int k = beg; k < end; ++k) {
-            const int d = lists.dest[a][k];              // z * nx + x of a rotated pixel whose source is (z0, x0)
-            const int z = d / nx, x = d - z * nx;
-            const float2* g = grot + (long long)a * batch_stride + (long long)z * slice_stride + (long long)y0 * nx + x;
-            any = true;
-            if (nyc == ROT_YCH) {
-                float2 v[ROT_YCH];
+        const int* __restrict__ off = lists.offsets[a];
+        const int* __restrict__ dst = lists.dest[a];
+        const float2* __restrict__ base = grot + (long long)a * batch_stride;
+        if (tid == 0) s_sum[0] = s_sum[1] = s_sum[2] = s_sum[3] = 0;
+        __syncthreads();
+        int beg[ROT_CPT], cnt[ROT_CPT], slot[ROT_CPT];
+        int sz = 0, sx = 0, sc = 0;
 #pragma unroll
-                for (int j = 0; j < ROT_YCH; ++j) v[j] = __ldcs(g + (long long)j * nx);
-#pragma unroll
-                for (int j = 0; j < ROT_YCH; ++j) { acc[j].x += v[j].x; acc[j].y += v[j].y; }
-            } else {
-#pragma unroll
-                for (int j = 0; j < ROT_YCH; ++j)
-                    if (j < nyc) { const float2 v = __ldcs(g + (long long)j * nx); acc[j].x += v.x; acc[j].y += v.y; }
+        for (int i = 0; i < ROT_CPT; ++i) {
+            beg[i] = ok[i] ? off[cell[i]] : 0;
+            cnt[i] = ok[i] ? off[cell[i] + 1] - beg[i] : 0;
+            slot[i] = -1;
+            if (cnt[i] > 0 && cnt[i] <= 2) { const int d = dst[beg[i]], z = d / nx; sz += z; sx += d - z * nx; ++sc; }    // ordinary cells centre the box
+            if (cnt[i] > 2) {
+                const int sl = atomicAdd(&s_sum[3], 1);              // slot order is arbitrary; every cell's sum is its own
+                if (sl < ROT_LONG) { slot[i] = sl; s_long_beg[sl] = beg[i] + 2; s_long_cnt[sl] = cnt[i] - 2; }
             }
         }
-    }
-    if (!any && accumulate) return;
-    float2* o = gobj + ((long long)z0 * ny + y0) * nx + x0;
+        sz = __reduce_add_sync(0xffffffffu, sz); sx = __reduce_add_sync(0xffffffffu, sx); sc = __reduce_add_sync(0xffffffffu, sc);
+        if (lane == 0 && sc > 0) { atomicAdd(&s_sum[0], sz); atomicAdd(&s_sum[1], sx); atomicAdd(&s_sum[2], sc); }
+        __syncthreads();
+        const int n_first = max(s_sum[2], 1);
+        if (s_sum[2] == 0 && s_sum[3] == 0) { __syncthreads(); continue; }  // nothing reads from this tile at this angle
+        const int zmn = max(0, min(s_sum[0] / n_first - ROT_BOX / 2, nz - ROT_BOX)), xmn = max(0, min(s_sum[1] / n_first - ROT_BOX / 2, nx - ROT_BOX)) & ~1;   // even: TMA boxes start on 16 bytes
+        const int bh = min(ROT_BOX, nz - zmn), bw = min(ROT_BOX, nx - xmn);
+        int s0[ROT_CPT], s1[ROT_CPT];                    // shared-memory offset of the first two readers, -1: outside the box
 #pragma unroll
-    for (int j = 0; j < ROT_YCH; ++j)
-        if (j < nyc) {
-            if (accumulate) { const float2 cur = o[(long long)j * nx]; acc[j].x += cur.x; acc[j].y += cur.y; }
-            o[(long long)j * nx] = acc[j];
+        for (int i = 0; i < ROT_CPT; ++i) {
+            s0[i] = s1[i] = -1;
+            if (cnt[i] > 0) {
+                const int d = dst[beg[i]], z = d / nx, x = d - z * nx;
+                if (z >= zmn && z < zmn + bh && x >= xmn && x < xmn + bw) s0[i] = (z - zmn) * ROT_BOX + (x - xmn);
+            }
+            if (cnt[i] > 1) {
+                const int d = dst[beg[i] + 1], z = d / nx, x = d - z * nx;
+                if (z >= zmn && z < zmn + bh && x >= xmn && x < xmn + bw) s1[i] = (z - zmn) * ROT_BOX + (x - xmn);
+            }
         }
+        auto add_readers = [&](int j, const float2* __restrict__ box) __attribute__((always_inline)) {
+            const int y = y0 + j;
+#pragma unroll
+            for (int i = 0; i < ROT_CPT; ++i) {
+                if (cnt[i] > 0) {
+                    float2 v;
+                    if (s0[i] >= 0) v = box[s0[i]];
+                    else { const int d = dst[beg[i]], z = d / nx, x = d - z * nx; v = __ldg(base + (long long)z * slice_stride + (long long)y * nx + x); }
+                    acc[i][j].x += v.x; acc[i][j].y += v.y;
+                }
+                if (cnt[i] > 1) {
+                    float2 v;
+                    if (s1[i] >= 0) v = box[s1[i]];
+                    else { const int d = dst[beg[i] + 1], z = d / nx, x = d - z * nx; v = __ldg(base + (long long)z * slice_stride + (long long)y * nx + x); }
+                    acc[i][j].x += v.x; acc[i][j].y += v.y;
+                }
+                if (cnt[i] > 2 && slot[i] < 0)           // work list overflow (not a rotation table): serial tail
+                    for (int k = 2; k < cnt[i]; ++k) {
+                        const int d = dst[beg[i] + k], z = d / nx, x = d - z * nx;
+                        const float2 v = __ldg(base + (long long)z * slice_stride + (long long)y * nx + x);
+                        acc[i][j].x += v.x; acc[i][j].y += v.y;
+                    }
+            }
+        };
+        if constexpr (TMA) {
+            // every buffer's previous readers are behind a __syncthreads (the one closing each row below)
+            if (tid == 0) { mbar_expect_tx(&bar[it & 1], ROT_BOX_BYTES); tma_load_4d(buf[it & 1], &tm_grot, 2 * xmn, y0, a, zmn, &bar[it & 1]); }
+#pragma unroll
+            for (int j = 0; j < ROT_YA; ++j) {
+                if (j < nyc) {                           // uniform over the CTA
+                    const int cur = it & 1;
+                    if (tid == 0 && j + 1 < nyc) {
+                        mbar_expect_tx(&bar[cur ^ 1], ROT_BOX_BYTES);
+                        tma_load_4d(buf[cur ^ 1], &tm_grot, 2 * xmn, y0 + j + 1, a, zmn, &bar[cur ^ 1]);
+                    }
+                    mbar_wait(&bar[cur], (it >> 1) & 1);
+                    add_readers(j, buf[cur]);
+                    ++it;
+                    __syncthreads();
+                }
+            }
+        } else {
+            const float2* origin = base + (long long)zmn * slice_stride + xmn;        // box element (r, c) of row y: origin + r slice_stride + y nx + c
+            float2 r[ROT_BPT];
+            rot_box_load(origin + (long long)y0 * nx, slice_stride, bh, bw, tid, r);
+            rot_box_store(buf[0], tid, r);
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < ROT_YA; ++j) {
+                if (j < nyc) {                           // uniform over the CTA
+                    const int cur = j & 1;
+                    if (j + 1 < nyc) rot_box_load(origin + (long long)(y0 + j + 1) * nx, slice_stride, bh, bw, tid, r);
+                    add_readers(j, buf[cur]);
+                    if (j + 1 < nyc) rot_box_store(buf[cur ^ 1], tid, r);
+                    __syncthreads();
+                }
+            }
+        }
+        const int n_long = min(s_sum[3], ROT_LONG);
+        if (n_long > 0) {                                // uniform over the CTA
+            for (int sl = warp; sl < n_long; sl += ROT_THREADS / 32) {
+                const int lb = s_long_beg[sl], lc = s_long_cnt[sl];
+                float2 part[ROT_YA];
+#pragma unroll
+                for (int j = 0; j < ROT_YA; ++j) part[j] = make_float2(0.f, 0.f);
+                for (int k = lane; k < lc; k += 32) {
+                    const int d = dst[lb + k], z = d / nx, x = d - z * nx;
+                    const float2* g = base + (long long)z * slice_stride + (long long)y0 * nx + x;
+#pragma unroll
+                    for (int j = 0; j < ROT_YA; ++j)
+                        if (j < nyc) { const float2 v = __ldg(g + (long long)j * nx); part[j].x += v.x; part[j].y += v.y; }
+                }
+#pragma unroll
+                for (int j = 0; j < ROT_YA; ++j) {
+#pragma unroll
+                    for (int m = 16; m > 0; m >>= 1) {
+                        part[j].x += __shfl_xor_sync(0xffffffffu, part[j].x, m);
+                        part[j].y += __shfl_xor_sync(0xffffffffu, part[j].y, m);
+                    }
+                    if (lane == 0) s_extra[sl][j] = part[j];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < ROT_CPT; ++i)
+                if (slot[i] >= 0) {
+#pragma unroll
+                    for (int j = 0; j < ROT_YA; ++j) { const float2 v = s_extra[slot[i]][j]; acc[i][j].x += v.x; acc[i][j].y += v.y; }
+                }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < ROT_CPT; ++i) {
+        if (!ok[i]) continue;
+        const int c = tid + ROT_THREADS * i;
+        float2* o = gobj + ((long long)(z0 + (c >> 5)) * ny + y0) * nx + x0 + (c & 31);
+#pragma unroll
+        for (int j = 0; j < ROT_YA; ++j)
+            if (j < nyc) {
+                float2 v = acc[i][j];
+                if (accumulate) { const float2 cur = o[(long long)j * nx]; v.x += cur.x; v.y += cur.y; }
+                o[(long long)j * nx] = v;
+            }
+    }
 }
 extern "C" int bdof_rotate_adjoint_csr_batch(const float* d_grad_rot_db, long long slice_stride_px, long long batch_stride_px, int n_angles,
                                              const int32_t* const* d_offsets, const int32_t* const* d_dest, float* d_grad_obj_db,
                                              int accumulate, int ny, int nx, int nz, void* st) {
     if (!d_grad_rot_db || !d_offsets || !d_dest || !d_grad_obj_db || ny < 1 || nx < 1 || nz < 1 || n_angles < 1) return fail(BDOF_E_BADARG, "bad argument");
-    if (ny > 65535 * ROT_YCH || nz > 65535) return fail(BDOF_E_UNSUPPORTED, "ny / nz too large");
-    dim3 grid((nx + 127) / 128, (ny + ROT_YCH - 1) / ROT_YCH, nz);
+    if (nx > 65535 * ROT_T || nz > 65535 * ROT_T) return fail(BDOF_E_UNSUPPORTED, "nx / nz too large");
+    dim3 grid((ny + ROT_YA - 1) / ROT_YA, (nx + ROT_T - 1) / ROT_T, (nz + ROT_T - 1) / ROT_T);
+    // TMA box loads need a tensor the descriptor can express: even nx (16-byte row pitch), sides at least one box, the
+    // minibatch laid out [z][angle][y][x] (a plan's db) or a single angle
+    const bool layout_ok = n_angles == 1 || (batch_stride_px == (long long)ny * nx && slice_stride_px >= (long long)n_angles * ny * nx);
+    const bool tma = rot_use_tma() && (nx % 2 == 0) && nx >= ROT_BOX && nz >= ROT_BOX && layout_ok && (reinterpret_cast<uintptr_t>(d_grad_rot_db) % 16 == 0) &&
+                     (slice_stride_px % 2 == 0) && (batch_stride_px % 2 == 0);
     for (int a0 = 0; a0 < n_angles; a0 += BDOF_ROT_MAX_ANGLES) {
         RotLists l;
         const int n = n_angles - a0 < BDOF_ROT_MAX_ANGLES ? n_angles - a0 : BDOF_ROT_MAX_ANGLES;
@@ -1669,9 +1932,22 @@ extern "C" int bdof_rotate_adjoint_csr_batch(const float* d_grad_rot_db, long lo
             if (!d_offsets[a0 + a] || !d_dest[a0 + a]) return fail(BDOF_E_BADARG, "null list");
             l.offsets[a] = d_offsets[a0 + a]; l.dest[a] = d_dest[a0 + a];
         }
-        k_rotate_adjoint_csr<<<grid, 128, 0, (cudaStream_t)st>>>(reinterpret_cast<const float2*>(d_grad_rot_db) + (long long)a0 * batch_stride_px,
-                                                               slice_stride_px, batch_stride_px, l, n, (accumulate || a0 > 0) ? 1 : 0,
-                                                               reinterpret_cast<float2*>(d_grad_obj_db), ny, nx, nz);
+        const float2* base = reinterpret_cast<const float2*>(d_grad_rot_db) + (long long)a0 * batch_stride_px;
+        const int acc = (accumulate || a0 > 0) ? 1 : 0;
+        alignas(64) CUtensorMap tm;
+        memset(&tm, 0, sizeof(tm));
+        if (tma) {
+            const long long bstride = n == 1 ? (long long)ny * nx : batch_stride_px;             // one angle: the dimension has extent 1
+            const long long dims[4] = {2LL * nx, ny, n, nz};
+            const long long strides[3] = {(long long)nx * 8, bstride * 8, slice_stride_px * 8};
+            const int box[4] = {2 * ROT_BOX, 1, 1, ROT_BOX};
+            BDOF_TRY(make_tensor_map_nd(&tm, base, 4, dims, strides, box));
+            k_rotate_adjoint_csr<true><<<grid, ROT_THREADS, 0, (cudaStream_t)st>>>(base, slice_stride_px, batch_stride_px, l, n, acc,
+                                                                                 reinterpret_cast<float2*>(d_grad_obj_db), ny, nx, nz, tm);
+        } else {
+            k_rotate_adjoint_csr<false><<<grid, ROT_THREADS, 0, (cudaStream_t)st>>>(base, slice_stride_px, batch_stride_px, l, n, acc,
+                                                                                  reinterpret_cast<float2*>(d_grad_obj_db), ny, nx, nz, tm);
+        }
         if (int r = launch_check("k_rotate_adjoint_csr")) return r;
     }
     return 0;
@@ -1683,10 +1959,22 @@ extern "C" int bdof_rotate_adjoint_csr(const float* d_grad_rot_db, long long sli
 extern "C" int bdof_rotate_gather(const float* d_obj_db, const int32_t* d_lookup_zx, float* d_out_db, long long out_slice_stride_px,
                                   int ny, int nx, int nz, void* st) {
     if (!d_obj_db || !d_lookup_zx || !d_out_db || ny < 1 || nx < 1 || nz < 1) return fail(BDOF_E_BADARG, "bad argument");
-    if (ny > 65535 * ROT_YCH || nz > 65535) return fail(BDOF_E_UNSUPPORTED, "ny / nz too large");
-    dim3 grid((nx + 127) / 128, (ny + ROT_YCH - 1) / ROT_YCH, nz);
-    k_rotate_gather<<<grid, 128, 0, (cudaStream_t)st>>>(reinterpret_cast<const float2*>(d_obj_db), reinterpret_cast<const int2*>(d_lookup_zx),
-                                                      reinterpret_cast<float2*>(d_out_db), out_slice_stride_px, ny, nx, nz);
+    if (nx > 65535 * ROT_T || nz > 65535 * ROT_T) return fail(BDOF_E_UNSUPPORTED, "nx / nz too large");
+    dim3 grid((ny + ROT_YB - 1) / ROT_YB, (nx + ROT_T - 1) / ROT_T, (nz + ROT_T - 1) / ROT_T);
+    const bool tma = rot_use_tma() && (nx % 2 == 0) && nx >= ROT_BOX && nz >= ROT_BOX && (reinterpret_cast<uintptr_t>(d_obj_db) % 16 == 0);
+    alignas(64) CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    if (tma) {
+        const long long dims[3] = {2LL * nx, ny, nz};
+        const long long strides[2] = {(long long)nx * 8, (long long)ny * nx * 8};
+        const int box[3] = {2 * ROT_BOX, 1, ROT_BOX};
+        BDOF_TRY(make_tensor_map_nd(&tm, d_obj_db, 3, dims, strides, box));
+        k_rotate_gather<true><<<grid, ROT_THREADS, 0, (cudaStream_t)st>>>(reinterpret_cast<const float2*>(d_obj_db), reinterpret_cast<const int2*>(d_lookup_zx),
+                                                                        reinterpret_cast<float2*>(d_out_db), out_slice_stride_px, ny, nx, nz, tm);
+    } else {
+        k_rotate_gather<false><<<grid, ROT_THREADS, 0, (cudaStream_t)st>>>(reinterpret_cast<const float2*>(d_obj_db), reinterpret_cast<const int2*>(d_lookup_zx),
+                                                                         reinterpret_cast<float2*>(d_out_db), out_slice_stride_px, ny, nx, nz, tm);
+    }
     return launch_check("k_rotate_gather");
 }
 extern "C" int bdof_rotate_scatter_add(const float* d_grad_rot_db, long long slice_stride_px, const int32_t* d_lookup_zx,

@@ -148,7 +148,7 @@ def test_apply_rotation_matches_reference_bit_exact(bd, gold_rot, tag):
 def test_rotation_adjoint_matches_oracle_ragged(bd):
     from beyond_dof_b200 import rotation
     rng = np.random.default_rng(71)
-    for (Y, X, Z), theta in (((5, 33, 33), 0.3), ((3, 64, 64), 2.1), ((2, 40, 40), 4.0), ((1, 8, 8), 0.0)):
+    for (Y, X, Z), theta in (((5, 33, 33), 0.3), ((3, 64, 64), 2.1), ((2, 40, 40), 4.0), ((1, 8, 8), 0.0), ((11, 160, 160), 0.7), ((9, 130, 130), 1.55), ((7, 101, 101), 2.4)):
         g = rng.standard_normal((Y, X, Z, 2)).astype(np.float32)
         tab = mo.rotation_lookup([Y, X, Z], theta)
         ref = mo.apply_rotation_adjoint(g.astype(np.float64), tab)
@@ -173,7 +173,7 @@ def test_rotation_adjoint_batch_sums_the_minibatch_in_one_pass(bd):
     from beyond_dof_b200 import rotation
     rng = np.random.default_rng(73)
     dev = torch.device('cuda')
-    for (Y, X, Z), n_ang in (((5, 33, 33), 3), ((19, 40, 40), 18), ((8, 64, 64), 10)):
+    for (Y, X, Z), n_ang in (((5, 33, 33), 3), ((19, 40, 40), 18), ((8, 64, 64), 10), ((6, 150, 150), 5), ((3, 97, 97), 4)):
         thetas = rng.random(n_ang) * 2 * np.pi
         tabs = [rotation.device_table([Y, X, Z], float(t), dev) for t in thetas]
         g = torch.as_tensor(rng.standard_normal((Z, n_ang, Y, X, 2)).astype(np.float32)).cuda()
