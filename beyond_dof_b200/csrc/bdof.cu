@@ -1742,12 +1742,9 @@ struct RotLists { const int* offsets[BDOF_ROT_MAX_ANGLES]; const int* dest[BDOF_
 // per-CTA work list that the warps sum cooperatively -- lanes stride the list, fixed shuffle tree, so still bit-reproducible.
 // (One thread walking such a list serially made the back-rotation 2.0-2.6 ms at 30-60 degrees against 0.9 ms below 30.)
 constexpr int ROT_LONG = 160;
-template <bool TMA>
 __global__ void __launch_bounds__(ROT_THREADS, 2) k_rotate_adjoint_csr(const float2* __restrict__ grot, long long slice_stride, long long batch_stride,
-                                     const RotLists lists, int n_ang, int accumulate, float2* __restrict__ gobj, int ny, int nx, int nz,
-                                     const __grid_constant__ CUtensorMap tm_grot) {
-    __shared__ __align__(128) float2 buf[2][ROT_BOX * ROT_BOX];
-    __shared__ __align__(8) unsigned long long bar[2];
+                                     const RotLists lists, int n_ang, int accumulate, float2* __restrict__ gobj, int ny, int nx, int nz) {
+    __shared__ float2 buf[2][ROT_BOX * ROT_BOX];
     __shared__ float2 s_extra[ROT_LONG][ROT_YA];
     __shared__ int s_long_beg[ROT_LONG], s_long_cnt[ROT_LONG];
     __shared__ int s_sum[4];                             // sum of z, sum of x, count over the first readers; number of long cells
@@ -1765,10 +1762,6 @@ __global__ void __launch_bounds__(ROT_THREADS, 2) k_rotate_adjoint_csr(const flo
 #pragma unroll
         for (int j = 0; j < ROT_YA; ++j) acc[i][j] = make_float2(0.f, 0.f);
     }
-    if constexpr (TMA) {
-        if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
-    }
-    [[maybe_unused]] int it = 0;                         // box loads issued so far: buffer it & 1, mbarrier parity (it >> 1) & 1
     for (int a = 0; a < n_ang; ++a) {
         const int* __restrict__ off = lists.offsets[a];
         const int* __restrict__ dst = lists.dest[a];
@@ -1832,24 +1825,7 @@ __global__ void __launch_bounds__(ROT_THREADS, 2) k_rotate_adjoint_csr(const flo
                     }
             }
         };
-        if constexpr (TMA) {
-            // every buffer's previous readers are behind a __syncthreads (the one closing each row below)
-            if (tid == 0) { mbar_expect_tx(&bar[it & 1], ROT_BOX_BYTES); tma_load_4d(buf[it & 1], &tm_grot, 2 * xmn, y0, a, zmn, &bar[it & 1]); }
-#pragma unroll
-            for (int j = 0; j < ROT_YA; ++j) {
-                if (j < nyc) {                           // uniform over the CTA
-                    const int cur = it & 1;
-                    if (tid == 0 && j + 1 < nyc) {
-                        mbar_expect_tx(&bar[cur ^ 1], ROT_BOX_BYTES);
-                        tma_load_4d(buf[cur ^ 1], &tm_grot, 2 * xmn, y0 + j + 1, a, zmn, &bar[cur ^ 1]);
-                    }
-                    mbar_wait(&bar[cur], (it >> 1) & 1);
-                    add_readers(j, buf[cur]);
-                    ++it;
-                    __syncthreads();
-                }
-            }
-        } else {
+        {
             const float2* origin = base + (long long)zmn * slice_stride + xmn;        // box element (r, c) of row y: origin + r slice_stride + y nx + c
             float2 r[ROT_BPT];
             rot_box_load(origin + (long long)y0 * nx, slice_stride, bh, bw, tid, r);
@@ -1914,6 +1890,235 @@ __global__ void __launch_bounds__(ROT_THREADS, 2) k_rotate_adjoint_csr(const flo
             }
     }
 }
+
+// ---- the TMA form of the same kernel.  The box origins of every (angle, tile) come from a small kernel of their own
+// (k_rot_origins), so the box loads do not wait for the lists: one thread streams the (angle, y) boxes of the CTA through a
+// ring of ROT_NBUF shared-memory buffers, ROT_NBUF loads in flight, while all threads read the next angle's lists.
+constexpr int ROT_NBUF = 4;
+// grow-only scratch per (device, stream): calls on one stream are ordered, calls on different streams never share a buffer
+// (a stream-ordered allocation per call cost 0.3-2 ms of host time)
+static int rot_scratch(int2** out, size_t bytes, cudaStream_t st) {
+    struct Buf { void* p; size_t n; };
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, Buf> bufs;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    Buf& b = bufs[std::make_pair(dev, st)];
+    if (b.n < bytes) {
+        if (b.p) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(b.p); b.p = nullptr; b.n = 0; }
+        const size_t want = bytes < 65536 ? 65536 : bytes;
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e != cudaSuccess) { b.p = nullptr; return bdof_fail(int(e), "cudaMalloc rotation scratch: %s", cudaGetErrorString(e)); }
+        b.n = want;
+    }
+    *out = static_cast<int2*>(b.p);
+    return 0;
+}
+__global__ void __launch_bounds__(ROT_THREADS) k_rot_origins(const RotLists lists, int nx, int nz, int2* __restrict__ origins) {
+    __shared__ int s_sum[4];
+    const int tid = threadIdx.x, a = blockIdx.z;
+    const int x0 = blockIdx.x * ROT_T, z0 = blockIdx.y * ROT_T;
+    const int* __restrict__ off = lists.offsets[a];
+    const int* __restrict__ dst = lists.dest[a];
+    if (tid == 0) s_sum[0] = s_sum[1] = s_sum[2] = s_sum[3] = 0;
+    __syncthreads();
+    int sz = 0, sx = 0, sc = 0, sl = 0;
+#pragma unroll
+    for (int i = 0; i < ROT_CPT; ++i) {
+        const int c = tid + ROT_THREADS * i, z = z0 + (c >> 5), x = x0 + (c & 31);
+        if (z < nz && x < nx) {
+            const int beg = off[z * nx + x], cnt = off[z * nx + x + 1] - beg;
+            if (cnt > 0 && cnt <= 2) { const int d = dst[beg], zz = d / nx; sz += zz; sx += d - zz * nx; ++sc; }    // ordinary cells centre the box
+            if (cnt > 2) ++sl;
+        }
+    }
+    sz = __reduce_add_sync(0xffffffffu, sz); sx = __reduce_add_sync(0xffffffffu, sx);
+    sc = __reduce_add_sync(0xffffffffu, sc); sl = __reduce_add_sync(0xffffffffu, sl);
+    if ((tid & 31) == 0) { atomicAdd(&s_sum[0], sz); atomicAdd(&s_sum[1], sx); atomicAdd(&s_sum[2], sc); atomicAdd(&s_sum[3], sl); }
+    __syncthreads();
+    if (tid == 0) {
+        int2 o = make_int2(-1, -1);                      // (z, x) of the box; x = -1: nothing reads from this tile at this angle
+        if (s_sum[2] > 0 || s_sum[3] > 0) {
+            const int n = max(s_sum[2], 1);
+            o.x = max(0, min(s_sum[0] / n - ROT_BOX / 2, nz - ROT_BOX));
+            o.y = max(0, min(s_sum[1] / n - ROT_BOX / 2, nx - ROT_BOX)) & ~1;         // even: TMA boxes start on 16 bytes
+        }
+        origins[((long long)a * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = o;
+    }
+}
+// d / nx for 0 <= d < 2^31 by multiplication: mul = ceil(2^(31 + sh) / nx), sh = ceil(log2 nx) (round-up method; the lists hold
+// z * nx + x, and a runtime integer division is ~25 instructions -- the per-angle code of the kernel is fetched, not looped)
+struct RotDiv { unsigned mul; int sh; int nx; };
+static RotDiv rot_div_make(int nx) {
+    RotDiv d; d.nx = nx; d.sh = 0;
+    while ((1LL << d.sh) < nx) ++d.sh;
+    d.mul = unsigned(((1ULL << (31 + d.sh)) + (unsigned long long)nx - 1) / (unsigned long long)nx);
+    return d;
+}
+__device__ __forceinline__ void rot_split(const RotDiv& dv, int d, int* z, int* x) {
+    const int q = int(((unsigned long long)(unsigned)d * dv.mul) >> (31 + dv.sh));
+    *z = q; *x = d - q * dv.nx;
+}
+// serial tail of one cell (work list overflow: not a rotation table); rare, kept out of line
+__device__ __noinline__ float2 rot_serial_tail(const float2* __restrict__ base, const int* __restrict__ dst, int beg, int n, long long slice_stride, int y, int nx) {
+    float2 a = make_float2(0.f, 0.f);
+    for (int k = 0; k < n; ++k) {
+        const int d = dst[beg + k], z = d / nx, x = d - z * nx;
+        const float2 v = __ldg(base + (long long)z * slice_stride + (long long)y * nx + x);
+        a.x += v.x; a.y += v.y;
+    }
+    return a;
+}
+__global__ void __launch_bounds__(ROT_THREADS, 2) k_rotate_adjoint_tma(const float2* __restrict__ grot, long long slice_stride, long long batch_stride,
+                                     const RotLists lists, int n_ang, int accumulate, float2* __restrict__ gobj, int ny, int nx, int nz,
+                                     const int2* __restrict__ origins, const RotDiv dv, const __grid_constant__ CUtensorMap tm_grot) {
+    extern __shared__ __align__(128) float2 ring[];      // ROT_NBUF boxes
+    __shared__ __align__(8) unsigned long long bar[ROT_NBUF];
+    __shared__ float2 s_extra[ROT_LONG][ROT_YA];
+    __shared__ int s_long_beg[ROT_LONG], s_long_cnt[ROT_LONG];
+    __shared__ int2 s_org[BDOF_ROT_MAX_ANGLES];          // box origin (z, x) of the angles that have readers, in angle order
+    __shared__ int s_ang[BDOF_ROT_MAX_ANGLES];
+    __shared__ int s_nv, s_nlong;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int y0 = blockIdx.x * ROT_YA, x0 = blockIdx.y * ROT_T, z0 = blockIdx.z * ROT_T;      // y fastest, as the gather
+    const int nyc = min(ROT_YA, ny - y0);
+    if (tid == 0) {
+        int nv = 0;
+        for (int a = 0; a < n_ang; ++a) {
+            const int2 o = origins[((long long)a * gridDim.z + blockIdx.z) * gridDim.y + blockIdx.y];
+            if (o.x >= 0) { s_org[nv] = o; s_ang[nv] = a; ++nv; }
+        }
+        s_nv = nv;
+        for (int b = 0; b < ROT_NBUF; ++b) mbar_init(&bar[b], 1);
+        fence_mbar_init();
+    }
+    float2 acc[ROT_CPT][ROT_YA];
+    bool ok[ROT_CPT];
+    int cell[ROT_CPT];
+#pragma unroll
+    for (int i = 0; i < ROT_CPT; ++i) {
+        const int c = tid + ROT_THREADS * i, z = z0 + (c >> 5), x = x0 + (c & 31);
+        ok[i] = z < nz && x < nx;
+        cell[i] = ok[i] ? z * nx + x : 0;
+#pragma unroll
+        for (int j = 0; j < ROT_YA; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    const int nv = s_nv, n_loads = nv * nyc;
+    // load q = (valid angle q / nyc, row q % nyc) goes to buffer q % ROT_NBUF; its mbarrier completes phase q / ROT_NBUF
+    auto issue = [&](int q) __attribute__((always_inline)) {
+        const int vi = q / nyc, j = q - vi * nyc, b = q % ROT_NBUF;
+        const int2 o = s_org[vi];
+        mbar_expect_tx(&bar[b], ROT_BOX_BYTES);
+        tma_load_4d(ring + b * (ROT_BOX * ROT_BOX), &tm_grot, 2 * o.y, y0 + j, s_ang[vi], o.x, &bar[b]);
+    };
+    if (tid == 0)
+        for (int q = 0; q < ROT_NBUF && q < n_loads; ++q) issue(q);
+    int q = 0;
+#pragma unroll 1
+    for (int vi = 0; vi < nv; ++vi) {
+        const int a = s_ang[vi], zmn = s_org[vi].x, xmn = s_org[vi].y;
+        const int* __restrict__ off = lists.offsets[a];
+        const int* __restrict__ dst = lists.dest[a];
+        const float2* __restrict__ base = grot + (long long)a * batch_stride;
+        if (tid == 0) s_nlong = 0;
+        __syncthreads();
+        // the first one or two readers of a cell come from the box; whatever is left (readers outside the box, the tails of
+        // the clipped border cells) goes to the CTA's work list
+        int s0[ROT_CPT], s1[ROT_CPT], slot[ROT_CPT], tail_beg[ROT_CPT], tail_n[ROT_CPT];
+#pragma unroll
+        for (int i = 0; i < ROT_CPT; ++i) {
+            const int beg = ok[i] ? off[cell[i]] : 0;
+            const int cnt = ok[i] ? off[cell[i] + 1] - beg : 0;
+            s0[i] = -1; s1[i] = -1; slot[i] = -1;
+            int nf = 0;                                  // leading readers served from the box
+            if (cnt > 0) {
+                int z, x;
+                rot_split(dv, dst[beg], &z, &x);
+                if (z >= zmn && z < zmn + ROT_BOX && x >= xmn && x < xmn + ROT_BOX) { s0[i] = (z - zmn) * ROT_BOX + (x - xmn); nf = 1; }
+            }
+            if (cnt > 1 && nf == 1) {
+                int z, x;
+                rot_split(dv, dst[beg + 1], &z, &x);
+                if (z >= zmn && z < zmn + ROT_BOX && x >= xmn && x < xmn + ROT_BOX) { s1[i] = (z - zmn) * ROT_BOX + (x - xmn); nf = 2; }
+            }
+            tail_beg[i] = beg + nf; tail_n[i] = cnt - nf;
+            if (tail_n[i] > 0) {
+                const int sl = atomicAdd(&s_nlong, 1);              // slot order is arbitrary; every cell's sum is its own
+                if (sl < ROT_LONG) { slot[i] = sl; s_long_beg[sl] = tail_beg[i]; s_long_cnt[sl] = tail_n[i]; }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < ROT_YA; ++j) {
+            if (j < nyc) {                               // uniform over the CTA
+                const int b = q % ROT_NBUF;
+                const float2* __restrict__ box = ring + b * (ROT_BOX * ROT_BOX);
+                mbar_wait(&bar[b], (q / ROT_NBUF) & 1);
+#pragma unroll
+                for (int i = 0; i < ROT_CPT; ++i) {
+                    if (s0[i] >= 0) { const float2 v = box[s0[i]]; acc[i][j].x += v.x; acc[i][j].y += v.y; }
+                    if (s1[i] >= 0) { const float2 v = box[s1[i]]; acc[i][j].x += v.x; acc[i][j].y += v.y; }
+                }
+                __syncthreads();                         // the buffer is free
+                if (tid == 0 && q + ROT_NBUF < n_loads) issue(q + ROT_NBUF);
+                ++q;
+            }
+        }
+        const int n_long = s_nlong;
+        if (n_long > 0) {                                // uniform over the CTA
+            for (int sl = warp; sl < min(n_long, ROT_LONG); sl += ROT_THREADS / 32) {
+                const int lb = s_long_beg[sl], lc = s_long_cnt[sl];
+                float2 part[ROT_YA];
+#pragma unroll
+                for (int j = 0; j < ROT_YA; ++j) part[j] = make_float2(0.f, 0.f);
+                for (int k = lane; k < lc; k += 32) {
+                    int z, x;
+                    rot_split(dv, dst[lb + k], &z, &x);
+                    const float2* g = base + (long long)z * slice_stride + (long long)y0 * nx + x;
+#pragma unroll
+                    for (int j = 0; j < ROT_YA; ++j)
+                        if (j < nyc) { const float2 v = __ldg(g + (long long)j * nx); part[j].x += v.x; part[j].y += v.y; }
+                }
+#pragma unroll
+                for (int j = 0; j < ROT_YA; ++j) {
+#pragma unroll
+                    for (int m = 16; m > 0; m >>= 1) {
+                        part[j].x += __shfl_xor_sync(0xffffffffu, part[j].x, m);
+                        part[j].y += __shfl_xor_sync(0xffffffffu, part[j].y, m);
+                    }
+                    if (lane == 0) s_extra[sl][j] = part[j];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < ROT_CPT; ++i) {
+                if (slot[i] >= 0) {
+#pragma unroll
+                    for (int j = 0; j < ROT_YA; ++j) { const float2 v = s_extra[slot[i]][j]; acc[i][j].x += v.x; acc[i][j].y += v.y; }
+                } else if (tail_n[i] > 0) {              // work list overflow
+#pragma unroll
+                    for (int j = 0; j < ROT_YA; ++j)
+                        if (j < nyc) { const float2 v = rot_serial_tail(base, dst, tail_beg[i], tail_n[i], slice_stride, y0 + j, nx); acc[i][j].x += v.x; acc[i][j].y += v.y; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < ROT_CPT; ++i) {
+        if (!ok[i]) continue;
+        const int c = tid + ROT_THREADS * i;
+        float2* o = gobj + ((long long)(z0 + (c >> 5)) * ny + y0) * nx + x0 + (c & 31);
+#pragma unroll
+        for (int j = 0; j < ROT_YA; ++j)
+            if (j < nyc) {
+                float2 v = acc[i][j];
+                if (accumulate) { const float2 cur = o[(long long)j * nx]; v.x += cur.x; v.y += cur.y; }
+                o[(long long)j * nx] = v;
+            }
+    }
+}
 extern "C" int bdof_rotate_adjoint_csr_batch(const float* d_grad_rot_db, long long slice_stride_px, long long batch_stride_px, int n_angles,
                                              const int32_t* const* d_offsets, const int32_t* const* d_dest, float* d_grad_obj_db,
                                              int accumulate, int ny, int nx, int nz, void* st) {
@@ -1934,19 +2139,29 @@ extern "C" int bdof_rotate_adjoint_csr_batch(const float* d_grad_rot_db, long lo
         }
         const float2* base = reinterpret_cast<const float2*>(d_grad_rot_db) + (long long)a0 * batch_stride_px;
         const int acc = (accumulate || a0 > 0) ? 1 : 0;
-        alignas(64) CUtensorMap tm;
-        memset(&tm, 0, sizeof(tm));
         if (tma) {
+            alignas(64) CUtensorMap tm;
             const long long bstride = n == 1 ? (long long)ny * nx : batch_stride_px;             // one angle: the dimension has extent 1
             const long long dims[4] = {2LL * nx, ny, n, nz};
             const long long strides[3] = {(long long)nx * 8, bstride * 8, slice_stride_px * 8};
             const int box[4] = {2 * ROT_BOX, 1, 1, ROT_BOX};
             BDOF_TRY(make_tensor_map_nd(&tm, base, 4, dims, strides, box));
-            k_rotate_adjoint_csr<true><<<grid, ROT_THREADS, 0, (cudaStream_t)st>>>(base, slice_stride_px, batch_stride_px, l, n, acc,
-                                                                                 reinterpret_cast<float2*>(d_grad_obj_db), ny, nx, nz, tm);
+            static bool attr_set = false;
+            const int ring_bytes = ROT_NBUF * int(ROT_BOX_BYTES);
+            if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_rotate_adjoint_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes)); attr_set = true; }
+            int2* origins = nullptr;                     // scratch [angle][tile z][tile x], one buffer per (device, stream)
+            BDOF_TRY(rot_scratch(&origins, sizeof(int2) * n * grid.y * grid.z, (cudaStream_t)st));
+            k_rot_origins<<<dim3(grid.y, grid.z, n), ROT_THREADS, 0, (cudaStream_t)st>>>(l, nx, nz, origins);
+            int r = launch_check("k_rot_origins");
+            if (!r) {
+                k_rotate_adjoint_tma<<<grid, ROT_THREADS, ring_bytes, (cudaStream_t)st>>>(base, slice_stride_px, batch_stride_px, l, n, acc,
+                                                                                        reinterpret_cast<float2*>(d_grad_obj_db), ny, nx, nz, origins, rot_div_make(nx), tm);
+                r = launch_check("k_rotate_adjoint_tma");
+            }
+            if (r) return r;
         } else {
-            k_rotate_adjoint_csr<false><<<grid, ROT_THREADS, 0, (cudaStream_t)st>>>(base, slice_stride_px, batch_stride_px, l, n, acc,
-                                                                                  reinterpret_cast<float2*>(d_grad_obj_db), ny, nx, nz, tm);
+            k_rotate_adjoint_csr<<<grid, ROT_THREADS, 0, (cudaStream_t)st>>>(base, slice_stride_px, batch_stride_px, l, n, acc,
+                                                                           reinterpret_cast<float2*>(d_grad_obj_db), ny, nx, nz);
         }
         if (int r = launch_check("k_rotate_adjoint_csr")) return r;
     }
