@@ -62,6 +62,7 @@ def build_lib(force=False, verbose=True):
     jobs.append((os.path.join(CSRC, 'genericfft.cu'), os.path.join(OBJ, 'genericfft.o'), [], os.path.join(OBJ, 'genericfft.log')))
     jobs.append((os.path.join(CSRC, 'tilehalo.cu'), os.path.join(OBJ, 'tilehalo.o'), [], os.path.join(OBJ, 'tilehalo.log')))
     jobs.append((os.path.join(CSRC, 'resident_inst.cu'), os.path.join(OBJ, 'resident_inst.o'), [], os.path.join(OBJ, 'resident_inst.log')))
+    jobs.append((os.path.join(CSRC, 'cluster_inst.cu'), os.path.join(OBJ, 'cluster_inst.o'), [], os.path.join(OBJ, 'cluster_inst.log')))
     for n in SIZES:
         jobs.append((os.path.join(CSRC, 'line_inst.cu'), os.path.join(OBJ, 'line_%d.o' % n), ['-DBDOF_N=%d' % n],
                      os.path.join(OBJ, 'line_%d.log' % n)))

@@ -142,6 +142,9 @@ namespace bdof { struct SweepParams; struct ResidentParams; }
 // resident small-field kernels (residentfft.cuh, resident_inst.cu): one CTA per field through all slices
 int bdof_resident_supported(int n);
 int bdof_launch_resident(int n, int adj, const bdof::ResidentParams& p, cudaStream_t st);
+// cluster-resident kernels (clusterfft.cuh): one cluster of 8 CTAs per 256 x 256 field; same parameters (BDOF_CLUSTER=0 disables)
+int bdof_cluster_supported(int n);
+int bdof_launch_cluster(int n, int adj, const bdof::ResidentParams& p, cudaStream_t st);
 // sweep kernels (sweepfft.cuh): col = 0 x kernel (rows), 1 y kernel (columns); adj = 0 forward, 1 adjoint;
 // the field is [rows][cols] complex64 row-major with rows = batch * ny
 #define BDOF_DECL_LINE(N) int bdof_launch_line_##N(int variant, const bdof::LineParams& p, long long n_lines, cudaStream_t st); \

@@ -64,11 +64,12 @@ static int launch_resident(int adj, const ResidentParams& p, cudaStream_t st) {
     return bdof_launch_check(adj ? "resident_adjoint_kernel" : "resident_forward_kernel");
 }
 
-int bdof_resident_supported(int n) { return n == 64 ? 1 : 0; }
+int bdof_resident_supported(int n) { return (n == 64 || bdof_cluster_supported(n)) ? 1 : 0; }
 
 int bdof_launch_resident(int n, int adj, const ResidentParams& p, cudaStream_t st) {
     switch (n) {
         case 64: return launch_resident<ResCfg<64>::C>(adj, p, st);
     }
+    if (bdof_cluster_supported(n)) return bdof_launch_cluster(n, adj, p, st);
     return bdof_fail(BDOF_E_UNSUPPORTED, "no resident kernel for %d x %d fields", n, n);
 }

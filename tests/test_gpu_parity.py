@@ -601,6 +601,28 @@ def test_resident_kernels_match_sweep_kernels_and_oracle(bd, case, in_place_stas
         assert rel_l2(a[1], gdo) < TOL_GRAD and rel_l2(a[2], gbo) < TOL_GRAD
 
 
+# cluster-resident kernels (clusterfft.cuh): a 256 x 256 field lives in the registers of a cluster of 8 CTAs, transposed through
+# distributed shared memory between slices.  Same A/B as above; batch 20 exceeds the clusters one GPU can hold at once.
+@pytest.mark.parametrize('case', [((2, 256, 256, 6), False, None), ((1, 256, 256, 7), True, 'inf'), ((20, 256, 256, 3), True, None),
+                                  ((3, 256, 256, 2), False, 1e-4), ((2, 256, 256, 9), True, 1e-4)])
+@pytest.mark.parametrize('in_place_stash', [False, True])
+def test_cluster_resident_kernels_match_sweep_kernels_and_oracle(bd, case, in_place_stash):
+    shape, propagate_last, free = case
+    gd, gb = mo.random_phantom(shape, seed=75, delta_scale=4e-4, beta_scale=4e-5)
+    pr, pi = mo.gaussian_probe(shape[1:3], 24., 20., 0.5) if free == 'inf' else mo.gaussian_probe(shape[1:3], 120., 100., 0.5)
+    rng = np.random.default_rng(76)
+    target = rng.random(shape[:3]) * (8 if free == 'inf' else 1.0) + 0.5
+    a = _run_plan_env(shape, gd, gb, pr, pi, target, {'BDOF_RESIDENT': '1'}, propagate_last, free, in_place_stash)
+    b = _run_plan_env(shape, gd, gb, pr, pi, target, {'BDOF_RESIDENT': '0'}, propagate_last, free, in_place_stash)
+    assert a[4] < b[4]                                        # one launch per direction instead of one per slice and direction
+    assert rel_l2(a[0], b[0]) < 2e-6
+    assert rel_l2(a[1], b[1]) < 2e-5 and rel_l2(a[2], b[2]) < 2e-5 and rel_l2(a[3], b[3]) < 2e-5
+    if shape[0] <= 3:
+        lo, gdo, gbo, psio = mo.loss_and_grad(gd, gb, pr, pi, 5000, 1e-7, target, free_prop_cm=free, propagate_last=propagate_last)
+        assert intensity_err(a[0], psio) < TOL_INTENSITY and abs(a[5] - lo) < 1e-5 * abs(lo)
+        assert rel_l2(a[1], gdo) < TOL_GRAD and rel_l2(a[2], gbo) < TOL_GRAD
+
+
 def test_resident_kernels_z_broadcast_and_forward_only(bd):
     shape = (4, 64, 64, 10)
     gd1, gb1 = mo.random_phantom((4, 64, 64, 1), seed=73, delta_scale=4e-4, beta_scale=4e-5)
