@@ -20,7 +20,7 @@ SYMBOLS = [
     'bdof_forward', 'bdof_loss_mag', 'bdof_adjoint', 'bdof_pack_db', 'bdof_unpack_db', 'bdof_patch_gather',
     'bdof_patch_scatter_add', 'bdof_cnn_forward', 'bdof_forward_host', 'bdof_plan_workspace_bytes',
     'bdof_free_prop', 'bdof_profile_begin', 'bdof_profile_end', 'bdof_debug_set_buffer', 'bdof_slice_step',
-    'bdof_plan_set_bucket_events', 'bdof_set_sm_reserve', 'bdof_rotate_gather', 'bdof_rotate_scatter_add', 'bdof_rotate_adjoint_csr', 'bdof_rotate_adjoint_csr_batch', 'bdof_adam_step',
+    'bdof_plan_set_bucket_events', 'bdof_set_sm_reserve', 'bdof_rotate_gather', 'bdof_rotate_scatter_add', 'bdof_rotate_adjoint_csr', 'bdof_rotate_adjoint_csr_batch', 'bdof_rotate_adjoint_csr_batch_range', 'bdof_adam_step',
     'bdof_finite_support', 'bdof_plan_set_t_stash', 'bdof_rotate_bilinear', 'bdof_rotate_bilinear_adjoint',
     'bdof_dp_create', 'bdof_dp_destroy', 'bdof_dp_handle_bytes', 'bdof_dp_export', 'bdof_dp_connect', 'bdof_dp_grad_ptr',
     'bdof_dp_bucket', 'bdof_dp_gather', 'bdof_dp_finish', 'bdof_plan_last_times', 'bdof_pack_db_rows', 'bdof_unpack_db_rows', 'bdof_plan_set_stream', 'bdof_debug_fft_gain', 'bdof_field_multiply', 'bdof_patch_gather_add', 'bdof_plan_set_windows', 'bdof_plan_is_resident', 'bdof_cnn_forward_store', 'bdof_cnn_adjoint', 'bdof_free_prop_adjoint',
@@ -81,6 +81,7 @@ def _load():
     lib.bdof_rotate_scatter_add.argtypes = [vp, i64, vp, vp, i32, i32, i32, vp]
     lib.bdof_rotate_adjoint_csr.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, vp]
     lib.bdof_rotate_adjoint_csr_batch.argtypes = [vp, i64, i64, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, i32, i32, i32, i32, vp]
+    lib.bdof_rotate_adjoint_csr_batch_range.argtypes = [vp, i64, i64, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, i32, i32, i32, i32, i32, i32, vp]
     lib.bdof_adam_step.argtypes = [vp, vp, vp, vp, i64, i32, f64, f64, f64, f64, vp]
     lib.bdof_finite_support.argtypes = [vp, vp, i64, f64, vp]
     lib.bdof_regularizers.argtypes = [vp, vp, i32, i32, i32, f64, f64, f64, vp, vp, vp]

@@ -1743,13 +1743,13 @@ struct RotLists { const int* offsets[BDOF_ROT_MAX_ANGLES]; const int* dest[BDOF_
 // (One thread walking such a list serially made the back-rotation 2.0-2.6 ms at 30-60 degrees against 0.9 ms below 30.)
 constexpr int ROT_LONG = 160;
 __global__ void __launch_bounds__(ROT_THREADS, 2) k_rotate_adjoint_csr(const float2* __restrict__ grot, long long slice_stride, long long batch_stride,
-                                     const RotLists lists, int n_ang, int accumulate, float2* __restrict__ gobj, int ny, int nx, int nz) {
+                                     const RotLists lists, int n_ang, int accumulate, float2* __restrict__ gobj, int ny, int nx, int nz, int z_tile0) {
     __shared__ float2 buf[2][ROT_BOX * ROT_BOX];
     __shared__ float2 s_extra[ROT_LONG][ROT_YA];
     __shared__ int s_long_beg[ROT_LONG], s_long_cnt[ROT_LONG];
     __shared__ int s_sum[4];                             // sum of z, sum of x, count over the first readers; number of long cells
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int y0 = blockIdx.x * ROT_YA, x0 = blockIdx.y * ROT_T, z0 = blockIdx.z * ROT_T;      // y fastest, as the gather
+    const int y0 = blockIdx.x * ROT_YA, x0 = blockIdx.y * ROT_T, z0 = (blockIdx.z + z_tile0) * ROT_T;      // y fastest, as the gather
     const int nyc = min(ROT_YA, ny - y0);
     float2 acc[ROT_CPT][ROT_YA];
     bool ok[ROT_CPT];
@@ -1915,10 +1915,10 @@ static int rot_scratch(int2** out, size_t bytes, cudaStream_t st) {
     *out = static_cast<int2*>(b.p);
     return 0;
 }
-__global__ void __launch_bounds__(ROT_THREADS) k_rot_origins(const RotLists lists, int nx, int nz, int2* __restrict__ origins) {
+__global__ void __launch_bounds__(ROT_THREADS) k_rot_origins(const RotLists lists, int nx, int nz, int z_tile0, int2* __restrict__ origins) {
     __shared__ int s_sum[4];
     const int tid = threadIdx.x, a = blockIdx.z;
-    const int x0 = blockIdx.x * ROT_T, z0 = blockIdx.y * ROT_T;
+    const int x0 = blockIdx.x * ROT_T, z0 = (blockIdx.y + z_tile0) * ROT_T;
     const int* __restrict__ off = lists.offsets[a];
     const int* __restrict__ dst = lists.dest[a];
     if (tid == 0) s_sum[0] = s_sum[1] = s_sum[2] = s_sum[3] = 0;
@@ -1972,7 +1972,7 @@ __device__ __noinline__ float2 rot_serial_tail(const float2* __restrict__ base, 
 }
 __global__ void __launch_bounds__(ROT_THREADS, 2) k_rotate_adjoint_tma(const float2* __restrict__ grot, long long slice_stride, long long batch_stride,
                                      const RotLists lists, int n_ang, int accumulate, float2* __restrict__ gobj, int ny, int nx, int nz,
-                                     const int2* __restrict__ origins, const RotDiv dv, const __grid_constant__ CUtensorMap tm_grot) {
+                                     int z_tile0, const int2* __restrict__ origins, const RotDiv dv, const __grid_constant__ CUtensorMap tm_grot) {
     extern __shared__ __align__(128) float2 ring[];      // ROT_NBUF boxes
     __shared__ __align__(8) unsigned long long bar[ROT_NBUF];
     __shared__ float2 s_extra[ROT_LONG][ROT_YA];
@@ -1981,7 +1981,7 @@ __global__ void __launch_bounds__(ROT_THREADS, 2) k_rotate_adjoint_tma(const flo
     __shared__ int s_ang[BDOF_ROT_MAX_ANGLES];
     __shared__ int s_nv, s_nlong;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int y0 = blockIdx.x * ROT_YA, x0 = blockIdx.y * ROT_T, z0 = blockIdx.z * ROT_T;      // y fastest, as the gather
+    const int y0 = blockIdx.x * ROT_YA, x0 = blockIdx.y * ROT_T, z0 = (blockIdx.z + z_tile0) * ROT_T;      // y fastest, as the gather
     const int nyc = min(ROT_YA, ny - y0);
     if (tid == 0) {
         int nv = 0;
@@ -2119,12 +2119,15 @@ __global__ void __launch_bounds__(ROT_THREADS, 2) k_rotate_adjoint_tma(const flo
             }
     }
 }
-extern "C" int bdof_rotate_adjoint_csr_batch(const float* d_grad_rot_db, long long slice_stride_px, long long batch_stride_px, int n_angles,
-                                             const int32_t* const* d_offsets, const int32_t* const* d_dest, float* d_grad_obj_db,
-                                             int accumulate, int ny, int nx, int nz, void* st) {
+extern "C" int bdof_rotate_adjoint_csr_batch_range(const float* d_grad_rot_db, long long slice_stride_px, long long batch_stride_px, int n_angles,
+                                                   const int32_t* const* d_offsets, const int32_t* const* d_dest, float* d_grad_obj_db,
+                                                   int accumulate, int ny, int nx, int nz, int z_begin, int z_end, void* st) {
     if (!d_grad_rot_db || !d_offsets || !d_dest || !d_grad_obj_db || ny < 1 || nx < 1 || nz < 1 || n_angles < 1) return fail(BDOF_E_BADARG, "bad argument");
+    if (z_begin < 0 || z_end > nz || z_begin >= z_end || z_begin % ROT_T != 0 || (z_end % ROT_T != 0 && z_end != nz))
+        return fail(BDOF_E_BADARG, "z range [%d, %d): bounds must be multiples of %d (or the last slice)", z_begin, z_end, ROT_T);
     if (nx > 65535 * ROT_T || nz > 65535 * ROT_T) return fail(BDOF_E_UNSUPPORTED, "nx / nz too large");
-    dim3 grid((ny + ROT_YA - 1) / ROT_YA, (nx + ROT_T - 1) / ROT_T, (nz + ROT_T - 1) / ROT_T);
+    const int z_tile0 = z_begin / ROT_T;
+    dim3 grid((ny + ROT_YA - 1) / ROT_YA, (nx + ROT_T - 1) / ROT_T, (z_end - z_begin + ROT_T - 1) / ROT_T);
     // TMA box loads need a tensor the descriptor can express: even nx (16-byte row pitch), sides at least one box, the
     // minibatch laid out [z][angle][y][x] (a plan's db) or a single angle
     const bool layout_ok = n_angles == 1 || (batch_stride_px == (long long)ny * nx && slice_stride_px >= (long long)n_angles * ny * nx);
@@ -2151,21 +2154,27 @@ extern "C" int bdof_rotate_adjoint_csr_batch(const float* d_grad_rot_db, long lo
             if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_rotate_adjoint_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes)); attr_set = true; }
             int2* origins = nullptr;                     // scratch [angle][tile z][tile x], one buffer per (device, stream)
             BDOF_TRY(rot_scratch(&origins, sizeof(int2) * n * grid.y * grid.z, (cudaStream_t)st));
-            k_rot_origins<<<dim3(grid.y, grid.z, n), ROT_THREADS, 0, (cudaStream_t)st>>>(l, nx, nz, origins);
+            k_rot_origins<<<dim3(grid.y, grid.z, n), ROT_THREADS, 0, (cudaStream_t)st>>>(l, nx, nz, z_tile0, origins);
             int r = launch_check("k_rot_origins");
             if (!r) {
                 k_rotate_adjoint_tma<<<grid, ROT_THREADS, ring_bytes, (cudaStream_t)st>>>(base, slice_stride_px, batch_stride_px, l, n, acc,
-                                                                                        reinterpret_cast<float2*>(d_grad_obj_db), ny, nx, nz, origins, rot_div_make(nx), tm);
+                                                                                        reinterpret_cast<float2*>(d_grad_obj_db), ny, nx, nz, z_tile0, origins, rot_div_make(nx), tm);
                 r = launch_check("k_rotate_adjoint_tma");
             }
             if (r) return r;
         } else {
             k_rotate_adjoint_csr<<<grid, ROT_THREADS, 0, (cudaStream_t)st>>>(base, slice_stride_px, batch_stride_px, l, n, acc,
-                                                                           reinterpret_cast<float2*>(d_grad_obj_db), ny, nx, nz);
+                                                                           reinterpret_cast<float2*>(d_grad_obj_db), ny, nx, nz, z_tile0);
         }
         if (int r = launch_check("k_rotate_adjoint_csr")) return r;
     }
     return 0;
+}
+extern "C" int bdof_rotate_adjoint_csr_batch(const float* d_grad_rot_db, long long slice_stride_px, long long batch_stride_px, int n_angles,
+                                             const int32_t* const* d_offsets, const int32_t* const* d_dest, float* d_grad_obj_db,
+                                             int accumulate, int ny, int nx, int nz, void* st) {
+    return bdof_rotate_adjoint_csr_batch_range(d_grad_rot_db, slice_stride_px, batch_stride_px, n_angles, d_offsets, d_dest, d_grad_obj_db, accumulate,
+                                               ny, nx, nz, 0, nz, st);
 }
 extern "C" int bdof_rotate_adjoint_csr(const float* d_grad_rot_db, long long slice_stride_px, const int32_t* d_offsets,
                                        const int32_t* d_dest, float* d_grad_obj_db, int ny, int nx, int nz, void* st) {

@@ -110,9 +110,11 @@ def rotate_db_adjoint(grad_rot, table_zx, grad_obj, atomic=False):
     return grad_obj
 
 
-def rotate_db_adjoint_batch(grad_rot_db, tables, grad_obj, accumulate=True):
+def rotate_db_adjoint_batch(grad_rot_db, tables, grad_obj, accumulate=True, z_range=None):
     """grad_obj [Z, Y, X, 2] += (accumulate=False: =) sum over the minibatch of transpose-of-rotation(grad_rot_db[:, b]) with tables[b]; grad_rot_db is a
-    plan's db [Z, B, Y, X, 2].  One pass over the object gradient (deterministic: the angles are summed in order in registers)."""
+    plan's db [Z, B, Y, X, 2].  One pass over the object gradient (deterministic: the angles are summed in order in registers).
+    z_range = (z_lo, z_hi), z_lo a multiple of 32: only those slices of grad_obj (the back-rotation in buckets, each all-reduced
+    while the next is computed)."""
     Z, Y, X, _ = grad_obj.shape
     B = len(tables)
     assert grad_rot_db.shape == (Z, B, Y, X, 2) and grad_rot_db.is_contiguous() and grad_obj.is_contiguous()
@@ -120,7 +122,9 @@ def rotate_db_adjoint_batch(grad_rot_db, tables, grad_obj, accumulate=True):
     offs = (ctypes.c_void_p * B)(*[o.data_ptr() for o, _ in lists])
     dests = (ctypes.c_void_p * B)(*[d.data_ptr() for _, d in lists])
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    check(lib.bdof_rotate_adjoint_csr_batch(_ptr(grad_rot_db), B * Y * X, Y * X, B, offs, dests, _ptr(grad_obj), 1 if accumulate else 0, Y, X, Z, st))
+    z_lo, z_hi = (0, Z) if z_range is None else (int(z_range[0]), int(z_range[1]))
+    check(lib.bdof_rotate_adjoint_csr_batch_range(_ptr(grad_rot_db), B * Y * X, Y * X, B, offs, dests, _ptr(grad_obj), 1 if accumulate else 0,
+                                                  Y, X, Z, z_lo, z_hi, st))
     return grad_obj
 
 

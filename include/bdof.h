@@ -208,6 +208,11 @@ int  bdof_rotate_adjoint_csr(const float* d_grad_rot_db, long long slice_stride_
 int  bdof_rotate_adjoint_csr_batch(const float* d_grad_rot_db, long long slice_stride_px, long long batch_stride_px, int n_angles,
                                    const int32_t* const* d_offsets, const int32_t* const* d_dest, float* d_grad_obj_db,
                                    int accumulate, int ny, int nx, int nz, void* cuda_stream);
+/* The same for the slices [z_begin, z_end) of the object gradient only (z_begin a multiple of 32): the back-rotation in z
+ * buckets, so that the all-reduce of one bucket can overlap the back-rotation of the next. */
+int  bdof_rotate_adjoint_csr_batch_range(const float* d_grad_rot_db, long long slice_stride_px, long long batch_stride_px, int n_angles,
+                                         const int32_t* const* d_offsets, const int32_t* const* d_dest, float* d_grad_obj_db,
+                                         int accumulate, int ny, int nx, int nz, int z_begin, int z_end, void* cuda_stream);
 
 /* SURVEY 8f-1, TF drivers: tf.contrib.image.rotate(stack([delta, beta], -1), theta, interpolation='BILINEAR')
  * (tensorflow_recon/fullfield.py:96, ptychography.py:39) on the native object d_obj_db [nz][ny][nx][2]: rotation by theta

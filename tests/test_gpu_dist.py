@@ -121,3 +121,38 @@ def _objective(rank, world):
 def test_data_parallel_objective_matches_serial_average():
     for err in spawn(_objective, 2):
         assert err < 1e-6
+
+
+def _tomography(rank, world):
+    # data-parallel TomographyObjective: the back-rotation runs in z buckets, each all-reduced on the communication stream under
+    # the next one; against the same update with the ranks' minibatches evaluated in one process and averaged
+    from beyond_dof_b200.models import TomographyObjective
+    n, mb = 64, 2
+    g = torch.Generator().manual_seed(7)
+    obj0 = torch.rand((n, n, n, 2), generator=g) * torch.tensor([8e-5, 5e-6])
+    probe = torch.ones((n, n), dtype=torch.complex64, device='cuda')
+    thetas = np.linspace(0.2, 2.9, mb * world)
+    prj = [0.9 + 0.1 * torch.rand((mb, n, n), generator=torch.Generator().manual_seed(90 + r)) for r in range(world)]
+    tomo = TomographyObjective(obj0.clone().cuda(), probe, 5000, 1e-7, minibatch_size=mb, free_prop_cm=None, propagate_last=True, step_size=1e-7)
+    tomo.enable_data_parallel(exchange='nccl', n_buckets=2)        # ('nccl' = torch.distributed all-reduce; the group here is gloo)
+    tomo.step(thetas[rank * mb:(rank + 1) * mb], prj[rank].cuda())
+    got_grad, got_obj = tomo.grad.clone(), tomo.obj.clone()
+    ref = torch.zeros_like(got_grad)
+    for r in range(world):
+        t = TomographyObjective(obj0.clone().cuda(), probe, 5000, 1e-7, minibatch_size=mb, free_prop_cm=None, propagate_last=True, step_size=1e-7)
+        t.loss_and_grad(thetas[r * mb:(r + 1) * mb], prj[r].cuda())
+        ref += t.grad
+    ref /= world
+    torch.cuda.synchronize()
+    e_grad = float((got_grad - ref).norm() / ref.norm())
+    # every rank holds the same object after the update
+    mine = got_obj.cpu()
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    same = all(torch.equal(gathered[0], x) for x in gathered)
+    return e_grad, same
+
+
+def test_data_parallel_tomography_buckets_match_serial_average():
+    for e_grad, same in spawn(_tomography, 2):
+        assert e_grad < 1e-6 and same
