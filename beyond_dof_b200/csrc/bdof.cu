@@ -2504,7 +2504,10 @@ extern "C" int bdof_plan_set_windows(bdof_plan* p, int oy, int ox, const int* d_
     p->stash_valid = false;
     return 0;
 }
-extern "C" int bdof_plan_is_resident(const bdof_plan* p) { return (p && p->have_kernel && use_resident(p)) ? 1 : 0; }
+extern "C" int bdof_plan_is_resident(const bdof_plan* p) {
+    if (!(p && p->have_kernel && use_resident(p))) return 0;
+    return p->nx == 64 ? 1 : 2;                          // 1: one CTA per field (window mode available), 2: one cluster per field
+}
 
 // One propagating slice whose input lines are read straight out of a larger pitched buffer (tiling: the windows of a block; the
 // cut is fused into the row pass): window b's first row starts d_in_offsets[b] elements into d_buf, rows are `pitch` elements

@@ -142,8 +142,13 @@ class MultislicePlan:
 
     # ---- compute ------------------------------------------------------------------------
     def is_resident(self):
-        """True when the plan runs the resident small-field kernels (one launch per direction, field on chip)."""
-        return bool(lib.bdof_plan_is_resident(self._h))
+        """True when the plan runs the resident small-field kernels (one CTA per 64 x 64 field, one launch per direction; window
+        mode available)."""
+        return int(lib.bdof_plan_is_resident(self._h)) == 1
+
+    def is_cluster_resident(self):
+        """True when the plan runs the cluster-resident kernels (one cluster of 8 CTAs per 256 x 256 field)."""
+        return int(lib.bdof_plan_is_resident(self._h)) == 2
 
     def set_windows(self, obj_shape_zyx, origin):
         """Window mode (resident plans only): the batch elements are windows of one object [Z,OY,OX,2]; origin [B,2] int32 CUDA

@@ -131,7 +131,8 @@ int  bdof_plan_set_t_stash(bdof_plan* p, float* d_stash);
  * object slice is L2 resident), so no [n_slice][batch][ny][nx] copy of the object is ever cut; bdof_adjoint writes the
  * per-window gradients to d_grad_out (required; accumulate them with bdof_patch_gather_add), which may also serve as the
  * transmission stash (bdof_plan_set_t_stash).
- * d_origin_yx = NULL switches the mode off.  bdof_plan_is_resident tells whether the plan runs the resident kernels. */
+ * d_origin_yx = NULL switches the mode off.  bdof_plan_is_resident: 0 = per-slice kernels, 1 = the resident kernels (one CTA per
+ * 64 x 64 field; window mode available), 2 = the cluster-resident kernels (one cluster of 8 CTAs per 256 x 256 field). */
 int  bdof_plan_set_windows(bdof_plan* p, int oy, int ox, const int* d_origin_yx);
 int  bdof_plan_is_resident(const bdof_plan* p);
 

@@ -623,6 +623,19 @@ def test_cluster_resident_kernels_match_sweep_kernels_and_oracle(bd, case, in_pl
         assert rel_l2(a[1], gdo) < TOL_GRAD and rel_l2(a[2], gbo) < TOL_GRAD
 
 
+def test_resident_kind_is_reported(bd):
+    from beyond_dof_b200.plan import MultislicePlan
+    p64 = MultislicePlan(64, 64, 2, 4, 5000, 1e-7, store_slices=True)
+    p256 = MultislicePlan(256, 256, 2, 4, 5000, 1e-7, store_slices=True)
+    p512 = MultislicePlan(512, 512, 1, 4, 5000, 1e-7, store_slices=True)
+    assert p64.is_resident() and not p64.is_cluster_resident()
+    assert p256.is_cluster_resident() and not p256.is_resident()            # window mode is a feature of the one-CTA kernels
+    assert not p512.is_resident() and not p512.is_cluster_resident()
+    with pytest.raises(Exception):
+        p256.set_windows((4, 300, 300), torch.zeros((2, 2), dtype=torch.int32, device='cuda'))
+        p256.forward(torch.zeros((4, 300, 300, 2), device='cuda'), torch.ones((256, 256), dtype=torch.complex64, device='cuda'))
+
+
 def test_resident_kernels_z_broadcast_and_forward_only(bd):
     shape = (4, 64, 64, 10)
     gd1, gb1 = mo.random_phantom((4, 64, 64, 1), seed=73, delta_scale=4e-4, beta_scale=4e-5)
