@@ -4,8 +4,9 @@
 // 256^3 tomography, tensorflow_recon/reconstruct_fullfield.py) is 512 KB -- too large for one SM, but not for the C = 8 SMs of a
 // cluster: CTA c owns N/C = 32 lines of the field, 16 elements per thread in registers, and between two slices the field is
 // transposed ACROSS THE CLUSTER through distributed shared memory: every thread pushes its elements into the receive buffers
-// of the CTAs that own them in the other layout (st.shared::cluster, 128-byte / 256-byte contiguous runs per warp), one
-// barrier.cluster per slice orders the pushes against the reads.  psi never touches HBM between slices; per slice the cluster
+// of the CTAs that own them in the other layout (st.async to shared::cluster, 128-byte / 256-byte contiguous runs per warp) and
+// reports the bytes to the receiver's mbarrier; a CTA starts its next step when its own 64 KB have arrived -- no cluster-wide
+// barrier in the slice loop.  psi never touches HBM between slices; per slice the cluster
 // streams only the side arrays: (delta, beta) in, the stored psi_i and the transmission stash out (forward); stash and psi_i in,
 // gradient out (adjoint).  One launch per direction replaces 2 x n_slice sweep-kernel launches, which at this size are bound by
 // launch latency (10.5 us per launch for 10 fields of 256^2, the same for 5 fields: tools/two_stream_probe.py).
@@ -20,8 +21,8 @@
 //            global accesses are 256-byte rows, interleaved exchange buffer Y[index][column]
 // Receive buffers (two, alternating by step parity; the one a step read its field from is that step's FFT scratch):
 //   for an x step: [R rows][PADDED] (what line_fft's exchange uses anyway); for a y step: [N rows][R columns].
-// A peer may be one step ahead at most (it cannot pass barrier s before every CTA has arrived there), so the pushes of step
-// s + 1 land in the buffer of the other parity while slow CTAs still work in this one.
+// A peer may be one step ahead at most (it needs every CTA's data of a step to finish that step), so the pushes of step s + 1
+// land in the buffer of the other parity while slow CTAs still work in this one (cluster_transpose).
 #pragma once
 #include "residentfft.cuh"
 
@@ -50,6 +51,12 @@ __device__ __forceinline__ unsigned mapa_shared(unsigned smem_addr, unsigned ran
 }
 __device__ __forceinline__ void st_cluster_f2(unsigned addr, float2 v) {
     asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+// asynchronous remote store of 8 bytes that also reports them to the mbarrier `bar` of the destination CTA (both shared::cluster
+// addresses): the receiver waits for its bytes, nobody waits for anybody's global stores
+__device__ __forceinline__ void st_async_f2(unsigned addr, float2 v, unsigned bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(addr), "f"(v.x), "f"(v.y), "r"(bar)
+                 : "memory");
 }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
@@ -122,34 +129,41 @@ __device__ __forceinline__ void cluster_conv(float2 (&v)[Cfg::E], const ClusterM
     static_for<E>([&](auto Q) __attribute__((always_inline)) { constexpr int q = decltype(Q)::value; v[q] = conjf2(v[q]); });
 }
 
-// Hand the field over to the layout of the other axis: push every element into the receive buffer `next` (a shared::cta
-// address, the same in every CTA) of the CTA that owns it there, then one cluster barrier, then read the own share.
-// T <= R, so element q of any thread goes to CTA (T q) / R -- known at compile time.
+// Hand the field over to the layout of the other axis: every element goes into the receive buffer `next` (a shared::cta address,
+// the same in every CTA) of the CTA that owns it there, as an asynchronous store that reports its 8 bytes to that CTA's
+// mbarrier `bar_next`; then wait until the own share (N * R elements) has arrived and read it.  T <= R, so element q of any
+// thread goes to CTA (T q) / R -- known at compile time.
+// No cluster-wide barrier: barrier.cluster.arrive.release is MEMBAR.ALL.GPU (it waited for the slab / stash stores of the step)
+// and its acquire side invalidates L1.  The data flow alone keeps the skew below one step: a CTA finishes step s + 1 -- and only
+// then pushes into the buffers of parity s -- after it received the step-(s + 1) data of EVERY peer, which a peer sends at the
+// end of its step s, when it is done with its parity-s buffer (its scratch during step s).  `phase` = uses of the barrier so far.
 template <class Cfg, int C, bool FROM_COL>
-__device__ __forceinline__ void cluster_transpose(float2 (&v)[Cfg::E], int tid, int rank, float2* next) {
+__device__ __forceinline__ void cluster_transpose(float2 (&v)[Cfg::E], int tid, int rank, float2* next, unsigned long long* bar_next, unsigned phase) {
     constexpr int E = Cfg::E, T = Cfg::T, N = Cfg::N, R = N / C, XP = ClusterSmem<Cfg, C>::XP;
     const ClusterMap<Cfg, C, FROM_COL> a(tid, rank);
     const ClusterMap<Cfg, C, !FROM_COL> b(tid, rank);
-    const unsigned base = smem_u32(next);
+    const unsigned base = smem_u32(next), bar = smem_u32(bar_next);
     static_for<E>([&](auto Q) __attribute__((always_inline)) {
         constexpr int q = decltype(Q)::value;
         constexpr int peer = (T * q) / R, off = (T * q) % R;      // a.t + off < R
-        const unsigned remote = mapa_shared(base, peer);
+        const unsigned remote = mapa_shared(base, peer), rbar = mapa_shared(bar, peer);
         if constexpr (FROM_COL) {
             // element (row k = a.t + T q, column rank R + a.l) -> x-step buffer of CTA k / R: [k % R][column]
-            st_cluster_f2(remote + unsigned(((a.t + off) * XP + rank * R + a.l) * sizeof(float2)), v[q]);
+            st_async_f2(remote + unsigned(((a.t + off) * XP + rank * R + a.l) * sizeof(float2)), v[q], rbar);
         } else {
             // element (row rank R + a.l, column k = a.t + T q) -> y-step buffer of CTA k / R: [row][k % R]
-            st_cluster_f2(remote + unsigned(((rank * R + a.l) * R + a.t + off) * sizeof(float2)), v[q]);
+            st_async_f2(remote + unsigned(((rank * R + a.l) * R + a.t + off) * sizeof(float2)), v[q], rbar);
         }
     });
-    cluster_arrive();
-    cluster_wait();
+    mbar_wait(bar_next, phase & 1);
+    // the next use of this barrier: armed before any of its bytes can complete it (they need this arrival)
+    if (tid == 0) mbar_expect_tx(bar_next, unsigned(N * R * sizeof(float2)));
     static_for<E>([&](auto Q) __attribute__((always_inline)) {
         constexpr int q = decltype(Q)::value;
         if constexpr (FROM_COL) v[q] = next[b.l * XP + b.t + T * q];           // now an x step: row b.l, column b.t + T q
         else v[q] = next[(b.t + T * q) * R + b.l];                              // now a y step: row b.t + T q, column b.l
     });
+    __syncthreads();                                   // step boundary inside the CTA (table staging, scratch of the y steps)
 }
 
 template <class Cfg>
@@ -174,7 +188,8 @@ __device__ __forceinline__ void cluster_prefetch_l2(const float2* base, const Cl
 // ------------------------------------------------------------------------------------------------------------------
 template <class Cfg, int C, bool COL>
 __device__ __forceinline__ void cluster_forward_step(const ResidentParams& p, int s, int n_steps, long long fbase, int tid, int rank,
-                                                     float2 (&v)[Cfg::E], float2* buf, float2* next, const float2* s_tw, float2* s_h) {
+                                                     float2 (&v)[Cfg::E], float2* buf, float2* next, unsigned long long* bar_next, unsigned phase,
+                                                     const float2* s_tw, float2* s_h) {
     constexpr int E = Cfg::E, N = Cfg::N, R = N / C, NT = R * Cfg::T;
     const ClusterMap<Cfg, C, COL> m(tid, rank);
     const int Z = p.n_slice;
@@ -183,15 +198,16 @@ __device__ __forceinline__ void cluster_forward_step(const ResidentParams& p, in
         cluster_prefetch_l2<Cfg, C, !COL>(p.db + (long long)(s + 1) * p.db_slice_stride + fbase, mn);
     }
     if (s + 1 < n_steps) cluster_stage_h<Cfg>(p, s + 1, tid, s_h);
-    // (delta, beta) of this slice: issued before the first convolution, consumed after it
-    float2 d[E];
-    if (s < Z) {
-        const float2* dp = p.db + (long long)s * p.db_slice_stride + fbase;
-#pragma unroll
-        for (int q = 0; q < E; ++q) d[q] = __ldg(dp + m.g(q));
-    }
     if (s > 0) cluster_conv<Cfg, C, COL>(v, m, buf, s_tw, s_h + (s & 1) * N);
     if (s < Z) {
+        // (delta, beta) of this slice: in L2 since the previous step; loaded where it is used (16 elements per thread leave no
+        // registers to hold it across a convolution under the 128-register cap of a 512-thread CTA)
+        float2 d[E];
+        {
+            const float2* dp = p.db + (long long)s * p.db_slice_stride + fbase;
+#pragma unroll
+            for (int q = 0; q < E; ++q) d[q] = __ldg(dp + m.g(q));
+        }
         if (p.store) {
             float2* sp = p.slab + (long long)s * p.slice_stride + fbase + (long long)rank * (NT * E) + tid;
 #pragma unroll
@@ -209,7 +225,7 @@ __device__ __forceinline__ void cluster_forward_step(const ResidentParams& p, in
         const bool prop = p.propagate_last ? (Z > 1) : (s < Z - 1);
         if (prop) cluster_conv<Cfg, C, COL>(v, m, buf, s_tw, s_h + (s & 1) * N);
     }
-    if (s + 1 < n_steps) cluster_transpose<Cfg, C, COL>(v, tid, rank, next);
+    if (s + 1 < n_steps) cluster_transpose<Cfg, C, COL>(v, tid, rank, next, bar_next, phase);
 }
 
 template <class Cfg, int C>
@@ -217,17 +233,26 @@ __global__ void __launch_bounds__((Cfg::N / C) * Cfg::T, 1) cluster_forward_kern
     using SM = ClusterSmem<Cfg, C>;
     constexpr int E = Cfg::E, N = Cfg::N;
     extern __shared__ __align__(16) float2 smem_cl[];
+    __shared__ __align__(8) unsigned long long bars[2];           // bytes received into the buffer of each parity
     float2* bufs = smem_cl;
     float2* s_tw = bufs + 2 * SM::BUF_ELEMS;
     float2* s_h = s_tw + SM::TW_ELEMS;
     const int tid = threadIdx.x, rank = int(cluster_ctarank());
     for (int i = tid; i < Cfg::TW_TOTAL; i += blockDim.x) s_tw[i] = p.tw[i];
+    if (tid == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+        fence_mbar_init();
+        mbar_expect_tx(&bars[0], unsigned(N * (N / C) * sizeof(float2)));
+        mbar_expect_tx(&bars[1], unsigned(N * (N / C) * sizeof(float2)));
+    }
+    unsigned uses0 = 0u, uses1 = 0u;                   // completed phases of the two barriers
     const int Z = p.n_slice;
     const bool trail = p.propagate_last && Z > 1;
     const int n_steps = Z + (trail ? 1 : 0);
     for (int b = int(cluster_id_x()); b < p.batch; b += int(n_clusters_x())) {
         const long long fbase = (long long)b * N * N;
-        // nobody pushes into a CTA that is still busy with the previous field (also orders the table staging)
+        // nobody pushes into a CTA that is still busy with the previous field or has not armed its barriers yet (also orders the
+        // table staging); the only cluster-wide barriers of the kernel are this one per field and the one before exit
         cluster_arrive();
         cluster_wait();
         cluster_stage_h<Cfg>(p, 0, tid, s_h);
@@ -240,10 +265,12 @@ __global__ void __launch_bounds__((Cfg::N / C) * Cfg::T, 1) cluster_forward_kern
         __syncthreads();
 #pragma unroll 1
         for (int s = 0; s < n_steps; ++s) {
+            const int pn = (s + 1) & 1;
             float2* buf = bufs + (s & 1) * SM::BUF_ELEMS;
-            float2* next = bufs + ((s + 1) & 1) * SM::BUF_ELEMS;
-            if (s & 1) cluster_forward_step<Cfg, C, true>(p, s, n_steps, fbase, tid, rank, v, buf, next, s_tw, s_h);
-            else       cluster_forward_step<Cfg, C, false>(p, s, n_steps, fbase, tid, rank, v, buf, next, s_tw, s_h);
+            float2* next = bufs + pn * SM::BUF_ELEMS;
+            if (s & 1) cluster_forward_step<Cfg, C, true>(p, s, n_steps, fbase, tid, rank, v, buf, next, &bars[pn], pn ? uses1 : uses0, s_tw, s_h);
+            else       cluster_forward_step<Cfg, C, false>(p, s, n_steps, fbase, tid, rank, v, buf, next, &bars[pn], pn ? uses1 : uses0, s_tw, s_h);
+            if (s + 1 < n_steps) { if (pn) ++uses1; else ++uses0; }
         }
         float2* op = p.out + fbase;
         if ((n_steps - 1) & 1) {
@@ -266,7 +293,8 @@ __global__ void __launch_bounds__((Cfg::N / C) * Cfg::T, 1) cluster_forward_kern
 // ------------------------------------------------------------------------------------------------------------------
 template <class Cfg, int C, bool COL>
 __device__ __forceinline__ void cluster_adjoint_step(const ResidentParams& p, int s, long long fbase, int tid, int rank,
-                                                     float2 (&v)[Cfg::E], float2* buf, float2* next, const float2* s_tw, float2* s_h) {
+                                                     float2 (&v)[Cfg::E], float2* buf, float2* next, unsigned long long* bar_next, unsigned phase,
+                                                     const float2* s_tw, float2* s_h) {
     constexpr int E = Cfg::E, N = Cfg::N, R = N / C, NT = R * Cfg::T;
     const ClusterMap<Cfg, C, COL> m(tid, rank);
     const int Z = p.n_slice;
@@ -307,7 +335,7 @@ __device__ __forceinline__ void cluster_adjoint_step(const ResidentParams& p, in
         }
         if (s > 0) cluster_conv<Cfg, C, COL>(v, m, buf, s_tw, h);
     }
-    if (s > 0) cluster_transpose<Cfg, C, COL>(v, tid, rank, next);
+    if (s > 0) cluster_transpose<Cfg, C, COL>(v, tid, rank, next, bar_next, phase);
 }
 
 template <class Cfg, int C>
@@ -315,11 +343,19 @@ __global__ void __launch_bounds__((Cfg::N / C) * Cfg::T, 1) cluster_adjoint_kern
     using SM = ClusterSmem<Cfg, C>;
     constexpr int E = Cfg::E, N = Cfg::N;
     extern __shared__ __align__(16) float2 smem_cl[];
+    __shared__ __align__(8) unsigned long long bars[2];           // bytes received into the buffer of each parity
     float2* bufs = smem_cl;
     float2* s_tw = bufs + 2 * SM::BUF_ELEMS;
     float2* s_h = s_tw + SM::TW_ELEMS;
     const int tid = threadIdx.x, rank = int(cluster_ctarank());
     for (int i = tid; i < Cfg::TW_TOTAL; i += blockDim.x) s_tw[i] = p.tw[i];
+    if (tid == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+        fence_mbar_init();
+        mbar_expect_tx(&bars[0], unsigned(N * (N / C) * sizeof(float2)));
+        mbar_expect_tx(&bars[1], unsigned(N * (N / C) * sizeof(float2)));
+    }
+    unsigned uses0 = 0u, uses1 = 0u;                   // completed phases of the two barriers
     const int Z = p.n_slice;
     const bool trail = p.propagate_last && Z > 1;
     const int s0 = trail ? Z : Z - 1;                  // first step executed
@@ -342,10 +378,12 @@ __global__ void __launch_bounds__((Cfg::N / C) * Cfg::T, 1) cluster_adjoint_kern
 #pragma unroll 1
         for (int s = s0; s >= 0; --s) {
             // buffer parity follows the step index, as in the forward kernel
+            const int pn = (s + 1) & 1;
             float2* buf = bufs + (s & 1) * SM::BUF_ELEMS;
-            float2* next = bufs + ((s + 1) & 1) * SM::BUF_ELEMS;
-            if (s & 1) cluster_adjoint_step<Cfg, C, true>(p, s, fbase, tid, rank, v, buf, next, s_tw, s_h);
-            else       cluster_adjoint_step<Cfg, C, false>(p, s, fbase, tid, rank, v, buf, next, s_tw, s_h);
+            float2* next = bufs + pn * SM::BUF_ELEMS;
+            if (s & 1) cluster_adjoint_step<Cfg, C, true>(p, s, fbase, tid, rank, v, buf, next, &bars[pn], pn ? uses1 : uses0, s_tw, s_h);
+            else       cluster_adjoint_step<Cfg, C, false>(p, s, fbase, tid, rank, v, buf, next, &bars[pn], pn ? uses1 : uses0, s_tw, s_h);
+            if (s > 0) { if (pn) ++uses1; else ++uses0; }
         }
         if (p.out != nullptr) {
             const ClusterMap<Cfg, C, false> m(tid, rank);  // step 0 is an x step
