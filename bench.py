@@ -744,6 +744,21 @@ def run_config4(args):
     value = units / (ms_step * 1e-3) / 1e9
     if rank == 0:
         clocks = sampler.stop()
+        # the multislice kernels of the last update (one event pair around each direction).  The cluster-resident kernels move
+        # 24 + 24 B per pixel*slice, the sweep kernels 96: the fraction says how far from an HBM bound they are
+        lt = tomo.plan.last_times()
+        peak, peak_src = measured_peaks()
+        cluster = tomo.plan.is_cluster_resident()
+        kernel_ms = lt['forward'][0] + lt['adjoint'][0]
+        alg_bytes = (48.0 if cluster else 96.0) * mb * n * n * n
+        roofline = {'bound': 'hbm',
+                    'kernel': 'cluster_forward_kernel + cluster_adjoint_kernel (one launch each per update)' if cluster else 'sweep kernels',
+                    'achieved': alg_bytes / (kernel_ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                    'frac': alg_bytes / (kernel_ms * 1e-3) / 1e9 / peak, 'traffic': None, 'alg_bytes_per_px_slice': 48 if cluster else 96,
+                    'forward_ms': lt['forward'][0], 'adjoint_ms': lt['adjoint'][0], 'kernel_ms_per_step': kernel_ms, 'ms_per_step': ms_step,
+                    'peak_source': peak_src,
+                    'note': 'not HBM-bound: ten 8-CTA clusters occupy 80 of 148 SMs and are bound by fp32 issue there '
+                            '(profiles/r02_cluster_kernels_256.txt); the rest of the step is the rotation stage, Adam and the exchange'}
         line = {
             'metric': 'multislice Gpixel*slice/s (forward + adjoint)', 'value': value, 'unit': 'Gpixel*slice/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
@@ -757,7 +772,7 @@ def run_config4(args):
             'e2e': {'value': value, 'unit': 'Gpixel*slice/s', 'h2d_bytes_per_step': prj_host.numel() * 4, 'd2h_bytes_per_step': 8,
                     'api': 'beyond_dof_b200.models.TomographyObjective.step(theta_batch, projections in pinned host memory) -> loss '
                            '(the timed region IS the public call: H2D copy, update, loss read-back)'},
-            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': None, 'cpu_baseline': None, 'loss': float(loss),
+            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': None, 'loss': float(loss),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
