@@ -530,7 +530,7 @@ struct bdof_plan {
     // window mode (bdof_plan_set_windows): d_db of bdof_forward / bdof_adjoint is the OBJECT, the batch its windows
     const int* win_origin = nullptr;
     int win_oy = 0, win_ox = 0;
-    bool grad_accumulate = false;   // bdof_adjoint ADDS to d_grad_out (bdof_plan_set_grad_accumulate; sweep kernels only)
+    bool grad_accumulate = false;   // bdof_adjoint ADDS to d_grad_out (bdof_plan_set_grad_accumulate)
     bool stash_valid = false;  // the last forward filled t_stash and nothing has overwritten it since
     double* partial = nullptr;
     std::complex<double> total_phase{1.0, 0.0};
@@ -1245,7 +1245,8 @@ extern "C" int bdof_adjoint(bdof_plan* p, float* d_db_inout, const float* d_grad
     if (p->win_origin && !d_grad_out) return fail(BDOF_E_BADARG, "window mode needs d_grad_out (the per-window gradients)");
     if (p->grad_accumulate) {
         if (!d_grad_out) return fail(BDOF_E_BADARG, "gradient accumulation needs d_grad_out (the accumulator)");
-        if (!use_sweep(p) || use_resident(p)) return fail(BDOF_E_UNSUPPORTED, "fused gradient accumulation is a sweep-kernel feature");
+        if (!use_sweep(p)) return fail(BDOF_E_UNSUPPORTED, "fused gradient accumulation is a feature of the sweep / resident kernels");
+        if (p->win_origin) return fail(BDOF_E_UNSUPPORTED, "window mode writes per-window gradients; accumulate them with bdof_patch_gather_add");
         if (p->stash_valid && p->t_stash == reinterpret_cast<float2*>(d_grad_out))
             return fail(BDOF_E_STATE, "the transmission stash must not live in the accumulator");
     }
@@ -1282,6 +1283,7 @@ extern "C" int bdof_adjoint(bdof_plan* p, float* d_db_inout, const float* d_grad
         q.db = db; q.db_slice_stride = zb ? 0 : p->F;
         q.tstash = p->stash_valid ? p->t_stash : nullptr;
         q.grad = gout ? gout : db;
+        q.accumulate = p->grad_accumulate ? 1 : 0;
         if (p->win_origin) {
             q.win = p->win_origin; q.oy = p->win_oy; q.ox = p->win_ox;
             q.db_slice_stride = zb ? 0 : (long long)p->win_oy * p->win_ox;

@@ -1,4 +1,5 @@
-// Instantiation unit and launcher of the cluster-resident kernels (clusterfft.cuh): 256 x 256 fields on clusters of 8 CTAs.
+// Instantiation unit and launcher of the cluster-resident kernels (clusterfft.cuh): 256 x 256 fields on clusters of 8 CTAs,
+// 128 x 128 fields on clusters of 4 (32 lines per CTA either way).
 #include "../../include/bdof.h"
 #include "common.h"
 #include "clusterfft.cuh"
@@ -40,12 +41,13 @@ static int launch_cluster(int adj, const ResidentParams& p, cudaStream_t st) {
 int bdof_cluster_supported(int n) {
     static int enabled = -1;
     if (enabled < 0) { const char* e = getenv("BDOF_CLUSTER"); enabled = (e && e[0] == '0') ? 0 : 1; }
-    return (enabled && n == 256) ? 1 : 0;
+    return (enabled && (n == 256 || n == 128)) ? 1 : 0;
 }
 
 int bdof_launch_cluster(int n, int adj, const ResidentParams& p, cudaStream_t st) {
     switch (n) {
         case 256: return launch_cluster<LineCfg<256, 16, 16, 16, 1>, 8>(adj, p, st);
+        case 128: return launch_cluster<LineCfg<128, 8, 16, 8, 1>, 4>(adj, p, st);
     }
     return bdof_fail(BDOF_E_UNSUPPORTED, "no cluster-resident kernel for %d x %d fields", n, n);
 }

@@ -229,7 +229,7 @@ __device__ __forceinline__ void cluster_forward_step(const ResidentParams& p, in
 }
 
 template <class Cfg, int C>
-__global__ void __launch_bounds__((Cfg::N / C) * Cfg::T, 1) cluster_forward_kernel(const ResidentParams p) {
+__global__ void __launch_bounds__((Cfg::N / C) * Cfg::T, ((Cfg::N / C) * Cfg::T <= 256 ? 2 : 1)) cluster_forward_kernel(const ResidentParams p) {
     using SM = ClusterSmem<Cfg, C>;
     constexpr int E = Cfg::E, N = Cfg::N;
     extern __shared__ __align__(16) float2 smem_cl[];
@@ -331,7 +331,8 @@ __device__ __forceinline__ void cluster_adjoint_step(const ResidentParams& p, in
             const float2 psi = __ldg(sp + q * NT);
             v[q] = cmulc1p(v[q], tau[q]);              // G = G_u conj(t)
             const float2 w = cmulc(psi, v[q]);         // psi conj(G)
-            gp[m.g(q)] = make_float2(-kdz * w.y, -kdz * w.x);
+            if (p.accumulate) red_add_f32x2_res(gp + m.g(q), -kdz * w.y, -kdz * w.x);
+            else gp[m.g(q)] = make_float2(-kdz * w.y, -kdz * w.x);
         }
         if (s > 0) cluster_conv<Cfg, C, COL>(v, m, buf, s_tw, h);
     }
@@ -339,7 +340,7 @@ __device__ __forceinline__ void cluster_adjoint_step(const ResidentParams& p, in
 }
 
 template <class Cfg, int C>
-__global__ void __launch_bounds__((Cfg::N / C) * Cfg::T, 1) cluster_adjoint_kernel(const ResidentParams p) {
+__global__ void __launch_bounds__((Cfg::N / C) * Cfg::T, ((Cfg::N / C) * Cfg::T <= 256 ? 2 : 1)) cluster_adjoint_kernel(const ResidentParams p) {
     using SM = ClusterSmem<Cfg, C>;
     constexpr int E = Cfg::E, N = Cfg::N;
     extern __shared__ __align__(16) float2 smem_cl[];

@@ -22,6 +22,11 @@
 
 namespace bdof {
 
+// fire-and-forget vector reduction at L2: *p += (a, b)
+__device__ __forceinline__ void red_add_f32x2_res(float2* p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
 struct ResidentParams {
     const float2* in;          // forward: probe [n][n] (shared by the batch); adjoint: G [batch][n][n]
     float2* out;               // forward: field after the object [batch][n][n]; adjoint: G at the entrance plane (nullable)
@@ -40,6 +45,7 @@ struct ResidentParams {
     int n_slice, batch;
     int propagate_last;        // TF semantics: the last slice propagates too
     int store;                 // forward: write the slab
+    int accumulate;            // adjoint: ADD the gradient to `grad` (bdof_plan_set_grad_accumulate: red.global.add.v2.f32 at L2)
     float k_dz;
 };
 
@@ -316,7 +322,8 @@ __device__ __forceinline__ void resident_adjoint_step(const ResidentParams& p, i
         for (int q = 0; q < E; ++q) {
             v[q] = cmulc1p(v[q], tau[q]);              // G = G_u conj(t)
             const float2 w = cmulc(psi[q], v[q]);      // psi conj(G)
-            gp[m.g(q)] = make_float2(-kdz * w.y, -kdz * w.x);
+            if (p.accumulate) red_add_f32x2_res(gp + m.g(q), -kdz * w.y, -kdz * w.x);
+            else gp[m.g(q)] = make_float2(-kdz * w.y, -kdz * w.x);
         }
         if (s > 0) resident_conv<Cfg, COL>(v, m, X, s_tw, h);
     }

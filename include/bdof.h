@@ -140,7 +140,8 @@ int  bdof_plan_is_resident(const bdof_plan* p);
  * angles before one exchange, reconstruct_fullfield.py:30): while on, bdof_adjoint ADDS its gradient to d_grad_out instead of
  * overwriting it -- vector reductions at L2 (red.global.add.v2.f32) from the row kernels, TMA reduce-stores
  * (cp.reduce.async.bulk.tensor) from the column kernels; one contribution per address and call, so the sum over calls is
- * deterministic.  Sweep-kernel plans only; the transmission stash must then live in another buffer. */
+ * deterministic.  Plans that run the sweep, resident or cluster-resident kernels (not the stepwise / mixed-radix / general-kernel
+ * passes, not window mode); the transmission stash must then live in another buffer. */
 int  bdof_plan_set_grad_accumulate(bdof_plan* p, int on);
 
 /* layout conversion: reference [B,Y,X,Z] float32 planes <-> slice-major interleaved db */

@@ -604,12 +604,14 @@ def test_resident_kernels_match_sweep_kernels_and_oracle(bd, case, in_place_stas
 # cluster-resident kernels (clusterfft.cuh): a 256 x 256 field lives in the registers of a cluster of 8 CTAs, transposed through
 # distributed shared memory between slices.  Same A/B as above; batch 20 exceeds the clusters one GPU can hold at once.
 @pytest.mark.parametrize('case', [((2, 256, 256, 6), False, None), ((1, 256, 256, 7), True, 'inf'), ((20, 256, 256, 3), True, None),
-                                  ((3, 256, 256, 2), False, 1e-4), ((2, 256, 256, 9), True, 1e-4)])
+                                  ((3, 256, 256, 2), False, 1e-4), ((2, 256, 256, 9), True, 1e-4),
+                                  ((3, 128, 128, 6), False, None), ((2, 128, 128, 7), True, 'inf'), ((50, 128, 128, 3), True, 1e-4)])
 @pytest.mark.parametrize('in_place_stash', [False, True])
 def test_cluster_resident_kernels_match_sweep_kernels_and_oracle(bd, case, in_place_stash):
     shape, propagate_last, free = case
     gd, gb = mo.random_phantom(shape, seed=75, delta_scale=4e-4, beta_scale=4e-5)
-    pr, pi = mo.gaussian_probe(shape[1:3], 24., 20., 0.5) if free == 'inf' else mo.gaussian_probe(shape[1:3], 120., 100., 0.5)
+    n = shape[1]
+    pr, pi = mo.gaussian_probe(shape[1:3], n / 10.7, n / 12.8, 0.5) if free == 'inf' else mo.gaussian_probe(shape[1:3], n / 2.13, n / 2.56, 0.5)
     rng = np.random.default_rng(76)
     target = rng.random(shape[:3]) * (8 if free == 'inf' else 1.0) + 0.5
     a = _run_plan_env(shape, gd, gb, pr, pi, target, {'BDOF_RESIDENT': '1'}, propagate_last, free, in_place_stash)
@@ -628,7 +630,9 @@ def test_resident_kind_is_reported(bd):
     p64 = MultislicePlan(64, 64, 2, 4, 5000, 1e-7, store_slices=True)
     p256 = MultislicePlan(256, 256, 2, 4, 5000, 1e-7, store_slices=True)
     p512 = MultislicePlan(512, 512, 1, 4, 5000, 1e-7, store_slices=True)
+    p128 = MultislicePlan(128, 128, 2, 4, 5000, 1e-7, store_slices=True)
     assert p64.is_resident() and not p64.is_cluster_resident()
+    assert p128.is_cluster_resident() and not p128.is_resident()
     assert p256.is_cluster_resident() and not p256.is_resident()            # window mode is a feature of the one-CTA kernels
     assert not p512.is_resident() and not p512.is_cluster_resident()
     with pytest.raises(Exception):
@@ -684,7 +688,8 @@ def test_unbatched_multislice_propagate_matches_oracle(bd, case):
     assert t.is_cuda and rel_l2(t.cpu().numpy(), ref) < 1e-5
 
 
-@pytest.mark.parametrize('shape', [(2, 64, 128, 5), (1, 256, 512, 4), (1, 1024, 2048, 3), (1, 4096, 1024, 2), (3, 128, 128, 3)])
+@pytest.mark.parametrize('shape', [(2, 64, 128, 5), (1, 256, 512, 4), (1, 1024, 2048, 3), (1, 4096, 1024, 2), (3, 128, 128, 3),
+                                   (2, 64, 64, 5), (3, 256, 256, 4)])      # the last three: resident and cluster-resident kernels
 def test_fused_gradient_accumulation_over_a_minibatch(bd, shape):
     # bdof_plan_set_grad_accumulate: the adjoint ADDS its gradient (L2 reductions from the row kernels, TMA reduce-stores from the
     # column kernels) -- the sum over the K fields of a minibatch (reconstruct_fullfield.py:30) without an extra pass
