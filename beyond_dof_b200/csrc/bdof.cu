@@ -2151,9 +2151,8 @@ extern "C" int bdof_rotate_adjoint_csr_batch_range(const float* d_grad_rot_db, l
             const long long strides[3] = {(long long)nx * 8, bstride * 8, slice_stride_px * 8};
             const int box[4] = {2 * ROT_BOX, 1, 1, ROT_BOX};
             BDOF_TRY(make_tensor_map_nd(&tm, base, 4, dims, strides, box));
-            static bool attr_set = false;
             const int ring_bytes = ROT_NBUF * int(ROT_BOX_BYTES);
-            if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_rotate_adjoint_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes)); attr_set = true; }
+            CUDA_TRY(cudaFuncSetAttribute(k_rotate_adjoint_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));   // per device: set every time
             int2* origins = nullptr;                     // scratch [angle][tile z][tile x], one buffer per (device, stream)
             BDOF_TRY(rot_scratch(&origins, sizeof(int2) * n * grid.y * grid.z, (cudaStream_t)st));
             k_rot_origins<<<dim3(grid.y, grid.z, n), ROT_THREADS, 0, (cudaStream_t)st>>>(l, nx, nz, z_tile0, origins);

@@ -1,3 +1,4 @@
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O2 -o tools/tma_probe tools/tma_probe.cu -lcuda
 // Developer probe: which 3-D TMA box shapes load correctly on this GPU (float32 tensor [nz][ny][2nx]).
 #include <cuda.h>
 #include <cuda_runtime.h>
