@@ -682,12 +682,18 @@ class PtychographyObjective:
         self.clip = bool(clip)
         self.i_batch = 0
         self._dp = None
+        self._n_buckets = 1
+        self._comm_stream = None
 
-    def enable_data_parallel(self):
-        """The object gradient (67 MB at 256 x 256 x 128) is averaged over the ranks with one NCCL all-reduce after the window
-        accumulation, when no multislice kernel is running (comm.Allreduce + grads / size, ptychography.py:302-306)."""
+    def enable_data_parallel(self, n_buckets=4):
+        """The object gradient (67 MB at 256 x 256 x 128) is averaged over the ranks with NCCL all-reduces (comm.Allreduce +
+        grads / size, ptychography.py:302-306), in `n_buckets` z buckets, each as soon as its part of the window accumulation
+        is done."""
         from . import dist as bdist
         self._dp = bdist
+        self._n_buckets = int(n_buckets)
+        self._comm_stream = torch.cuda.Stream(device=self.obj.device)
+        self._bucket_events = [torch.cuda.Event() for _ in range(max(1, self._n_buckets))]
         return self
 
     def loss_and_grad(self, pos_batch, target_dev):
@@ -709,6 +715,19 @@ class PtychographyObjective:
             loss, g = self.plan.loss_mag(self.exit, target_dev, loss_scale=self.scale)
             self.plan.adjoint(self.patches, g)
         self.grad.zero_()
+        if self._dp is not None and self._n_buckets > 1 and Z >= 2 * self._n_buckets:
+            # window accumulation in z buckets: the all-reduce of a bucket runs on the communication stream under the next one
+            step = (Z + self._n_buckets - 1) // self._n_buckets
+            buckets = []
+            for k, z_lo in enumerate(range(0, Z, step)):
+                z_hi = min(Z, z_lo + step)
+                check(lib.bdof_patch_gather_add(_ptr(self.patches[z_lo:z_hi]), z_hi - z_lo, OY, OX, _ptr(self.origin), self.n, self.py, self.px,
+                                                _ptr(self.grad[z_lo:z_hi]), st))
+                self._bucket_events[k].record()
+                buckets.append((z_lo, z_hi, self._bucket_events[k]))
+            works = self._dp.allreduce_gradient(self.grad, average=True, buckets=buckets, comm_stream=self._comm_stream)
+            self._dp.finish_allreduce(self.grad, works, comm_stream=self._comm_stream)
+            return loss
         check(lib.bdof_patch_gather_add(_ptr(self.patches), Z, OY, OX, _ptr(self.origin), self.n, self.py, self.px, _ptr(self.grad), st))
         if self._dp is not None:
             self._dp.finish_allreduce(self.grad, self._dp.allreduce_gradient(self.grad, average=True))

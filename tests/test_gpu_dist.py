@@ -156,3 +156,34 @@ def _tomography(rank, world):
 def test_data_parallel_tomography_buckets_match_serial_average():
     for e_grad, same in spawn(_tomography, 2):
         assert e_grad < 1e-6 and same
+
+
+def _ptychography(rank, world):
+    # data-parallel PtychographyObjective: the window accumulation runs in z buckets, each all-reduced under the next; against
+    # the mean of the ranks' gradients evaluated in one process
+    from beyond_dof_b200.models import PtychographyObjective
+    Z, OY, OX, n = 8, 96, 96, 4
+    g = torch.Generator().manual_seed(11)
+    obj0 = torch.rand((Z, OY, OX, 2), generator=g) * torch.tensor([3e-4, 3e-5])
+    xs = torch.linspace(-1, 1, 64)
+    probe = torch.exp(-(xs[:, None] ** 2 + xs[None, :] ** 2) / 0.08).to(torch.complex64)
+    pos = [np.array([(32 + 7 * (r * n + i), 40 + 5 * i) for i in range(n)]) for r in range(world)]
+    prj = [1.0 + torch.rand((n, 64, 64), generator=torch.Generator().manual_seed(70 + r)) for r in range(world)]
+    pty = PtychographyObjective(obj0.clone().cuda(), probe, (64, 64), 5000, 1e-7, n_pos_per_step=n, n_pos_total=n * world, step_size=1e-7)
+    pty.enable_data_parallel(n_buckets=4)
+    pty.loss_and_grad(pos[rank], prj[rank].cuda())
+    torch.cuda.synchronize()
+    got = pty.grad.clone()
+    ref = torch.zeros_like(got)
+    for r in range(world):
+        q = PtychographyObjective(obj0.clone().cuda(), probe, (64, 64), 5000, 1e-7, n_pos_per_step=n, n_pos_total=n * world, step_size=1e-7)
+        q.loss_and_grad(pos[r], prj[r].cuda())
+        ref += q.grad
+    ref /= world
+    torch.cuda.synchronize()
+    return float((got - ref).norm() / ref.norm())
+
+
+def test_data_parallel_ptychography_buckets_match_serial_average():
+    for err in spawn(_ptychography, 2):
+        assert err < 1e-6
