@@ -18,6 +18,7 @@ PY
 #   c35      config3 + config5 only
 #   c4       config4 only
 if [ "$MODE" = "c4" ]; then run config4 --workload config4 --steps 10 --warmup 3; exit 0; fi
+if [ "$MODE" = "c3" ]; then run config3 --workload config3 --steps 10 --warmup 3; exit 0; fi
 if [ "$MODE" != "c35" ]; then run default --steps 5 --warmup 3; fi
 if [ "$MODE" = "c35" ]; then
   run config3 --workload config3 --steps 10 --warmup 3
