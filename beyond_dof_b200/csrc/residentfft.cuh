@@ -322,8 +322,14 @@ __device__ __forceinline__ void resident_adjoint_step(const ResidentParams& p, i
         for (int q = 0; q < E; ++q) {
             v[q] = cmulc1p(v[q], tau[q]);              // G = G_u conj(t)
             const float2 w = cmulc(psi[q], v[q]);      // psi conj(G)
-            if (p.accumulate) red_add_f32x2_res(gp + m.g(q), -kdz * w.y, -kdz * w.x);
-            else gp[m.g(q)] = make_float2(-kdz * w.y, -kdz * w.x);
+            tau[q] = make_float2(-kdz * w.y, -kdz * w.x);
+        }
+        if (p.accumulate) {                            // the branch outside the loops: no asm volatile among the arithmetic
+#pragma unroll
+            for (int q = 0; q < E; ++q) red_add_f32x2_res(gp + m.g(q), tau[q].x, tau[q].y);
+        } else {
+#pragma unroll
+            for (int q = 0; q < E; ++q) gp[m.g(q)] = tau[q];
         }
         if (s > 0) resident_conv<Cfg, COL>(v, m, X, s_tw, h);
     }
