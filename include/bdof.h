@@ -116,10 +116,10 @@ int  bdof_loss_mag(bdof_plan* p, const float* d_exit, const float* d_target_mag,
 int  bdof_adjoint(bdof_plan* p, float* d_db_inout, const float* d_grad_exit, float* d_grad_out,
                   float* d_grad_probe);
 
-/* Transmission stash (optional, sweep kernels only).  d_stash [n_slice][batch][ny][nx] complex64, caller-owned, or NULL to
- * switch off: bdof_forward (plans with BDOF_STORE_SLICES) then leaves t_i = exp(i k delta_i - k beta_i) of every slice there and
- * the next bdof_adjoint lands t_i instead of (delta, beta) and skips recomputing it (the exponentials are ~12 % of an
- * adjoint kernel).  Intended use: pass the buffer the adjoint writes the gradient to -- d_grad_out, or d_db_inout itself for
+/* Transmission stash (optional; plans that run the sweep, resident or cluster-resident kernels).  d_stash
+ * [n_slice][batch][ny][nx] complex64, caller-owned, or NULL to switch off: bdof_forward (plans with BDOF_STORE_SLICES) then leaves
+ * tau_i = exp(i k delta_i - k beta_i) - 1 of every slice there and the next bdof_adjoint lands it instead of (delta, beta) and
+ * skips recomputing it (the exponentials are ~12 % of an adjoint kernel).  Intended use: pass the buffer the adjoint writes the gradient to -- d_grad_out, or d_db_inout itself for
  * the in-place adjoint (db then holds t between forward and adjoint; not with BDOF_Z_BROADCAST) -- so that it costs no
  * memory: every tile of t is read just before the gradient of the same tile replaces it. */
 int  bdof_plan_set_t_stash(bdof_plan* p, float* d_stash);
