@@ -23,7 +23,7 @@ SYMBOLS = [
     'bdof_plan_set_bucket_events', 'bdof_set_sm_reserve', 'bdof_rotate_gather', 'bdof_rotate_scatter_add', 'bdof_rotate_adjoint_csr', 'bdof_rotate_adjoint_csr_batch', 'bdof_rotate_adjoint_csr_batch_range', 'bdof_adam_step',
     'bdof_finite_support', 'bdof_plan_set_t_stash', 'bdof_rotate_bilinear', 'bdof_rotate_bilinear_adjoint',
     'bdof_dp_create', 'bdof_dp_destroy', 'bdof_dp_handle_bytes', 'bdof_dp_export', 'bdof_dp_connect', 'bdof_dp_grad_ptr',
-    'bdof_dp_bucket', 'bdof_dp_gather', 'bdof_dp_finish', 'bdof_plan_last_times', 'bdof_pack_db_rows', 'bdof_unpack_db_rows', 'bdof_plan_set_stream', 'bdof_debug_fft_gain', 'bdof_field_multiply', 'bdof_patch_gather_add', 'bdof_plan_set_windows', 'bdof_plan_is_resident', 'bdof_cnn_forward_store', 'bdof_cnn_adjoint', 'bdof_free_prop_adjoint',
+    'bdof_dp_bucket', 'bdof_dp_gather', 'bdof_dp_finish', 'bdof_plan_last_times', 'bdof_pack_db_rows', 'bdof_unpack_db_rows', 'bdof_plan_set_stream', 'bdof_debug_fft_gain', 'bdof_debug_rot_split', 'bdof_field_multiply', 'bdof_patch_gather_add', 'bdof_plan_set_windows', 'bdof_plan_is_resident', 'bdof_cnn_forward_store', 'bdof_cnn_adjoint', 'bdof_free_prop_adjoint',
     'bdof_tiles_create', 'bdof_tiles_destroy', 'bdof_tiles_handle_bytes', 'bdof_tiles_export', 'bdof_tiles_connect',
     'bdof_tiles_block_ptr', 'bdof_tiles_cut', 'bdof_tiles_paste', 'bdof_tiles_halo_exchange', 'bdof_slice_step_seq', 'bdof_plan_set_grad_accumulate', 'bdof_regularizers', 'bdof_slice_step_windows',
 ]
@@ -113,6 +113,7 @@ def _load():
     lib.bdof_plan_last_times.argtypes = [vp, vp, vp]
     lib.bdof_plan_set_stream.argtypes = [vp, vp]
     lib.bdof_debug_fft_gain.argtypes = [i32, vp]
+    lib.bdof_debug_rot_split.argtypes = [i32, i32, vp, vp]
     lib.bdof_field_multiply.argtypes = [vp, vp, vp, i32, i64, vp]
     lib.bdof_plan_set_windows.argtypes = [vp, i32, i32, vp]
     lib.bdof_plan_is_resident.argtypes = [vp]

@@ -1958,9 +1958,16 @@ static RotDiv rot_div_make(int nx) {
     d.mul = unsigned(((1ULL << (31 + d.sh)) + (unsigned long long)nx - 1) / (unsigned long long)nx);
     return d;
 }
-__device__ __forceinline__ void rot_split(const RotDiv& dv, int d, int* z, int* x) {
+__host__ __device__ __forceinline__ void rot_split(const RotDiv& dv, int d, int* z, int* x) {
     const int q = int(((unsigned long long)(unsigned)d * dv.mul) >> (31 + dv.sh));
     *z = q; *x = d - q * dv.nx;
+}
+// the same arithmetic on the host, for the CPU tests (d = z * nx + x of a list entry -> z, x)
+extern "C" int bdof_debug_rot_split(int nx, int d, int* z, int* x) {
+    if (nx < 1 || d < 0 || !z || !x) return bdof_fail(BDOF_E_BADARG, "bad argument");
+    const RotDiv dv = rot_div_make(nx);
+    rot_split(dv, d, z, x);
+    return 0;
 }
 // serial tail of one cell (work list overflow: not a rotation table); rare, kept out of line
 __device__ __noinline__ float2 rot_serial_tail(const float2* __restrict__ base, const int* __restrict__ dst, int beg, int n, long long slice_stride, int y, int nx) {

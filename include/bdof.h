@@ -321,6 +321,9 @@ int  bdof_set_sm_reserve(int n_sms);
  * constants) from the exact DFT -- that the multiplier tables are divided by.  gain_out: n complex128 (re, im).  All ones for
  * lengths the model does not cover (mixed radix, 4096, 8192). */
 int  bdof_debug_fft_gain(int n, double* gain_out);
+/* Host evaluation of the multiply-shift division the back-rotation kernel uses to split a reader-list entry d = z*nx + x
+ * (0 <= d < 2^31), for the CPU tests. */
+int  bdof_debug_rot_split(int nx, int d, int* z, int* x);
 
 /* Developer hook: device buffer that instrumented builds (-DBDOF_PHASE_TIMING) fill with clock64()
  * phase stamps; ignored by the production build. */

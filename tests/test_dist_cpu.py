@@ -190,3 +190,18 @@ def test_axis_tiles_cover_the_block_with_the_requested_halo():
     # restricted choice of lengths (bench --tile-lengths)
     L, tiles, _ = axis_tiles(8192, 8, (2048,))
     assert L == 2048 and len(tiles) == 5
+
+
+def test_back_rotation_list_entries_split_exactly():
+    """The back-rotation kernel splits a reader-list entry d = z * nx + x with a multiply and a shift (bdof.cu: RotDiv); the same
+    arithmetic evaluated on the host must be the exact division for every d a table can hold."""
+    import ctypes
+    from beyond_dof_b200 import capi
+    z, x = ctypes.c_int(), ctypes.c_int()
+    rng = np.random.default_rng(5)
+    for nx in (1, 2, 3, 18, 64, 72, 97, 256, 1000, 2048, 4097, 46340):
+        top = min(nx * nx, 2 ** 31 - 1)
+        ds = np.unique(np.concatenate([np.arange(0, min(top, 3000)), rng.integers(0, top, 3000), [top - 1, max(top - nx, 0), 2 ** 31 - 1]]))
+        for d in ds:
+            assert capi.lib.bdof_debug_rot_split(nx, int(d), ctypes.byref(z), ctypes.byref(x)) == 0
+            assert (z.value, x.value) == (int(d) // nx, int(d) % nx), (nx, int(d))
