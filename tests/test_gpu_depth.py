@@ -50,10 +50,19 @@ def intensity_err(psi, ref):
     return rel_l2(np.abs(psi) ** 2, np.abs(ref) ** 2)
 
 
-def _gpu_forward_and_operator_adjoint(gd, gb, pr, pi, G, free, propagate_last, energy=5000, psize=1e-7):
+def _gpu_forward_and_operator_adjoint(gd, gb, pr, pi, G, free, propagate_last, energy=5000, psize=1e-7, env=None):
     from beyond_dof_b200.plan import MultislicePlan
     B, Y, X, Z = gd.shape
-    plan = MultislicePlan(Y, X, B, Z, energy, psize, free_prop_cm=free, propagate_last=propagate_last, store_slices=True)
+    old = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})                                     # kernel selection is read when the plan is created
+    try:
+        plan = MultislicePlan(Y, X, B, Z, energy, psize, free_prop_cm=free, propagate_last=propagate_last, store_slices=True)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
     db = plan.pack(torch.as_tensor(gd).cuda(), torch.as_tensor(gb).cuda())
     probe = torch.as_tensor((np.asarray(pr) + 1j * np.asarray(pi)).astype(np.complex64)).cuda()
     plan.set_t_stash(db)
@@ -82,6 +91,12 @@ def test_depth_256_forward_and_operator_gradient(bd, n_slice, propagate_last):
            grad_beta=e_b, tol_intensity=TOL_INTENSITY, tol_grad=TOL_GRAD)
     assert e_i < TOL_INTENSITY
     assert e_d < TOL_GRAD and e_b < TOL_GRAD
+    if n_slice == 256:
+        # 256 x 256 fields run the cluster-resident kernels by default; the per-slice sweep kernels at the same depth
+        psi, g_d, g_b = _gpu_forward_and_operator_adjoint(gd, gb, one, zero, G, None, propagate_last, env={'BDOF_RESIDENT': '0'})
+        e_i, e_d, e_b = intensity_err(psi, psio), rel_l2(g_d, gdo), rel_l2(g_b, gbo)
+        record('depth_256x256x%d_%s_per_slice_kernels' % (n_slice, 'tf' if propagate_last else 'numpy'), intensity=e_i, grad_delta=e_d, grad_beta=e_b)
+        assert e_i < TOL_INTENSITY and e_d < TOL_GRAD and e_b < TOL_GRAD
 
 
 TOL_INTENSITY_STRONG = 1e-4
